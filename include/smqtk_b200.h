@@ -1,0 +1,146 @@
+/*
+ * smqtk_b200.h -- C ABI of the B200-native LSH nearest-neighbour hot path.
+ *
+ * One shared library (libsmqtk_b200.so), plain C linkage, raw device pointers
+ * and sizes only (no torch / C++ types).  This is the boundary a maintainer of
+ * SMQTK-Indexing binds (ctypes stub in INTEGRATION.md) to replace the pure
+ * Python/numpy arithmetic of:
+ *
+ *   stage 1  ItqFunctor.get_hash             smqtk_indexing/impls/lsh_functor/itq.py:389-408
+ *            + bit_vector_to_int_large       smqtk_indexing/utils/bits.py:4-20
+ *   stage 2  LinearHashIndex._nn             smqtk_indexing/impls/hash_index/linear.py:206-244
+ *            + hamming_distance              smqtk_indexing/utils/metrics.py:140-155
+ *   stage 3  LSHNearestNeighborIndex._nn re-rank   smqtk_indexing/impls/nn_index/lsh.py:507-519
+ *            + euclidean/cosine/hik          smqtk_indexing/utils/metrics.py:49-137
+ *   build    LinearHashIndex._build_index / LSH _build_index (unique codes, code->rows)
+ *                                            linear.py:148-165, lsh.py:316-329
+ *   train    ItqFunctor.fit GEMMs            itq.py:338-383, 239-289
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *     the library never synchronises, allocates or frees caller-visible memory:
+ *     scratch space is passed in, its size comes from the *_workspace_bytes query;
+ *   - return value 0 = success, otherwise an SB_ERR_* code; sb_last_error()
+ *     gives a thread-local message;
+ *   - no global mutable state: calls on different streams may run concurrently.
+ *
+ * Hash-code layout (device): uint32[rows][W], each row is the INTEGER VALUE of
+ * the reference's big-endian bit vector (bits.py:17-20) written in W 32-bit
+ * words, word 0 most significant; W in {1,2,4,8,16,32}.  Bit j of a b-bit code
+ * is integer bit p=b-1-j: word W-1-p/32, bit p%32.
+ *
+ * Packed result key: uint64 = (hamming_distance << 40) | global_row, so that
+ * unsigned comparison is the canonical order "ascending distance, ties by row";
+ * SB_KEY_EMPTY marks "no neighbour" (fewer than k rows).
+ */
+#ifndef SMQTK_B200_H
+#define SMQTK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SB_API __attribute__((visibility("default")))
+#else
+#define SB_API
+#endif
+
+#define SB_OK 0
+#define SB_ERR_INVALID_ARGUMENT 1
+#define SB_ERR_CUDA 2
+#define SB_ERR_WORKSPACE 3
+#define SB_ERR_UNSUPPORTED 4
+
+#define SB_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define SB_KEY_ROW_BITS 40
+
+/* norm_kind for sb_itq_hash (ItqFunctor(normalize=...), itq.py:172-191) */
+#define SB_NORM_NONE 0  /* normalize=None                         */
+#define SB_NORM_LP 1    /* numpy.linalg.norm(v, ord=p), p finite >0 */
+#define SB_NORM_INF 2   /* ord=inf: max |v_i|                     */
+#define SB_NORM_L0 3    /* ord=0: count of non-zeros              */
+
+/* metric for sb_rerank / sb_pairwise_distance (lsh.py:236-255) */
+#define SB_METRIC_EUCLIDEAN 0 /* metrics.py:73-86   sqrt(sum (a-b)^2)                 */
+#define SB_METRIC_COSINE 1    /* metrics.py:120-137 2*acos(clip(cos_sim,-1,1))/pi      */
+#define SB_METRIC_HIK 2       /* metrics.py:49-70   1 - sum min(a,b)                   */
+
+SB_API int sb_version(void);
+SB_API const char* sb_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench bookkeeping). */
+SB_API uint64_t sb_launch_count(void);
+
+/* ---- stage 1: ITQ hashing ------------------------------------------------
+ * codes[r] = pack( ((X[r] / norm(X[r])) - mean) . R >= 0 )        itq.py:404-408
+ * X: f32[n][ldx] (first D columns used); mean: f32[D] or NULL (= zeros);
+ * R: f32[D][b] row-major; codes_out: u32[n][W] (W >= ceil(b/32), layout above);
+ * z_out: optional f32[n][b] projections (tests / epsilon masks), may be NULL.
+ * variant: 0 = auto, 1 = FP32 FFMA kernel (any shape), 2 = tcgen05 3xTF32 GEMM
+ *          (needs D % 32 == 0, b % 32 == 0, b <= 256, ldx % 4 == 0).
+ */
+SB_API int sb_itq_hash(const float* X, int64_t n, int32_t D, int64_t ldx,
+                const float* mean, const float* R, int32_t b,
+                int32_t norm_kind, float norm_p,
+                uint32_t* codes_out, int32_t W, float* z_out,
+                int32_t variant, void* stream);
+
+/* ---- stage 2: Hamming scan + top-k -----------------------------------------
+ * For each of Q query codes: the k rows of db with the smallest
+ * popcount(q xor row), canonical order (distance, idx_base + row).
+ * db: u32[U][W]; q: u32[Q][W]; keys_out: u64[Q][k] ascending, padded with
+ * SB_KEY_EMPTY when U < k.   linear.py:232-240 (heapq.nsmallest over the set).
+ */
+SB_API size_t sb_hamming_scan_workspace_bytes(int64_t U, int32_t W, int32_t Q, int32_t k);
+SB_API int sb_hamming_scan(const uint32_t* db, int64_t U, int32_t W,
+                    const uint32_t* q, int32_t Q, int32_t k, int64_t idx_base,
+                    uint64_t* keys_out, void* workspace, size_t workspace_bytes,
+                    void* stream);
+/* Same, choosing the popcount formulation: variant 0 = default (carry-save adder
+ * tree + 5 POPC per 256 bits), 1 = plain POPC per word.  Results are identical. */
+SB_API int sb_hamming_scan_variant(const uint32_t* db, int64_t U, int32_t W,
+                            const uint32_t* q, int32_t Q, int32_t k, int64_t idx_base,
+                            uint64_t* keys_out, void* workspace, size_t workspace_bytes,
+                            int32_t variant, void* stream);
+
+/* Merge `parts` sorted key lists per query (keys_in: u64[parts][Q][k], e.g. the
+ * all-gathered per-GPU results) into the global top-k and decode:
+ * out_dist i32[Q][k] (-1 = empty), out_idx i64[Q][k] (-1 = empty); either of
+ * out_keys (u64[Q][k]) / out_dist / out_idx may be NULL. */
+SB_API int sb_topk_merge(const uint64_t* keys_in, int32_t parts, int32_t Q, int32_t k,
+                  uint64_t* out_keys, int32_t* out_dist, int64_t* out_idx, void* stream);
+
+/* Convenience: sb_hamming_scan + decode in one call (single device). */
+SB_API int sb_hamming_topk(const uint32_t* db, int64_t U, int32_t W,
+                    const uint32_t* q, int32_t Q, int32_t k, int64_t idx_base,
+                    int32_t* out_dist, int64_t* out_idx,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- stage 3: candidate re-rank ----------------------------------------------
+ * out[j] = metric(q[query_of(j)], db[cand_idx[j]]) for j in [cand_off[0], cand_off[Q]),
+ * candidates of query i are j in [cand_off[i], cand_off[i+1]).  Element math is
+ * FP32 FFMA with error-free (hi, lo) accumulation, the per-candidate scalar tail
+ * (sqrt / divide / acos) is FP64; lsh.py:507-511 + metrics.py.
+ * db: f32[N][ldd]; q: f32[Q][ldq]; cand_idx: i64[M]; cand_off: i64[Q+1]; out: f64[M]
+ * (NaN for an out-of-range row, and for cosine against a zero vector as in the reference).
+ */
+SB_API int sb_rerank(const float* db, int64_t N, int32_t D, int64_t ldd,
+              const float* q, int32_t Q, int64_t ldq,
+              const int64_t* cand_idx, const int64_t* cand_off, int64_t M,
+              int32_t metric, double* out, void* stream);
+
+/* Per query: order its candidates by (distance, candidate position) and keep
+ * the first n (lsh.py:513-519: stable sort by distance, slice).  out_pos i64[Q][n]
+ * = position j into cand_idx (-1 = fewer than n candidates), out_dist f64[Q][n]
+ * (NaN distances order last). */
+SB_API int sb_rerank_select(const double* dist, const int64_t* cand_off, int32_t Q, int32_t n,
+                     int64_t* out_pos, double* out_dist, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMQTK_B200_H */

@@ -1,0 +1,87 @@
+"""
+ctypes binding of ``libsmqtk_b200.so`` (declared in ``include/smqtk_b200.h``).
+
+The library is the ONLY implementation of the compute path: there is no numpy
+or torch fallback.  If it is missing (not built) every entry point raises.
+"""
+import ctypes
+import os
+import re
+import threading
+from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from typing import Dict, List
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libsmqtk_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "smqtk_b200.h")
+
+SB_OK = 0
+KEY_EMPTY = 0xFFFFFFFFFFFFFFFF
+KEY_ROW_BITS = 40
+NORM_NONE, NORM_LP, NORM_INF, NORM_L0 = 0, 1, 2, 3
+METRIC_EUCLIDEAN, METRIC_COSINE, METRIC_HIK = 0, 1, 2
+METRICS = {"euclidean": METRIC_EUCLIDEAN, "cosine": METRIC_COSINE, "hik": METRIC_HIK}
+
+_P = c_void_p
+# name -> (restype, argtypes); mirrors include/smqtk_b200.h one to one
+SIGNATURES: Dict[str, tuple] = {
+    "sb_version": (c_int32, []),
+    "sb_last_error": (c_char_p, []),
+    "sb_launch_count": (c_uint64, []),
+    "sb_itq_hash": (c_int32, [_P, c_int64, c_int32, c_int64, _P, _P, c_int32, c_int32, c_float,
+                              _P, c_int32, _P, c_int32, _P]),
+    "sb_hamming_scan_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
+    "sb_hamming_scan": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P, c_size_t, _P]),
+    "sb_hamming_scan_variant": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P,
+                                          c_size_t, c_int32, _P]),
+    "sb_topk_merge": (c_int32, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
+    "sb_hamming_topk": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P, _P, c_size_t, _P]),
+    "sb_rerank": (c_int32, [_P, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64, c_int32, _P, _P]),
+    "sb_rerank_select": (c_int32, [_P, _P, c_int32, c_int32, _P, _P, _P]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class LibraryMissingError(RuntimeError):
+    pass
+
+
+def declared_symbols() -> List[str]:
+    """Function names declared (``SB_API``) in include/smqtk_b200.h."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    return re.findall(r"^SB_API\s+[\w\s\*]+?\b(sb_\w+)\s*\(", text, flags=re.M)
+
+
+def load() -> ctypes.CDLL:
+    """Load the C-ABI library (once).  Raises ``LibraryMissingError`` when it has
+    not been built -- by design there is no fallback implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise LibraryMissingError(
+                    "%s not found: build it with `python -m smqtk_indexing_b200.build` "
+                    "(or __graft_entry__.build()).  The CUDA library is the only "
+                    "implementation of the LSH hot path; there is no CPU fallback." % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != SB_OK:
+        msg = load().sb_last_error()
+        raise RuntimeError("libsmqtk_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def launch_count() -> int:
+    return int(load().sb_launch_count())

@@ -1,0 +1,201 @@
+"""
+Device plumbing: torch owns HBM allocations and streams, the kernels are called
+through the C ABI with raw pointers (``tensor.data_ptr()``) on torch's current
+stream.  Nothing here computes; every function is a thin typed wrapper around
+one ``sb_*`` entry point.
+
+Storage conventions (torch has no unsigned 32/64-bit arithmetic types worth
+using, so raw bits are carried in signed tensors of the same width):
+  codes  uint32[rows, W]  -> torch.int32
+  keys   uint64[...]      -> torch.int64
+"""
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("smqtk_indexing_b200 needs a CUDA device (B200): the LSH "
+                           "hot path has no CPU implementation.")
+    _lib.load()
+
+
+def device(dev: Optional[object] = None) -> torch.device:
+    require_cuda()
+    if dev is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(dev)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor" % name)
+    if t.dtype != dtype:
+        raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def codes_to_device(words: np.ndarray, dev: Optional[object] = None) -> torch.Tensor:
+    """uint32[n, W] numpy -> int32 CUDA tensor (bit pattern preserved)."""
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    return torch.from_numpy(w.view(np.int32)).to(device(dev), non_blocking=False)
+
+
+def codes_to_host(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy().view(np.uint32)
+
+
+# --------------------------------------------------------------------- stage 1
+def norm_spec(normalize) -> Tuple[int, float]:
+    """Map ``ItqFunctor(normalize=...)`` (an ``ord`` for numpy.linalg.norm over a
+    1-D vector, reference itq.py:184) onto the kernel's (kind, p)."""
+    if normalize is None:
+        return _lib.NORM_NONE, 0.0
+    if isinstance(normalize, str):
+        raise ValueError("normalize=%r is not a valid vector norm order" % (normalize,))
+    o = float(normalize)
+    if o == float("inf"):
+        return _lib.NORM_INF, 0.0
+    if o == 0.0:
+        return _lib.NORM_L0, 0.0
+    if o > 0.0:
+        return _lib.NORM_LP, o
+    raise ValueError("normalize=%r: only ord in {None, 0, p > 0, inf} is supported on the device" % (normalize,))
+
+
+def itq_hash(X: torch.Tensor, mean: Optional[torch.Tensor], R: torch.Tensor, normalize=None,
+             words: Optional[int] = None, want_z: bool = False, variant: int = 0):
+    """codes = pack(((X / norm(X)) - mean) @ R >= 0).  X f32[n, D] (row stride may
+    exceed D), mean f32[D] | None, R f32[D, b].  Returns codes int32[n, W]
+    (and z f32[n, b] when ``want_z``)."""
+    require_cuda()
+    if X.dim() != 2 or X.dtype != torch.float32 or not X.is_cuda or X.stride(1) != 1:
+        raise ValueError("X must be a 2-D float32 CUDA tensor with unit column stride")
+    _chk(R, torch.float32, "R")
+    n, D = X.shape
+    if R.shape[0] != D:
+        raise ValueError("R has %d rows, X has %d columns" % (R.shape[0], D))
+    b = R.shape[1]
+    if mean is not None:
+        _chk(mean, torch.float32, "mean")
+        if mean.numel() != D:
+            raise ValueError("mean has %d entries, X has %d columns" % (mean.numel(), D))
+    from .utils.bits import words_for_bits
+    W = words or words_for_bits(b)
+    kind, p = norm_spec(normalize)
+    codes = torch.empty((n, W), dtype=torch.int32, device=X.device)
+    z = torch.empty((n, b), dtype=torch.float32, device=X.device) if want_z else None
+    ldx = X.stride(0) if n > 1 else max(D, X.stride(0))
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.load().sb_itq_hash(_ptr(X), n, D, ldx, _ptr(mean), _ptr(R), b, kind, p,
+                                           _ptr(codes), W, _ptr(z), variant, _stream()))
+    return (codes, z) if want_z else codes
+
+
+# --------------------------------------------------------------------- stage 2
+def hamming_scan_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0,
+                      variant: int = 0) -> torch.Tensor:
+    """Local top-k as packed keys int64[Q, k] (uint64 bit pattern, ascending,
+    SB_KEY_EMPTY padded)."""
+    require_cuda()
+    _chk(db, torch.int32, "db")
+    _chk(q, torch.int32, "q")
+    U, W = db.shape
+    Q = q.shape[0]
+    if q.shape[1] != W:
+        raise ValueError("query codes have %d words, table has %d" % (q.shape[1], W))
+    lib = _lib.load()
+    ws_bytes = lib.sb_hamming_scan_workspace_bytes(U, W, Q, k)
+    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=db.device)
+    keys = torch.empty((Q, k), dtype=torch.int64, device=db.device)
+    with torch.cuda.device(db.device):
+        _lib.check(lib.sb_hamming_scan_variant(_ptr(db), U, W, _ptr(q), Q, k, idx_base, _ptr(keys),
+                                               _ptr(ws), ws_bytes, variant, _stream()))
+    return keys
+
+
+def topk_merge(keys: torch.Tensor, want_keys: bool = False):
+    """keys int64[parts, Q, k] -> (dist int32[Q, k], idx int64[Q, k]) in canonical
+    (distance, row) order; -1 marks empty slots."""
+    require_cuda()
+    _chk(keys, torch.int64, "keys")
+    parts, Q, k = keys.shape
+    dist = torch.empty((Q, k), dtype=torch.int32, device=keys.device)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=keys.device)
+    okeys = torch.empty((Q, k), dtype=torch.int64, device=keys.device) if want_keys else None
+    with torch.cuda.device(keys.device):
+        _lib.check(_lib.load().sb_topk_merge(_ptr(keys), parts, Q, k, _ptr(okeys), _ptr(dist), _ptr(idx), _stream()))
+    return (dist, idx, okeys) if want_keys else (dist, idx)
+
+
+def hamming_topk(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0):
+    """(dist int32[Q, k], idx int64[Q, k]); -1 where the table has fewer than k rows."""
+    require_cuda()
+    _chk(db, torch.int32, "db")
+    _chk(q, torch.int32, "q")
+    U, W = db.shape
+    Q = q.shape[0]
+    if q.shape[1] != W:
+        raise ValueError("query codes have %d words, table has %d" % (q.shape[1], W))
+    lib = _lib.load()
+    ws_bytes = lib.sb_hamming_scan_workspace_bytes(U, W, Q, k)
+    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=db.device)
+    dist = torch.empty((Q, k), dtype=torch.int32, device=db.device)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=db.device)
+    with torch.cuda.device(db.device):
+        _lib.check(lib.sb_hamming_topk(_ptr(db), U, W, _ptr(q), Q, k, idx_base, _ptr(dist), _ptr(idx),
+                                       _ptr(ws), ws_bytes, _stream()))
+    return dist, idx
+
+
+# --------------------------------------------------------------------- stage 3
+def rerank(db: torch.Tensor, q: torch.Tensor, cand_idx: torch.Tensor, cand_off: torch.Tensor,
+           metric: str) -> torch.Tensor:
+    """float64[M] distances of each candidate row to its query."""
+    require_cuda()
+    if db.dtype != torch.float32 or q.dtype != torch.float32 or db.stride(1) != 1 or q.stride(1) != 1:
+        raise ValueError("db and q must be float32 with unit column stride")
+    _chk(cand_idx, torch.int64, "cand_idx")
+    _chk(cand_off, torch.int64, "cand_off")
+    if metric not in _lib.METRICS:
+        raise ValueError("Invalid distance method label. Must be one of "
+                         "['euclidean' | 'cosine' | 'hik']")
+    N, D = db.shape
+    Q = q.shape[0]
+    if q.shape[1] != D or cand_off.numel() != Q + 1:
+        raise ValueError("shape mismatch between db, q and cand_off")
+    M = cand_idx.numel()
+    out = torch.empty((M,), dtype=torch.float64, device=db.device)
+    with torch.cuda.device(db.device):
+        _lib.check(_lib.load().sb_rerank(_ptr(db), N, D, max(db.stride(0), D), _ptr(q), Q, max(q.stride(0), D),
+                                         _ptr(cand_idx), _ptr(cand_off), M, _lib.METRICS[metric], _ptr(out),
+                                         _stream()))
+    return out
+
+
+def rerank_select(dist: torch.Tensor, cand_off: torch.Tensor, n: int):
+    """Per query the first ``n`` candidates by (distance, position):
+    (pos int64[Q, n] into the candidate list or -1, dist float64[Q, n])."""
+    require_cuda()
+    _chk(dist, torch.float64, "dist")
+    _chk(cand_off, torch.int64, "cand_off")
+    Q = cand_off.numel() - 1
+    pos = torch.empty((Q, n), dtype=torch.int64, device=dist.device)
+    od = torch.empty((Q, n), dtype=torch.float64, device=dist.device)
+    with torch.cuda.device(dist.device):
+        _lib.check(_lib.load().sb_rerank_select(_ptr(dist), _ptr(cand_off), Q, n, _ptr(pos), _ptr(od), _stream()))
+    return pos, od

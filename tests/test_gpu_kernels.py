@@ -1,0 +1,233 @@
+"""
+GPU parity tests at the C-ABI level: every kernel against the oracle on the same
+seeded inputs.  Integer results must be bit exact; floating-point tolerances
+are written next to each assertion.
+"""
+import numpy as np
+import pytest
+
+import golden_inputs as gi
+import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from smqtk_indexing_b200 import device as D
+    D.require_cuda()
+    return D
+
+
+def _rand_table(rng, U, b, W, dup=False):
+    bits = rng.rand(U, b) > 0.5
+    if dup:                       # heavy ties: few distinct bits set
+        bits = rng.rand(U, b) > 0.9
+    return O.pack_codes(bits, W)
+
+
+def _run_topk(dev, table, q, k, idx_base=0):
+    dt = dev.codes_to_device(table)
+    dq = dev.codes_to_device(q)
+    d, i = dev.hamming_topk(dt, dq, k, idx_base)
+    torch.cuda.synchronize()
+    return d.cpu().numpy(), i.cpu().numpy()
+
+
+@pytest.mark.parametrize("b,W", [(1, 1), (5, 1), (32, 1), (33, 2), (64, 2), (100, 4), (128, 4),
+                                 (256, 8), (500, 16), (1024, 32)])
+def test_hamming_topk_bit_exact(dev, b, W):
+    rng = np.random.RandomState(b)
+    for U, Q, k in [(1, 1, 1), (7, 3, 10), (1000, 5, 10), (4097, 33, 10), (20000, 130, 7), (3000, 2, 100)]:
+        table = _rand_table(rng, U, b, W)
+        q = O.pack_codes(rng.rand(Q, b) > 0.5, W)
+        q[0] = table[U // 2]
+        od, oi = O.hamming_topk(table, q, k, idx_base=5)
+        d, i = _run_topk(dev, table, q, k, idx_base=5)
+        kk = od.shape[1]
+        assert np.array_equal(d[:, :kk], od), (b, U, Q, k)
+        assert np.array_equal(i[:, :kk], oi), (b, U, Q, k)
+        assert (d[:, kk:] == -1).all() and (i[:, kk:] == -1).all()
+
+
+def test_hamming_topk_heavy_ties(dev):
+    rng = np.random.RandomState(7)
+    for b, W in [(8, 1), (32, 1), (256, 8)]:
+        table = _rand_table(rng, 50000, b, W, dup=True)
+        q = O.pack_codes(rng.rand(16, b) > 0.9, W)
+        od, oi = O.hamming_topk(table, q, 25)
+        d, i = _run_topk(dev, table, q, 25)
+        assert np.array_equal(d, od) and np.array_equal(i, oi)
+
+
+def test_hamming_variants_agree(dev):
+    rng = np.random.RandomState(11)
+    table = _rand_table(rng, 100000, 256, 8)
+    q = O.pack_codes(rng.rand(64, 256) > 0.5, 8)
+    dt, dq = dev.codes_to_device(table), dev.codes_to_device(q)
+    k0 = dev.hamming_scan_keys(dt, dq, 10, variant=0)
+    k1 = dev.hamming_scan_keys(dt, dq, 10, variant=1)
+    assert torch.equal(k0, k1)
+    od, oi = O.hamming_topk(table, q, 10)
+    d, i = dev.topk_merge(k0.unsqueeze(0).contiguous())
+    assert np.array_equal(d.cpu().numpy(), od) and np.array_equal(i.cpu().numpy(), oi)
+
+
+def test_hamming_large_k(dev):
+    rng = np.random.RandomState(13)
+    table = _rand_table(rng, 5000, 64, 2)
+    q = O.pack_codes(rng.rand(3, 64) > 0.5, 2)
+    for k in (33, 500, 1000, 2048):
+        od, oi = O.hamming_topk(table, q, k)
+        d, i = _run_topk(dev, table, q, k)
+        assert np.array_equal(d, od) and np.array_equal(i, oi), k
+
+
+def test_sharded_scan_merge_equals_single(dev):
+    """row-sharded table, per-shard top-k keys, sb_topk_merge == single scan."""
+    rng = np.random.RandomState(17)
+    table = _rand_table(rng, 30011, 256, 8)
+    q = O.pack_codes(rng.rand(40, 256) > 0.5, 8)
+    dq = dev.codes_to_device(q)
+    cuts = np.linspace(0, len(table), 9).astype(int)
+    keys = [dev.hamming_scan_keys(dev.codes_to_device(table[a:b]), dq, 10, idx_base=int(a))
+            for a, b in zip(cuts[:-1], cuts[1:])]
+    d, i = dev.topk_merge(torch.stack(keys).contiguous())
+    od, oi = O.hamming_topk(table, q, 10)
+    assert np.array_equal(d.cpu().numpy(), od) and np.array_equal(i.cpu().numpy(), oi)
+
+
+def test_hamming_empty_table(dev):
+    q = dev.codes_to_device(np.zeros((2, 8), np.uint32))
+    db = torch.empty((0, 8), dtype=torch.int32, device=q.device)
+    d, i = dev.hamming_topk(db, q, 3)
+    assert (d.cpu().numpy() == -1).all() and (i.cpu().numpy() == -1).all()
+
+
+# --------------------------------------------------------------------- ITQ hash
+#: |z_gpu - z_ref| <= HASH_EPS * |x - m|_2 * |r_j|_2 (fp32 inputs + fp32 FFMA
+#: accumulation, D <= 4096); bits may only differ where |z_ref| is below that.
+HASH_EPS = 1e-5
+
+
+def _check_hash(dev, x, mean, rot, normalize, variant=1):
+    b = rot.shape[1]
+    W = (b + 31) // 32
+    W = [w for w in (1, 2, 4, 8, 16, 32) if w >= W][0]
+    X = torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda()
+    m = torch.from_numpy(np.ascontiguousarray(mean, np.float32)).cuda()
+    R = torch.from_numpy(np.ascontiguousarray(rot, np.float32)).cuda()
+    codes, z = dev.itq_hash(X, m, R, normalize=normalize, want_z=True, variant=variant)
+    torch.cuda.synchronize()
+    z_ref = O.itq_project(np.asarray(x, np.float64), mean, rot, normalize)
+    a = O.norm_vector(np.asarray(x, np.float64), normalize) - mean
+    scale = np.linalg.norm(a, axis=1)[:, None] * np.linalg.norm(rot, axis=0)[None, :]
+    err = np.abs(z.cpu().numpy() - z_ref)
+    assert (err <= HASH_EPS * scale + 1e-30).all(), float((err / (scale + 1e-30)).max())
+    bits_ref = z_ref >= 0
+    got = dev.codes_to_host(codes)
+    want = O.pack_codes(bits_ref, W)
+    if not np.array_equal(got, want):
+        from smqtk_indexing_b200.utils.bits import unpack_bits
+        diff = unpack_bits(got, b) != bits_ref
+        assert (np.abs(z_ref[diff]) <= HASH_EPS * scale[diff]).all()
+    return np.mean(unpack_ok(got, want))
+
+
+def unpack_ok(a, b):
+    return a == b
+
+
+def test_itq_hash_golden_models(dev, golden):
+    g = golden("itq")
+    for ci, (N, D, b, it, norm, seed, isz) in enumerate(g["cases"]):
+        x, q = gi.itq_inputs(ci)
+        normalize = None if norm < 0 else int(norm)
+        for data in (x, q):
+            _check_hash(dev, data, np.real(g["c%d_mean" % ci]), np.real(g["c%d_rot" % ci]), normalize)
+
+
+def test_itq_hash_known_answer(dev):
+    # reference tests/impls/lsh_functor/test_itq.py:304-336 incl. z == 0 -> True
+    mean = np.zeros(2)
+    rot = np.array([[1 / np.sqrt(2)], [1 / np.sqrt(2)]])
+    pts = np.array([[1, 1], [-1, -1], [-1, 1], [-1.001, 1], [-1, 1.001], [1, -1], [1, -1.001], [1.001, -1]], float)
+    X = torch.from_numpy(pts.astype(np.float32)).cuda()
+    codes = dev.itq_hash(X, torch.zeros(2, device="cuda"), torch.from_numpy(rot.astype(np.float32)).cuda())
+    assert list(dev.codes_to_host(codes)[:, 0]) == [1, 0, 1, 0, 1, 1, 0, 1]
+
+
+@pytest.mark.parametrize("n,D,b", [(1, 2, 1), (3, 5, 5), (70, 33, 31), (129, 64, 33), (1000, 512, 256),
+                                   (257, 100, 100), (65, 4096, 64), (100, 48, 1000)])
+def test_itq_hash_shapes(dev, n, D, b):
+    rng = np.random.RandomState(n + D + b)
+    x = rng.rand(n, D).astype(np.float32)
+    mean = x.mean(0).astype(np.float64)
+    rot = np.linalg.qr(rng.randn(max(D, b), max(D, b)))[0][:D, :b]
+    for normalize in (None, 2, 1, np.inf):
+        _check_hash(dev, x, mean, rot, normalize)
+
+
+# --------------------------------------------------------------------- re-rank
+#: distances: |d_gpu - d_ref| <= 1e-5 * |d_ref| + atol (inputs are fp32-representable).
+#: cosine's atol is the float64 reference's own conditioning floor: acos near 1
+#: turns the last-ulp error of the similarity (1e-16) into sqrt(2e-16)*2/pi ~ 1e-8
+#: (the reference itself returns 1.6e-8, not 0, for identical vectors).
+RERANK_RTOL = 1e-5
+RERANK_ATOL = {"euclidean": 1e-12, "hik": 1e-12, "cosine": 5e-8}
+
+
+def test_rerank_metrics_golden(dev, golden):
+    g = golden("metrics")
+    for ci, D in enumerate(g["cases"]):
+        q, c, qh, ch = gi.metrics_inputs(int(D))
+        for metric, qq, cc in (("euclidean", q, c), ("cosine", q, c), ("hik", qh, ch)):
+            q32 = qq.astype(np.float32)
+            c32 = cc.astype(np.float32)
+            db = torch.from_numpy(c32).cuda()
+            tq = torch.from_numpy(q32[None, :]).cuda()
+            idx = torch.arange(len(c32), device="cuda")
+            off = torch.tensor([0, len(c32)], device="cuda")
+            out = dev.rerank(db, tq, idx, off, metric).cpu().numpy()
+            with np.errstate(all="ignore"):
+                ref = np.atleast_1d(O.DISTANCE_FUNCTIONS[metric](q32.astype(np.float64), c32.astype(np.float64)))
+            assert np.array_equal(np.isnan(out), np.isnan(ref))
+            ok = ~np.isnan(ref)
+            np.testing.assert_allclose(out[ok], ref[ok], rtol=RERANK_RTOL, atol=RERANK_ATOL[metric], err_msg=metric)
+
+
+def test_rerank_known_answers(dev):
+    # reference tests/impls/nn_index/test_lsh.py:102-136
+    def one(metric, a, b):
+        db = torch.tensor([b], dtype=torch.float32, device="cuda")
+        q = torch.tensor([a], dtype=torch.float32, device="cuda")
+        return float(dev.rerank(db, q, torch.zeros(1, dtype=torch.int64, device="cuda"),
+                                torch.tensor([0, 1], device="cuda"), metric)[0])
+    assert one("euclidean", [0, 0], [0, 1]) == 1.0
+    assert abs(one("cosine", [1, 0], [0, 1]) - 1.0) < 1e-12
+    assert abs(one("cosine", [1, 0], [1, 1]) - 0.5) < 1e-7
+    assert one("hik", [0, 0], [0, 1]) == 1.0
+    assert one("hik", [1, 0], [0, 1]) == 1.0
+    assert one("hik", [1, 1], [0, 1]) == 0.0
+    assert one("euclidean", [3, 4], [3, 4]) == 0.0
+    assert one("cosine", [3, 4], [3, 4]) == 0.0
+
+
+def test_rerank_select_order(dev):
+    rng = np.random.RandomState(3)
+    sizes = [0, 1, 5, 300, 5000, 17]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    d = rng.rand(off[-1])
+    d[off[3]:off[3] + 50] = 0.25            # ties -> position order
+    d[off[4] + 7] = np.nan                  # NaN sorts last
+    pos, od = dev.rerank_select(torch.from_numpy(d).cuda(), torch.from_numpy(off).cuda(), 20)
+    pos, od = pos.cpu().numpy(), od.cpu().numpy()
+    for qi, m in enumerate(sizes):
+        seg = d[off[qi]:off[qi + 1]]
+        key = np.where(np.isnan(seg), np.inf, seg)
+        o = np.lexsort((np.arange(m), key))[:20]
+        assert list(pos[qi][:len(o)]) == list(o + off[qi])
+        assert (pos[qi][len(o):] == -1).all()
+        np.testing.assert_array_equal(od[qi][:len(o)], seg[o])
