@@ -140,6 +140,35 @@ SB_API int sb_rerank(const float* db, int64_t N, int32_t D, int64_t ldd,
 SB_API int sb_rerank_select(const double* dist, const int64_t* cand_off, int32_t Q, int32_t n,
                      int64_t* out_pos, double* out_dist, void* stream);
 
+/* ---- training: N-scaled contractions of ItqFunctor.fit (itq.py:338-383, 239-289) ----
+ * FP64 accumulation, deterministic two-stage row reductions.  Matrix operands are
+ * (pointer, kind, row pitch, columns, div, mean[, bits]):
+ *   kind 0 = f32, kind 1 = f64: element value = x / div[r] - mean[c] (div, mean optional: NULL)
+ *   kind 2 = packed sign bits u32[n][pitch] of `bits`-bit codes: value = bit ? +1 : -1
+ */
+/* div_out[r] = norm(X[r]) (1 where the norm is 0); itq.py:184-189 */
+SB_API int sb_fit_row_div(const void* X, int32_t x_kind, int64_t n, int32_t D, int64_t ldx,
+                          int32_t norm_kind, double norm_p, double* div_out, void* stream);
+/* scratch size for sb_fit_col_mean / sb_fit_gram with output Ma x Mb over n rows */
+SB_API size_t sb_fit_workspace_bytes(int64_t n, int32_t Ma, int32_t Mb);
+/* mean_out[c] = mean_r (X[r][c] / div[r]); itq.py:343 */
+SB_API int sb_fit_col_mean(const void* X, int32_t x_kind, int64_t n, int32_t D, int64_t ldx,
+                           const double* div, double* mean_out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+/* out f64[Ma][Mb] = scale * sum_r opA(r)^T opB(r): covariance (itq.py:351) and UX^T V (itq.py:274) */
+SB_API int sb_fit_gram(const void* A, int32_t a_kind, int64_t lda, int32_t Ma,
+                       const double* a_div, const double* a_mean, int32_t a_bits,
+                       const void* B, int32_t b_kind, int64_t ldb, int32_t Mb,
+                       const double* b_div, const double* b_mean, int32_t b_bits,
+                       int64_t n, double scale, double* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* opA[n][K] . Bm f64[K][M] -> out_f64 f64[n][M] and/or sign bits out_codes u32[n][Wc]
+ * (projection itq.py:378; Z = V.R with the sign step itq.py:270-272, 285-287) */
+SB_API int sb_fit_project(const void* A, int32_t a_kind, int64_t lda, int32_t K,
+                          const double* a_div, const double* a_mean,
+                          const double* Bm, int32_t M, int64_t n,
+                          double* out_f64, uint32_t* out_codes, int32_t Wc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

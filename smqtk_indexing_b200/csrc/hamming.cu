@@ -342,6 +342,50 @@ hamming_scan_kernel(const uint32_t* __restrict__ db, long long U, const uint32_t
   }
 }
 
+// ---- threshold seeding ----------------------------------------------------------
+// One warp per query scans a small prefix sample of the table and publishes the
+// sample's k-th smallest distance as the query's initial threshold.  The sample
+// is part of the table, so its k-th distance bounds the table's k-th distance.
+constexpr int SEED_WARPS = 4;
+
+template <int W>
+__global__ void __launch_bounds__(SEED_WARPS * 32)
+tau_seed_kernel(const uint32_t* __restrict__ db, int S, const uint32_t* __restrict__ qcodes, int Q, int k,
+                int* __restrict__ tau_g) {
+  constexpr int MAXD = 32 * W;
+  extern __shared__ int seed_hist[];  // [SEED_WARPS][MAXD + 1]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * SEED_WARPS + warp;
+  int* h = seed_hist + warp * (MAXD + 1);
+  for (int i = lane; i <= MAXD; i += 32) h[i] = 0;
+  __syncwarp();
+  if (q >= Q) return;
+  uint32_t qw[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) qw[i] = qcodes[(size_t)q * W + i];
+  for (int r = lane; r < S; r += 32) {
+    uint32_t c[W];
+    load_words<W>(c, db + (size_t)r * W);
+    atomicAdd(&h[hamming<W, 1>(c, qw)], 1);
+  }
+  __syncwarp();
+  // k-th smallest distance of the sample
+  int acc = 0, found = -1;
+  for (int base = 0; base <= MAXD && found < 0; base += 32) {
+    const int bin = base + lane;
+    int cum = (bin <= MAXD) ? h[bin] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(sb::FULL_MASK, cum, o);
+      if (lane >= o) cum += t;
+    }
+    const unsigned ok = __ballot_sync(sb::FULL_MASK, acc + cum >= k);
+    if (ok) found = base + __ffs(ok) - 1;
+    acc += __shfl_sync(sb::FULL_MASK, cum, 31);
+  }
+  if (lane == 0 && found >= 0) tau_g[q] = found;
+}
+
 // ---- merge: P sorted k-lists per query -> top-k ------------------------------
 // Exact selection by distance histogram: distances are small integers (<= 32*W
 // <= 1024), so one pass counts keys per distance, a scan finds the distance d*
@@ -489,18 +533,21 @@ ScanPlan make_plan(long long U, int W, int Q, int k) {
   // than one CTA pass (WARPS warp tiles) per chunk
   const long long pass = (long long)WARPS * tile_codes(W);
   const long long max_chunks = max(1ll, (U + pass - 1) / pass);
-  // one wave for short scans (warm-up of the k-lists is per CTA), up to 4 for long ones
-  const double pairs_per_slot = (double)U * (double)Q / ((double)sms * 2);
-  const int waves = pairs_per_slot > 4.0e8 ? 4 : (pairs_per_slot > 1.0e8 ? 2 : 1);
-  long long want = (long long)sms * 2 * waves;
-  long long chunks = (want + p.nqt - 1) / p.nqt;
-  if (p.nqt * chunks < (long long)sms * 2) chunks = ((long long)sms * 2 + p.nqt - 1) / p.nqt;
-  chunks = max(1ll, min(chunks, max_chunks));
+  // Grid = nqt * chunks CTAs.  Keep it at (just under) a whole number of waves of
+  // the 2-CTA/SM residency so no SM idles behind a partial last wave; thresholds
+  // are global, so extra waves cost almost nothing and shorten the tail.
+  const long long slots = (long long)sms * 2;
+  const double total_pairs = (double)U * (double)Q;
+  int waves = (int)(total_pairs / ((double)slots * 2.0e6));
+  waves = max(1, min(8, waves));
+  long long chunks = (slots * waves) / p.nqt;          // floor: never spill into an extra wave
+  if (chunks < 1) chunks = 1;
+  chunks = min(chunks, max_chunks);
   // round the chunk length up to whole CTA passes so only the last chunk has a tail
   long long cpc = (U + chunks - 1) / chunks;
   cpc = ((cpc + pass - 1) / pass) * pass;
   if (cpc < pass) cpc = pass;
-  chunks = max(1ll, (U + cpc - 1) / cpc);
+  chunks = max(1ll, (U + cpc - 1) / cpc);              // rounding up cpc can only lower this
   p.chunks = (int)chunks;
   p.codes_per_chunk = cpc;
   p.P = p.chunks;
@@ -514,6 +561,17 @@ ScanPlan make_plan(long long U, int W, int Q, int k) {
 template <int W>
 int launch_scan(const ScanPlan& p, int mode, const uint32_t* db, long long U, const uint32_t* q, int Q, int k,
                 long long idx_base, uint64_t* part, int* tau_g, int* hist_g, cudaStream_t st) {
+  {
+    // sample = table prefix, large enough to hold k rows several times over
+    const long long S = min(U, max(2048ll, 4ll * k));
+    if (S >= k) {
+      const size_t sh = (size_t)SEED_WARPS * (32 * W + 1) * sizeof(int);
+      tau_seed_kernel<W><<<(Q + SEED_WARPS - 1) / SEED_WARPS, SEED_WARPS * 32, sh, st>>>(db, (int)S, q, Q, k, tau_g);
+      sb::count_launch();
+      int rc = sb::check_launch("tau_seed_kernel");
+      if (rc) return rc;
+    }
+  }
   dim3 grid(p.chunks, p.nqt);
   const int q_tma_ok = ((reinterpret_cast<uintptr_t>(q) & 15u) == 0 && ((size_t)p.QT * W * 4) % 16 == 0) ? 1 : 0;
   if (mode == 0) {

@@ -1,0 +1,445 @@
+"""
+B200 ``LSHNearestNeighborIndex``: locality-sensitive-hashing nearest-neighbour
+index whose arithmetic (hashing, Hamming scan / top-k, candidate re-rank) runs on
+the GPU through ``libsmqtk_b200``.
+
+Drop-in for ``smqtk_indexing.impls.nn_index.lsh.LSHNearestNeighborIndex``
+(reference: smqtk_indexing/impls/nn_index/lsh.py:39-519): same constructor and
+config keys, same collaborators (``DescriptorSet``, ``KeyValueStore``,
+``HashIndex``, ``LshFunctor``), same state after build / update / remove, same
+exceptions.  Two query entry points:
+
+* ``nn(d, n)`` -- the reference API, one ``DescriptorElement`` per call; walks the
+  collaborator containers exactly like lsh.py:470-519 and uses the GPU for the
+  three arithmetic stages.
+* ``nn_batch(X, n)`` -- the throughput API: a ``[Q, D]`` matrix of queries against
+  the device-resident mirror of the index (descriptor matrix, packed codes, unique
+  code table, code -> rows CSR); nothing leaves HBM between stages.
+
+Ordering contract (the reference leaves ties to set-iteration order): near codes
+come in (Hamming distance, code value) order, candidates in (code rank, row)
+order, results in (distance, candidate position) order.
+"""
+import logging
+import threading
+from typing import Any, Callable, Dict, Hashable, Iterable, List, Optional, Sequence, Set, Tuple, Type, TypeVar
+
+import numpy
+
+from smqtk_core.configuration import from_config_dict, make_default_config, to_config_dict
+from smqtk_core.dict import merge_dict
+from smqtk_dataprovider import KeyValueStore
+from smqtk_dataprovider.exceptions import ReadOnlyError
+from smqtk_descriptors import DescriptorElement, DescriptorSet
+
+from smqtk_indexing_b200.interfaces import HashIndex, LshFunctor, NearestNeighborsIndex
+from smqtk_indexing_b200.impls.hash_index.linear import LinearHashIndex
+from smqtk_indexing_b200.utils import bits as bitutil
+from smqtk_indexing_b200.utils import metrics
+
+LOG = logging.getLogger(__name__)
+T_LSH = TypeVar("T_LSH", bound="LSHNearestNeighborIndex")
+
+
+class _DeviceMirror:
+    """Device-resident copy of the index used by ``nn_batch``:
+    descriptor matrix, per-row codes, unique code table and code->rows CSR."""
+
+    def __init__(self) -> None:
+        self.x = None                       # float32[N, D]
+        self.codes = None                   # int32[N, W]
+        self.uuids: List[Hashable] = []     # row -> uuid
+        self.row_of: Dict[Hashable, int] = {}
+        self.table = None                   # int32[U, W] sorted unique
+        self.csr_off = None                 # int64[U + 1]
+        self.csr_rows = None                # int64[N]
+        self.row_code = None                # int64[N] row -> table row
+
+    def clear(self) -> None:
+        self.__init__()
+
+    def count(self) -> int:
+        return len(self.uuids)
+
+    def reindex(self) -> None:
+        """Recompute table / CSR from ``codes``."""
+        from smqtk_indexing_b200 import codes as codeops
+        if self.codes is None or self.codes.shape[0] == 0:
+            self.table = self.csr_off = self.csr_rows = self.row_code = None
+            return
+        self.table, self.row_code = codeops.sort_unique(self.codes, return_inverse=True)
+        self.csr_off, self.csr_rows = codeops.group_rows(self.row_code, self.table.shape[0])
+
+
+class LSHNearestNeighborIndex(NearestNeighborsIndex):
+    """LSH nearest-neighbour index (hash functor + unique-code Hamming index +
+    descriptor re-rank)."""
+
+    @classmethod
+    def is_usable(cls) -> bool:
+        return True
+
+    @classmethod
+    def get_default_config(cls) -> Dict[str, Any]:
+        default = super(LSHNearestNeighborIndex, cls).get_default_config()
+        default['lsh_functor'] = make_default_config(LshFunctor.get_impls())
+        default['descriptor_set'] = make_default_config(DescriptorSet.get_impls())
+        default['hash2uuids_kvstore'] = make_default_config(KeyValueStore.get_impls())
+        default['hash_index'] = make_default_config(HashIndex.get_impls())
+        return default
+
+    @classmethod
+    def from_config(cls: Type[T_LSH], config_dict: Dict, merge_default: bool = True) -> T_LSH:
+        if merge_default:
+            cfg = cls.get_default_config()
+            merge_dict(cfg, config_dict)
+        else:
+            cfg = config_dict
+        cfg['lsh_functor'] = from_config_dict(cfg['lsh_functor'], LshFunctor.get_impls())
+        cfg['descriptor_set'] = from_config_dict(cfg['descriptor_set'], DescriptorSet.get_impls())
+        cfg['hash2uuids_kvstore'] = from_config_dict(cfg['hash2uuids_kvstore'], KeyValueStore.get_impls())
+        if cfg['hash_index'] and cfg['hash_index']['type']:
+            cfg['hash_index'] = from_config_dict(cfg['hash_index'], HashIndex.get_impls())
+        else:
+            cfg['hash_index'] = None
+        if 'hash_index_comment' in cfg:
+            del cfg['hash_index_comment']
+        return super(LSHNearestNeighborIndex, cls).from_config(cfg, False)
+
+    def __init__(
+        self,
+        lsh_functor: LshFunctor,
+        descriptor_set: DescriptorSet,
+        hash2uuids_kvstore: KeyValueStore,
+        hash_index: Optional[HashIndex] = None,
+        distance_method: str = 'cosine',
+        read_only: bool = False
+    ):
+        super(LSHNearestNeighborIndex, self).__init__()
+        self.lsh_functor = lsh_functor
+        self.descriptor_set = descriptor_set
+        self.hash_index = hash_index
+        self.hash2uuids_kvstore = hash2uuids_kvstore
+        self.distance_method = distance_method
+        self.read_only = read_only
+        # In-process lock (the reference uses a multiprocessing.RLock because its
+        # containers may live in other processes; device state cannot).
+        self._model_lock = threading.RLock()
+        self._distance_function = self._get_dist_func(self.distance_method)
+        self._mirror = _DeviceMirror()
+
+    @staticmethod
+    def _get_dist_func(distance_method: str) -> Callable[[numpy.ndarray, numpy.ndarray], float]:
+        """Distance function for a method label (reference lsh.py:236-255).
+
+        :raises ValueError: unknown label."""
+        if distance_method == "euclidean":
+            return metrics.euclidean_distance
+        elif distance_method == "cosine":
+            return metrics.cosine_distance
+        elif distance_method == 'hik':
+            return metrics.histogram_intersection_distance_fast
+        else:
+            raise ValueError("Invalid distance method label. Must be one of "
+                             "['euclidean' | 'cosine' | 'hik']")
+
+    def get_config(self) -> Dict[str, Any]:
+        hi_conf = None
+        if self.hash_index is not None:
+            hi_conf = to_config_dict(self.hash_index)
+        return {
+            "lsh_functor": to_config_dict(self.lsh_functor),
+            "descriptor_set": to_config_dict(self.descriptor_set),
+            "hash_index": hi_conf,
+            "hash2uuids_kvstore": to_config_dict(self.hash2uuids_kvstore),
+            "distance_method": self.distance_method,
+            "read_only": self.read_only,
+        }
+
+    def count(self) -> int:
+        """Number of descriptors reachable through the hash -> uuids map
+        (reference lsh.py:271-281: sums the KVS value sets)."""
+        with self._model_lock:
+            c = 0
+            for set_v in self.hash2uuids_kvstore.values():
+                c += len(set_v)
+            return c
+
+    # ------------------------------------------------------------------ hashing helpers
+    def _hash_matrix(self, x: numpy.ndarray):
+        """[n, D] host matrix -> (packed codes on device int32[n, W], bit length b)."""
+        f = self.lsh_functor
+        if hasattr(f, "get_hash_packed"):
+            codes = f.get_hash_packed(x)
+            rot = numpy.asarray(f.rotation)
+            b = rot.reshape(rot.shape[0], -1).shape[1]
+            return codes, b
+        # foreign functor: one host call per vector, pack + upload
+        from smqtk_indexing_b200 import device
+        hv = [numpy.asarray(f.get_hash(v)).astype(bool).ravel() for v in x]
+        b = max(max(len(h) for h in hv), 1)          # lengths may differ (value semantics, like the reference's ints)
+        ints = [bitutil.bit_vector_to_int_large(h) for h in hv]
+        return device.codes_to_device(bitutil.ints_to_words(ints, bitutil.words_for_bits(b))), b
+
+    @staticmethod
+    def _vectors(descriptors: Sequence[DescriptorElement]) -> numpy.ndarray:
+        return numpy.asarray([d.vector() for d in descriptors])
+
+    def _push_hashes(self, op: str, codes_host: numpy.ndarray, bits: int, table=None) -> None:
+        """Forward hash codes to the configured ``hash_index`` (reference
+        lsh.py:326-329, 381-383, 444-447)."""
+        hi = self.hash_index
+        if hi is None:
+            return
+        if isinstance(hi, LinearHashIndex) and op == "build" and table is not None:
+            hi.set_code_table(table)
+            hi.save_cache()
+            return
+        vectors = bitutil.unpack_bits(codes_host, bits)
+        getattr(hi, {"build": "build_index", "update": "update_index", "remove": "remove_from_index"}[op])(vectors)
+
+    # ------------------------------------------------------------------ build / update / remove
+    def _build_index(self, descriptors: Iterable[DescriptorElement]) -> None:
+        from smqtk_indexing_b200 import device
+        with self._model_lock:
+            if self.read_only:
+                raise ReadOnlyError("Cannot modify container attributes due to being in read-only mode.")
+            LOG.debug("Clearing and adding new descriptor elements")
+            self.descriptor_set.clear()
+            self.descriptor_set.add_many_descriptors(descriptors)
+
+            LOG.debug("Generating hash codes")
+            self.hash2uuids_kvstore.clear()
+            elems = list(self.descriptor_set)
+            self._mirror.clear()
+            if not elems:
+                return
+            x = self._vectors(elems)
+            codes, bits = self._hash_matrix(x)
+            m = self._mirror
+            import torch
+            m.x = torch.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32)).to(codes.device)
+            m.codes = codes
+            m.uuids = [d.uuid() for d in elems]
+            m.row_of = {u: i for i, u in enumerate(m.uuids)}
+            m.reindex()
+
+            # hash -> uuids map, one add_many (reference lsh.py:313-324)
+            table_ints = bitutil.words_to_ints(device.codes_to_host(m.table))
+            row_code = m.row_code.cpu().numpy()
+            kvstore_update: Dict[Hashable, Set[Hashable]] = {h: set() for h in table_ints}
+            for r, c in enumerate(row_code):
+                kvstore_update[table_ints[c]].add(m.uuids[r])
+            self.hash2uuids_kvstore.add_many(kvstore_update)
+
+            self._push_hashes("build", device.codes_to_host(m.table), bits, table=m.table)
+
+    def _update_index(self, descriptors: Iterable[DescriptorElement]) -> None:
+        from smqtk_indexing_b200 import device
+        import torch
+        with self._model_lock:
+            if self.read_only:
+                raise ReadOnlyError("Cannot modify container attributes due to being in read-only mode.")
+            new = list(descriptors)
+            LOG.debug("Updating descriptor index.")
+            self.descriptor_set.add_many_descriptors(new)
+
+            LOG.debug("Generating hash codes for new descriptors")
+            x = self._vectors(new)
+            codes, bits = self._hash_matrix(x)
+            codes_host = device.codes_to_host(codes)
+            ints = bitutil.words_to_ints(codes_host)
+            kvstore_update: Dict[Hashable, Set[Hashable]] = {}
+            for d, h_int in zip(new, ints):
+                if h_int not in kvstore_update:
+                    kvstore_update[h_int] = self.hash2uuids_kvstore.get(h_int, set())
+                kvstore_update[h_int] |= {d.uuid()}
+            LOG.debug("Updating kv-store with new hash codes")
+            self.hash2uuids_kvstore.add_many(kvstore_update)
+
+            # device mirror: append new uuids, overwrite re-added ones
+            m = self._mirror
+            xt = torch.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32)).to(codes.device)
+            if m.x is None:
+                m.x, m.codes = xt[:0], codes[:0]
+            if m.codes.shape[1] != codes.shape[1]:
+                from smqtk_indexing_b200 import codes as codeops
+                w = max(m.codes.shape[1], codes.shape[1])
+                m.codes, codes = codeops.widen(m.codes, w), codeops.widen(codes, w)
+            last = {d.uuid(): i for i, d in enumerate(new)}   # a uuid given twice keeps its last vector
+            app_rows = []
+            for u, i in last.items():
+                r = m.row_of.get(u)
+                if r is None:
+                    m.row_of[u] = len(m.uuids)
+                    m.uuids.append(u)
+                    app_rows.append(i)
+                else:
+                    m.x[r] = xt[i]
+                    m.codes[r] = codes[i]
+            if app_rows:
+                sel = torch.tensor(app_rows, dtype=torch.int64, device=codes.device)
+                m.x = torch.cat([m.x, xt[sel]], dim=0)
+                m.codes = torch.cat([m.codes, codes[sel]], dim=0)
+            m.reindex()
+
+            if self.hash_index is not None:
+                LOG.debug("Updating hash index structure.")
+                self._push_hashes("update", codes_host, bits)
+
+    def _remove_from_index(self, uids: Iterable[Hashable]) -> None:
+        from smqtk_indexing_b200 import device
+        import torch
+        with self._model_lock:
+            if self.read_only:
+                raise ReadOnlyError("Cannot modify container attributes due to being in read-only mode.")
+            uids = list(uids)
+            # KeyError here (unknown uid) leaves everything untouched (lsh.py:407-416)
+            descrs = list(self.descriptor_set.get_many_descriptors(uids))
+            codes, bits = self._hash_matrix(self._vectors(descrs))
+            codes_host = device.codes_to_host(codes)
+            h_ints = bitutil.words_to_ints(codes_host)
+
+            removal_rows: List[int] = []
+            kvs_update: Dict[Hashable, Set[Hashable]] = {}
+            kvs_remove = set()
+            for i, (uid, h_int) in enumerate(zip(uids, h_ints)):
+                if h_int not in kvs_update:
+                    kvs_update[h_int] = self.hash2uuids_kvstore.get(h_int, set())
+                kvs_update[h_int] -= {uid}
+                if not kvs_update[h_int]:
+                    del kvs_update[h_int]
+                    kvs_remove.add(h_int)
+                    removal_rows.append(i)
+            self.hash2uuids_kvstore.add_many(kvs_update)
+            self.hash2uuids_kvstore.remove_many(kvs_remove)
+
+            if self.hash_index and removal_rows:
+                self._push_hashes("remove", codes_host[removal_rows], bits)
+
+            self.descriptor_set.remove_many_descriptors(uids)
+
+            m = self._mirror
+            gone = {m.row_of[u] for u in uids if u in m.row_of}
+            if gone:
+                keep = [r for r in range(len(m.uuids)) if r not in gone]
+                sel = torch.tensor(keep, dtype=torch.int64, device=m.codes.device)
+                m.x, m.codes = m.x[sel], m.codes[sel]
+                m.uuids = [m.uuids[r] for r in keep]
+                m.row_of = {u: i for i, u in enumerate(m.uuids)}
+                m.reindex()
+
+    # ------------------------------------------------------------------ queries
+    def _nn(self, d: DescriptorElement, n: int = 1) -> Tuple[Tuple[DescriptorElement, ...], Tuple[float, ...]]:
+        """Reference-shaped query (lsh.py:452-519)."""
+        from smqtk_indexing_b200 import device
+        import torch
+        LOG.debug("generating hash for descriptor")
+        d_v = d.vector()
+        d_h = self.lsh_functor.get_hash(d_v)
+
+        with self._model_lock:
+            LOG.debug("getting near hashes")
+            hi = self.hash_index
+            if hi is None:
+                # on-the-fly linear index over the KVS keys (lsh.py:481-486)
+                hi = LinearHashIndex()
+                hi.index = self.hash2uuids_kvstore.keys()
+            near_hashes, _ = hi.nn(d_h, n)
+
+            LOG.debug("getting UUIDs of descriptors for nearby hashes")
+            neighbor_uuids: List[Hashable] = []
+            for h_int in map(bitutil.bit_vector_to_int_large, near_hashes):
+                neighbor_uuids.extend(self.hash2uuids_kvstore.get(h_int, set()))
+            LOG.debug("-- matched %d UUIDs", len(neighbor_uuids))
+            neighbors = list(self.descriptor_set.get_many_descriptors(neighbor_uuids))
+
+        # lock released: re-rank (lsh.py:503-519)
+        if not neighbors:
+            return (), ()
+        dev = device.device()
+        cand = torch.from_numpy(numpy.ascontiguousarray(self._vectors(neighbors), dtype=numpy.float32)).to(dev)
+        q = torch.from_numpy(numpy.ascontiguousarray(numpy.asarray(d_v, dtype=numpy.float32))[None, :]).to(dev)
+        m = len(neighbors)
+        idx = torch.arange(m, dtype=torch.int64, device=dev)
+        off = torch.tensor([0, m], dtype=torch.int64, device=dev)
+        dist = device.rerank(cand, q, idx, off, self.distance_method)
+        pos, od = device.rerank_select(dist, off, min(n, m))
+        pos = pos[0].cpu().numpy()
+        od = od[0].cpu().numpy()
+        r_descrs = tuple(neighbors[p] for p in pos if p >= 0)
+        r_dists = tuple(float(v) for v, p in zip(od, pos) if p >= 0)
+        return r_descrs, r_dists
+
+    def nn_batch(self, queries, n: int = 1, return_device: bool = False):
+        """Batched LSH query against the device-resident index.
+
+        :param queries: ``[Q, D]`` float array (host) or float32 CUDA tensor.
+        :param n: neighbours per query (also the number of nearest unique codes
+            whose descriptors form the candidate pool, as in the reference).
+        :return: ``(rows int64[Q, n], dists float64[Q, n])`` -- rows index
+            :meth:`mirror_uuids`; -1 / NaN pad queries with fewer than ``n``
+            candidates.  Device tensors when ``return_device``.
+        :raises ValueError: the index is empty.
+        """
+        import torch
+        from smqtk_indexing_b200 import device
+        with self._model_lock:
+            m = self._mirror
+            if m.table is None:
+                raise ValueError("No index currently set to query from!")
+            dev = m.x.device
+            if isinstance(queries, torch.Tensor):
+                q = queries.to(dev, torch.float32)
+            else:
+                q = torch.from_numpy(numpy.ascontiguousarray(queries, dtype=numpy.float32)).to(dev, non_blocking=True)
+            if q.dim() == 1:
+                q = q.unsqueeze(0)
+            rows, dists = lsh_query_device(self.lsh_functor, m, q, n, self.distance_method)
+        if return_device:
+            return rows, dists
+        return rows.cpu().numpy(), dists.cpu().numpy()
+
+    def mirror_uuids(self) -> List[Hashable]:
+        """row -> uuid for the rows returned by :meth:`nn_batch`."""
+        return self._mirror.uuids
+
+
+def expand_candidates(code_rows, csr_off, csr_rows):
+    """Ragged expansion ``near codes -> descriptor rows`` on the device.
+
+    :param code_rows: int64[Q, n] rows of the unique-code table (-1 = none)
+    :return: (cand_idx int64[M], cand_off int64[Q + 1])
+    """
+    import torch
+    Q, n = code_rows.shape
+    flat = code_rows.reshape(-1)
+    ok = flat >= 0
+    safe = torch.where(ok, flat, torch.zeros_like(flat))
+    start = csr_off[safe]
+    cnt = torch.where(ok, csr_off[safe + 1] - start, torch.zeros_like(start))
+    seg_end = torch.cumsum(cnt, 0)
+    total = int(seg_end[-1].item()) if flat.numel() else 0
+    cand_off = torch.zeros(Q + 1, dtype=torch.int64, device=flat.device)
+    cand_off[1:] = seg_end.reshape(Q, n)[:, -1]
+    if total == 0:
+        return torch.empty(0, dtype=torch.int64, device=flat.device), cand_off
+    seg = torch.repeat_interleave(torch.arange(flat.numel(), device=flat.device), cnt, output_size=total)
+    within = torch.arange(total, device=flat.device) - (seg_end - cnt)[seg]
+    return csr_rows[start[seg] + within], cand_off
+
+
+def lsh_query_device(functor, mirror: _DeviceMirror, q, n: int, distance_method: str):
+    """hash -> Hamming top-n unique codes -> candidate rows -> re-rank -> top-n,
+    entirely on the device (reference lsh.py:470-519 for a batch of queries)."""
+    import torch
+    from smqtk_indexing_b200 import codes as codeops, device
+    q_codes = functor.get_hash_packed(q)
+    table = mirror.table
+    w = max(table.shape[1], q_codes.shape[1])
+    _, code_rows = device.hamming_topk(codeops.widen(table, w), codeops.widen(q_codes, w).contiguous(), n)
+    cand_idx, cand_off = expand_candidates(code_rows, mirror.csr_off, mirror.csr_rows)
+    dist = device.rerank(mirror.x, q, cand_idx, cand_off, distance_method)
+    pos, od = device.rerank_select(dist, cand_off, n)
+    rows = torch.where(pos >= 0, cand_idx[pos.clamp(min=0)] if cand_idx.numel() else pos, pos)
+    return rows, od

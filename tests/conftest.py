@@ -8,6 +8,8 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+import smqtk_indexing_b200  # noqa: E402,F401  (activates the smqtk_* compat shim)
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

@@ -1,0 +1,282 @@
+"""
+CPU-only checks of the host side: C-ABI library presence / exported symbols,
+bit marshalling against the reference's golden vectors, plugin discovery,
+configuration round trips and the exception contract that needs no compute.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from smqtk_core.configuration import configuration_test_helper
+from smqtk_dataprovider.exceptions import ReadOnlyError
+from smqtk_dataprovider.impls.data_element.memory import DataMemoryElement
+from smqtk_dataprovider.impls.key_value_store.memory import MemoryKeyValueStore
+from smqtk_descriptors.impls.descriptor_element.memory import DescriptorMemoryElement
+from smqtk_descriptors.impls.descriptor_set.memory import MemoryDescriptorSet
+
+from smqtk_indexing_b200 import _lib
+from smqtk_indexing_b200.interfaces import HashIndex, LshFunctor, NearestNeighborsIndex
+from smqtk_indexing_b200.impls.hash_index.linear import LinearHashIndex
+from smqtk_indexing_b200.impls.lsh_functor.itq import ItqFunctor
+from smqtk_indexing_b200.impls.nn_index.lsh import LSHNearestNeighborIndex
+from smqtk_indexing_b200.utils import bits as B
+
+
+# ------------------------------------------------------------------ C ABI
+def test_library_loads_and_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 16
+    for name in declared:
+        assert hasattr(raw, name), "missing export %s" % name
+    assert set(declared) == set(_lib.SIGNATURES), "ctypes table out of sync with include/smqtk_b200.h"
+    lib = _lib.load()
+    assert lib.sb_version() >= 100
+    assert lib.sb_launch_count() == 0          # no compute happened
+
+
+def test_workspace_query_needs_no_device():
+    lib = _lib.load()
+    assert lib.sb_hamming_scan_workspace_bytes(10_000_000, 8, 4096, 10) > 0
+    assert lib.sb_hamming_scan_workspace_bytes(10, 3, 1, 1) == 0      # unsupported word count
+
+
+def test_no_silent_cpu_fallback():
+    """Without a CUDA device every compute entry point must raise."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    f = ItqFunctor(bit_length=1)
+    f.mean_vec = np.zeros(2)
+    f.rotation = np.ones((2, 1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        f.get_hash(np.array([1., 2.]))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        LinearHashIndex().build_index([[0, 1, 0]])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        LSHNearestNeighborIndex._get_dist_func("euclidean")(np.zeros(2), np.ones(2))
+
+
+def test_product_does_not_import_the_oracle():
+    import smqtk_indexing_b200
+    root = os.path.dirname(smqtk_indexing_b200.__file__)
+    for dp, _, files in os.walk(root):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dp, fn)).read()
+                assert "np_oracle" not in src and "import oracle" not in src and "from oracle" not in src, fn
+
+
+# ------------------------------------------------------------------ bit marshalling
+def test_bits_against_reference_golden(golden):
+    g = golden("bits")
+    for b, pv, hx in zip(g["lens"], g["vec_packed"], g["ints_hex"]):
+        v = np.unpackbits(pv, count=int(b)).astype(bool)
+        i = int(str(hx), 16)
+        assert B.bit_vector_to_int_large(v) == i
+        assert np.array_equal(B.int_to_bit_vector_large(i, int(b)), v)
+        w = B.pack_bits(v, B.words_for_bits(int(b)))
+        assert B.words_to_ints(w) == [i]
+        assert np.array_equal(B.ints_to_words([i], w.shape[1]), w)
+        assert np.array_equal(B.unpack_bits(w, int(b))[0], v)
+    for hx, bits, ln, pv in zip(g["back_int_hex"], g["back_bits"], g["back_len"], g["back_vec_packed"]):
+        v = B.int_to_bit_vector_large(int(str(hx), 16), int(bits))
+        assert len(v) == ln and np.array_equal(v, np.unpackbits(pv, count=int(ln)).astype(bool))
+
+
+def test_bits_errors_and_widths():
+    with pytest.raises(ValueError):
+        B.int_to_bit_vector_large(8, 3)
+    with pytest.raises(ValueError):
+        B.unpack_bits(np.array([[8]], np.uint32), 3)
+    with pytest.raises(ValueError):
+        B.words_for_bits(0)
+    with pytest.raises(ValueError):
+        B.words_for_bits(B.MAX_BITS + 1)
+    assert [B.words_for_bits(b) for b in (1, 32, 33, 64, 65, 256, 257, 1024)] == [1, 1, 2, 2, 4, 8, 16, 32]
+    w = B.pack_bits(np.array([[1, 0, 1]], bool), 1)
+    assert w[0, 0] == 5
+    assert np.array_equal(B.widen_words(w, 4), [[0, 0, 0, 5]])
+    assert np.array_equal(B.unpack_bits(B.widen_words(w, 4), 3), [[True, False, True]])
+
+
+# ------------------------------------------------------------------ plugins / config
+def test_plugins_are_discoverable():
+    assert LinearHashIndex in HashIndex.get_impls()
+    assert ItqFunctor in LshFunctor.get_impls()
+    assert LSHNearestNeighborIndex in NearestNeighborsIndex.get_impls()
+    assert LinearHashIndex.is_usable() and ItqFunctor.is_usable() and LSHNearestNeighborIndex.is_usable()
+
+
+def test_linear_config():
+    c = LinearHashIndex.get_default_config()
+    assert len(c) == 1 and c['cache_element']['type'] is None
+    i = LinearHashIndex.from_config(c)
+    assert i.cache_element is None and i.index == set() and i.count() == 0
+    assert i.get_config() == c
+    c['cache_element']['type'] = 'smqtk_dataprovider.impls.data_element.memory.DataMemoryElement'
+    i = LinearHashIndex.from_config(c)
+    assert isinstance(i.cache_element, DataMemoryElement)
+    assert i.get_config()['cache_element']['type'] == c['cache_element']['type']
+    for inst in configuration_test_helper(LinearHashIndex(DataMemoryElement())):
+        assert isinstance(inst.cache_element, DataMemoryElement)
+
+
+def test_itq_config_roundtrip():
+    c = ItqFunctor.get_default_config()
+    assert ItqFunctor.from_config(c).get_config() == c
+    f = ItqFunctor(DataMemoryElement(), DataMemoryElement(), bit_length=153, itq_iterations=7,
+                   normalize=2, random_seed=58)
+    for inst in configuration_test_helper(f):
+        assert (inst.bit_length, inst.itq_iterations, inst.normalize, inst.random_seed) == (153, 7, 2, 58)
+        assert isinstance(inst.mean_vec_cache_elem, DataMemoryElement)
+        assert isinstance(inst.rotation_cache_elem, DataMemoryElement)
+
+
+def test_itq_model_cache_bytes_are_npy(tmp_path):
+    from io import BytesIO
+    mean, rot = np.array([1., 2., 3.]), np.eye(3)
+    mb, rb = BytesIO(), BytesIO()
+    np.save(mb, mean)
+    np.save(rb, rot)
+    f = ItqFunctor(DataMemoryElement(mb.getvalue()), DataMemoryElement(rb.getvalue()), bit_length=3)
+    assert f.has_model()
+    np.testing.assert_array_equal(f.mean_vec, mean)
+    np.testing.assert_array_equal(f.rotation, rot)
+    # written caches are byte-identical .npy blobs (reference itq.py:222-237)
+    g = ItqFunctor(DataMemoryElement(), DataMemoryElement(), bit_length=3)
+    g.mean_vec, g.rotation = mean, rot
+    g.save_model()
+    assert g.mean_vec_cache_elem.get_bytes() == mb.getvalue()
+    assert g.rotation_cache_elem.get_bytes() == rb.getvalue()
+
+
+def test_itq_errors_without_compute():
+    f = ItqFunctor(bit_length=8)
+    with pytest.raises(Exception, match="mean vector is none"):
+        f.get_hash(np.zeros(4))
+    f.mean_vec = np.zeros(4)
+    with pytest.raises(Exception, match="rotation matrix is none"):
+        f.get_hash(np.zeros(4))
+    descr = [DescriptorMemoryElement(i).set_vector([-1. + i, -1. + i]) for i in range(3)]
+    g = ItqFunctor(bit_length=8)
+    for arg in (descr, iter(descr)):
+        with pytest.raises(ValueError, match="fewer features than requested bit encoding"):
+            g.fit(arg)
+        assert g.mean_vec is None and g.rotation is None
+    h = ItqFunctor(bit_length=1)
+    h.mean_vec, h.rotation = np.zeros(2), np.ones((2, 1))
+    with pytest.raises(RuntimeError, match="already been loaded"):
+        h.fit(descr)
+    with pytest.raises(ValueError):
+        ItqFunctor(normalize="fro")
+
+
+def test_itq_norm_vector_known_answers():
+    f = ItqFunctor(normalize=2)
+    np.testing.assert_array_almost_equal(f._norm_vector(np.array([0, 1])), [0, 1])
+    np.testing.assert_array_almost_equal(f._norm_vector(np.array([[3., 4.], [0., 0.]])), [[.6, .8], [0, 0]])
+    v = np.array([1., 2.])
+    assert ItqFunctor()._norm_vector(v) is v
+
+
+def test_lsh_config():
+    i = LSHNearestNeighborIndex(lsh_functor=ItqFunctor(), descriptor_set=MemoryDescriptorSet(),
+                                hash2uuids_kvstore=MemoryKeyValueStore(), hash_index=LinearHashIndex(),
+                                distance_method='euclidean', read_only=True)
+    for inst in configuration_test_helper(i):
+        assert isinstance(inst.lsh_functor, ItqFunctor)
+        assert isinstance(inst.descriptor_set, MemoryDescriptorSet)
+        assert isinstance(inst.hash_index, LinearHashIndex)
+        assert isinstance(inst.hash2uuids_kvstore, MemoryKeyValueStore)
+        assert inst.distance_method == 'euclidean' and inst.read_only is True
+
+    c = LSHNearestNeighborIndex.get_default_config()
+    assert json.loads(json.dumps(c)) == c
+    c['lsh_functor']['type'] = 'smqtk_indexing_b200.impls.lsh_functor.itq.ItqFunctor'
+    c['descriptor_set']['type'] = 'smqtk_descriptors.impls.descriptor_set.memory.MemoryDescriptorSet'
+    c['hash2uuids_kvstore']['type'] = 'smqtk_dataprovider.impls.key_value_store.memory.MemoryKeyValueStore'
+    c['hash_index']['type'] = None
+    c['hash_index_comment'] = "ignored"
+    idx = LSHNearestNeighborIndex.from_config(c)
+    assert isinstance(idx.lsh_functor, ItqFunctor) and idx.hash_index is None
+    assert json.loads(json.dumps(idx.get_config())) == idx.get_config()
+
+
+def test_lsh_dist_func_label_and_count():
+    with pytest.raises(ValueError, match="Invalid distance method"):
+        LSHNearestNeighborIndex._get_dist_func('not-valid-string')
+    with pytest.raises(ValueError):
+        LSHNearestNeighborIndex(ItqFunctor(), MemoryDescriptorSet(), MemoryKeyValueStore(), distance_method="nope")
+    import types
+    for m in ("euclidean", "cosine", "hik"):
+        assert isinstance(LSHNearestNeighborIndex._get_dist_func(m), types.FunctionType)
+    # count() sums the KVS value sets, not the descriptor set (reference lsh.py:271-281)
+    kvs = MemoryKeyValueStore()
+    idx = LSHNearestNeighborIndex(ItqFunctor(), MemoryDescriptorSet(), kvs)
+    assert idx.count() == 0
+    kvs.add(0, {0}).add(1, {1, 2}).add(2, frozenset({3, 4, 5}))
+    assert idx.count() == 6 and len(idx) == 6
+
+
+def test_validation_errors_need_no_device():
+    idx = LSHNearestNeighborIndex(ItqFunctor(), MemoryDescriptorSet(), MemoryKeyValueStore())
+    for call in (idx.build_index, idx.update_index, idx.remove_from_index):
+        with pytest.raises(ValueError, match="No DescriptorElement"):
+            call([])
+    with pytest.raises(ValueError, match="did not have a vector"):
+        idx.nn(DescriptorMemoryElement(0))
+    with pytest.raises(ValueError, match="No index currently set"):
+        idx.nn(DescriptorMemoryElement(0).set_vector([1., 2.]))
+    hi = LinearHashIndex()
+    for call in (hi.build_index, hi.update_index, hi.remove_from_index):
+        with pytest.raises(ValueError, match="No hash vectors"):
+            call([])
+    with pytest.raises(ValueError, match="No index currently set"):
+        hi.nn(np.zeros(3, bool))
+    ro = LSHNearestNeighborIndex(ItqFunctor(), MemoryDescriptorSet(), MemoryKeyValueStore(), read_only=True)
+    d = [DescriptorMemoryElement(0).set_vector([1., 2.])]
+    for call, arg in ((ro.build_index, d), (ro.update_index, d), (ro.remove_from_index, [0])):
+        with pytest.raises(ReadOnlyError):
+            call(arg)
+
+
+def test_linear_index_attribute_roundtrip_on_host():
+    """`index` get/set works on ints without a device (upload is lazy)."""
+    hi = LinearHashIndex()
+    hi.index = {1, 2, 3, 4, 2 ** 70 + 5}
+    assert hi.count() == 5 and hi.index == {1, 2, 3, 4, 2 ** 70 + 5}
+    hi.index = set()
+    assert hi.count() == 0
+
+
+def test_linear_cache_formats():
+    from io import BytesIO
+    ce = DataMemoryElement()
+    hi = LinearHashIndex(ce)
+    hi.index = {1, 2, 3, 4}
+    hi.save_cache()
+    # narrow codes: the reference's 1-D integer .npy (linear.py:131-142)
+    assert set(np.load(BytesIO(ce.get_bytes()))) == {1, 2, 3, 4}
+    assert LinearHashIndex(ce).index == {1, 2, 3, 4}
+    # wide codes: packed table (the reference format cannot represent them)
+    ce2 = DataMemoryElement()
+    h2 = LinearHashIndex(ce2)
+    wide = {2 ** 255 + 7, 2 ** 64, 3}
+    h2.index = wide
+    h2.save_cache()
+    arr = np.load(BytesIO(ce2.get_bytes()))
+    assert arr.ndim == 2 and arr.dtype == np.uint32
+    assert LinearHashIndex(ce2).index == wide
+    # a cache written by the reference itself
+    b = BytesIO()
+    np.save(b, tuple({5, 9, 12}))
+    assert LinearHashIndex(DataMemoryElement(b.getvalue())).index == {5, 9, 12}
+    ro = LinearHashIndex(DataMemoryElement(readonly=True))
+    ro.index = {1}
+    with pytest.raises(ValueError, match="is read-only"):
+        ro.save_cache()
