@@ -1,0 +1,149 @@
+"""
+Multi-GPU LSH index: one process per GPU (``torch.distributed``, NCCL over
+NVLink 5 / NVSwitch; gloo on CPU for tests).
+
+Sharding (DESIGN.md section "Multi-GPU"):
+  * the descriptor matrix is sharded by ROW RANGE: rank r holds the rows it
+    ingested; global row id = rank-major concatenation;
+  * per-row codes are all-gathered once at build time (32 B per row at 256 bits)
+    and every rank derives the SAME global sorted-unique code table and
+    code -> rows CSR -- exactly the single-GPU structures;
+  * the Hamming scan is range-partitioned over that table: rank r scans table
+    rows [lo_r, hi_r) with ``idx_base = lo_r``, so its keys are already global.
+
+Per query batch there are two small collectives:
+  1. all-gather of the per-rank top-n keys (Q*n*8 bytes per rank) followed by
+     ``sb_topk_merge`` -> the global n nearest unique codes, identical on all ranks;
+  2. all-gather of candidate distances: every rank re-ranks the candidate rows
+     that live in its descriptor shard, the owner's value is selected per candidate.
+Because keys and candidate order are global, the result is bit-identical to the
+single-GPU index, ties included.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import codes as codeops
+from .engine import _stage, expand_candidates
+
+
+class DeviceOps:
+    """The CUDA implementation of the per-rank compute steps (default)."""
+
+    def __init__(self, functor, distance_method: str) -> None:
+        self.functor = functor
+        self.distance_method = distance_method
+
+    def hash(self, x: torch.Tensor) -> torch.Tensor:
+        return self.functor.get_hash_packed(x)
+
+    def scan_keys(self, table: torch.Tensor, q_codes: torch.Tensor, n: int, idx_base: int) -> torch.Tensor:
+        from . import device
+        return device.hamming_scan_keys(table, q_codes, n, idx_base)
+
+    def merge_keys(self, keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        from . import device
+        return device.topk_merge(keys)
+
+    def rerank(self, x, q, cand_idx, cand_off) -> torch.Tensor:
+        from . import device
+        return device.rerank(x, q, cand_idx, cand_off, self.distance_method)
+
+    def rerank_select(self, d, cand_off, n):
+        from . import device
+        return device.rerank_select(d, cand_off, n)
+
+
+def _all_gather_rows(t: torch.Tensor, group) -> Tuple[torch.Tensor, List[int]]:
+    """Concatenate row blocks of differing length from all ranks (rank-major)."""
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0), sizes
+
+
+def partition_bounds(total: int, world: int, align: int = 4) -> List[int]:
+    """``world + 1`` ascending cut points over ``total`` table rows; interior cuts
+    are multiples of ``align`` rows so every slice starts 16-byte aligned."""
+    cuts = [0]
+    for r in range(1, world):
+        c = (total * r // world) // align * align
+        cuts.append(max(c, cuts[-1]))
+    cuts.append(total)
+    return cuts
+
+
+class ShardedLshIndex:
+    """Row-sharded descriptors, range-partitioned Hamming scan, exact merge."""
+
+    def __init__(self, functor, distance_method: str = "euclidean", group=None, ops=None) -> None:
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.ops = ops if ops is not None else DeviceOps(functor, distance_method)
+        self.x_local: Optional[torch.Tensor] = None
+        self.row_bounds: List[int] = []
+        self.table = self.csr_off = self.csr_rows = None
+        self.scan_lo = self.scan_hi = 0
+
+    @property
+    def num_rows(self) -> int:
+        return self.row_bounds[-1] if self.row_bounds else 0
+
+    @property
+    def num_codes(self) -> int:
+        return 0 if self.table is None else int(self.table.shape[0])
+
+    def build(self, x_local: torch.Tensor) -> None:
+        """Collective: every rank passes the descriptor rows it owns."""
+        self.x_local = x_local
+        codes_local = self.ops.hash(x_local)
+        codes_all, sizes = _all_gather_rows(codes_local, self.group)
+        self.row_bounds = [0]
+        for s in sizes:
+            self.row_bounds.append(self.row_bounds[-1] + s)
+        self.table, row_code = codeops.sort_unique(codes_all, return_inverse=True)
+        self.csr_off, self.csr_rows = codeops.group_rows(row_code, self.table.shape[0])
+        cuts = partition_bounds(int(self.table.shape[0]), self.world)
+        self.scan_lo, self.scan_hi = cuts[self.rank], cuts[self.rank + 1]
+
+    def near_codes(self, q_codes: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Global n nearest unique codes: local scan, all-gather, merge."""
+        with _stage("hamming_scan"):
+            keys = self.ops.scan_keys(self.table[self.scan_lo:self.scan_hi], q_codes, n, self.scan_lo)
+        with _stage("allgather_merge"):
+            gathered = [torch.empty_like(keys) for _ in range(self.world)]
+            dist.all_gather(gathered, keys.contiguous(), group=self.group)
+            return self.ops.merge_keys(torch.stack(gathered).contiguous())
+
+    def query(self, q: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Collective: all ranks pass the SAME queries; all get the full result
+        (global rows int64[Q, n], dists f64[Q, n])."""
+        with _stage("itq_hash"):
+            q_codes = self.ops.hash(q)
+        _, code_rows = self.near_codes(q_codes, n)
+        with _stage("expand"):
+            cand_idx, cand_off = expand_candidates(code_rows, self.csr_off, self.csr_rows)
+        with _stage("rerank"):
+            lo = self.row_bounds[self.rank]
+            # rows outside this rank's shard fall out of range -> NaN, replaced below
+            local = self.ops.rerank(self.x_local, q, (cand_idx - lo).contiguous(), cand_off)
+        with _stage("allgather_dist"):
+            parts = [torch.empty_like(local) for _ in range(self.world)]
+            dist.all_gather(parts, local, group=self.group)
+            bounds = torch.tensor(self.row_bounds[1:], dtype=torch.int64, device=cand_idx.device)
+            owner = torch.bucketize(cand_idx, bounds, right=True)
+            d = torch.stack(parts)[owner, torch.arange(cand_idx.numel(), device=cand_idx.device)] \
+                if cand_idx.numel() else local
+        with _stage("rerank"):
+            pos, od = self.ops.rerank_select(d, cand_off, n)
+        rows = torch.where(pos >= 0, cand_idx[pos.clamp(min=0)], pos) if cand_idx.numel() else pos
+        return rows, od

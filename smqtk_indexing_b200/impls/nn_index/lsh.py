@@ -32,6 +32,7 @@ from smqtk_dataprovider import KeyValueStore
 from smqtk_dataprovider.exceptions import ReadOnlyError
 from smqtk_descriptors import DescriptorElement, DescriptorSet
 
+from smqtk_indexing_b200.engine import DeviceLshIndex
 from smqtk_indexing_b200.interfaces import HashIndex, LshFunctor, NearestNeighborsIndex
 from smqtk_indexing_b200.impls.hash_index.linear import LinearHashIndex
 from smqtk_indexing_b200.utils import bits as bitutil
@@ -41,34 +42,16 @@ LOG = logging.getLogger(__name__)
 T_LSH = TypeVar("T_LSH", bound="LSHNearestNeighborIndex")
 
 
-class _DeviceMirror:
-    """Device-resident copy of the index used by ``nn_batch``:
-    descriptor matrix, per-row codes, unique code table and code->rows CSR."""
+class _DeviceMirror(DeviceLshIndex):
+    """Device index + the row <-> uuid maps of the plugin layer."""
 
     def __init__(self) -> None:
-        self.x = None                       # float32[N, D]
-        self.codes = None                   # int32[N, W]
+        super().__init__()
         self.uuids: List[Hashable] = []     # row -> uuid
         self.row_of: Dict[Hashable, int] = {}
-        self.table = None                   # int32[U, W] sorted unique
-        self.csr_off = None                 # int64[U + 1]
-        self.csr_rows = None                # int64[N]
-        self.row_code = None                # int64[N] row -> table row
-
-    def clear(self) -> None:
-        self.__init__()
 
     def count(self) -> int:
         return len(self.uuids)
-
-    def reindex(self) -> None:
-        """Recompute table / CSR from ``codes``."""
-        from smqtk_indexing_b200 import codes as codeops
-        if self.codes is None or self.codes.shape[0] == 0:
-            self.table = self.csr_off = self.csr_rows = self.row_code = None
-            return
-        self.table, self.row_code = codeops.sort_unique(self.codes, return_inverse=True)
-        self.csr_off, self.csr_rows = codeops.group_rows(self.row_code, self.table.shape[0])
 
 
 class LSHNearestNeighborIndex(NearestNeighborsIndex):
@@ -371,6 +354,45 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
         r_dists = tuple(float(v) for v, p in zip(od, pos) if p >= 0)
         return r_descrs, r_dists
 
+    def build_index_matrix(self, x, uuids: Optional[Sequence[Hashable]] = None) -> None:
+        """Bulk build straight from a ``[N, D]`` matrix (numpy or float32 CUDA
+        tensor, adopted without a copy): hash -> unique codes -> CSR, all on the
+        device.  ``uuids[r]`` names row ``r`` (default: the row number).
+
+        This is the ingest path for tables too large for per-element Python
+        containers: the ``descriptor_set`` / ``hash2uuids_kvstore`` collaborators
+        are NOT populated (use ``build_index`` for that), so only ``nn_batch`` /
+        ``count_rows`` see these rows.  The configured ``hash_index`` receives the
+        unique-code table.
+
+        :raises ReadOnlyError: read-only index.  :raises ValueError: empty matrix.
+        """
+        import torch
+        from smqtk_indexing_b200 import device
+        with self._model_lock:
+            if self.read_only:
+                raise ReadOnlyError("Cannot modify container attributes due to being in read-only mode.")
+            if x is None or len(x) == 0:
+                raise self._empty_iterable_exception()
+            if not isinstance(x, torch.Tensor):
+                x = torch.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32))
+            if not x.is_cuda:
+                x = x.to(device.device())
+            if x.dtype != torch.float32:
+                x = x.to(torch.float32)
+            m = self._mirror
+            m.clear()
+            codes = self.lsh_functor.get_hash_packed(x)
+            m.uuids = list(uuids) if uuids is not None else range(x.shape[0])  # type: ignore
+            m.row_of = {}
+            m.set_rows(x, codes)
+            if isinstance(self.hash_index, LinearHashIndex):
+                self.hash_index.set_code_table(m.table)
+
+    def count_rows(self) -> int:
+        """Descriptor rows in the device-resident index (see ``build_index_matrix``)."""
+        return self._mirror.num_rows
+
     def nn_batch(self, queries, n: int = 1, return_device: bool = False):
         """Batched LSH query against the device-resident index.
 
@@ -395,7 +417,7 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
                 q = torch.from_numpy(numpy.ascontiguousarray(queries, dtype=numpy.float32)).to(dev, non_blocking=True)
             if q.dim() == 1:
                 q = q.unsqueeze(0)
-            rows, dists = lsh_query_device(self.lsh_functor, m, q, n, self.distance_method)
+            rows, dists = m.query(self.lsh_functor, q, n, self.distance_method)
         if return_device:
             return rows, dists
         return rows.cpu().numpy(), dists.cpu().numpy()
@@ -403,43 +425,3 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
     def mirror_uuids(self) -> List[Hashable]:
         """row -> uuid for the rows returned by :meth:`nn_batch`."""
         return self._mirror.uuids
-
-
-def expand_candidates(code_rows, csr_off, csr_rows):
-    """Ragged expansion ``near codes -> descriptor rows`` on the device.
-
-    :param code_rows: int64[Q, n] rows of the unique-code table (-1 = none)
-    :return: (cand_idx int64[M], cand_off int64[Q + 1])
-    """
-    import torch
-    Q, n = code_rows.shape
-    flat = code_rows.reshape(-1)
-    ok = flat >= 0
-    safe = torch.where(ok, flat, torch.zeros_like(flat))
-    start = csr_off[safe]
-    cnt = torch.where(ok, csr_off[safe + 1] - start, torch.zeros_like(start))
-    seg_end = torch.cumsum(cnt, 0)
-    total = int(seg_end[-1].item()) if flat.numel() else 0
-    cand_off = torch.zeros(Q + 1, dtype=torch.int64, device=flat.device)
-    cand_off[1:] = seg_end.reshape(Q, n)[:, -1]
-    if total == 0:
-        return torch.empty(0, dtype=torch.int64, device=flat.device), cand_off
-    seg = torch.repeat_interleave(torch.arange(flat.numel(), device=flat.device), cnt, output_size=total)
-    within = torch.arange(total, device=flat.device) - (seg_end - cnt)[seg]
-    return csr_rows[start[seg] + within], cand_off
-
-
-def lsh_query_device(functor, mirror: _DeviceMirror, q, n: int, distance_method: str):
-    """hash -> Hamming top-n unique codes -> candidate rows -> re-rank -> top-n,
-    entirely on the device (reference lsh.py:470-519 for a batch of queries)."""
-    import torch
-    from smqtk_indexing_b200 import codes as codeops, device
-    q_codes = functor.get_hash_packed(q)
-    table = mirror.table
-    w = max(table.shape[1], q_codes.shape[1])
-    _, code_rows = device.hamming_topk(codeops.widen(table, w), codeops.widen(q_codes, w).contiguous(), n)
-    cand_idx, cand_off = expand_candidates(code_rows, mirror.csr_off, mirror.csr_rows)
-    dist = device.rerank(mirror.x, q, cand_idx, cand_off, distance_method)
-    pos, od = device.rerank_select(dist, cand_off, n)
-    rows = torch.where(pos >= 0, cand_idx[pos.clamp(min=0)] if cand_idx.numel() else pos, pos)
-    return rows, od
