@@ -74,6 +74,13 @@ SB_API int sb_version(void);
 SB_API const char* sb_last_error(void);
 /* Number of kernels this library has launched in the calling process (bench bookkeeping). */
 SB_API uint64_t sb_launch_count(void);
+/* Per-launch device timing for bench.py (no profiler needed): while enabled, every
+ * kernel launch of this library is bracketed by CUDA events on its stream.
+ * sb_profile_fetch waits for them, returns the number of launches recorded since
+ * the last fetch and fills up to `cap` (kernel name, milliseconds) pairs in launch
+ * order; `names[i]` points at static storage. */
+SB_API int sb_profile_enable(int on);
+SB_API int64_t sb_profile_fetch(const char** host_names, float* host_ms, int64_t cap);
 
 /* ---- stage 1: ITQ hashing ------------------------------------------------
  * codes[r] = pack( ((X[r] / norm(X[r])) - mean) . R >= 0 )        itq.py:404-408

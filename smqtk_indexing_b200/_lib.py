@@ -28,6 +28,8 @@ SIGNATURES: Dict[str, tuple] = {
     "sb_version": (c_int32, []),
     "sb_last_error": (c_char_p, []),
     "sb_launch_count": (c_uint64, []),
+    "sb_profile_enable": (c_int32, [c_int32]),
+    "sb_profile_fetch": (c_int64, [_P, _P, c_int64]),
     "sb_itq_hash": (c_int32, [_P, c_int64, c_int32, c_int64, _P, _P, c_int32, c_int32, c_float,
                               _P, c_int32, _P, c_int32, _P]),
     "sb_hamming_scan_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
@@ -92,3 +94,16 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(load().sb_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    """Bracket every kernel launch of the library with CUDA events (bench only)."""
+    load().sb_profile_enable(1 if on else 0)
+
+
+def profile_fetch(cap: int = 1 << 16):
+    """[(kernel name, milliseconds)] of the launches recorded since the last fetch."""
+    names = (c_char_p * cap)()
+    ms = (c_float * cap)()
+    n = int(load().sb_profile_fetch(ctypes.cast(names, c_void_p), ctypes.cast(ms, c_void_p), cap))
+    return [(names[i].decode(), float(ms[i])) for i in range(min(n, cap))]

@@ -47,4 +47,14 @@ constexpr int NUM_SMS_B200 = 148;
 // Cached device properties (SM count) for the current device.
 int sm_count();
 
+// Optional per-launch timing (sb_profile_enable): when on, a ProfScope records a
+// CUDA event on `st` before and after the launch it brackets; sb_profile_fetch
+// turns the pairs into milliseconds.  Off (default) it costs one relaxed load.
+struct ProfScope {
+  ProfScope(const char* name, cudaStream_t st);
+  ~ProfScope();
+  int slot_;
+  cudaStream_t st_;
+};
+
 }  // namespace sb

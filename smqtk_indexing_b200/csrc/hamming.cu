@@ -566,6 +566,7 @@ int launch_scan(const ScanPlan& p, int mode, const uint32_t* db, long long U, co
     const long long S = min(U, max(2048ll, 4ll * k));
     if (S >= k) {
       const size_t sh = (size_t)SEED_WARPS * (32 * W + 1) * sizeof(int);
+      sb::ProfScope prof("tau_seed_kernel", st);
       tau_seed_kernel<W><<<(Q + SEED_WARPS - 1) / SEED_WARPS, SEED_WARPS * 32, sh, st>>>(db, (int)S, q, Q, k, tau_g);
       sb::count_launch();
       int rc = sb::check_launch("tau_seed_kernel");
@@ -574,6 +575,7 @@ int launch_scan(const ScanPlan& p, int mode, const uint32_t* db, long long U, co
   }
   dim3 grid(p.chunks, p.nqt);
   const int q_tma_ok = ((reinterpret_cast<uintptr_t>(q) & 15u) == 0 && ((size_t)p.QT * W * 4) % 16 == 0) ? 1 : 0;
+  sb::ProfScope prof("hamming_scan_kernel", st);
   if (mode == 0) {
     SB_CUDA_TRY(cudaFuncSetAttribute(hamming_scan_kernel<W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)p.smem_bytes));
@@ -593,6 +595,7 @@ int launch_merge(const uint64_t* lists, int P, int Q, int k, int q_major, uint64
                  int64_t* out_idx, cudaStream_t st) {
   const size_t dyn = merge_smem_bytes(k);
   SB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  sb::ProfScope prof("merge_kernel", st);
   merge_kernel<<<Q, MERGE_THREADS, dyn, st>>>(lists, P, Q, k, q_major, out_keys, out_dist,
                                               reinterpret_cast<long long*>(out_idx));
   sb::count_launch();

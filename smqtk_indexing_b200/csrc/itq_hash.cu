@@ -191,6 +191,7 @@ extern "C" int sb_itq_hash(const float* X, int64_t n, int32_t D, int64_t ldx, co
 
   SB_CUDA_TRY(cudaMemsetAsync(codes_out, 0, (size_t)n * W * sizeof(uint32_t), st));
   dim3 grid((unsigned)((n + BM - 1) / BM), (unsigned)((b + BN - 1) / BN));
+  sb::ProfScope prof("itq_hash_simt_kernel", st);
   itq_hash_simt_kernel<<<grid, THREADS, 0, st>>>(X, n, D, ldx, mean, R, b, norm_kind, norm_p, codes_out, W, z_out);
   sb::count_launch();
   return sb::check_launch("itq_hash_simt_kernel");

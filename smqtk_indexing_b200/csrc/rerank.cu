@@ -175,6 +175,7 @@ int sb_rerank(const float* db, int64_t N, int32_t D, int64_t ldd, const float* q
   const unsigned grid = (unsigned)((M + RR_WARPS - 1) / RR_WARPS);
   const long long* ci = reinterpret_cast<const long long*>(cand_idx);
   const long long* co = reinterpret_cast<const long long*>(cand_off);
+  sb::ProfScope prof("rerank_kernel", st);
   switch (metric) {
     case SB_METRIC_EUCLIDEAN:
       rerank_kernel<SB_METRIC_EUCLIDEAN><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok);
@@ -195,6 +196,7 @@ int sb_rerank_select(const double* dist, const int64_t* cand_off, int32_t Q, int
   SB_REQUIRE(Q >= 1 && n >= 1, "sb_rerank_select: bad sizes");
   SB_REQUIRE(cand_off && out_pos && out_dist, "sb_rerank_select: NULL pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  sb::ProfScope prof("rerank_select_kernel", st);
   rerank_select_kernel<<<Q, SEL_THREADS, 0, st>>>(dist, reinterpret_cast<const long long*>(cand_off), Q, n,
                                                   reinterpret_cast<long long*>(out_pos), out_dist);
   sb::count_launch();
