@@ -87,14 +87,29 @@ SB_API int64_t sb_profile_fetch(const char** host_names, float* host_ms, int64_t
  * X: f32[n][ldx] (first D columns used); mean: f32[D] or NULL (= zeros);
  * R: f32[D][b] row-major; codes_out: u32[n][W] (W >= ceil(b/32), layout above);
  * z_out: optional f32[n][b] projections (tests / epsilon masks), may be NULL.
- * variant: 0 = auto, 1 = FP32 FFMA kernel (any shape), 2 = tcgen05 3xTF32 GEMM
- *          (needs D % 32 == 0, b % 32 == 0, b <= 256, ldx % 4 == 0).
+ * FP32 FFMA kernel, any shape.  variant: 0 or 1 (reserved).
  */
 SB_API int sb_itq_hash(const float* X, int64_t n, int32_t D, int64_t ldx,
                 const float* mean, const float* R, int32_t b,
                 int32_t norm_kind, float norm_p,
                 uint32_t* codes_out, int32_t W, float* z_out,
                 int32_t variant, void* stream);
+
+/* Tensor-core hashing (tcgen05.mma kind::tf32, 3xTF32 split, FP32 accumulation in
+ * tensor memory, fused sign/bit-pack epilogue) for aligned shapes:
+ *   D % 16 == 0, b % 32 == 0, 32 <= b <= 256, ldx % 4 == 0, 16-byte aligned pointers.
+ * The rotation is pre-split ONCE per model into the kernel's shared-memory image
+ * (hi/lo TF32 parts, UMMA core-matrix order): image_out holds
+ * sb_itq_rotation_image_bytes(D, b) bytes (0 = shape not supported).
+ * row_div: optional f32[n] row divisors (the norms of itq.py:184-189, 1 where 0),
+ * NULL = no normalisation.  Same outputs as sb_itq_hash. */
+SB_API int sb_itq_row_div(const float* X, int64_t n, int32_t D, int64_t ldx,
+                   int32_t norm_kind, float norm_p, float* div_out, void* stream);
+SB_API size_t sb_itq_rotation_image_bytes(int32_t D, int32_t b);
+SB_API int sb_itq_rotation_image(const float* R, int32_t D, int32_t b, void* image_out, void* stream);
+SB_API int sb_itq_hash_tc(const float* X, int64_t n, int32_t D, int64_t ldx,
+                   const float* mean, const void* r_image, int32_t b, const float* row_div,
+                   uint32_t* codes_out, int32_t W, float* z_out, void* stream);
 
 /* ---- stage 2: Hamming scan + top-k -----------------------------------------
  * For each of Q query codes: the k rows of db with the smallest

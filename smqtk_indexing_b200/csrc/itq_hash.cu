@@ -10,18 +10,11 @@
 // tile is staged, the sign test and the big-endian bit-pack happen in the
 // epilogue (shared-memory OR, then one global atomicOr per row/word/CTA).
 // The tcgen05 3xTF32 tensor-core kernel for aligned shapes lives in
-// itq_hash_tc.cu; sb_itq_hash dispatches between them.
+// itq_hash_tc.cu (sb_itq_hash_tc); it needs the rotation pre-split into its
+// shared-memory image, so it has its own entry points.
 #include <math.h>
 
 #include "common.cuh"
-
-namespace sb {
-// implemented in itq_hash_tc.cu
-int itq_hash_tc_supported(int64_t n, int32_t D, int64_t ldx, int32_t b, const float* X, const float* R);
-int itq_hash_tc_launch(const float* X, int64_t n, int32_t D, int64_t ldx, const float* mean, const float* R,
-                       int32_t b, int32_t norm_kind, float norm_p, uint32_t* codes_out, int32_t W, float* z_out,
-                       cudaStream_t st);
-}  // namespace sb
 
 namespace {
 
@@ -164,7 +157,41 @@ itq_hash_simt_kernel(const float* __restrict__ X, long long n, int D, long long 
   }
 }
 
+// One warp per row: div[r] = norm(X[r]) (1 when 0), the divisor of itq.py:184-189.
+__global__ void __launch_bounds__(256)
+row_div_f32_kernel(const float* __restrict__ X, long long n, int D, long long ldx, int norm_kind, float norm_p,
+                   float* __restrict__ div_out) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = X + row * ldx;
+  float acc = 0.0f;
+  for (int d = lane; d < D; d += 32) {
+    const float t = norm_term(xr[d], norm_kind, norm_p);
+    acc = (norm_kind == SB_NORM_INF) ? fmaxf(acc, t) : acc + t;
+  }
+  for (int o = 16; o; o >>= 1) {
+    const float t = __shfl_xor_sync(sb::FULL_MASK, acc, o);
+    acc = (norm_kind == SB_NORM_INF) ? fmaxf(acc, t) : acc + t;
+  }
+  if (lane == 0) div_out[row] = finish_norm(acc, norm_kind, norm_p);
+}
+
 }  // namespace
+
+extern "C" int sb_itq_row_div(const float* X, int64_t n, int32_t D, int64_t ldx, int32_t norm_kind, float norm_p,
+                              float* div_out, void* stream) {
+  SB_REQUIRE(n >= 0 && D >= 1 && ldx >= D, "sb_itq_row_div: bad sizes");
+  SB_REQUIRE(norm_kind >= SB_NORM_LP && norm_kind <= SB_NORM_L0, "sb_itq_row_div: bad norm_kind %d", norm_kind);
+  SB_REQUIRE(norm_kind != SB_NORM_LP || norm_p > 0.0f, "sb_itq_row_div: Lp norm needs p > 0");
+  if (n == 0) return SB_OK;
+  SB_REQUIRE(X != nullptr && div_out != nullptr, "sb_itq_row_div: NULL pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  sb::ProfScope prof("row_div_f32_kernel", st);
+  row_div_f32_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(X, n, D, ldx, norm_kind, norm_p, div_out);
+  sb::count_launch();
+  return sb::check_launch("row_div_f32_kernel");
+}
 
 extern "C" int sb_itq_hash(const float* X, int64_t n, int32_t D, int64_t ldx, const float* mean, const float* R,
                            int32_t b, int32_t norm_kind, float norm_p, uint32_t* codes_out, int32_t W, float* z_out,
@@ -176,18 +203,9 @@ extern "C" int sb_itq_hash(const float* X, int64_t n, int32_t D, int64_t ldx, co
   SB_REQUIRE(R != nullptr && codes_out != nullptr, "sb_itq_hash: NULL pointer");
   SB_REQUIRE(norm_kind >= SB_NORM_NONE && norm_kind <= SB_NORM_L0, "sb_itq_hash: bad norm_kind %d", norm_kind);
   SB_REQUIRE(norm_kind != SB_NORM_LP || norm_p > 0.0f, "sb_itq_hash: Lp norm needs p > 0");
-  SB_REQUIRE(variant >= 0 && variant <= 2, "sb_itq_hash: bad variant %d", variant);
+  SB_REQUIRE(variant == 0 || variant == 1, "sb_itq_hash: bad variant %d (the tensor-core kernel is sb_itq_hash_tc)", variant);
   if (n == 0) return SB_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-
-  const int tc_ok = sb::itq_hash_tc_supported(n, D, ldx, b, X, R);
-  if (variant == 2 && !tc_ok) {
-    sb::set_error("sb_itq_hash: tensor-core variant needs D%%32==0, b%%32==0, 32<=b<=256, ldx%%4==0, 16B-aligned X");
-    return SB_ERR_UNSUPPORTED;
-  }
-  if (variant == 2 || (variant == 0 && tc_ok && n >= 1024)) {
-    return sb::itq_hash_tc_launch(X, n, D, ldx, mean, R, b, norm_kind, norm_p, codes_out, W, z_out, st);
-  }
 
   SB_CUDA_TRY(cudaMemsetAsync(codes_out, 0, (size_t)n * W * sizeof(uint32_t), st));
   dim3 grid((unsigned)((n + BM - 1) / BM), (unsigned)((b + BN - 1) / BN));

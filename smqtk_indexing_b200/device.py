@@ -77,11 +77,42 @@ def norm_spec(normalize) -> Tuple[int, float]:
     raise ValueError("normalize=%r: only ord in {None, 0, p > 0, inf} is supported on the device" % (normalize,))
 
 
+TC_MIN_ROWS = 512     # below this the FFMA kernel's launch is as fast as the tensor-core one
+
+
+def itq_rotation_image(R: torch.Tensor) -> Optional[torch.Tensor]:
+    """Pre-split rotation (hi/lo TF32, UMMA core-matrix order) for ``sb_itq_hash_tc``;
+    None when the shape is not supported by the tensor-core kernel."""
+    require_cuda()
+    _chk(R, torch.float32, "R")
+    D, b = R.shape
+    lib = _lib.load()
+    nbytes = lib.sb_itq_rotation_image_bytes(D, b)
+    if nbytes == 0:
+        return None
+    img = torch.empty((nbytes,), dtype=torch.uint8, device=R.device)
+    with torch.cuda.device(R.device):
+        _lib.check(lib.sb_itq_rotation_image(_ptr(R), D, b, _ptr(img), _stream()))
+    return img
+
+
+def itq_tc_supported(X: torch.Tensor, b: int) -> bool:
+    n, D = X.shape
+    ldx = X.stride(0) if n > 1 else max(D, X.stride(0))
+    return (n >= 1 and D % 16 == 0 and D >= 16 and b % 32 == 0 and 32 <= b <= 256 and ldx % 4 == 0
+            and X.data_ptr() % 16 == 0)
+
+
 def itq_hash(X: torch.Tensor, mean: Optional[torch.Tensor], R: torch.Tensor, normalize=None,
-             words: Optional[int] = None, want_z: bool = False, variant: int = 0):
+             words: Optional[int] = None, want_z: bool = False, variant: int = 0,
+             r_image: Optional[torch.Tensor] = None):
     """codes = pack(((X / norm(X)) - mean) @ R >= 0).  X f32[n, D] (row stride may
     exceed D), mean f32[D] | None, R f32[D, b].  Returns codes int32[n, W]
-    (and z f32[n, b] when ``want_z``)."""
+    (and z f32[n, b] when ``want_z``).
+
+    variant 0 = auto (tensor-core kernel when ``r_image`` is given, the shape is
+    aligned and n >= TC_MIN_ROWS, else the FFMA kernel), 1 = FFMA kernel,
+    2 = tensor-core kernel (raises when the shape is not supported)."""
     require_cuda()
     if X.dim() != 2 or X.dtype != torch.float32 or not X.is_cuda or X.stride(1) != 1:
         raise ValueError("X must be a 2-D float32 CUDA tensor with unit column stride")
@@ -100,9 +131,24 @@ def itq_hash(X: torch.Tensor, mean: Optional[torch.Tensor], R: torch.Tensor, nor
     codes = torch.empty((n, W), dtype=torch.int32, device=X.device)
     z = torch.empty((n, b), dtype=torch.float32, device=X.device) if want_z else None
     ldx = X.stride(0) if n > 1 else max(D, X.stride(0))
+    lib = _lib.load()
+    use_tc = variant == 2 or (variant == 0 and r_image is not None and n >= TC_MIN_ROWS and itq_tc_supported(X, b))
     with torch.cuda.device(X.device):
-        _lib.check(_lib.load().sb_itq_hash(_ptr(X), n, D, ldx, _ptr(mean), _ptr(R), b, kind, p,
-                                           _ptr(codes), W, _ptr(z), variant, _stream()))
+        if use_tc:
+            if r_image is None:
+                r_image = itq_rotation_image(R)
+            if r_image is None or not itq_tc_supported(X, b):
+                raise ValueError("tensor-core hashing needs D % 16 == 0, b % 32 == 0, 32 <= b <= 256 and 16-byte "
+                                 "aligned rows (D=%d, b=%d)" % (D, b))
+            div = None
+            if kind != _lib.NORM_NONE:
+                div = torch.empty((n,), dtype=torch.float32, device=X.device)
+                _lib.check(lib.sb_itq_row_div(_ptr(X), n, D, ldx, kind, p, _ptr(div), _stream()))
+            _lib.check(lib.sb_itq_hash_tc(_ptr(X), n, D, ldx, _ptr(mean), _ptr(r_image), b, _ptr(div),
+                                          _ptr(codes), W, _ptr(z), _stream()))
+        else:
+            _lib.check(lib.sb_itq_hash(_ptr(X), n, D, ldx, _ptr(mean), _ptr(R), b, kind, p,
+                                       _ptr(codes), W, _ptr(z), 0, _stream()))
     return (codes, z) if want_z else codes
 
 

@@ -164,7 +164,8 @@ class ItqFunctor(LshFunctor):
             rot = np.real(np.asarray(self.rotation))
             rot = rot.reshape(rot.shape[0], -1)
             rotation = torch.from_numpy(np.ascontiguousarray(rot, dtype=np.float32)).to(d)
-            self._dev_model = (d, mean, rotation)
+            # rotation pre-split for the tensor-core kernel (None: shape not supported)
+            self._dev_model = (d, mean, rotation, device.itq_rotation_image(rotation))
         return self._dev_model[1], self._dev_model[2]
 
     def get_hash_packed(self, descriptors, variant: int = 0):
@@ -185,7 +186,8 @@ class ItqFunctor(LshFunctor):
         if x.stride(-1) != 1:
             x = x.contiguous()
         mean, rotation = self.device_model(x.device)
-        return device.itq_hash(x, mean, rotation, normalize=self.normalize, variant=variant)
+        return device.itq_hash(x, mean, rotation, normalize=self.normalize, variant=variant,
+                               r_image=self._dev_model[3])
 
     def get_hash(self, descriptor: np.ndarray) -> np.ndarray:
         """Hash one descriptor ``[D]`` (or a matrix ``[n, D]``) -> ``bool[b]``

@@ -170,6 +170,47 @@ def test_itq_hash_shapes(dev, n, D, b):
         _check_hash(dev, x, mean, rot, normalize)
 
 
+@pytest.mark.parametrize("n,D,b", [(256, 16, 32), (1000, 512, 256), (777, 64, 64), (4096, 512, 256),
+                                   (300, 128, 96), (5000, 256, 128), (40000, 48, 160), (513, 4096, 64)])
+def test_itq_hash_tensor_core(dev, n, D, b):
+    """tcgen05 3xTF32 kernel: same epsilon bar as the FFMA kernel, against the float64 oracle."""
+    rng = np.random.RandomState(n + D + b)
+    x = rng.rand(n, D).astype(np.float32)
+    mean = x.mean(0).astype(np.float32).astype(np.float64)
+    rot = np.linalg.qr(rng.randn(max(D, b), max(D, b)))[0][:D, :b]
+    for normalize in (None, 2):
+        _check_hash(dev, x, mean, rot, normalize, variant=2)
+
+
+def test_itq_hash_tensor_core_matches_ffma(dev):
+    """Both kernels give the same codes except where |z| is at rounding level; row
+    pitch larger than D, zero rows and the z == 0 -> 1 rule included."""
+    rng = np.random.RandomState(5)
+    n, D, b = 3000, 128, 64
+    big = torch.from_numpy(rng.rand(n, D + 32).astype(np.float32)).cuda()
+    X = big[:, :D]
+    X[7] = 0.0
+    m = torch.zeros(D, device="cuda")
+    R = torch.from_numpy(np.linalg.qr(rng.randn(D, D))[0][:, :b].astype(np.float32)).cuda()
+    c1, z1 = dev.itq_hash(X, m, R, want_z=True, variant=1)
+    c2, z2 = dev.itq_hash(X, m, R, want_z=True, variant=2)
+    torch.cuda.synchronize()
+    assert (dev.codes_to_host(c2)[7] == 0xFFFFFFFF).all()           # z == 0 -> bit set
+    z1, z2 = z1.cpu().numpy(), z2.cpu().numpy()
+    np.testing.assert_allclose(z2, z1, rtol=0, atol=1e-5)
+    from smqtk_indexing_b200.utils.bits import unpack_bits
+    d = unpack_bits(dev.codes_to_host(c1), b) != unpack_bits(dev.codes_to_host(c2), b)
+    assert (np.abs(z1[d]) < 1e-5).all()
+
+
+def test_itq_hash_tensor_core_rejects_unaligned(dev):
+    X = torch.rand(600, 20, device="cuda")
+    R = torch.rand(20, 32, device="cuda")
+    assert dev.itq_rotation_image(R) is None
+    with pytest.raises(ValueError):
+        dev.itq_hash(X, None, R, variant=2)
+
+
 # --------------------------------------------------------------------- re-rank
 #: distances: |d_gpu - d_ref| <= 1e-5 * |d_ref| + atol (inputs are fp32-representable).
 #: cosine's atol is the float64 reference's own conditioning floor: acos near 1
