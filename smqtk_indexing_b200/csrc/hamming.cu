@@ -20,6 +20,8 @@
 //
 // Exactness: integer arithmetic only; keys (distance<<40 | row) are unique, the
 // merge is a pure selection, so the result is independent of chunking.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -40,11 +42,21 @@ __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
   return r;
 }
 
-// popcount of 8 xor-ed words.  MODE 0: 8 POPC.  MODE 1: three carry-save adders
-// fold the 8 words into 2 weight-1 and 3 weight-2 words -> 5 POPC + 6 LOP3
-// (POPC issues at a quarter of the LOP3 rate, so trading 3 POPC for 6 LOP3 wins).
+// a * m + b as an IMAD: `m` is an opaque register holding 1 (a kernel argument), so the
+// add is issued to the FMA pipe, which the scan otherwise leaves idle, instead of the
+// ALU pipe that carries the LOP3 stream.
+__device__ __forceinline__ int fma_add(int a, int b, int m) { return a * m + b; }
+
+// popcount of 8 xor-ed words.
+//   MODE 0: 8 POPC.
+//   MODE 1: three carry-save adders fold the 8 words into 2 weight-1 and 3 weight-2
+//           words -> 5 POPC + 6 LOP3.
+//   MODE 2: a fourth adder folds the weight-2 words -> 4 POPC + 8 LOP3, sums on the FMA
+//           pipe.  POPC runs on the XU pipe at 16 lanes/clk/SM, LOP3 on the ALU pipe at
+//           64: per pair MODE 2 is 32 XU cycles vs 2*(8 XOR + 8 LOP3 + 1 ISETP) = 34
+//           ALU cycles -- the two pipes finish together.
 template <int MODE>
-__device__ __forceinline__ int popc8(const uint32_t* x) {
+__device__ __forceinline__ int popc8(const uint32_t* x, int one) {
   if (MODE == 0) {
     return (__popc(x[0]) + __popc(x[1]) + __popc(x[2])) + (__popc(x[3]) + __popc(x[4]) + __popc(x[5])) +
            (__popc(x[6]) + __popc(x[7]));
@@ -52,14 +64,21 @@ __device__ __forceinline__ int popc8(const uint32_t* x) {
     uint32_t s1 = xor3(x[0], x[1], x[2]), c1 = maj3(x[0], x[1], x[2]);
     uint32_t s2 = xor3(x[3], x[4], x[5]), c2 = maj3(x[3], x[4], x[5]);
     uint32_t s3 = xor3(s1, s2, x[6]), c3 = maj3(s1, s2, x[6]);
-    int ones = __popc(s3) + __popc(x[7]);
-    int twos = __popc(c1) + __popc(c2) + __popc(c3);
-    return ones + 2 * twos;
+    if (MODE == 1) {
+      int ones = __popc(s3) + __popc(x[7]);
+      int twos = __popc(c1) + __popc(c2) + __popc(c3);
+      return ones + 2 * twos;
+    } else {
+      uint32_t s4 = xor3(c1, c2, c3), c4 = maj3(c1, c2, c3);     // weight 2, weight 4
+      int d = fma_add(__popc(s3), __popc(x[7]), one);
+      d = __popc(s4) * 2 + d;
+      return __popc(c4) * 4 + d;
+    }
   }
 }
 
 template <int W, int MODE>
-__device__ __forceinline__ int hamming(const uint32_t (&c)[W], const uint32_t (&q)[W]) {
+__device__ __forceinline__ int hamming(const uint32_t (&c)[W], const uint32_t (&q)[W], int one) {
   uint32_t x[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) x[i] = c[i] ^ q[i];
@@ -70,11 +89,11 @@ __device__ __forceinline__ int hamming(const uint32_t (&c)[W], const uint32_t (&
   } else if constexpr (W == 4) {
     if (MODE == 0) return __popc(x[0]) + __popc(x[1]) + __popc(x[2]) + __popc(x[3]);
     uint32_t s = xor3(x[0], x[1], x[2]), cy = maj3(x[0], x[1], x[2]);
-    return __popc(s) + __popc(x[3]) + 2 * __popc(cy);
+    return __popc(cy) * 2 + fma_add(__popc(s), __popc(x[3]), one);
   } else {
     int d = 0;
 #pragma unroll
-    for (int g = 0; g + 8 <= W; g += 8) d += popc8<MODE>(x + g);
+    for (int g = 0; g + 8 <= W; g += 8) d = fma_add(popc8<MODE>(x + g, one), d, one);
     return d;
   }
 }
@@ -160,6 +179,38 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                : "memory");
 }
 
+// ---- fold the CTA's 8 warp lists into one list per query: part[q][chunk][k] ----
+// Keys are unique, so the rank of a key among all 8*k candidates is the sum of its
+// lower bounds in the 8 sorted lists; ranks < k are written straight to HBM.
+__device__ __forceinline__ void fold_lists(const uint64_t* lists, int QT, int nq, int k, uint64_t* __restrict__ part,
+                                           int P, int qt0, int tid) {
+  __syncthreads();
+  for (int i = tid; i < nq * k; i += THREADS) {
+    const int qi = i / k, j = i - qi * k;
+    part[((size_t)(qt0 + qi) * P + blockIdx.x) * k + j] = SB_KEY_EMPTY;
+  }
+  __syncthreads();
+  const int per_q = WARPS * k;
+  for (int i = tid; i < nq * per_q; i += THREADS) {
+    const int qi = i / per_q, r = i - qi * per_q;
+    const int w = r / k, j = r - w * k;
+    const uint64_t key = lists[((size_t)w * QT + qi) * k + j];
+    if (key == SB_KEY_EMPTY) continue;
+    int rank = 0;
+#pragma unroll
+    for (int ww = 0; ww < WARPS; ++ww) {
+      const uint64_t* l = lists + ((size_t)ww * QT + qi) * k;
+      int lo = 0, hi = k;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (l[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) part[((size_t)(qt0 + qi) * P + blockIdx.x) * k + rank] = key;
+  }
+}
+
 template <int W>
 struct ScanCfg {
   static constexpr int C = (W <= 4) ? 8 : (W == 8 ? 4 : (W == 16 ? 2 : 1));  // codes per lane
@@ -170,7 +221,7 @@ template <int W, int MODE>
 __global__ void __launch_bounds__(THREADS, 2)
 hamming_scan_kernel(const uint32_t* __restrict__ db, long long U, const uint32_t* __restrict__ qcodes, int Q, int QT,
                     int k, long long idx_base, long long codes_per_chunk, uint64_t* __restrict__ part, int P,
-                    int* __restrict__ tau_g, int* __restrict__ hist_g, int q_tma_ok) {
+                    int* __restrict__ tau_g, int* __restrict__ hist_g, int q_tma_ok, int one) {
   constexpr int C = ScanCfg<W>::C;
   constexpr int TILE = ScanCfg<W>::TILE;
   constexpr int MAXD = 32 * W;       // largest possible distance
@@ -237,6 +288,8 @@ hamming_scan_kernel(const uint32_t* __restrict__ db, long long U, const uint32_t
     }
 
     // Two queries per trip: one warp vote (and one dependent branch) per 2*C pairs.
+    auto scan_queries = [&](auto full_c) {
+    constexpr bool FULL = decltype(full_c)::value;              // no per-pair tail masking on whole tiles
     for (int qi = 0; qi < nq; qi += 2) {
       const bool two = (qi + 1 < nq);
       uint32_t qa[W], qb[W];
@@ -248,9 +301,9 @@ hamming_scan_kernel(const uint32_t* __restrict__ db, long long U, const uint32_t
       bool any = false;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        da[c] = hamming<W, MODE>(code[c], qa);
-        dbb[c] = hamming<W, MODE>(code[c], qb);
-        if (!full) {
+        da[c] = hamming<W, MODE>(code[c], qa, one);
+        dbb[c] = hamming<W, MODE>(code[c], qb, one);
+        if (!FULL) {
           const bool ok = (valid >> c) & 1u;
           da[c] = ok ? da[c] : D_INVALID;
           dbb[c] = ok ? dbb[c] : D_INVALID;
@@ -310,36 +363,119 @@ hamming_scan_kernel(const uint32_t* __restrict__ db, long long U, const uint32_t
         }
       }
     }
+    };
+    if (full) scan_queries(std::true_type{}); else scan_queries(std::false_type{});
+
   }
 
-  // ---- fold the CTA's 8 warp lists into one list per query: part[q][chunk][k] ----
-  // Keys are unique, so the rank of a key among all 8*k candidates is the sum of its
-  // lower bounds in the 8 sorted lists; ranks < k are written straight to HBM.
+  fold_lists(lists, QT, nq, k, part, P, qt0, tid);
+}
+
+// ---- few-queries scan (Q <= FEW_Q): the LinearHashIndex.nn call shape ---------------
+// One query does ~20 integer ops per 32-byte code, so this regime is HBM-bound: the
+// table is streamed exactly once.  Same chunk / warp-tile decomposition and per-warp
+// k-lists as the batched kernel, but every warp keeps TWO tiles of codes in flight
+// (register double buffer): the loads of tile i+1 are issued before the XOR/POPC of
+// tile i, which is what keeps enough bytes in flight to cover HBM latency.
+constexpr int FEW_Q = 4;
+
+template <int W>
+__global__ void __launch_bounds__(THREADS, 2)
+hamming_scan_few_kernel(const uint32_t* __restrict__ db, long long U, const uint32_t* __restrict__ qcodes, int Q, int k,
+                        long long idx_base, long long codes_per_chunk, uint64_t* __restrict__ part, int P,
+                        int* __restrict__ tau_g) {
+  constexpr int C = ScanCfg<W>::C;
+  constexpr int TILE = ScanCfg<W>::TILE;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [queries FEW_Q*W u32][tau FEW_Q i32][lists WARPS*FEW_Q*k u64]
+  uint32_t* sq = reinterpret_cast<uint32_t*>(smem_raw);
+  int* stau = reinterpret_cast<int*>(sq + FEW_Q * W);
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)FEW_Q * W * 4 + FEW_Q * 4 + 7) / 8) * 8);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nq = Q;
+
+  for (int i = tid; i < nq * W; i += THREADS) sq[i] = qcodes[i];
+  for (int i = tid; i < FEW_Q; i += THREADS) stau[i] = (i < nq) ? min(TAU_INIT, tau_g[i]) : TAU_INIT;
+  for (int i = tid; i < WARPS * FEW_Q * k; i += THREADS) lists[i] = SB_KEY_EMPTY;
   __syncthreads();
-  for (int i = tid; i < nq * k; i += THREADS) {
-    const int qi = i / k, j = i - qi * k;
-    part[((size_t)(qt0 + qi) * P + blockIdx.x) * k + j] = SB_KEY_EMPTY;
-  }
-  __syncthreads();
-  const int per_q = WARPS * k;
-  for (int i = tid; i < nq * per_q; i += THREADS) {
-    const int qi = i / per_q, r = i - qi * per_q;
-    const int w = r / k, j = r - w * k;
-    const uint64_t key = lists[((size_t)w * QT + qi) * k + j];
-    if (key == SB_KEY_EMPTY) continue;
-    int rank = 0;
+
+  const long long chunk_begin = (long long)blockIdx.x * codes_per_chunk;
+  const long long chunk_end = min(U, chunk_begin + codes_per_chunk);
+  uint64_t* mylists = lists + (size_t)warp * FEW_Q * k;
+  volatile int* vtau = stau;
+
+  auto load_tile = [&](uint32_t (&dst)[C][W], long long tb) {
 #pragma unroll
-    for (int ww = 0; ww < WARPS; ++ww) {
-      const uint64_t* l = lists + ((size_t)ww * QT + qi) * k;
-      int lo = 0, hi = k;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (l[mid] < key) lo = mid + 1; else hi = mid;
+    for (int c = 0; c < C; ++c) {
+      const long long r = tb + c * 32 + lane;
+      if (r < chunk_end) {
+        load_words<W>(dst[c], db + (size_t)r * W);
+      } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) dst[c][i] = 0u;
       }
-      rank += lo;
     }
-    if (rank < k) part[((size_t)(qt0 + qi) * P + blockIdx.x) * k + rank] = key;
+  };
+
+  uint32_t cur[C][W], nxt[C][W];
+  long long tb = chunk_begin + (long long)warp * TILE;
+  if (tb < chunk_end) load_tile(cur, tb);
+  while (tb < chunk_end) {
+    const long long tn = tb + (long long)WARPS * TILE;
+    if (tn < chunk_end) load_tile(nxt, tn);                     // in flight while `cur` is processed
+    if (lane < nq) {
+      const int g = __ldcg(tau_g + lane);
+      if (g < vtau[lane]) atomicMin(&stau[lane], g);
+    }
+    const long long row0 = idx_base + tb + lane;
+    for (int qi = 0; qi < nq; ++qi) {
+      uint32_t qw[W];
+      load_words_shared<W>(qw, sq + (size_t)qi * W);
+      const int tau = vtau[qi];
+      int d[C];
+      bool any = false;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        d[c] = hamming<W, 1>(cur[c], qw, 1);
+        if (tb + c * 32 + lane >= chunk_end) d[c] = D_INVALID;
+        any |= (d[c] <= tau);
+      }
+      if (__any_sync(sb::FULL_MASK, any)) {
+        uint64_t* list = mylists + (size_t)qi * k;
+        bool touched = false;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const uint64_t mykey = ((uint64_t)(uint32_t)d[c] << SB_KEY_ROW_BITS) | (uint64_t)(row0 + c * 32);
+          unsigned m = __ballot_sync(sb::FULL_MASK, d[c] <= tau && mykey < list[k - 1]);
+          while (m) {
+            const int src = __ffs(m) - 1;
+            const uint64_t key = __shfl_sync(sb::FULL_MASK, mykey, src);
+            warp_insert(list, k, key, lane);
+            touched = true;
+            m &= m - 1;
+            m &= __ballot_sync(sb::FULL_MASK, mykey < list[k - 1]);
+          }
+        }
+        if (touched) {
+          const uint64_t kth = list[k - 1];
+          if (lane == 0 && kth != SB_KEY_EMPTY) {
+            const int bound = (int)(kth >> SB_KEY_ROW_BITS);
+            if (bound < tau && bound < atomicMin(&stau[qi], bound)) atomicMin(tau_g + qi, bound);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int i = 0; i < W; ++i) cur[c][i] = nxt[c][i];
+    tb = tn;
   }
+  fold_lists(lists, FEW_Q, nq, k, part, P, 0, tid);
+}
+
+size_t few_smem_bytes(int W, int k) {
+  return (((size_t)FEW_Q * W * 4 + FEW_Q * 4 + 7) / 8) * 8 + (size_t)WARPS * FEW_Q * k * 8;
 }
 
 // ---- threshold seeding ----------------------------------------------------------
@@ -366,7 +502,7 @@ tau_seed_kernel(const uint32_t* __restrict__ db, int S, const uint32_t* __restri
   for (int r = lane; r < S; r += 32) {
     uint32_t c[W];
     load_words<W>(c, db + (size_t)r * W);
-    atomicAdd(&h[hamming<W, 1>(c, qw)], 1);
+    atomicAdd(&h[hamming<W, 1>(c, qw, 1)], 1);
   }
   __syncwarp();
   // k-th smallest distance of the sample
@@ -573,20 +709,30 @@ int launch_scan(const ScanPlan& p, int mode, const uint32_t* db, long long U, co
       if (rc) return rc;
     }
   }
+  if (Q <= FEW_Q && few_smem_bytes(W, k) <= 100 * 1024) {
+    const size_t sh = few_smem_bytes(W, k);
+    SB_CUDA_TRY(cudaFuncSetAttribute(hamming_scan_few_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    sb::ProfScope prof("hamming_scan_kernel", st);
+    hamming_scan_few_kernel<W><<<p.chunks, THREADS, sh, st>>>(db, U, q, Q, k, idx_base, p.codes_per_chunk, part, p.P,
+                                                              tau_g);
+    sb::count_launch();
+    return sb::check_launch("hamming_scan_few_kernel");
+  }
   dim3 grid(p.chunks, p.nqt);
   const int q_tma_ok = ((reinterpret_cast<uintptr_t>(q) & 15u) == 0 && ((size_t)p.QT * W * 4) % 16 == 0) ? 1 : 0;
   sb::ProfScope prof("hamming_scan_kernel", st);
-  if (mode == 0) {
-    SB_CUDA_TRY(cudaFuncSetAttribute(hamming_scan_kernel<W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)p.smem_bytes));
-    hamming_scan_kernel<W, 0><<<grid, THREADS, p.smem_bytes, st>>>(db, U, q, Q, p.QT, k, idx_base, p.codes_per_chunk,
-                                                                     part, p.P, tau_g, hist_g, q_tma_ok);
-  } else {
-    SB_CUDA_TRY(cudaFuncSetAttribute(hamming_scan_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)p.smem_bytes));
-    hamming_scan_kernel<W, 1><<<grid, THREADS, p.smem_bytes, st>>>(db, U, q, Q, p.QT, k, idx_base, p.codes_per_chunk,
-                                                                     part, p.P, tau_g, hist_g, q_tma_ok);
-  }
+#define SB_SCAN_LAUNCH(M)                                                                                          \
+  do {                                                                                                            \
+    SB_CUDA_TRY(cudaFuncSetAttribute(hamming_scan_kernel<W, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                     (int)p.smem_bytes));                                                        \
+    hamming_scan_kernel<W, M><<<grid, THREADS, p.smem_bytes, st>>>(db, U, q, Q, p.QT, k, idx_base,                \
+                                                                     p.codes_per_chunk, part, p.P, tau_g, hist_g, \
+                                                                     q_tma_ok, /*one=*/1);                        \
+  } while (0)
+  if (mode == 0) SB_SCAN_LAUNCH(0);
+  else if (mode == 1) SB_SCAN_LAUNCH(1);
+  else SB_SCAN_LAUNCH(2);
+#undef SB_SCAN_LAUNCH
   sb::count_launch();
   return sb::check_launch("hamming_scan_kernel");
 }
@@ -626,7 +772,8 @@ int scan_impl(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q, int32
   uint64_t* part = reinterpret_cast<uint64_t*>(static_cast<unsigned char*>(workspace) + p.tau_bytes + p.hist_bytes);
   SB_CUDA_TRY(cudaMemsetAsync(tau_g, 0x7f, p.tau_bytes, st));  // 0x7f7f7f7f: "no bound yet"
   SB_CUDA_TRY(cudaMemsetAsync(hist_g, 0, p.hist_bytes, st));
-  const int mode = (variant == 1) ? 0 : 1;  // variant 1 = plain POPC, otherwise CSA
+  // variant 0 (default) = 4-POPC adder tree, 1 = plain POPC per word, 2 = 5-POPC adder tree
+  const int mode = (variant == 1) ? 0 : (variant == 2 ? 1 : 2);
   int rc;
   switch (W) {
     case 1: rc = launch_scan<1>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, st); break;
