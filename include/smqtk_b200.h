@@ -162,6 +162,23 @@ SB_API int sb_rerank(const float* db, int64_t N, int32_t D, int64_t ldd,
 SB_API int sb_rerank_select(const double* dist, const int64_t* cand_off, int32_t Q, int32_t n,
                      int64_t* out_pos, double* out_dist, void* stream);
 
+/* Same selection, fused with the row gather: out_rows[q][i] = cand_idx[position]
+ * (-1 = fewer than n candidates).  cand_cnt (optional, i64[Q]) limits each query to
+ * the first cand_cnt[q] entries of its segment (fixed-pitch layout below). */
+SB_API int sb_rerank_select_rows(const double* dist, const int64_t* cand_off, const int64_t* cand_cnt,
+                          const int64_t* cand_idx, int32_t Q, int32_t n,
+                          int64_t* out_rows, double* out_dist, void* stream);
+
+/* Candidate expansion (lsh.py:490-496): the descriptor rows of each query's near codes,
+ * in (code rank, row) order.  code_rows i64[Q][n] = rows of the unique-code table
+ * (-1 = none); csr_off i64[U+1] / csr_rows i64[N] = code -> rows map.  Output in a
+ * FIXED-PITCH layout (no host round trip for the total): cand_idx i64[Q][pitch] padded
+ * with -1, cand_off i64[Q+1] = q*pitch, cand_cnt i64[Q] = rows present.  pitch must be
+ * >= n * (max rows per code); surplus rows are dropped.  n <= 2048. */
+SB_API int sb_expand_candidates(const int64_t* code_rows, int32_t Q, int32_t n,
+                         const int64_t* csr_off, const int64_t* csr_rows, int64_t pitch,
+                         int64_t* cand_idx, int64_t* cand_off, int64_t* cand_cnt, void* stream);
+
 /* ---- training: N-scaled contractions of ItqFunctor.fit (itq.py:338-383, 239-289) ----
  * FP64 accumulation, deterministic two-stage row reductions.  Matrix operands are
  * (pointer, kind, row pitch, columns, div, mean[, bits]):

@@ -127,13 +127,17 @@ __device__ __forceinline__ bool before(double da, long long ia, double db_, long
   return ia < ib;
 }
 
+// cand_cnt (optional): candidates actually present in the query's segment (fixed-pitch
+// layout of sb_expand_candidates); cand_idx (optional): write candidate ROWS instead of
+// positions.
 __global__ void __launch_bounds__(SEL_THREADS)
-rerank_select_kernel(const double* __restrict__ dist, const long long* __restrict__ cand_off, int Q, int n,
+rerank_select_kernel(const double* __restrict__ dist, const long long* __restrict__ cand_off,
+                     const long long* __restrict__ cand_cnt, const long long* __restrict__ cand_idx, int Q, int n,
                      long long* __restrict__ out_pos, double* __restrict__ out_dist) {
   __shared__ double s_d[SEL_CAP];
   const int qi = blockIdx.x, tid = threadIdx.x;
   const long long beg = cand_off[qi], end = cand_off[qi + 1];
-  const long long m = end - beg;
+  const long long m = cand_cnt ? min(cand_cnt[qi], end - beg) : end - beg;
   for (int i = tid; i < n; i += SEL_THREADS) {
     out_pos[(long long)qi * n + i] = -1;
     out_dist[(long long)qi * n + i] = nan("");
@@ -151,10 +155,77 @@ rerank_select_kernel(const double* __restrict__ dist, const long long* __restric
       for (long long jx = 0; jx < m; ++jx) rank += before(dist[beg + jx], jx, di, i) ? 1 : 0;
     }
     if (rank < n) {
-      out_pos[(long long)qi * n + rank] = beg + i;
+      out_pos[(long long)qi * n + rank] = cand_idx ? cand_idx[beg + i] : beg + i;
       out_dist[(long long)qi * n + rank] = di;
     }
   }
+}
+
+// ---- candidate expansion: near codes -> descriptor rows (lsh.py:490-496) ------------
+// One CTA per query.  Segment q of cand_idx is [q*pitch, (q+1)*pitch): the rows of the
+// query's near codes in (code rank, row) order, then -1 padding.
+constexpr int EXP_THREADS = 128;
+constexpr int EXP_MAX_N = 2048;
+
+__global__ void __launch_bounds__(EXP_THREADS)
+expand_kernel(const long long* __restrict__ code_rows, int Q, int n, const long long* __restrict__ csr_off,
+              const long long* __restrict__ csr_rows, long long pitch, long long* __restrict__ cand_idx,
+              long long* __restrict__ cand_off, long long* __restrict__ cand_cnt) {
+  __shared__ long long s_start[EXP_MAX_N];   // first csr position of code j
+  __shared__ long long s_dst[EXP_MAX_N + 1];  // exclusive prefix of the counts
+  __shared__ long long s_carry;
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  long long* seg = cand_idx + (long long)qi * pitch;
+  if (tid == 0) {
+    s_carry = 0;
+    cand_off[qi] = (long long)qi * pitch;
+    if (qi == Q - 1) cand_off[Q] = (long long)Q * pitch;
+  }
+  __syncthreads();
+  // counts, then a chunked block scan (EXP_THREADS codes per pass)
+  for (int base = 0; base < n; base += EXP_THREADS) {
+    const int j = base + tid;
+    long long cnt = 0, start = 0;
+    if (j < n) {
+      const long long c = code_rows[(long long)qi * n + j];
+      if (c >= 0) {
+        start = csr_off[c];
+        cnt = csr_off[c + 1] - start;
+      }
+      s_start[j] = start;
+    }
+    // inclusive warp scan + cross-warp carry through shared memory
+    long long inc = cnt;
+    const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(sb::FULL_MASK, inc, o);
+      if (lane >= o) inc += t;
+    }
+    __shared__ long long s_wsum[EXP_THREADS / 32];
+    if (lane == 31) s_wsum[w] = inc;
+    __syncthreads();
+    long long woff = s_carry;
+    for (int ww = 0; ww < w; ++ww) woff += s_wsum[ww];
+    if (j < n) s_dst[j] = woff + inc - cnt;
+    __syncthreads();
+    if (tid == EXP_THREADS - 1) s_carry = woff + inc;
+    __syncthreads();
+  }
+  const long long total = min(s_carry, pitch);
+  if (tid == 0) {
+    s_dst[n] = s_carry;
+    cand_cnt[qi] = total;
+  }
+  __syncthreads();
+  // copy: one warp per code, lanes over its rows
+  const int lane = tid & 31, w = tid >> 5;
+  for (int j = w; j < n; j += EXP_THREADS / 32) {
+    const long long d0 = s_dst[j], cnt = s_dst[j + 1] - d0, src = s_start[j];
+    for (long long i = lane; i < cnt; i += 32)
+      if (d0 + i < pitch) seg[d0 + i] = csr_rows[src + i];
+  }
+  for (long long i = total + tid; i < pitch; i += EXP_THREADS) seg[i] = -1;
 }
 
 }  // namespace
@@ -197,10 +268,40 @@ int sb_rerank_select(const double* dist, const int64_t* cand_off, int32_t Q, int
   SB_REQUIRE(cand_off && out_pos && out_dist, "sb_rerank_select: NULL pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   sb::ProfScope prof("rerank_select_kernel", st);
-  rerank_select_kernel<<<Q, SEL_THREADS, 0, st>>>(dist, reinterpret_cast<const long long*>(cand_off), Q, n,
-                                                  reinterpret_cast<long long*>(out_pos), out_dist);
+  rerank_select_kernel<<<Q, SEL_THREADS, 0, st>>>(dist, reinterpret_cast<const long long*>(cand_off), nullptr, nullptr, Q,
+                                                  n, reinterpret_cast<long long*>(out_pos), out_dist);
   sb::count_launch();
   return sb::check_launch("rerank_select_kernel");
+}
+
+int sb_rerank_select_rows(const double* dist, const int64_t* cand_off, const int64_t* cand_cnt, const int64_t* cand_idx,
+                          int32_t Q, int32_t n, int64_t* out_rows, double* out_dist, void* stream) {
+  SB_REQUIRE(Q >= 1 && n >= 1, "sb_rerank_select_rows: bad sizes");
+  SB_REQUIRE(cand_off && cand_idx && out_rows && out_dist, "sb_rerank_select_rows: NULL pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  sb::ProfScope prof("rerank_select_kernel", st);
+  rerank_select_kernel<<<Q, SEL_THREADS, 0, st>>>(dist, reinterpret_cast<const long long*>(cand_off),
+                                                  reinterpret_cast<const long long*>(cand_cnt),
+                                                  reinterpret_cast<const long long*>(cand_idx), Q, n,
+                                                  reinterpret_cast<long long*>(out_rows), out_dist);
+  sb::count_launch();
+  return sb::check_launch("rerank_select_kernel");
+}
+
+int sb_expand_candidates(const int64_t* code_rows, int32_t Q, int32_t n, const int64_t* csr_off, const int64_t* csr_rows,
+                         int64_t pitch, int64_t* cand_idx, int64_t* cand_off, int64_t* cand_cnt, void* stream) {
+  SB_REQUIRE(Q >= 1 && n >= 1 && pitch >= 1, "sb_expand_candidates: bad sizes");
+  SB_REQUIRE(n <= EXP_MAX_N, "sb_expand_candidates: n=%d exceeds the supported maximum of %d", n, EXP_MAX_N);
+  SB_REQUIRE(code_rows && csr_off && csr_rows && cand_idx && cand_off && cand_cnt, "sb_expand_candidates: NULL pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  sb::ProfScope prof("expand_kernel", st);
+  expand_kernel<<<Q, EXP_THREADS, 0, st>>>(reinterpret_cast<const long long*>(code_rows), Q, n,
+                                           reinterpret_cast<const long long*>(csr_off),
+                                           reinterpret_cast<const long long*>(csr_rows), pitch,
+                                           reinterpret_cast<long long*>(cand_idx), reinterpret_cast<long long*>(cand_off),
+                                           reinterpret_cast<long long*>(cand_cnt));
+  sb::count_launch();
+  return sb::check_launch("expand_kernel");
 }
 
 }  // extern "C"

@@ -233,6 +233,40 @@ def rerank(db: torch.Tensor, q: torch.Tensor, cand_idx: torch.Tensor, cand_off: 
     return out
 
 
+def expand_candidates(code_rows: torch.Tensor, csr_off: torch.Tensor, csr_rows: torch.Tensor, pitch: int):
+    """Fixed-pitch candidate expansion on the device (no host sync):
+    (cand_idx int64[Q * pitch] padded with -1, cand_off int64[Q + 1], cand_cnt int64[Q])."""
+    require_cuda()
+    _chk(code_rows, torch.int64, "code_rows")
+    _chk(csr_off, torch.int64, "csr_off")
+    _chk(csr_rows, torch.int64, "csr_rows")
+    Q, n = code_rows.shape
+    cand_idx = torch.empty((Q * pitch,), dtype=torch.int64, device=code_rows.device)
+    cand_off = torch.empty((Q + 1,), dtype=torch.int64, device=code_rows.device)
+    cand_cnt = torch.empty((Q,), dtype=torch.int64, device=code_rows.device)
+    with torch.cuda.device(code_rows.device):
+        _lib.check(_lib.load().sb_expand_candidates(_ptr(code_rows), Q, n, _ptr(csr_off), _ptr(csr_rows), pitch,
+                                                    _ptr(cand_idx), _ptr(cand_off), _ptr(cand_cnt), _stream()))
+    return cand_idx, cand_off, cand_cnt
+
+
+def rerank_select_rows(dist: torch.Tensor, cand_off: torch.Tensor, cand_cnt: Optional[torch.Tensor],
+                       cand_idx: torch.Tensor, n: int):
+    """Per query the first ``n`` candidates by (distance, position), as candidate ROWS:
+    (rows int64[Q, n] or -1, dist float64[Q, n])."""
+    require_cuda()
+    _chk(dist, torch.float64, "dist")
+    _chk(cand_off, torch.int64, "cand_off")
+    _chk(cand_idx, torch.int64, "cand_idx")
+    Q = cand_off.numel() - 1
+    rows = torch.empty((Q, n), dtype=torch.int64, device=dist.device)
+    od = torch.empty((Q, n), dtype=torch.float64, device=dist.device)
+    with torch.cuda.device(dist.device):
+        _lib.check(_lib.load().sb_rerank_select_rows(_ptr(dist), _ptr(cand_off), _ptr(cand_cnt), _ptr(cand_idx), Q, n,
+                                                     _ptr(rows), _ptr(od), _stream()))
+    return rows, od
+
+
 def rerank_select(dist: torch.Tensor, cand_off: torch.Tensor, n: int):
     """Per query the first ``n`` candidates by (distance, position):
     (pos int64[Q, n] into the candidate list or -1, dist float64[Q, n])."""

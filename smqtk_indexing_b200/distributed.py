@@ -54,6 +54,14 @@ class DeviceOps:
         from . import device
         return device.rerank_select(d, cand_off, n)
 
+    def expand(self, code_rows, csr_off, csr_rows, pitch):
+        from . import device
+        return device.expand_candidates(code_rows.contiguous(), csr_off, csr_rows, pitch)
+
+    def rerank_select_rows(self, d, cand_off, cand_cnt, cand_idx, n):
+        from . import device
+        return device.rerank_select_rows(d, cand_off, cand_cnt, cand_idx, n)
+
 
 def _all_gather_rows(t: torch.Tensor, group) -> Tuple[torch.Tensor, List[int]]:
     """Concatenate row blocks of differing length from all ranks (rank-major)."""
@@ -92,6 +100,7 @@ class ShardedLshIndex:
         self.x_local: Optional[torch.Tensor] = None
         self.row_bounds: List[int] = []
         self.table = self.csr_off = self.csr_rows = None
+        self.max_rows_per_code = 0
         self.scan_lo = self.scan_hi = 0
 
     @property
@@ -112,6 +121,7 @@ class ShardedLshIndex:
             self.row_bounds.append(self.row_bounds[-1] + s)
         self.table, row_code = codeops.sort_unique(codes_all, return_inverse=True)
         self.csr_off, self.csr_rows = codeops.group_rows(row_code, self.table.shape[0])
+        self.max_rows_per_code = int((self.csr_off[1:] - self.csr_off[:-1]).max().item()) if len(self.table) else 0
         cuts = partition_bounds(int(self.table.shape[0]), self.world)
         self.scan_lo, self.scan_hi = cuts[self.rank], cuts[self.rank + 1]
 
@@ -130,8 +140,15 @@ class ShardedLshIndex:
         with _stage("itq_hash"):
             q_codes = self.ops.hash(q)
         _, code_rows = self.near_codes(q_codes, n)
+        from .engine import FIXED_PITCH_LIMIT
+        pitch = n * max(self.max_rows_per_code, 1)
+        fixed = hasattr(self.ops, "expand") and n <= 2048 and q.shape[0] * pitch <= FIXED_PITCH_LIMIT
+        cand_cnt = None
         with _stage("expand"):
-            cand_idx, cand_off = expand_candidates(code_rows, self.csr_off, self.csr_rows)
+            if fixed:       # device-only, fixed-pitch segments padded with -1 (no host round trip)
+                cand_idx, cand_off, cand_cnt = self.ops.expand(code_rows, self.csr_off, self.csr_rows, pitch)
+            else:
+                cand_idx, cand_off = expand_candidates(code_rows, self.csr_off, self.csr_rows)
         with _stage("rerank"):
             lo = self.row_bounds[self.rank]
             # rows outside this rank's shard fall out of range -> NaN, replaced below
@@ -140,10 +157,12 @@ class ShardedLshIndex:
             parts = [torch.empty_like(local) for _ in range(self.world)]
             dist.all_gather(parts, local, group=self.group)
             bounds = torch.tensor(self.row_bounds[1:], dtype=torch.int64, device=cand_idx.device)
-            owner = torch.bucketize(cand_idx, bounds, right=True)
+            owner = torch.bucketize(cand_idx, bounds, right=True).clamp_(max=self.world - 1)
             d = torch.stack(parts)[owner, torch.arange(cand_idx.numel(), device=cand_idx.device)] \
                 if cand_idx.numel() else local
         with _stage("rerank"):
+            if fixed:
+                return self.ops.rerank_select_rows(d, cand_off, cand_cnt, cand_idx, n)
             pos, od = self.ops.rerank_select(d, cand_off, n)
         rows = torch.where(pos >= 0, cand_idx[pos.clamp(min=0)], pos) if cand_idx.numel() else pos
         return rows, od

@@ -16,6 +16,9 @@ import torch
 from . import codes as codeops
 from . import device
 
+#: Largest Q * pitch (candidate slots) served by the fixed-pitch device path.
+FIXED_PITCH_LIMIT = 1 << 25
+
 #: When set to a list, every query stage appends (name, start_event, end_event)
 #: recorded on the current stream -- used by bench.py to attribute step time to
 #: kernels without a profiler.  None (default) = no events are recorded.
@@ -74,6 +77,7 @@ class DeviceLshIndex:
         self.row_code: Optional[torch.Tensor] = None   # int64[N] row -> table row
         self.csr_off: Optional[torch.Tensor] = None    # int64[U + 1]
         self.csr_rows: Optional[torch.Tensor] = None   # int64[N]
+        self.max_rows_per_code: int = 0
 
     def clear(self) -> None:
         self.__init__()
@@ -98,6 +102,8 @@ class DeviceLshIndex:
             return
         self.table, self.row_code = codeops.sort_unique(self.codes, return_inverse=True)
         self.csr_off, self.csr_rows = codeops.group_rows(self.row_code, self.table.shape[0])
+        # most rows sharing one code: sizes the fixed-pitch candidate segments (one sync per re-index)
+        self.max_rows_per_code = int((self.csr_off[1:] - self.csr_off[:-1]).max().item())
 
     # ------------------------------------------------------------------ query stages
     def near_codes(self, q_codes: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -109,6 +115,17 @@ class DeviceLshIndex:
 
     def rerank(self, q: torch.Tensor, code_rows: torch.Tensor, n: int, distance_method: str):
         """Candidate rows of the given codes, re-ranked: (rows int64[Q, n], dists f64[Q, n])."""
+        Q = code_rows.shape[0]
+        pitch = n * max(self.max_rows_per_code, 1)
+        if n <= 2048 and Q * pitch <= FIXED_PITCH_LIMIT:
+            # device-only path: fixed-pitch segments, no host round trip
+            with _stage("expand"):
+                cand_idx, cand_off, cand_cnt = device.expand_candidates(code_rows.contiguous(), self.csr_off,
+                                                                        self.csr_rows, pitch)
+            with _stage("rerank"):
+                dist = device.rerank(self.x, q, cand_idx, cand_off, distance_method)
+                return device.rerank_select_rows(dist, cand_off, cand_cnt, cand_idx, n)
+        # heavy code collisions: exact-size ragged expansion (needs the total on the host)
         with _stage("expand"):
             cand_idx, cand_off = expand_candidates(code_rows, self.csr_off, self.csr_rows)
         with _stage("rerank"):

@@ -272,3 +272,47 @@ def test_rerank_select_order(dev):
         assert list(pos[qi][:len(o)]) == list(o + off[qi])
         assert (pos[qi][len(o):] == -1).all()
         np.testing.assert_array_equal(od[qi][:len(o)], seg[o])
+
+
+# --------------------------------------------------------------------- candidate expansion
+@pytest.mark.parametrize("n", [1, 7, 130, 300])
+def test_expand_candidates_fixed_pitch_equals_ragged(dev, n):
+    """sb_expand_candidates (+ sb_rerank_select_rows) against the ragged torch expansion
+    (+ position select): same candidates in the same (code rank, row) order."""
+    from smqtk_indexing_b200 import engine
+    rng = np.random.RandomState(n)
+    U, Q = 500, 37
+    counts = rng.randint(1, 6, size=U)
+    counts[rng.randint(0, U, 5)] = 40                      # a few crowded codes
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    rows = rng.permutation(int(off[-1])).astype(np.int64)
+    code_rows = rng.randint(0, U, size=(Q, n)).astype(np.int64)
+    code_rows[rng.rand(Q, n) < 0.1] = -1
+    code_rows[3] = -1                                       # a query without candidates
+    t = lambda a: torch.from_numpy(a).cuda()
+    ci_r, co_r = engine.expand_candidates(t(code_rows), t(off), t(rows))
+    pitch = n * int(counts.max())
+    ci, co, cc = dev.expand_candidates(t(code_rows), t(off), t(rows), pitch)
+    torch.cuda.synchronize()
+    ci, co, cc, ci_r, co_r = (x.cpu().numpy() for x in (ci, co, cc, ci_r, co_r))
+    assert np.array_equal(co, np.arange(Q + 1) * pitch)
+    assert np.array_equal(cc, np.diff(co_r))
+    for q in range(Q):
+        seg = ci[q * pitch:(q + 1) * pitch]
+        assert np.array_equal(seg[:cc[q]], ci_r[co_r[q]:co_r[q + 1]])
+        assert (seg[cc[q]:] == -1).all()
+    # selection on random distances (with ties and NaNs)
+    d = rng.randint(0, 50, size=Q * pitch).astype(np.float64)
+    d[rng.rand(Q * pitch) < 0.05] = np.nan
+    k = min(n, 9)
+    r_rows, r_d = dev.rerank_select_rows(t(d), t(co), t(cc), t(ci), k)
+    pos, pd = dev.rerank_select(t(d), t(co), k)
+    torch.cuda.synchronize()
+    r_rows, r_d, pos, pd = (x.cpu().numpy() for x in (r_rows, r_d, pos, pd))
+    for q in range(Q):
+        m = min(k, cc[q])
+        seg_d = d[q * pitch:q * pitch + cc[q]]
+        o = np.lexsort((np.arange(cc[q]), np.where(np.isnan(seg_d), np.inf, seg_d)))[:m]
+        assert np.array_equal(r_rows[q, :m], ci[q * pitch + o])
+        np.testing.assert_array_equal(r_d[q, :m], seg_d[o])
+        assert (r_rows[q, m:] == -1).all()
