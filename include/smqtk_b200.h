@@ -155,6 +155,14 @@ SB_API int sb_rerank(const float* db, int64_t N, int32_t D, int64_t ldd,
               const int64_t* cand_idx, const int64_t* cand_off, int64_t M,
               int32_t metric, double* out, void* stream);
 
+/* Row-sharded variant: db holds the GLOBAL rows [row_base, row_base + N); candidates
+ * owned by another shard (and -1 padding) get 0.0, so that one all-reduce(SUM) over
+ * the shards assembles every distance exactly (x + 0 + ... + 0 == x). */
+SB_API int sb_rerank_shard(const float* db, int64_t N, int64_t row_base, int32_t D, int64_t ldd,
+                    const float* q, int32_t Q, int64_t ldq,
+                    const int64_t* cand_idx, const int64_t* cand_off, int64_t M,
+                    int32_t metric, double* out, void* stream);
+
 /* Per query: order its candidates by (distance, candidate position) and keep
  * the first n (lsh.py:513-519: stable sort by distance, slice).  out_pos i64[Q][n]
  * = position j into cand_idx (-1 = fewer than n candidates), out_dist f64[Q][n]

@@ -43,6 +43,8 @@ SIGNATURES: Dict[str, tuple] = {
     "sb_topk_merge": (c_int32, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "sb_hamming_topk": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P, _P, c_size_t, _P]),
     "sb_rerank": (c_int32, [_P, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64, c_int32, _P, _P]),
+    "sb_rerank_shard": (c_int32, [_P, c_int64, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64,
+                                  c_int32, _P, _P]),
     "sb_rerank_select": (c_int32, [_P, _P, c_int32, c_int32, _P, _P, _P]),
     "sb_rerank_select_rows": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, _P, _P, _P]),
     "sb_expand_candidates": (c_int32, [_P, c_int32, c_int32, _P, _P, c_int64, _P, _P, _P, _P]),

@@ -228,6 +228,7 @@ int sb_fit_row_div(const void* X, int32_t x_kind, int64_t n, int32_t D, int64_t 
   Operand x;
   if (int rc = make_operand(x, X, x_kind, ldx, D, nullptr, nullptr, 0)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  sb::ProfScope prof("row_div_kernel", st);
   row_div_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x, n, norm_kind, norm_p, div_out);
   sb::count_launch();
   return sb::check_launch("row_div_kernel");
@@ -256,6 +257,7 @@ int sb_fit_col_mean(const void* X, int32_t x_kind, int64_t n, int32_t D, int64_t
   double* partial = static_cast<double*>(workspace);
   const long long rpb = (n + parts - 1) / parts;
   dim3 grid((D + 127) / 128, parts);
+  sb::ProfScope prof("col_mean_kernels", st);
   col_sum_partial_kernel<<<grid, 128, 0, st>>>(x, n, rpb, partial);
   reduce_partials_kernel<<<(D + 255) / 256, 256, 0, st>>>(partial, parts, D, 1.0 / (double)n, mean_out);
   sb::count_launch(2);
@@ -281,6 +283,7 @@ int sb_fit_gram(const void* A, int32_t a_kind, int64_t lda, int32_t Ma, const do
   long long rpb = (n + chunks - 1) / chunks;
   rpb = ((rpb + GK - 1) / GK) * GK;
   dim3 grid((Ma + GT - 1) / GT, (Mb + GT - 1) / GT, chunks);
+  sb::ProfScope prof("gram_kernels", st);
   gram_partial_kernel<<<grid, 256, 0, st>>>(a, b, n, rpb, partial);
   const long long elems = (long long)Ma * Mb;
   reduce_partials_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(partial, chunks, elems, scale, out);
@@ -301,6 +304,7 @@ int sb_fit_project(const void* A, int32_t a_kind, int64_t lda, int32_t K, const 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (out_codes) SB_CUDA_TRY(cudaMemsetAsync(out_codes, 0, (size_t)n * Wc * sizeof(uint32_t), st));
   dim3 grid((unsigned)((n + GT - 1) / GT), (M + GT - 1) / GT);
+  sb::ProfScope prof("project_kernel", st);
   project_kernel<<<grid, 256, 0, st>>>(a, Bm, M, n, out_f64, out_codes, Wc);
   sb::count_launch();
   return sb::check_launch("project_kernel");

@@ -20,6 +20,8 @@
 //
 // Exactness: integer arithmetic only; keys (distance<<40 | row) are unique, the
 // merge is a pure selection, so the result is independent of chunking.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -665,8 +667,9 @@ ScanPlan make_plan(long long U, int W, int Q, int k) {
   p.QT = (Q + p.nqt - 1) / p.nqt;                       // balance the tiles
   if (qt_cap >= 4) p.QT = min(qt_cap & ~3, ((p.QT + 3) / 4) * 4);  // keep tile offsets 16-byte aligned
   p.nqt = (Q + p.QT - 1) / p.QT;
-  // code chunks: ~4 waves of 2 CTAs/SM when there is enough work, never less
-  // than one CTA pass (WARPS warp tiles) per chunk
+  // code chunks: up to 4 waves of 2 CTAs/SM when there is enough work (measured best at
+  // U = 1.25M, 2.5M and 10M rows x 4096 queries), never less than one CTA pass
+  // (WARPS warp tiles) per chunk
   const long long pass = (long long)WARPS * tile_codes(W);
   const long long max_chunks = max(1ll, (U + pass - 1) / pass);
   // Grid = nqt * chunks CTAs.  Keep it at (just under) a whole number of waves of
@@ -675,7 +678,8 @@ ScanPlan make_plan(long long U, int W, int Q, int k) {
   const long long slots = (long long)sms * 2;
   const double total_pairs = (double)U * (double)Q;
   int waves = (int)(total_pairs / ((double)slots * 2.0e6));
-  waves = max(1, min(8, waves));
+  waves = max(1, min(4, waves));
+  if (const char* e = getenv("SB_SCAN_WAVES")) waves = max(1, atoi(e));   // tuning knob
   long long chunks = (slots * waves) / p.nqt;          // floor: never spill into an extra wave
   if (chunks < 1) chunks = 1;
   chunks = min(chunks, max_chunks);

@@ -66,7 +66,7 @@ template <int METRIC>
 __global__ void __launch_bounds__(RR_WARPS * 32)
 rerank_kernel(const float* __restrict__ db, long long N, int D, long long ldd, const float* __restrict__ q, int Q,
               long long ldq, const long long* __restrict__ cand_idx, const long long* __restrict__ cand_off,
-              long long M, double* __restrict__ out, int vec_ok) {
+              long long M, double* __restrict__ out, int vec_ok, long long row_base, double miss_value) {
   const int lane = threadIdx.x & 31;
   const long long j = (long long)blockIdx.x * RR_WARPS + (threadIdx.x >> 5);
   if (j >= M) return;
@@ -76,9 +76,9 @@ rerank_kernel(const float* __restrict__ db, long long N, int D, long long ldd, c
     int mid = (lo + hi) >> 1;
     if (cand_off[mid] <= j) lo = mid; else hi = mid;
   }
-  const long long row = cand_idx[j];
+  const long long row = cand_idx[j] - row_base;              // db holds global rows [row_base, row_base + N)
   if (row < 0 || row >= N) {
-    if (lane == 0) out[j] = nan("");
+    if (lane == 0) out[j] = miss_value;
     return;
   }
   const float* a = q + (long long)lo * ldq;
@@ -232,9 +232,9 @@ expand_kernel(const long long* __restrict__ code_rows, int Q, int n, const long 
 
 extern "C" {
 
-int sb_rerank(const float* db, int64_t N, int32_t D, int64_t ldd, const float* q, int32_t Q, int64_t ldq,
-              const int64_t* cand_idx, const int64_t* cand_off, int64_t M, int32_t metric, double* out,
-              void* stream) {
+static int rerank_impl(const float* db, int64_t N, int32_t D, int64_t ldd, const float* q, int32_t Q, int64_t ldq,
+                       const int64_t* cand_idx, const int64_t* cand_off, int64_t M, int32_t metric, double* out,
+                       int64_t row_base, double miss_value, void* stream) {
   SB_REQUIRE(D >= 1 && Q >= 1 && M >= 0 && N >= 0, "sb_rerank: bad sizes");
   SB_REQUIRE(ldd >= D && ldq >= D, "sb_rerank: leading dimension smaller than D");
   SB_REQUIRE(metric >= SB_METRIC_EUCLIDEAN && metric <= SB_METRIC_HIK, "sb_rerank: bad metric %d", metric);
@@ -249,17 +249,32 @@ int sb_rerank(const float* db, int64_t N, int32_t D, int64_t ldd, const float* q
   sb::ProfScope prof("rerank_kernel", st);
   switch (metric) {
     case SB_METRIC_EUCLIDEAN:
-      rerank_kernel<SB_METRIC_EUCLIDEAN><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok);
+      rerank_kernel<SB_METRIC_EUCLIDEAN><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok,
+                                                                         row_base, miss_value);
       break;
     case SB_METRIC_COSINE:
-      rerank_kernel<SB_METRIC_COSINE><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok);
+      rerank_kernel<SB_METRIC_COSINE><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok,
+                                                                      row_base, miss_value);
       break;
     default:
-      rerank_kernel<SB_METRIC_HIK><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok);
+      rerank_kernel<SB_METRIC_HIK><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok,
+                                                                   row_base, miss_value);
       break;
   }
   sb::count_launch();
   return sb::check_launch("rerank_kernel");
+}
+
+int sb_rerank(const float* db, int64_t N, int32_t D, int64_t ldd, const float* q, int32_t Q, int64_t ldq,
+              const int64_t* cand_idx, const int64_t* cand_off, int64_t M, int32_t metric, double* out,
+              void* stream) {
+  return rerank_impl(db, N, D, ldd, q, Q, ldq, cand_idx, cand_off, M, metric, out, 0, nan(""), stream);
+}
+
+int sb_rerank_shard(const float* db, int64_t N, int64_t row_base, int32_t D, int64_t ldd, const float* q, int32_t Q,
+                    int64_t ldq, const int64_t* cand_idx, const int64_t* cand_off, int64_t M, int32_t metric,
+                    double* out, void* stream) {
+  return rerank_impl(db, N, D, ldd, q, Q, ldq, cand_idx, cand_off, M, metric, out, row_base, 0.0, stream);
 }
 
 int sb_rerank_select(const double* dist, const int64_t* cand_off, int32_t Q, int32_t n, int64_t* out_pos,

@@ -233,6 +233,26 @@ def rerank(db: torch.Tensor, q: torch.Tensor, cand_idx: torch.Tensor, cand_off: 
     return out
 
 
+def rerank_shard(db: torch.Tensor, row_base: int, q: torch.Tensor, cand_idx: torch.Tensor, cand_off: torch.Tensor,
+                 metric: str) -> torch.Tensor:
+    """float64[M] distances of the candidates whose GLOBAL row lies in
+    [row_base, row_base + len(db)); 0.0 for the others (sum over shards = all distances)."""
+    require_cuda()
+    if db.dtype != torch.float32 or q.dtype != torch.float32 or db.stride(1) != 1 or q.stride(1) != 1:
+        raise ValueError("db and q must be float32 with unit column stride")
+    _chk(cand_idx, torch.int64, "cand_idx")
+    _chk(cand_off, torch.int64, "cand_off")
+    N, D = db.shape
+    Q = q.shape[0]
+    M = cand_idx.numel()
+    out = torch.empty((M,), dtype=torch.float64, device=db.device)
+    with torch.cuda.device(db.device):
+        _lib.check(_lib.load().sb_rerank_shard(_ptr(db), N, row_base, D, max(db.stride(0), D), _ptr(q), Q,
+                                               max(q.stride(0), D), _ptr(cand_idx), _ptr(cand_off), M,
+                                               _lib.METRICS[metric], _ptr(out), _stream()))
+    return out
+
+
 def expand_candidates(code_rows: torch.Tensor, csr_off: torch.Tensor, csr_rows: torch.Tensor, pitch: int):
     """Fixed-pitch candidate expansion on the device (no host sync):
     (cand_idx int64[Q * pitch] padded with -1, cand_off int64[Q + 1], cand_cnt int64[Q])."""

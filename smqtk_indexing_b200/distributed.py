@@ -14,8 +14,8 @@ Sharding (DESIGN.md section "Multi-GPU"):
 Per query batch there are two small collectives:
   1. all-gather of the per-rank top-n keys (Q*n*8 bytes per rank) followed by
      ``sb_topk_merge`` -> the global n nearest unique codes, identical on all ranks;
-  2. all-gather of candidate distances: every rank re-ranks the candidate rows
-     that live in its descriptor shard, the owner's value is selected per candidate.
+  2. all-reduce (SUM) of candidate distances: every rank re-ranks the candidate rows
+     that live in its descriptor shard and contributes an exact 0.0 for the others.
 Because keys and candidate order are global, the result is bit-identical to the
 single-GPU index, ties included.
 """
@@ -53,6 +53,10 @@ class DeviceOps:
     def rerank_select(self, d, cand_off, n):
         from . import device
         return device.rerank_select(d, cand_off, n)
+
+    def rerank_shard(self, x, row_base, q, cand_idx, cand_off) -> torch.Tensor:
+        from . import device
+        return device.rerank_shard(x, row_base, q, cand_idx, cand_off, self.distance_method)
 
     def expand(self, code_rows, csr_off, csr_rows, pitch):
         from . import device
@@ -128,19 +132,20 @@ class ShardedLshIndex:
     def near_codes(self, q_codes: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Global n nearest unique codes: local scan, all-gather, merge."""
         with _stage("hamming_scan"):
-            keys = self.ops.scan_keys(self.table[self.scan_lo:self.scan_hi], q_codes, n, self.scan_lo)
+            keys = self.ops.scan_keys(self.table[self.scan_lo:self.scan_hi], q_codes, n, self.scan_lo).contiguous()
         with _stage("allgather_merge"):
-            gathered = [torch.empty_like(keys) for _ in range(self.world)]
-            dist.all_gather(gathered, keys.contiguous(), group=self.group)
-            return self.ops.merge_keys(torch.stack(gathered).contiguous())
+            Q = keys.shape[0]
+            gathered = torch.empty((self.world * Q,) + tuple(keys.shape[1:]), dtype=keys.dtype, device=keys.device)
+            dist.all_gather_into_tensor(gathered, keys, group=self.group)      # rank-major concatenation
+            return self.ops.merge_keys(gathered.view((self.world, Q) + tuple(keys.shape[1:])))
 
     def query(self, q: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Collective: all ranks pass the SAME queries; all get the full result
         (global rows int64[Q, n], dists f64[Q, n])."""
+        from .engine import FIXED_PITCH_LIMIT
         with _stage("itq_hash"):
             q_codes = self.ops.hash(q)
         _, code_rows = self.near_codes(q_codes, n)
-        from .engine import FIXED_PITCH_LIMIT
         pitch = n * max(self.max_rows_per_code, 1)
         fixed = hasattr(self.ops, "expand") and n <= 2048 and q.shape[0] * pitch <= FIXED_PITCH_LIMIT
         cand_cnt = None
@@ -149,17 +154,18 @@ class ShardedLshIndex:
                 cand_idx, cand_off, cand_cnt = self.ops.expand(code_rows, self.csr_off, self.csr_rows, pitch)
             else:
                 cand_idx, cand_off = expand_candidates(code_rows, self.csr_off, self.csr_rows)
+        lo, hi = self.row_bounds[self.rank], self.row_bounds[self.rank + 1]
         with _stage("rerank"):
-            lo = self.row_bounds[self.rank]
-            # rows outside this rank's shard fall out of range -> NaN, replaced below
-            local = self.ops.rerank(self.x_local, q, (cand_idx - lo).contiguous(), cand_off)
-        with _stage("allgather_dist"):
-            parts = [torch.empty_like(local) for _ in range(self.world)]
-            dist.all_gather(parts, local, group=self.group)
-            bounds = torch.tensor(self.row_bounds[1:], dtype=torch.int64, device=cand_idx.device)
-            owner = torch.bucketize(cand_idx, bounds, right=True).clamp_(max=self.world - 1)
-            d = torch.stack(parts)[owner, torch.arange(cand_idx.numel(), device=cand_idx.device)] \
-                if cand_idx.numel() else local
+            # every candidate row lives in exactly one shard: its owner computes the distance, the
+            # others contribute an exact 0.0, so a SUM all-reduce assembles the vector bit-exactly
+            if hasattr(self.ops, "rerank_shard"):
+                d = self.ops.rerank_shard(self.x_local, lo, q, cand_idx, cand_off)
+            else:
+                d = self.ops.rerank(self.x_local, q, (cand_idx - lo).contiguous(), cand_off)
+                d = torch.where((cand_idx >= lo) & (cand_idx < hi), d, torch.zeros_like(d))
+        with _stage("allreduce_dist"):
+            if d.numel():
+                dist.all_reduce(d, op=dist.ReduceOp.SUM, group=self.group)
         with _stage("rerank"):
             if fixed:
                 return self.ops.rerank_select_rows(d, cand_off, cand_cnt, cand_idx, n)
