@@ -19,25 +19,69 @@ def _flip(t: torch.Tensor) -> torch.Tensor:
     return torch.bitwise_xor(t, torch.tensor(_SIGN, dtype=torch.int32, device=t.device))
 
 
+def lex_order(codes: torch.Tensor) -> torch.Tensor:
+    """Permutation that sorts the rows ascending by (unsigned) integer value; STABLE, so
+    rows with equal codes keep their relative order.  LSD radix over 64-bit digits:
+    W/2 stable device sorts of int64 keys instead of a comparison sort over rows."""
+    n, w = codes.shape
+    order = None
+    mask = 0xFFFFFFFF
+    for j in range(w, 0, -2):                       # least significant word pair first
+        lo = codes[:, j - 1].to(torch.int64) & mask
+        if j >= 2:
+            key = ((codes[:, j - 2].to(torch.int64) & mask) << 32) | lo
+        else:
+            key = lo
+        key = key ^ (-2 ** 63)                       # unsigned order through a signed sort
+        if order is not None:
+            key = key[order]
+        idx = torch.sort(key, stable=True).indices
+        order = idx if order is None else order[idx]
+    return order
+
+
+def build_table(codes: torch.Tensor):
+    """Everything the index derives from per-row codes, in one pass:
+
+    :return: (table int32[U, W] sorted unique, row_code int64[rows] -> table row,
+              csr_off int64[U + 1], csr_rows int64[rows]) with the rows of each code in
+              ascending row order.
+    """
+    if codes.dim() != 2 or codes.dtype != torch.int32:
+        raise ValueError("codes must be int32[rows, W]")
+    n = codes.shape[0]
+    dev = codes.device
+    if n == 0:
+        e = torch.empty(0, dtype=torch.int64, device=dev)
+        return codes.clone(), e, torch.zeros(1, dtype=torch.int64, device=dev), e.clone()
+    order = lex_order(codes)
+    s = codes[order]
+    new = torch.ones(n, dtype=torch.bool, device=dev)
+    if n > 1:
+        new[1:] = (s[1:] != s[:-1]).any(dim=1)
+    first = torch.nonzero(new).reshape(-1)           # position of each code's first row
+    table = s[first].contiguous()
+    code_of_sorted = torch.cumsum(new.to(torch.int64), 0) - 1
+    row_code = torch.empty(n, dtype=torch.int64, device=dev)
+    row_code[order] = code_of_sorted
+    csr_off = torch.empty(first.numel() + 1, dtype=torch.int64, device=dev)
+    csr_off[:-1] = first
+    csr_off[-1] = n
+    return table, row_code, csr_off, order
+
+
 def sort_unique(codes: torch.Tensor, return_inverse: bool = False, return_counts: bool = False):
     """Rows of ``codes`` sorted ascending by integer value, duplicates removed.
 
     :return: table int32[U, W] (+ inverse int64[rows] -> table row, + counts int64[U])
     """
-    if codes.dim() != 2 or codes.dtype != torch.int32:
-        raise ValueError("codes must be int32[rows, W]")
-    if codes.shape[0] == 0:
-        out = [codes.clone()]
-        if return_inverse:
-            out.append(torch.empty(0, dtype=torch.int64, device=codes.device))
-        if return_counts:
-            out.append(torch.empty(0, dtype=torch.int64, device=codes.device))
-        return out[0] if len(out) == 1 else tuple(out)
-    res = torch.unique(_flip(codes), dim=0, sorted=True, return_inverse=return_inverse,
-                       return_counts=return_counts)
-    if isinstance(res, tuple):
-        return (_flip(res[0]).contiguous(),) + tuple(res[1:])
-    return _flip(res).contiguous()
+    table, row_code, csr_off, _ = build_table(codes)
+    out = [table]
+    if return_inverse:
+        out.append(row_code)
+    if return_counts:
+        out.append(csr_off[1:] - csr_off[:-1])
+    return out[0] if len(out) == 1 else tuple(out)
 
 
 def union(table: torch.Tensor, new_codes: torch.Tensor) -> torch.Tensor:

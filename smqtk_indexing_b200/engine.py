@@ -100,8 +100,7 @@ class DeviceLshIndex:
         if self.codes is None or self.codes.shape[0] == 0:
             self.table = self.csr_off = self.csr_rows = self.row_code = None
             return
-        self.table, self.row_code = codeops.sort_unique(self.codes, return_inverse=True)
-        self.csr_off, self.csr_rows = codeops.group_rows(self.row_code, self.table.shape[0])
+        self.table, self.row_code, self.csr_off, self.csr_rows = codeops.build_table(self.codes)
         # most rows sharing one code: sizes the fixed-pitch candidate segments (one sync per re-index)
         self.max_rows_per_code = int((self.csr_off[1:] - self.csr_off[:-1]).max().item())
 

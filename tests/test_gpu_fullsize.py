@@ -192,7 +192,7 @@ def test_c1_pipeline_100k_x_128_itq64_euclidean_k10():
 def test_c4_pipeline_hik_4096d_itq256_k50():
     rows, dists = _pipeline_case(20_000, 4096, 256, 50, "hik", n_queries=64, n_check=12, seed=4,
                                  normalise_rows=True, fit_rows=5_000)
-    assert rows[0][0] == 17 and abs(dists[0][0]) < 1e-12
+    assert rows[0][0] == 17 and abs(dists[0][0]) < 1e-6      # 1 - sum(fp32 row): not exactly 0
 
 
 def test_c5_fit_and_build_throughput_shape():

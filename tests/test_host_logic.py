@@ -280,3 +280,21 @@ def test_linear_cache_formats():
     ro.index = {1}
     with pytest.raises(ValueError, match="is read-only"):
         ro.save_cache()
+
+
+def test_code_table_build_matches_oracle():
+    """codes.build_table (radix sort / unique / CSR; torch plumbing, runs on CPU tensors too)
+    vs the oracle's unique_code_table, including codes with the top bit set (unsigned order)."""
+    import torch
+    import np_oracle as O
+    from smqtk_indexing_b200 import codes as C
+    rng = np.random.RandomState(0)
+    for W in (1, 2, 4, 8):
+        cw = rng.randint(0, 3, size=(4000, W)).astype(np.uint32)
+        cw[:, 0] |= rng.randint(0, 2, size=4000).astype(np.uint32) << 31
+        t, inv, off, rows = O.unique_code_table(cw)
+        tt, ri, co, cr = C.build_table(torch.from_numpy(cw.view(np.int32)))
+        assert np.array_equal(tt.numpy().view(np.uint32), t)
+        assert np.array_equal(ri.numpy(), inv) and np.array_equal(co.numpy(), off) and np.array_equal(cr.numpy(), rows)
+    e = C.build_table(torch.empty((0, 4), dtype=torch.int32))
+    assert e[0].shape == (0, 4) and e[2].tolist() == [0]
