@@ -524,6 +524,37 @@ tau_seed_kernel(const uint32_t* __restrict__ db, int S, const uint32_t* __restri
   if (lane == 0 && found >= 0) tau_g[q] = found;
 }
 
+// Cheaper seeding for k <= 32: no histogram, no atomics.  Every lane keeps the smallest
+// distance among the sample rows it visits; the 32 lane minima belong to 32 distinct
+// rows, so their k-th smallest bounds the table's k-th distance.  With S rows per query
+// this is as tight as the exact k-th of the sample (both sit near the k/S quantile).
+template <int W>
+__global__ void __launch_bounds__(SEED_WARPS * 32)
+tau_seed_min_kernel(const uint32_t* __restrict__ db, int S, const uint32_t* __restrict__ qcodes, int Q, int k,
+                    int* __restrict__ tau_g) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * SEED_WARPS + warp;
+  if (q >= Q) return;
+  uint32_t qw[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) qw[i] = qcodes[(size_t)q * W + i];
+  int best = D_INVALID;
+#pragma unroll 4
+  for (int r = lane; r < S; r += 32) {
+    uint32_t c[W];
+    load_words<W>(c, db + (size_t)r * W);
+    best = min(best, hamming<W, 1>(c, qw, 1));
+  }
+  // rank of this lane's minimum among the 32 (ties by lane): the lane of rank k-1 publishes
+  int rank = 0;
+#pragma unroll
+  for (int o = 0; o < 32; ++o) {
+    const int other = __shfl_sync(sb::FULL_MASK, best, o);
+    rank += (other < best || (other == best && o < lane)) ? 1 : 0;
+  }
+  if (rank == k - 1 && best != D_INVALID) tau_g[q] = best;
+}
+
 // ---- merge: P sorted k-lists per query -> top-k ------------------------------
 // Exact selection by distance histogram: distances are small integers (<= 32*W
 // <= 1024), so one pass counts keys per distance, a scan finds the distance d*
@@ -701,7 +732,17 @@ ScanPlan make_plan(long long U, int W, int Q, int k) {
 template <int W>
 int launch_scan(const ScanPlan& p, int mode, const uint32_t* db, long long U, const uint32_t* q, int Q, int k,
                 long long idx_base, uint64_t* part, int* tau_g, int* hist_g, cudaStream_t st) {
-  {
+  if (k <= 32 && U >= 32) {
+    // lane-minima seed over a table prefix (the prefix is part of the table, so any k of
+    // its rows bound the k-th distance from above)
+    long long S = min(U, 8192ll);
+    if (const char* e = getenv("SB_SEED_ROWS")) S = min(U, max((long long)atoi(e), 32ll));   // tuning knob
+    sb::ProfScope prof("tau_seed_kernel", st);
+    tau_seed_min_kernel<W><<<(Q + SEED_WARPS - 1) / SEED_WARPS, SEED_WARPS * 32, 0, st>>>(db, (int)S, q, Q, k, tau_g);
+    sb::count_launch();
+    int rc = sb::check_launch("tau_seed_min_kernel");
+    if (rc) return rc;
+  } else {
     // sample = table prefix, large enough to hold k rows several times over
     const long long S = min(U, max(2048ll, 4ll * k));
     if (S >= k) {

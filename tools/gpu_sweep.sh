@@ -1,8 +1,16 @@
-for U in 1.25e6 2.5e6 1e7; do for w in 1 2 3 4 6 8 12 16; do echo -n "U=$U waves=$w: "; SB_SCAN_WAVES=$w timeout 120 python tools/scan_bench.py $U 4096 2>&1 | grep "variant 0" | sed 's/.*scan kernel//'; done; done
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/b2.json 2> gpurun_out/b2.err; echo "bench n2 rc=$?"
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fullsize.py -m gpu -x -q -k "hamming or sharded or c2_scan or c2_few or c2_shard" 2>&1 | tail -3
+for U in 1.25e6 1e7; do for s in 4096 8192 16384; do echo -n "U=$U seed=$s: "; SB_SEED_ROWS=$s timeout 120 python tools/scan_bench.py $U 4096 2>&1 | grep "variant 0" | sed 's/.*scan kernel//'; done; done
 python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/b2.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['kernel_ms'], d['kernel_ms_per_step'])
+import torch, sys
+sys.path.insert(0,'.')
+from smqtk_indexing_b200 import device as D, _lib
+db = torch.randint(-2**31, 2**31-1, (1_250_000, 8), dtype=torch.int32, device="cuda")
+q = torch.randint(-2**31, 2**31-1, (4096, 8), dtype=torch.int32, device="cuda")
+for _ in range(3): D.hamming_scan_keys(db, q, 10)
+_lib.profile_fetch(); _lib.profile_enable(True)
+for _ in range(5): D.hamming_scan_keys(db, q, 10)
+_lib.profile_enable(False)
+agg={}
+for n,ms in _lib.profile_fetch(): agg.setdefault(n,[]).append(ms)
+print({k: sum(v)/len(v) for k,v in agg.items()})
 PY
-tail -3 gpurun_out/b2.err
