@@ -155,6 +155,13 @@ SB_API int sb_rerank(const float* db, int64_t N, int32_t D, int64_t ldd,
               const int64_t* cand_idx, const int64_t* cand_off, int64_t M,
               int32_t metric, double* out, void* stream);
 
+/* Like sb_rerank with cand_idx holding GLOBAL rows of a table whose rows [row_base, row_base + N)
+ * are in db (NaN outside). */
+SB_API int sb_rerank_base(const float* db, int64_t N, int64_t row_base, int32_t D, int64_t ldd,
+                   const float* q, int32_t Q, int64_t ldq,
+                   const int64_t* cand_idx, const int64_t* cand_off, int64_t M,
+                   int32_t metric, double* out, void* stream);
+
 /* Row-sharded variant: db holds the GLOBAL rows [row_base, row_base + N); candidates
  * owned by another shard (and -1 padding) get 0.0, so that one all-reduce(SUM) over
  * the shards assembles every distance exactly (x + 0 + ... + 0 == x). */
@@ -172,9 +179,10 @@ SB_API int sb_rerank_select(const double* dist, const int64_t* cand_off, int32_t
 
 /* Same selection, fused with the row gather: out_rows[q][i] = cand_idx[position]
  * (-1 = fewer than n candidates).  cand_cnt (optional, i64[Q]) limits each query to
- * the first cand_cnt[q] entries of its segment (fixed-pitch layout below). */
+ * the first cand_cnt[q] entries of its segment (fixed-pitch layout below).
+ * tie_by_row != 0: equal distances are ordered by candidate row instead of position. */
 SB_API int sb_rerank_select_rows(const double* dist, const int64_t* cand_off, const int64_t* cand_cnt,
-                          const int64_t* cand_idx, int32_t Q, int32_t n,
+                          const int64_t* cand_idx, int32_t Q, int32_t n, int32_t tie_by_row,
                           int64_t* out_rows, double* out_dist, void* stream);
 
 /* Candidate expansion (lsh.py:490-496): the descriptor rows of each query's near codes,
@@ -186,6 +194,25 @@ SB_API int sb_rerank_select_rows(const double* dist, const int64_t* cand_off, co
 SB_API int sb_expand_candidates(const int64_t* code_rows, int32_t Q, int32_t n,
                          const int64_t* csr_off, const int64_t* csr_rows, int64_t pitch,
                          int64_t* cand_idx, int64_t* cand_off, int64_t* cand_cnt, void* stream);
+
+/* ---- flat index: exact L2 k-nearest rows (reference impls/nn_index/faiss.py:751-831
+ * with 'IDMap,Flat' + metrics.py:73-86).  Tensor-core filter (3xTF32 |x|^2+|q|^2-2x.q against
+ * per-query thresholds, chunked) + exact FP32 error-free re-rank of the survivors; result =
+ * the k rows with the smallest euclidean distance in (distance, row) order.
+ *   sb_l2_prepare: xn_out f32[N] = |row|^2, xn_max_out f32[1] = max (once per table).
+ *   sb_l2_topk:    out_idx i64[Q][k] (-1 = fewer than k rows), out_dist f64[Q][k] (NaN);
+ *                  overflow_out i32[Q] != 0 marks a query whose survivor buffer overflowed
+ *                  (massive near-ties): the caller re-does it with sb_rerank over all rows.
+ * Needs D % 16 == 0, ldd % 4 == 0, 16-byte aligned db, k <= 256 (sb_l2_topk_supported). */
+SB_API int sb_l2_prepare(const float* db, int64_t N, int32_t D, int64_t ldd,
+                  float* xn_out, float* xn_max_out, void* stream);
+SB_API int sb_l2_topk_supported(int64_t N, int32_t D, int64_t ldd, int32_t k);
+SB_API size_t sb_l2_topk_workspace_bytes(int32_t D, int32_t Q, int32_t k);
+SB_API int sb_l2_topk(const float* db, int64_t N, int32_t D, int64_t ldd,
+               const float* xn, const float* xn_max,
+               const float* q, int32_t Q, int64_t ldq, int32_t k,
+               int64_t* out_idx, double* out_dist, int32_t* overflow_out,
+               void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- training: N-scaled contractions of ItqFunctor.fit (itq.py:338-383, 239-289) ----
  * FP64 accumulation, deterministic two-stage row reductions.  Matrix operands are

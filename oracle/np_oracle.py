@@ -246,6 +246,26 @@ def cosine_distance(i: np.ndarray, j: np.ndarray, pos_vectors: bool = True) -> n
     return out[0] if out.size == 1 else out
 
 
+def l2_topk(x_db: np.ndarray, q: np.ndarray, k: int):
+    """Exact flat L2 k-nearest rows: what impls/nn_index/faiss.py:751-831 returns for an
+    'IDMap,Flat' L2 index whose search is exact -- rows ordered by
+    utils/metrics.py:73-86 euclidean_distance (float64), ties broken by row (FAISS and the
+    reference's sorted() leave tie order unspecified).
+
+    :return: (rows int64[Q, k'], dist float64[Q, k']), k' = min(k, N)
+    """
+    x_db = np.asarray(x_db, np.float64)
+    q = np.atleast_2d(np.asarray(q, np.float64))
+    kk = min(k, len(x_db))
+    rows = np.empty((len(q), kk), np.int64)
+    dist = np.empty((len(q), kk), np.float64)
+    for i in range(len(q)):
+        d = euclidean_distance(q[i], x_db) if len(x_db) else np.empty(0)
+        o = np.lexsort((np.arange(len(d)), d))[:kk]
+        rows[i], dist[i] = o, d[o]
+    return rows, dist
+
+
 DISTANCE_FUNCTIONS = {
     "euclidean": euclidean_distance,
     "cosine": cosine_distance,

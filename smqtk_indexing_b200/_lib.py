@@ -46,8 +46,15 @@ SIGNATURES: Dict[str, tuple] = {
     "sb_rerank_shard": (c_int32, [_P, c_int64, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64,
                                   c_int32, _P, _P]),
     "sb_rerank_select": (c_int32, [_P, _P, c_int32, c_int32, _P, _P, _P]),
-    "sb_rerank_select_rows": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, _P, _P, _P]),
+    "sb_rerank_select_rows": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
+    "sb_rerank_base": (c_int32, [_P, c_int64, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64,
+                                 c_int32, _P, _P]),
     "sb_expand_candidates": (c_int32, [_P, c_int32, c_int32, _P, _P, c_int64, _P, _P, _P, _P]),
+    "sb_l2_prepare": (c_int32, [_P, c_int64, c_int32, c_int64, _P, _P, _P]),
+    "sb_l2_topk_supported": (c_int32, [c_int64, c_int32, c_int64, c_int32]),
+    "sb_l2_topk_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "sb_l2_topk": (c_int32, [_P, c_int64, c_int32, c_int64, _P, _P, _P, c_int32, c_int64, c_int32,
+                             _P, _P, _P, _P, c_size_t, _P]),
     "sb_fit_row_div": (c_int32, [_P, c_int32, c_int64, c_int32, c_int64, c_int32, c_double, _P, _P]),
     "sb_fit_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "sb_fit_col_mean": (c_int32, [_P, c_int32, c_int64, c_int32, c_int64, _P, _P, _P, c_size_t, _P]),

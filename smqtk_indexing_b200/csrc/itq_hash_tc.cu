@@ -138,6 +138,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- one-off: split R into the per-stage shared-memory image ------------------
 // image[kc][part][chunk][n][4] (part 0 = hi, 1 = lo): exactly the bytes a stage's R
 // region holds, so the main kernel fetches a stage with ONE bulk copy.
@@ -170,9 +181,25 @@ struct TcParams {
   float* z_out;           // may be NULL
   int stages;
   int tmem_cols;
+  // column blocks: a tile is (column block jb, 256-row tile rt); block jb uses the image at
+  // r_image + jb * image_block_words.  Hashing has one block.
+  int col_blocks;
+  long long image_block_words;
+  // EPI_L2 only: approximate squared-L2 filter (flat_l2.cu)
+  const float* xn;        // f32[n]  |x|^2 per row
+  const float* tq;        // f32[col_blocks * 256]  pass threshold per query (tau + margin) baked into the image
+  unsigned long long* cand_buf;   // u64[queries][cap]: (float bits of d2) << 32 | row
+  int* cand_cnt;          // i32[queries]
+  int cap;
+  unsigned int row_base;  // added to the row stored in the key
+  int passes;             // 3 = 3xTF32 everywhere; 1 = single TF32 pass on the data chunks (EPI_L2: the
+                          // synthetic threshold chunk always gets the full split)
 };
 
-template <bool HAS_DIV>
+constexpr int EPI_HASH = 0;   // sign test + bit-pack (ItqFunctor.get_hash)
+constexpr int EPI_L2 = 1;     // d2 = |x|^2 + |q|^2 - 2 x.q against a per-query threshold (flat L2 index)
+
+template <bool HAS_DIV, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) itq_hash_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -189,8 +216,11 @@ __global__ void __launch_bounds__(THREADS, 1) itq_hash_tc_kernel(const TcParams 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_raw + (2 * MAX_STAGES + 2) * 8);
   const uint32_t smem0 = smem_u32(smem);
 
-  const long long tiles = (p.n + TILE_M - 1) / TILE_M;
-  const int nk = p.D / KC;
+  const long long row_tiles = (p.n + TILE_M - 1) / TILE_M;
+  const long long tiles = row_tiles * p.col_blocks;            // flat index t = jb * row_tiles + rt
+  // EPI_L2 appends one synthetic K chunk: A = (-|x|^2/2, 1, 0...), B = (1, -h[query], 0...), so that
+  // the accumulator is x.q - |x|^2/2 - h and the threshold test is a sign test
+  const int nk = p.D / KC + (EPI == EPI_L2 ? 1 : 0);
   // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
   const long long my_tiles = (tiles > (long long)blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long long items = my_tiles * nk;                       // (tile, k-chunk) pipeline items
@@ -224,7 +254,8 @@ __global__ void __launch_bounds__(THREADS, 1) itq_hash_tc_kernel(const TcParams 
     float4 buf[PF][XF_ROWGROUPS];
     float4 mbuf[PF];
     float dbuf[PF][XF_ROWGROUPS];
-    long long ld_tile = blockIdx.x;                             // load cursor
+    long long ld_tile = blockIdx.x % row_tiles;                 // load cursor: ROW tile of flat tile blockIdx.x
+    const long long ld_step = gridDim.x % row_tiles;
     int ld_kc = 0;
     long long ld_left = items;
     auto load_next = [&](float4 (&dst)[XF_ROWGROUPS], float4& m4, float (&dv)[XF_ROWGROUPS]) {
@@ -235,15 +266,24 @@ __global__ void __launch_bounds__(THREADS, 1) itq_hash_tc_kernel(const TcParams 
 #pragma unroll
       for (int i = 0; i < XF_ROWGROUPS; ++i) {
         const long long row = row0 + i * 8;
-        dst[i] = (row < p.n) ? ldg_stream(src + (long long)i * 8 * p.ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI == EPI_L2 && ld_kc == nk - 1) {
+          dst[i] = (row < p.n && c == 0) ? make_float4(-0.5f * __ldg(p.xn + row), 1.0f, 0.f, 0.f)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          dst[i] = (row < p.n) ? ldg_stream(src + (long long)i * 8 * p.ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (HAS_DIV) dv[i] = (row < p.n) ? __ldg(p.row_div + row) : 1.0f;
       }
       m4 = p.mean ? __ldg(reinterpret_cast<const float4*>(p.mean + ld_kc * KC + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (++ld_kc == nk) { ld_kc = 0; ld_tile += gridDim.x; }
+      if (++ld_kc == nk) {
+        ld_kc = 0;
+        ld_tile += ld_step;
+        if (ld_tile >= row_tiles) ld_tile -= row_tiles;
+      }
     };
 #pragma unroll
     for (int q = 0; q < PF; ++q) load_next(buf[q], mbuf[q], dbuf[q]);
-    int stage = 0;
+    int stage = 0, st_kc = 0;
     uint32_t phase = 0;
     const uint32_t st_off = (uint32_t)c * A_PLANE + (uint32_t)(xw * (XF_ROWGROUPS * 8) + r8) * 16;
     for (long long base = 0; base < items; base += PF) {
@@ -251,6 +291,8 @@ __global__ void __launch_bounds__(THREADS, 1) itq_hash_tc_kernel(const TcParams 
       for (int q = 0; q < PF; ++q) {
         if (base + q < items) {
           const float4 m4 = mbuf[q];
+          const bool need_lo = (p.passes == 3) || (EPI == EPI_L2 && st_kc == nk - 1);
+          if (++st_kc == nk) st_kc = 0;
           mbar_wait(empty0 + stage * 8, phase ^ 1);
           unsigned char* a_hi = smem + (size_t)stage * stage_bytes + st_off;
 #pragma unroll
@@ -264,12 +306,14 @@ __global__ void __launch_bounds__(THREADS, 1) itq_hash_tc_kernel(const TcParams 
             const float a0 = v.x - m4.x, a1 = v.y - m4.y, a2 = v.z - m4.z, a3 = v.w - m4.w;
             uint4 hi, lo;
             hi.x = to_tf32_finite(a0); hi.y = to_tf32_finite(a1); hi.z = to_tf32_finite(a2); hi.w = to_tf32_finite(a3);
-            lo.x = to_tf32_finite(a0 - __uint_as_float(hi.x));
-            lo.y = to_tf32_finite(a1 - __uint_as_float(hi.y));
-            lo.z = to_tf32_finite(a2 - __uint_as_float(hi.z));
-            lo.w = to_tf32_finite(a3 - __uint_as_float(hi.w));
             *reinterpret_cast<uint4*>(a_hi + i * 128) = hi;
-            *reinterpret_cast<uint4*>(a_hi + A_PART + i * 128) = lo;
+            if (need_lo) {
+              lo.x = to_tf32_finite(a0 - __uint_as_float(hi.x));
+              lo.y = to_tf32_finite(a1 - __uint_as_float(hi.y));
+              lo.z = to_tf32_finite(a2 - __uint_as_float(hi.z));
+              lo.w = to_tf32_finite(a3 - __uint_as_float(hi.w));
+              *reinterpret_cast<uint4*>(a_hi + A_PART + i * 128) = lo;
+            }
           }
           fence_proxy_async();                                  // generic-proxy stores -> visible to the tensor core
           __syncwarp();
@@ -284,14 +328,21 @@ __global__ void __launch_bounds__(THREADS, 1) itq_hash_tc_kernel(const TcParams 
     if (lane == 0) {
       int stage = 0, kc = 0;
       uint32_t phase = 0;
+      long long t = blockIdx.x;
+      const uint32_t* img = p.r_image + (t / row_tiles) * p.image_block_words;
       for (long long it = 0; it < items; ++it) {
         mbar_wait(empty0 + stage * 8, phase ^ 1);
-        mbar_expect_tx(full0 + stage * 8, 2 * b_part);
+        // hi part only when the chunk runs a single TF32 pass
+        const uint32_t bytes = ((p.passes == 3) || (EPI == EPI_L2 && kc == nk - 1)) ? 2 * b_part : b_part;
+        mbar_expect_tx(full0 + stage * 8, bytes);
         tma_bulk_g2s(smem0 + stage * stage_bytes + 2 * A_PART,
-                     reinterpret_cast<const unsigned char*>(p.r_image) + (size_t)kc * 2 * b_part, 2 * b_part,
-                     full0 + stage * 8);
+                     reinterpret_cast<const unsigned char*>(img) + (size_t)kc * 2 * b_part, bytes, full0 + stage * 8);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        if (++kc == nk) kc = 0;
+        if (++kc == nk) {
+          kc = 0;
+          t += gridDim.x;
+          img = p.r_image + (t / row_tiles) * p.image_block_words;
+        }
       }
     }
   } else if (warp == MMA_WARP) {
@@ -320,9 +371,13 @@ __global__ void __launch_bounds__(THREADS, 1) itq_hash_tc_kernel(const TcParams 
               const uint64_t dal = umma_desc(a_lo + a_off, A_PLANE, 128);
               const uint64_t dbh = umma_desc(r_hi + b_off, (uint32_t)b * 16, 128);
               const uint64_t dbl = umma_desc(r_lo + b_off, (uint32_t)b * 16, 128);
-              umma_tf32(d_tmem, dal, dbh, idesc, (kc | ks) ? 1u : 0u);   // small terms first
-              umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-              umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+              if ((p.passes == 3) || (EPI == EPI_L2 && kc == nk - 1)) {
+                umma_tf32(d_tmem, dal, dbh, idesc, (kc | ks) ? 1u : 0u);   // small terms first
+                umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+              } else {
+                umma_tf32(d_tmem, dah, dbh, idesc, (kc | ks) ? 1u : 0u);
+              }
             }
           }
           umma_commit(empty0 + stage * 8);                      // frees the stage when these MMAs retire
@@ -335,55 +390,103 @@ __global__ void __launch_bounds__(THREADS, 1) itq_hash_tc_kernel(const TcParams 
   } else {
     // =========================== epilogue (warps 0-3 = TMEM lane quadrants) ===========================
     const int nb = b >> 5;                                      // 32-column groups
-    const int wpad = p.W - nb;                                  // leading zero words when W > b/32
     uint32_t acc_phase = 0;
-    for (long long t = 0; t < my_tiles; ++t) {
-      const long long tile = blockIdx.x + t * gridDim.x;
-      mbar_wait(acc_full, acc_phase);
-      tc_fence_after();
+    if constexpr (EPI == EPI_HASH) {
+      const int wpad = p.W - nb;                                // leading zero words when W > b/32
+      for (long long t = 0; t < my_tiles; ++t) {
+        const long long tile = blockIdx.x + t * gridDim.x;      // one column block: flat tile == row tile
+        mbar_wait(acc_full, acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int sub = 0; sub < 2; ++sub) {
-        const long long row = tile * TILE_M + sub * UMMA_M + warp * 32 + lane;
-        uint32_t words[8];
+        for (int sub = 0; sub < 2; ++sub) {
+          const long long row = tile * TILE_M + sub * UMMA_M + warp * 32 + lane;
+          uint32_t words[8];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          words[g] = 0u;
-          if (g < nb) {
-            uint32_t w = 0u;
+          for (int g = 0; g < 8; ++g) {
+            words[g] = 0u;
+            if (g < nb) {
+              uint32_t w = 0u;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {                       // 16 accumulator columns per TMEM load
-              uint32_t v[16];
-              tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * b + g * 32 + h * 16), v);
+              for (int h = 0; h < 2; ++h) {                     // 16 accumulator columns per TMEM load
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * b + g * 32 + h * 16), v);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) w |= (__uint_as_float(v[j]) >= 0.0f) ? (0x80000000u >> (h * 16 + j)) : 0u;
-              if (p.z_out && row < p.n) {
-                float4* zo = reinterpret_cast<float4*>(p.z_out + row * (long long)b + g * 32 + h * 16);
+                for (int j = 0; j < 16; ++j) w |= (__uint_as_float(v[j]) >= 0.0f) ? (0x80000000u >> (h * 16 + j)) : 0u;
+                if (p.z_out && row < p.n) {
+                  float4* zo = reinterpret_cast<float4*>(p.z_out + row * (long long)b + g * 32 + h * 16);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  zo[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                  for (int j = 0; j < 4; ++j)
+                    zo[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                }
+              }
+              words[g] = w;
+            }
+          }
+          if (row < p.n) {
+            uint32_t* out = p.codes + row * p.W;
+            for (int i = 0; i < wpad; ++i) out[i] = 0u;
+            if (nb == 8 && wpad == 0) {
+              reinterpret_cast<uint4*>(out)[0] = make_uint4(words[0], words[1], words[2], words[3]);
+              reinterpret_cast<uint4*>(out)[1] = make_uint4(words[4], words[5], words[6], words[7]);
+            } else {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                if (g < nb) out[wpad + g] = words[g];
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+        acc_phase ^= 1;
+      }
+    } else {
+      // ---- flat L2 filter: the accumulator is x.q - |x|^2/2 - (|q|^2 - tq)/2, so a pair passes its
+      // query's threshold (d2 <= tq) iff the accumulator is >= 0: a sign test like the hash epilogue.
+      // Survivors (rare after the first chunk) are appended to the query's candidate buffer.
+      for (long long t = 0; t < my_tiles; ++t) {
+        const long long tile = blockIdx.x + t * gridDim.x;
+        const long long jb = tile / row_tiles, rt = tile - jb * row_tiles;
+        mbar_wait(acc_full, acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          const long long row = rt * TILE_M + sub * UMMA_M + warp * 32 + lane;
+          const bool rvalid = row < p.n;
+          const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * b);
+          uint32_t cur[16], nxt[16];
+          tmem_ld16(tbase, cur);
+#pragma unroll 1
+          for (int g16 = 0; g16 < 2 * nb; ++g16) {               // 16 accumulator columns per TMEM load
+            if (g16 + 1 < 2 * nb) tmem_ld16_nowait(tbase + (uint32_t)((g16 + 1) * 16), nxt);
+            unsigned pass = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pass |= (__uint_as_float(cur[j]) >= 0.0f) ? (1u << j) : 0u;
+            if (!rvalid) pass = 0u;
+            if (pass) {                                          // rare after the first chunk
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {                     // static register indices only
+                if (pass & (1u << j)) {
+                  const long long qg = jb * 256 + g16 * 16 + j;
+                  const float d2 = fmaxf(fmaf(-2.0f, __uint_as_float(cur[j]), __ldcg(p.tq + qg)), 0.0f);
+                  const int slot = atomicAdd(p.cand_cnt + qg, 1);
+                  if (slot < p.cap)
+                    p.cand_buf[qg * p.cap + slot] =
+                        ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(p.row_base + (unsigned)row);
+                }
               }
             }
-            words[g] = w;
-          }
-        }
-        if (row < p.n) {
-          uint32_t* out = p.codes + row * p.W;
-          for (int i = 0; i < wpad; ++i) out[i] = 0u;
-          if (nb == 8 && wpad == 0) {
-            reinterpret_cast<uint4*>(out)[0] = make_uint4(words[0], words[1], words[2], words[3]);
-            reinterpret_cast<uint4*>(out)[1] = make_uint4(words[4], words[5], words[6], words[7]);
-          } else {
+            tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              if (g < nb) out[wpad + g] = words[g];
+            for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+        acc_phase ^= 1;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
-      acc_phase ^= 1;
     }
   }
 
@@ -408,6 +511,34 @@ int pick_stages(int b, size_t* smem_bytes) {
 }  // namespace
 
 namespace sb {
+
+// Flat-L2 filter pass (flat_l2.cu): rows [0, n) of X against `col_blocks` blocks of 256
+// query columns whose hi/lo images (same layout as the rotation image, b = 256, plus one
+// synthetic K chunk carrying the thresholds) start at q_image + jb * (D + 16) * 512 words.
+// Pairs with |x|^2 + |q|^2 - 2 x.q <= tq[query] are appended to cand_buf[query][cap]
+// (key = d2 bits << 32 | row_base + row), counted in cand_cnt.
+int tc_l2_filter(const float* X, int64_t n, int32_t D, int64_t ldx, const uint32_t* q_image, int col_blocks,
+                 const float* xn, const float* tq, unsigned long long* cand_buf, int* cand_cnt, int cap,
+                 unsigned row_base, int passes, cudaStream_t st) {
+  TcParams p;
+  p.X = X; p.n = n; p.D = D; p.ldx = ldx; p.mean = nullptr; p.row_div = nullptr;
+  p.r_image = q_image; p.b = 256; p.codes = nullptr; p.W = 8; p.z_out = nullptr;
+  size_t smem_bytes = 0;
+  p.stages = pick_stages(256, &smem_bytes);
+  p.tmem_cols = 512;
+  p.col_blocks = col_blocks;
+  p.image_block_words = (long long)(D + KC) * 256 * 2;         // D/16 data chunks + the synthetic chunk
+  p.passes = passes;
+  p.xn = xn; p.tq = tq; p.cand_buf = cand_buf; p.cand_cnt = cand_cnt; p.cap = cap; p.row_base = row_base;
+  const long long tiles = ((n + TILE_M - 1) / TILE_M) * col_blocks;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  SB_CUDA_TRY(cudaFuncSetAttribute(itq_hash_tc_kernel<false, EPI_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem_bytes));
+  ProfScope prof("l2_filter_tc_kernel", st);
+  itq_hash_tc_kernel<false, EPI_L2><<<grid, THREADS, smem_bytes, st>>>(p);
+  count_launch();
+  return check_launch("l2_filter_tc_kernel");
+}
 
 int itq_hash_tc_supported(int64_t n, int32_t D, int64_t ldx, int32_t b, const float* X) {
   return n >= 1 && D >= KC && D % KC == 0 && b >= 32 && b <= 256 && b % 32 == 0 && ldx % 4 == 0 &&
@@ -456,6 +587,9 @@ int sb_itq_hash_tc(const float* X, int64_t n, int32_t D, int64_t ldx, const floa
   p.X = X; p.n = n; p.D = D; p.ldx = ldx; p.mean = mean; p.row_div = row_div;
   p.r_image = reinterpret_cast<const uint32_t*>(r_image);
   p.b = b; p.codes = codes_out; p.W = W; p.z_out = z_out;
+  p.col_blocks = 1; p.image_block_words = 0;
+  p.xn = nullptr; p.tq = nullptr; p.cand_buf = nullptr; p.cand_cnt = nullptr; p.cap = 0; p.row_base = 0;
+  p.passes = 3;
   size_t smem_bytes = 0;
   p.stages = pick_stages(b, &smem_bytes);
   int cols = 32;
@@ -465,11 +599,13 @@ int sb_itq_hash_tc(const float* X, int64_t n, int32_t D, int64_t ldx, const floa
   const int grid = (int)(tiles < sb::sm_count() ? tiles : sb::sm_count());
   sb::ProfScope prof("itq_hash_tc_kernel", st);
   if (row_div) {
-    SB_CUDA_TRY(cudaFuncSetAttribute(itq_hash_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    itq_hash_tc_kernel<true><<<grid, THREADS, smem_bytes, st>>>(p);
+    SB_CUDA_TRY(cudaFuncSetAttribute(itq_hash_tc_kernel<true, EPI_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes));
+    itq_hash_tc_kernel<true, EPI_HASH><<<grid, THREADS, smem_bytes, st>>>(p);
   } else {
-    SB_CUDA_TRY(cudaFuncSetAttribute(itq_hash_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    itq_hash_tc_kernel<false><<<grid, THREADS, smem_bytes, st>>>(p);
+    SB_CUDA_TRY(cudaFuncSetAttribute(itq_hash_tc_kernel<false, EPI_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes));
+    itq_hash_tc_kernel<false, EPI_HASH><<<grid, THREADS, smem_bytes, st>>>(p);
   }
   sb::count_launch();
   return sb::check_launch("itq_hash_tc_kernel");

@@ -49,10 +49,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 template <int METRIC>
 __device__ __forceinline__ void accumulate(F2& s0, F2& s1, F2& s2, float a, float b) {
   if (METRIC == SB_METRIC_EUCLIDEAN) {
-    // a - b: exact for near-equal values (Sterbenz), one rounding otherwise; the
-    // squared term is split exactly.
-    float t = a - b;
+    // a - b = t + e exactly (TwoSum), (t + e)^2 = t^2 + 2 t e + O(e^2): t^2 is split
+    // exactly, the cross term goes to the low word -- ~2^-45 relative per term.
+    const float t = a - b;
+    const float bv = t - a;
+    const float e = (a - (t - bv)) + (-b - bv);
     acc_prod(s0, t, t);
+    s0.lo = fmaf(2.0f * t, e, s0.lo);
   } else if (METRIC == SB_METRIC_COSINE) {
     acc_prod(s0, a, b);
     acc_prod(s1, a, a);
@@ -130,10 +133,11 @@ __device__ __forceinline__ bool before(double da, long long ia, double db_, long
 // cand_cnt (optional): candidates actually present in the query's segment (fixed-pitch
 // layout of sb_expand_candidates); cand_idx (optional): write candidate ROWS instead of
 // positions.
+// tie_by_row: equal distances are ordered by candidate ROW (cand_idx value) instead of position.
 __global__ void __launch_bounds__(SEL_THREADS)
 rerank_select_kernel(const double* __restrict__ dist, const long long* __restrict__ cand_off,
                      const long long* __restrict__ cand_cnt, const long long* __restrict__ cand_idx, int Q, int n,
-                     long long* __restrict__ out_pos, double* __restrict__ out_dist) {
+                     long long* __restrict__ out_pos, double* __restrict__ out_dist, int tie_by_row) {
   __shared__ double s_d[SEL_CAP];
   const int qi = blockIdx.x, tid = threadIdx.x;
   const long long beg = cand_off[qi], end = cand_off[qi + 1];
@@ -149,7 +153,11 @@ rerank_select_kernel(const double* __restrict__ dist, const long long* __restric
   for (long long i = tid; i < m; i += SEL_THREADS) {
     const double di = staged ? s_d[i] : dist[beg + i];
     long long rank = 0;
-    if (staged) {
+    if (tie_by_row) {
+      const long long ri = cand_idx[beg + i];
+      for (long long jx = 0; jx < m; ++jx)
+        rank += before(staged ? s_d[jx] : dist[beg + jx], cand_idx[beg + jx], di, ri) ? 1 : 0;
+    } else if (staged) {
       for (long long jx = 0; jx < m; ++jx) rank += before(s_d[jx], jx, di, i) ? 1 : 0;
     } else {
       for (long long jx = 0; jx < m; ++jx) rank += before(dist[beg + jx], jx, di, i) ? 1 : 0;
@@ -271,6 +279,12 @@ int sb_rerank(const float* db, int64_t N, int32_t D, int64_t ldd, const float* q
   return rerank_impl(db, N, D, ldd, q, Q, ldq, cand_idx, cand_off, M, metric, out, 0, nan(""), stream);
 }
 
+int sb_rerank_base(const float* db, int64_t N, int64_t row_base, int32_t D, int64_t ldd, const float* q, int32_t Q,
+                   int64_t ldq, const int64_t* cand_idx, const int64_t* cand_off, int64_t M, int32_t metric,
+                   double* out, void* stream) {
+  return rerank_impl(db, N, D, ldd, q, Q, ldq, cand_idx, cand_off, M, metric, out, row_base, nan(""), stream);
+}
+
 int sb_rerank_shard(const float* db, int64_t N, int64_t row_base, int32_t D, int64_t ldd, const float* q, int32_t Q,
                     int64_t ldq, const int64_t* cand_idx, const int64_t* cand_off, int64_t M, int32_t metric,
                     double* out, void* stream) {
@@ -284,13 +298,13 @@ int sb_rerank_select(const double* dist, const int64_t* cand_off, int32_t Q, int
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   sb::ProfScope prof("rerank_select_kernel", st);
   rerank_select_kernel<<<Q, SEL_THREADS, 0, st>>>(dist, reinterpret_cast<const long long*>(cand_off), nullptr, nullptr, Q,
-                                                  n, reinterpret_cast<long long*>(out_pos), out_dist);
+                                                  n, reinterpret_cast<long long*>(out_pos), out_dist, 0);
   sb::count_launch();
   return sb::check_launch("rerank_select_kernel");
 }
 
 int sb_rerank_select_rows(const double* dist, const int64_t* cand_off, const int64_t* cand_cnt, const int64_t* cand_idx,
-                          int32_t Q, int32_t n, int64_t* out_rows, double* out_dist, void* stream) {
+                          int32_t Q, int32_t n, int32_t tie_by_row, int64_t* out_rows, double* out_dist, void* stream) {
   SB_REQUIRE(Q >= 1 && n >= 1, "sb_rerank_select_rows: bad sizes");
   SB_REQUIRE(cand_off && cand_idx && out_rows && out_dist, "sb_rerank_select_rows: NULL pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -298,7 +312,7 @@ int sb_rerank_select_rows(const double* dist, const int64_t* cand_off, const int
   rerank_select_kernel<<<Q, SEL_THREADS, 0, st>>>(dist, reinterpret_cast<const long long*>(cand_off),
                                                   reinterpret_cast<const long long*>(cand_cnt),
                                                   reinterpret_cast<const long long*>(cand_idx), Q, n,
-                                                  reinterpret_cast<long long*>(out_rows), out_dist);
+                                                  reinterpret_cast<long long*>(out_rows), out_dist, tie_by_row ? 1 : 0);
   sb::count_launch();
   return sb::check_launch("rerank_select_kernel");
 }

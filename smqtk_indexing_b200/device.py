@@ -271,7 +271,7 @@ def expand_candidates(code_rows: torch.Tensor, csr_off: torch.Tensor, csr_rows: 
 
 
 def rerank_select_rows(dist: torch.Tensor, cand_off: torch.Tensor, cand_cnt: Optional[torch.Tensor],
-                       cand_idx: torch.Tensor, n: int):
+                       cand_idx: torch.Tensor, n: int, tie_by_row: bool = False):
     """Per query the first ``n`` candidates by (distance, position), as candidate ROWS:
     (rows int64[Q, n] or -1, dist float64[Q, n])."""
     require_cuda()
@@ -283,7 +283,7 @@ def rerank_select_rows(dist: torch.Tensor, cand_off: torch.Tensor, cand_cnt: Opt
     od = torch.empty((Q, n), dtype=torch.float64, device=dist.device)
     with torch.cuda.device(dist.device):
         _lib.check(_lib.load().sb_rerank_select_rows(_ptr(dist), _ptr(cand_off), _ptr(cand_cnt), _ptr(cand_idx), Q, n,
-                                                     _ptr(rows), _ptr(od), _stream()))
+                                                     1 if tie_by_row else 0, _ptr(rows), _ptr(od), _stream()))
     return rows, od
 
 
@@ -299,3 +299,67 @@ def rerank_select(dist: torch.Tensor, cand_off: torch.Tensor, n: int):
     with torch.cuda.device(dist.device):
         _lib.check(_lib.load().sb_rerank_select(_ptr(dist), _ptr(cand_off), Q, n, _ptr(pos), _ptr(od), _stream()))
     return pos, od
+
+
+# --------------------------------------------------------------------- flat L2 index
+def l2_prepare(db: torch.Tensor):
+    """(xn f32[N] = |row|^2, xn_max f32[1]) of a float32 table (once per table)."""
+    require_cuda()
+    if db.dtype != torch.float32 or db.dim() != 2 or db.stride(1) != 1:
+        raise ValueError("db must be float32[N, D] with unit column stride")
+    N, D = db.shape
+    xn = torch.empty((N,), dtype=torch.float32, device=db.device)
+    xmax = torch.empty((1,), dtype=torch.float32, device=db.device)
+    with torch.cuda.device(db.device):
+        _lib.check(_lib.load().sb_l2_prepare(_ptr(db), N, D, max(db.stride(0), D), _ptr(xn), _ptr(xmax), _stream()))
+    return xn, xmax
+
+
+def l2_brute_force(db: torch.Tensor, q: torch.Tensor, k: int):
+    """Exact L2 top-k by the re-rank kernel over EVERY row (any shape; the fallback of
+    ``l2_topk`` and the path for shapes the tensor-core filter does not take).
+    (idx int64[Q, k], dist float64[Q, k]); -1 / NaN when the table has fewer than k rows."""
+    N = db.shape[0]
+    Q = q.shape[0]
+    idx = torch.full((Q, k), -1, dtype=torch.int64, device=db.device)
+    dist = torch.full((Q, k), float("nan"), dtype=torch.float64, device=db.device)
+    if N == 0:
+        return idx, dist
+    all_rows = torch.arange(N, dtype=torch.int64, device=db.device)
+    off = torch.tensor([0, N], dtype=torch.int64, device=db.device)
+    for qi in range(Q):                      # one query at a time: N candidate slots each
+        d = rerank(db, q[qi:qi + 1], all_rows, off, "euclidean")
+        r, od = rerank_select_rows(d, off, None, all_rows, k, tie_by_row=True)
+        idx[qi], dist[qi] = r[0], od[0]
+    return idx, dist
+
+
+def l2_topk(db: torch.Tensor, q: torch.Tensor, k: int, prepared=None):
+    """Exact k nearest rows by euclidean distance, (distance, row) order:
+    (idx int64[Q, k], dist float64[Q, k]).  ``prepared`` = ``l2_prepare(db)`` (cached by the
+    index).  Queries whose survivor buffer overflowed are redone by brute force."""
+    require_cuda()
+    if db.dtype != torch.float32 or q.dtype != torch.float32 or db.stride(1) != 1 or q.stride(1) != 1:
+        raise ValueError("db and q must be float32 with unit column stride")
+    N, D = db.shape
+    Q = q.shape[0]
+    if q.shape[1] != D:
+        raise ValueError("query dimension %d != table dimension %d" % (q.shape[1], D))
+    lib = _lib.load()
+    ldd = max(db.stride(0), D)
+    if not lib.sb_l2_topk_supported(N, D, ldd, k) or db.data_ptr() % 16 != 0:
+        return l2_brute_force(db, q, k)
+    xn, xmax = prepared if prepared is not None else l2_prepare(db)
+    ws_bytes = lib.sb_l2_topk_workspace_bytes(D, Q, k)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=db.device)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=db.device)
+    dist = torch.empty((Q, k), dtype=torch.float64, device=db.device)
+    overflow = torch.empty((Q,), dtype=torch.int32, device=db.device)
+    with torch.cuda.device(db.device):
+        _lib.check(lib.sb_l2_topk(_ptr(db), N, D, ldd, _ptr(xn), _ptr(xmax), _ptr(q), Q, max(q.stride(0), D), k,
+                                  _ptr(idx), _ptr(dist), _ptr(overflow), _ptr(ws), ws_bytes, _stream()))
+    bad = torch.nonzero(overflow).reshape(-1)
+    if bad.numel():
+        bi, bd = l2_brute_force(db, q[bad].contiguous(), k)
+        idx[bad], dist[bad] = bi, bd
+    return idx, dist

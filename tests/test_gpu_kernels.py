@@ -316,3 +316,56 @@ def test_expand_candidates_fixed_pitch_equals_ragged(dev, n):
         assert np.array_equal(r_rows[q, :m], ci[q * pitch + o])
         np.testing.assert_array_equal(r_d[q, :m], seg_d[o])
         assert (r_rows[q, m:] == -1).all()
+
+
+# --------------------------------------------------------------------- flat L2 index (row N1)
+def _check_l2(dev, x, q, k):
+    X = torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda()
+    Qt = torch.from_numpy(np.ascontiguousarray(q, np.float32)).cuda()
+    idx, dist = dev.l2_topk(X, Qt, k)
+    torch.cuda.synchronize()
+    orow, od = O.l2_topk(x.astype(np.float32), q.astype(np.float32), k)
+    kk = od.shape[1]
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    np.testing.assert_allclose(dist[:, :kk], od, rtol=1e-5, atol=1e-12)
+    assert (idx[:, kk:] == -1).all()
+    for i in range(len(q)):
+        # identical neighbours wherever the float64 distances are distinct at the 1e-9 level
+        gaps = np.diff(od[i])
+        if len(gaps) == 0 or gaps.min() > 1e-9 * max(od[i].max(), 1e-30):
+            assert list(idx[i, :kk]) == list(orow[i]), i
+        else:
+            assert set(idx[i, :kk][od[i] < od[i][-1] - 1e-9]) <= set(orow[i])
+    return idx, dist
+
+
+@pytest.mark.parametrize("N,D,Q,k", [(5000, 128, 33, 10), (40000, 64, 300, 100), (3000, 16, 7, 256),
+                                     (100, 32, 5, 10), (1, 16, 2, 3), (70000, 256, 64, 50)])
+def test_l2_topk_matches_oracle(dev, N, D, Q, k):
+    rng = np.random.RandomState(N + D)
+    x = rng.rand(N, D).astype(np.float32)
+    q = rng.rand(Q, D).astype(np.float32)
+    q[0] = x[N // 2]                                           # an indexed vector: distance 0
+    idx, dist = _check_l2(dev, x, q, k)
+    assert idx[0, 0] == N // 2 and dist[0, 0] == 0.0
+
+
+def test_l2_topk_duplicates_ties_and_brute_force_path(dev):
+    rng = np.random.RandomState(9)
+    x = rng.rand(6000, 48).astype(np.float32)
+    x[100:140] = x[7]                                          # 41 identical rows: ties broken by row
+    q = np.vstack([x[7], x[7] * 1.0001, rng.rand(3, 48)]).astype(np.float32)
+    idx, dist = _check_l2(dev, x, q, 20)
+    assert list(idx[0]) == [7] + list(range(100, 119)) and (dist[0] == 0).all()
+    # D not a multiple of 16: the exact kernel over all rows
+    xo = rng.rand(900, 37).astype(np.float32)
+    _check_l2(dev, xo, rng.rand(6, 37).astype(np.float32), 12)
+
+
+def test_l2_topk_overflow_falls_back(dev):
+    """More near-ties than the survivor buffer holds: flagged and redone exactly."""
+    rng = np.random.RandomState(2)
+    x = np.tile(rng.rand(1, 32).astype(np.float32), (30000, 1))
+    x[::7] += 1e-3 * rng.rand(len(x[::7]), 32).astype(np.float32)
+    q = x[:3].copy()
+    idx, dist = _check_l2(dev, x, q, 10)

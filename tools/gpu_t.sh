@@ -1,2 +1,2 @@
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 600 python tools/fit_bench.py 1e7 256 256 1 2>&1 | tail -3
+python tools/l2_prof.py > gpurun_out/l2_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:itq_hash_tc_kernel -s 14 -c 1 -o gpurun_out/r1_l2_filter_full python tools/l2_prof.py > gpurun_out/l2_ncu.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/l2_ncu.log
