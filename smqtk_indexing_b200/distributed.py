@@ -171,3 +171,74 @@ class ShardedLshIndex:
             pos, od = self.ops.rerank_select(d, cand_off, n)
         rows = torch.where(pos >= 0, cand_idx[pos.clamp(min=0)], pos) if cand_idx.numel() else pos
         return rows, od
+
+
+# ----------------------------------------------------------------------------- flat L2 index
+class DeviceFlatOps:
+    """CUDA implementation of the per-rank steps of the sharded flat L2 index."""
+
+    def prepare(self, x: torch.Tensor):
+        from . import device
+        return device.l2_prepare(x) if len(x) else None
+
+    def l2_topk(self, x, q, n, prepared):
+        from . import device
+        if len(x) == 0:
+            return (torch.full((q.shape[0], n), -1, dtype=torch.int64, device=q.device),
+                    torch.full((q.shape[0], n), float("nan"), dtype=torch.float64, device=q.device))
+        return device.l2_topk(x, q, n, prepared=prepared)
+
+    def select(self, dist_all: torch.Tensor, idx_all: torch.Tensor, n: int):
+        """Per query the n best of ``m`` (distance, global row) pairs, ties by row; NaN / -1 last."""
+        from . import device
+        Q, m = dist_all.shape
+        off = torch.arange(Q + 1, dtype=torch.int64, device=dist_all.device) * m
+        return device.rerank_select_rows(dist_all.reshape(-1).contiguous(), off, None,
+                                         idx_all.reshape(-1).contiguous(), n, tie_by_row=True)
+
+
+class ShardedFlatL2Index:
+    """Row-sharded exact L2 index (BASELINE config 3: 100M x 128-d over 8 GPUs).  Each rank
+    searches its own rows (local exact top-n), one all-gather of ``Q*n*(8+8)`` bytes per rank,
+    then the (distance, global row) merge -- identical to the single-device result."""
+
+    def __init__(self, group=None, ops=None) -> None:
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.ops = ops if ops is not None else DeviceFlatOps()
+        self.x_local: Optional[torch.Tensor] = None
+        self.prepared = None
+        self.row_bounds: List[int] = []
+
+    @property
+    def num_rows(self) -> int:
+        return self.row_bounds[-1] if self.row_bounds else 0
+
+    def build(self, x_local: torch.Tensor) -> None:
+        """Collective: every rank passes the descriptor rows it owns (rank-major global rows)."""
+        self.x_local = x_local
+        n_local = torch.tensor([x_local.shape[0]], dtype=torch.int64, device=x_local.device)
+        sizes = [torch.zeros_like(n_local) for _ in range(self.world)]
+        dist.all_gather(sizes, n_local, group=self.group)
+        self.row_bounds = [0]
+        for s in sizes:
+            self.row_bounds.append(self.row_bounds[-1] + int(s.item()))
+        self.prepared = self.ops.prepare(x_local)
+
+    def query(self, q: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Collective: all ranks pass the SAME queries; all get (global rows int64[Q, n], dists f64[Q, n])."""
+        lo = self.row_bounds[self.rank]
+        with _stage("l2_topk"):
+            idx, d = self.ops.l2_topk(self.x_local, q, n, self.prepared)
+            idx = torch.where(idx >= 0, idx + lo, idx)
+        with _stage("allgather_merge"):
+            Q = q.shape[0]
+            g_idx = torch.empty((self.world * Q, n), dtype=idx.dtype, device=idx.device)
+            g_d = torch.empty((self.world * Q, n), dtype=d.dtype, device=d.device)
+            dist.all_gather_into_tensor(g_idx, idx.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(g_d, d.contiguous(), group=self.group)
+            # [world, Q, n] -> [Q, world * n]
+            g_idx = g_idx.view(self.world, Q, n).permute(1, 0, 2).reshape(Q, self.world * n)
+            g_d = g_d.view(self.world, Q, n).permute(1, 0, 2).reshape(Q, self.world * n)
+            return self.ops.select(g_d, g_idx, n)

@@ -145,3 +145,69 @@ def test_partition_bounds():
             assert len(c) == world + 1 and c[0] == 0 and c[-1] == total
             assert all(a <= b for a, b in zip(c[:-1], c[1:]))
             assert all(x % 4 == 0 for x in c[1:-1])
+
+
+# ----------------------------------------------------------------------------- sharded flat L2 index
+class OracleFlatOps:
+    """CPU stand-in for DeviceFlatOps (tests only)."""
+
+    def prepare(self, x):
+        return None
+
+    def l2_topk(self, x, q, n, prepared):
+        rows, d = O.l2_topk(x.numpy(), q.numpy(), n)
+        idx = np.full((len(q), n), -1, np.int64)
+        dd = np.full((len(q), n), np.nan)
+        idx[:, :rows.shape[1]] = rows
+        dd[:, :d.shape[1]] = d
+        return torch.from_numpy(idx), torch.from_numpy(dd)
+
+    def select(self, dist_all, idx_all, n):
+        d, i = dist_all.numpy(), idx_all.numpy()
+        Q = d.shape[0]
+        rows = np.full((Q, n), -1, np.int64)
+        od = np.full((Q, n), np.nan)
+        for q in range(Q):
+            ok = np.flatnonzero(i[q] >= 0)
+            o = ok[np.lexsort((i[q][ok], d[q][ok]))][:n]
+            rows[q, :len(o)] = i[q][o]
+            od[q, :len(o)] = d[q][o]
+        return torch.from_numpy(rows), torch.from_numpy(od)
+
+
+def _flat_worker(rank, world, port, cuts, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from smqtk_indexing_b200.distributed import ShardedFlatL2Index
+        x, q, _, _ = _data()
+        x[40:60] = x[3]                                  # duplicates spread over the shards
+        idx = ShardedFlatL2Index(ops=OracleFlatOps())
+        idx.build(torch.from_numpy(x[cuts[rank]:cuts[rank + 1]]))
+        res = {n: tuple(t.numpy() for t in idx.query(torch.from_numpy(q), n)) for n in (1, 7, 30)}
+        out_q.put((rank, idx.num_rows, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,cuts", [(2, [0, 50, 1500]), (3, [0, 45, 45, 1500])])
+def test_sharded_flat_l2_equals_single_index(world, cuts):
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_flat_worker, args=(r, world, port, cuts, out_q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out_q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, q, _, _ = _data()
+    x[40:60] = x[3]
+    for rank, nrows, res in results:
+        assert nrows == len(x)
+        for n, (rows, d) in res.items():
+            orow, od = O.l2_topk(x, q, n)
+            assert np.array_equal(rows, orow), (rank, n)
+            np.testing.assert_array_equal(d, od)

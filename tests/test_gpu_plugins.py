@@ -497,3 +497,61 @@ def test_lsh_nn_batch_matches_oracle_pipeline():
         np.testing.assert_allclose(dists[qi][:len(od)], od, rtol=1e-5, atol=1e-9)
         if np.diff(od).min() > 1e-6:
             assert list(rows[qi][:len(od)]) == list(orows)
+
+
+# --------------------------------------------------------------------- flat L2 index (row N1)
+def test_flat_l2_index_build_update_remove_nn():
+    """State semantics of the reference's flat index (faiss.py:486-679) + exact neighbours."""
+    from smqtk_indexing_b200.impls.nn_index.flat import FlatL2NearestNeighborsIndex
+    rng = np.random.RandomState(11)
+    x = rng.rand(600, 32)
+    idx = FlatL2NearestNeighborsIndex(MemoryDescriptorSet())
+    idx.build_index(_descr(x[:400]))
+    assert idx.count() == 400 and idx._descriptor_set.count() == 400
+    # self query, known order
+    r, d = idx.nn(DescriptorMemoryElement(9000).set_vector(x[5]), 3)
+    assert r[0].uuid() == 5 and d[0] == 0.0 and list(d) == sorted(d)
+    orow, od = O.l2_topk(x[:400].astype(np.float32), x[5].astype(np.float32), 3)
+    assert [e.uuid() for e in r] == list(orow[0])
+    np.testing.assert_allclose(d, od[0], rtol=1e-5)
+    # update: new rows appended, an existing uuid overwritten in place
+    changed = DescriptorMemoryElement(7).set_vector(x[500])
+    idx.update_index(_descr(x[400:], start=400) + [changed])
+    assert idx.count() == 600
+    truth = x.copy()
+    truth[7] = x[500]
+    qs = rng.rand(5, 32).astype(np.float32)
+    rows, dists = idx.nn_batch(qs, 10)
+    orow, od = O.l2_topk(truth.astype(np.float32), qs, 10)
+    uu = idx.row_uuids()
+    assert [[uu[i] for i in row] for row in rows] == [list(o) for o in orow]
+    np.testing.assert_allclose(dists, od, rtol=1e-5)
+    # remove: KeyError is non-mutating, then rows vanish from results
+    with pytest.raises(KeyError):
+        idx.remove_from_index([3, 99999])
+    assert idx.count() == 600
+    near = [int(u) for u in orow[0][:4]]
+    idx.remove_from_index(near)
+    assert idx.count() == 596 and idx._descriptor_set.count() == 596
+    r, d = idx.nn(DescriptorMemoryElement(9001).set_vector(qs[0]), 6)
+    assert [e.uuid() for e in r] == list(orow[0][4:10])
+    # n larger than the index
+    r, d = idx.nn(DescriptorMemoryElement(9002).set_vector(qs[1]), 1000)
+    assert len(r) == 596 and list(d) == sorted(d)
+    idx.remove_from_index([u for u in idx.row_uuids()])
+    assert idx.count() == 0
+    with pytest.raises(ValueError):
+        idx.nn(DescriptorMemoryElement(9003).set_vector(qs[1]), 1)
+
+
+def test_flat_l2_index_matrix_build_and_batch():
+    from smqtk_indexing_b200.impls.nn_index.flat import FlatL2NearestNeighborsIndex
+    rng = np.random.RandomState(12)
+    x = rng.rand(30000, 128).astype(np.float32)
+    idx = FlatL2NearestNeighborsIndex(MemoryDescriptorSet())
+    idx.build_index_matrix(x)
+    qs = rng.rand(40, 128).astype(np.float32)
+    rows, dists = idx.nn_batch(qs, 100)
+    orow, od = O.l2_topk(x, qs, 100)
+    assert np.array_equal(rows, orow)
+    np.testing.assert_allclose(dists, od, rtol=1e-9)

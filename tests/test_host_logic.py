@@ -298,3 +298,30 @@ def test_code_table_build_matches_oracle():
         assert np.array_equal(ri.numpy(), inv) and np.array_equal(co.numpy(), off) and np.array_equal(cr.numpy(), rows)
     e = C.build_table(torch.empty((0, 4), dtype=torch.int32))
     assert e[0].shape == (0, 4) and e[2].tolist() == [0]
+
+
+def test_flat_l2_index_config_and_errors_need_no_device():
+    from smqtk_descriptors.impls.descriptor_set.memory import MemoryDescriptorSet
+    from smqtk_dataprovider.exceptions import ReadOnlyError
+    from smqtk_indexing_b200.impls.nn_index.flat import FlatL2NearestNeighborsIndex
+    assert FlatL2NearestNeighborsIndex in NearestNeighborsIndex.get_impls()
+    c = FlatL2NearestNeighborsIndex.get_default_config()
+    assert c["read_only"] is False and "type" in c["descriptor_set"]
+    json.dumps(c)
+    c["descriptor_set"]["type"] = "smqtk_descriptors.impls.descriptor_set.memory.MemoryDescriptorSet"
+    idx = FlatL2NearestNeighborsIndex.from_config(c)
+    assert idx.count() == 0
+    c2 = idx.get_config()
+    json.dumps(c2)
+    assert FlatL2NearestNeighborsIndex.from_config(c2).get_config() == c2
+    with pytest.raises(ValueError):
+        idx.build_index([])
+    with pytest.raises(ValueError):                       # empty index
+        idx.nn(DescriptorMemoryElement(0).set_vector(np.zeros(4)), 1)
+    ro = FlatL2NearestNeighborsIndex(MemoryDescriptorSet(), read_only=True)
+    with pytest.raises(ReadOnlyError):
+        ro.build_index([DescriptorMemoryElement(0).set_vector(np.zeros(4))])
+    with pytest.raises(ReadOnlyError):
+        ro.update_index([DescriptorMemoryElement(0).set_vector(np.zeros(4))])
+    with pytest.raises(ReadOnlyError):
+        ro.remove_from_index([0])
