@@ -26,6 +26,13 @@
 #include "common.cuh"
 
 namespace sb {
+int tc_l2_tma_supported(int32_t D, int64_t ldd, const float* db);
+size_t tc_l2_tma_image_bytes(int32_t D, int col_blocks);
+int tc_l2_tma_query_image(const float* q, int Q, int D, long long ldq, int col_blocks, void* img, float* qn, cudaStream_t st);
+int tc_l2_tma_threshold_image(int Q, int cols, int D, const float* qn, const float* tq, void* img, cudaStream_t st);
+int tc_l2_filter_tma(const float* X, int64_t n, int32_t D, int64_t ldx, const void* image, int col_blocks, const float* xn,
+                     const float* tq, unsigned long long* cand_buf, int* cand_cnt, int cap, unsigned row_base,
+                     cudaStream_t st);
 int tc_l2_filter(const float* X, int64_t n, int32_t D, int64_t ldx, const uint32_t* q_image, int col_blocks,
                  const float* xn, const float* tq, unsigned long long* cand_buf, int* cand_cnt, int cap,
                  unsigned row_base, int passes, cudaStream_t st);
@@ -42,6 +49,9 @@ constexpr int QB = 256;                   // query columns per block
 //           (Cauchy-Schwarz) -> d2 error <= 2^-9 |x||q| <= 2^-10 (|x|^2 + |q|^2) -> eps = 2^-9 + 4e-5
 constexpr float L2_EPS_3X = 4e-5f;
 constexpr float L2_EPS_1X = 0.001953125f + 4e-5f;
+//   TMA variant: A is raw FP32 TRUNCATED to TF32 by the tensor core (2^-10), B rounded (2^-11):
+//           |dz| <= 1.5 * 2^-10 |x||q| -> d2 error <= 1.5 * 2^-10 (|x|^2 + |q|^2)   -> eps = 3 * 2^-10 + 4e-5
+constexpr float L2_EPS_TMA = 0.0029296875f + 4e-5f;
 constexpr int L2_PASSES = 1;              // single TF32 pass on the data chunks (the exact stage restores exactness)
 constexpr int FIRST_CHUNK_MAX = 2048;
 constexpr int GROWTH = 8;
@@ -100,13 +110,13 @@ __global__ void query_image_kernel(const float* __restrict__ q, int Q, int D, lo
 
 __global__ void l2_init_kernel(int Q, int cols, const float* __restrict__ qn, const int* __restrict__ xn_max_bits,
                                float* __restrict__ tau, float* __restrict__ margin, float* __restrict__ tq,
-                               int* __restrict__ cnt, int* __restrict__ overflow) {
+                               int* __restrict__ cnt, int* __restrict__ overflow, float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cols) return;
   const float xmax = __int_as_float(*xn_max_bits);
   // no row can be farther than |q| + max|x|: a finite threshold that the whole first chunk passes
   const float far = sqrtf(qn[i]) + sqrtf(xmax);
-  margin[i] = (L2_PASSES == 3 ? L2_EPS_3X : L2_EPS_1X) * (qn[i] + xmax);
+  margin[i] = eps * (qn[i] + xmax);
   tau[i] = far * far * 1.0001f;
   tq[i] = tau[i] + margin[i];
   cnt[i] = 0;
@@ -207,9 +217,12 @@ struct L2Plan {
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
+// Survivor slots per query.  A chunk GROWTH x the rows seen so far appends ~GROWTH * k survivors
+// plus the rows inside the margin band (about as many again with the single-pass TF32 margins),
+// on top of the ~k kept ones; 4 * (GROWTH + 1) * k leaves a 2x cushion over that.
 int l2_cap(int k) {
   int cap = 2048;
-  while (cap < 2 * (GROWTH + 1) * k) cap <<= 1;
+  while (cap < 4 * (GROWTH + 1) * k) cap <<= 1;
   return cap;
 }
 
@@ -295,13 +308,20 @@ int sb_l2_topk(const float* db, int64_t N, int32_t D, int64_t ldd, const float* 
   long long* cand_cnt = reinterpret_cast<long long*>(ws + p.off_cand_cnt);
   double* dist = reinterpret_cast<double*>(ws + p.off_dist);
 
+  // D <= 128: TMA-fed kernel with the query block resident in shared memory; else the register-staged one
+  const bool use_tma = sb::tc_l2_tma_supported(D, ldd, db) != 0;
   {
-    sb::ProfScope prof("l2_query_image_kernel", st);
-    query_image_kernel<<<1184, 256, 0, st>>>(q, Q, D, ldq, p.col_blocks, img, qn);
-    sb::count_launch();
-    if (int rc = sb::check_launch("query_image_kernel")) return rc;
+    if (use_tma) {
+      if (int rc = sb::tc_l2_tma_query_image(q, Q, D, ldq, p.col_blocks, img, qn, st)) return rc;
+    } else {
+      sb::ProfScope prof("l2_query_image_kernel", st);
+      query_image_kernel<<<1184, 256, 0, st>>>(q, Q, D, ldq, p.col_blocks, img, qn);
+      sb::count_launch();
+      if (int rc = sb::check_launch("query_image_kernel")) return rc;
+    }
+    const float eps = use_tma ? L2_EPS_TMA : (L2_PASSES == 3 ? L2_EPS_3X : L2_EPS_1X);
     l2_init_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, qn, reinterpret_cast<const int*>(xn_max), tau, margin, tq,
-                                                        cnt, overflow_out);
+                                                        cnt, overflow_out, eps);
     sb::count_launch();
     if (int rc = sb::check_launch("l2_init_kernel")) return rc;
   }
@@ -313,12 +333,19 @@ int sb_l2_topk(const float* db, int64_t N, int32_t D, int64_t ldd, const float* 
     int64_t len = (done == 0) ? FIRST_CHUNK_MAX : done * (GROWTH - 1);
     if (done == 0 && len > p.cap) len = p.cap;
     if (len > N - done) len = N - done;
-    l2_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, D, qn, tq, img);
-    sb::count_launch();
-    if (int rc = sb::check_launch("l2_threshold_image_kernel")) return rc;
-    if (int rc = sb::tc_l2_filter(db + done * ldd, len, D, ldd, img, p.col_blocks, xn + done, tq, buf, cnt, p.cap,
-                                  (unsigned)done, L2_PASSES, st))
-      return rc;
+    if (use_tma) {
+      if (int rc = sb::tc_l2_tma_threshold_image(Q, p.cols, D, qn, tq, img, st)) return rc;
+      if (int rc = sb::tc_l2_filter_tma(db + done * ldd, len, D, ldd, img, p.col_blocks, xn + done, tq, buf, cnt, p.cap,
+                                        (unsigned)done, st))
+        return rc;
+    } else {
+      l2_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, D, qn, tq, img);
+      sb::count_launch();
+      if (int rc = sb::check_launch("l2_threshold_image_kernel")) return rc;
+      if (int rc = sb::tc_l2_filter(db + done * ldd, len, D, ldd, img, p.col_blocks, xn + done, tq, buf, cnt, p.cap,
+                                    (unsigned)done, L2_PASSES, st))
+        return rc;
+    }
     done += len;
     const int final = (done >= N) ? 1 : 0;
     sb::ProfScope prof("l2_compact_kernel", st);

@@ -1,0 +1,364 @@
+// Flat-L2 filter pass, TMA-fed variant for D <= 128 (D % 32 == 0) -- BASELINE config 3's shape.
+//
+// Same contract as sb::tc_l2_filter (itq_hash_tc.cu, EPI_L2): append every (row, query) pair
+// whose approximate squared distance passes the query's threshold to the query's candidate
+// buffer.  What changes is how the operands reach the tensor core:
+//   * A (the database rows) is NOT staged through registers: a 2-D TMA tensor copy with
+//     CU_TENSOR_MAP_SWIZZLE_128B drops 128 rows x 32 floats of raw FP32 straight into the
+//     canonical SWIZZLE_128B K-major UMMA layout; kind::tf32 reads the top 19 bits of each
+//     word.  No LSU loads, no L1 miss-queue limit on bytes in flight: the kernel streams the
+//     table at HBM speed (the register-staged producers of itq_hash_tc.cu top out near
+//     1.9 TB/s).
+//   * B (256 queries, rounded to TF32) is RESIDENT in shared memory for the whole pass over
+//     the rows (<= 128 KB), pre-swizzled by query_image_sw128_kernel.
+//   * The threshold rides in one extra K step: A_syn = (-|x|^2/2 split hi/lo, 1, 1),
+//     B_syn = (1, 1, -h split hi/lo) with h = (|q|^2 - tq)/2, so the accumulator is
+//     x.q - |x|^2/2 - h and "d2 <= tq" is a sign test.
+//   * Tile = 128 rows x 256 queries, accumulators double-buffered in TMEM (2 x 256 columns):
+//     the epilogue of tile t overlaps the MMAs of tile t+1.
+// Warp roles (8 warps): 0 TMA producer (A ring), 1 MMA issue + TMEM alloc, 2 B loader,
+// 3 synthetic-A writer, 4-7 epilogue (TMEM lane quadrants).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+using namespace tcptx;
+
+namespace {
+
+constexpr int TM = 128;                     // rows per tile (UMMA M)
+constexpr int QB = 256;                     // query columns per block (UMMA N)
+constexpr int GK = 32;                      // K elements per A stage / B group (128 bytes per row)
+constexpr int A_STAGE = TM * 128;           // 16 KB
+constexpr int B_GROUP = QB * 128;           // 32 KB
+constexpr int B_SYN = 2 * QB * 16;          // 8 KB  (no-swizzle, 2 K chunks)
+constexpr int A_SYN = 2 * TM * 16;          // 4 KB  (no-swizzle, 2 K chunks)
+constexpr int STAGES = 4;
+constexpr int PF_TILES = 4;                 // L2 prefetch distance of the A stream, in tiles
+constexpr int THREADS = 256;
+
+struct TmaL2Params {
+  long long n;                 // rows in this chunk
+  int G;                       // D / 32
+  int col_blocks;
+  const unsigned char* image;  // per block: G x B_GROUP (SW128) then B_SYN
+  const float* xn;             // |x|^2 per row of the chunk
+  const float* tq;             // pass thresholds (for the survivors' d2)
+  unsigned long long* cand_buf;
+  int* cand_cnt;
+  int cap;
+  unsigned int row_base;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // SWIZZLE_128B atoms need 1024-byte alignment in the shared WINDOW: align by hand (1 KB of slack allocated)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = p.G;
+  // layout (offsets are multiples of 1024): [B data G x 32 KB][A ring][B_syn][A_syn x 2][barriers]
+  unsigned char* s_b = smem;
+  unsigned char* s_a = s_b + (size_t)G * B_GROUP;
+  unsigned char* s_bsyn = s_a + (size_t)STAGES * A_STAGE;
+  unsigned char* s_asyn = s_bsyn + B_SYN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_asyn + 2 * A_SYN);
+  const uint32_t a_full = smem_u32(bars), a_empty = a_full + STAGES * 8;
+  const uint32_t syn_full = a_empty + STAGES * 8, syn_empty = syn_full + 16;
+  const uint32_t acc_full = syn_empty + 16, acc_empty = acc_full + 16;
+  const uint32_t b_full = acc_empty + 16, b_empty = b_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
+
+  const long long row_tiles = (p.n + TM - 1) / TM;
+  const long long my_tiles = (row_tiles > (long long)blockIdx.x) ? (row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(a_full + s * 8, 1); mbar_init(a_empty + s * 8, 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(syn_full + b * 8, 1); mbar_init(syn_empty + b * 8, 1);
+      mbar_init(acc_full + b * 8, 1); mbar_init(acc_empty + b * 8, 4);
+    }
+    mbar_init(b_full, 1); mbar_init(b_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== A ring: TMA tensor copies ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int jb = 0; jb < p.col_blocks; ++jb)
+        for (long long i = 0; i < my_tiles; ++i) {
+          const long long rt = blockIdx.x + i * gridDim.x;
+          // The ring holds one tile (64 KB) -- too little to cover HBM latency on its own, so the
+          // tile PF_TILES ahead is pulled into L2 now and the ring is refilled from L2.
+          if (i + PF_TILES < my_tiles) {
+            const long long rp = rt + (long long)PF_TILES * gridDim.x;
+            for (int g = 0; g < G; ++g) tma_tensor_2d_prefetch_l2(&tmap, g * GK, (int)(rp * TM));
+          }
+          for (int g = 0; g < G; ++g) {
+            mbar_wait(a_empty + stage * 8, phase ^ 1);
+            mbar_expect_tx(a_full + stage * 8, A_STAGE);
+            tma_tensor_2d_g2s(smem_u32(s_a + (size_t)stage * A_STAGE), &tmap, g * GK, (int)(rt * TM), a_full + stage * 8);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issue ===========================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(QB >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      const uint64_t bsyn_desc = umma_desc(smem_u32(s_bsyn), QB * 16, 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      long long t = 0;
+      for (int jb = 0; jb < p.col_blocks; ++jb) {
+        mbar_wait(b_full, jb & 1);
+        tc_fence_after();
+        for (long long i = 0; i < my_tiles; ++i, ++t) {
+          const int buf = (int)(t & 1);
+          const uint32_t use = (uint32_t)((t >> 1) & 1);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * QB);
+          mbar_wait(acc_empty + buf * 8, use ^ 1);
+          tc_fence_after();
+          for (int g = 0; g < G; ++g) {
+            mbar_wait(a_full + stage * 8, phase);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(s_a + (size_t)stage * A_STAGE), b0 = smem_u32(s_b + (size_t)g * B_GROUP);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32(d_tmem, umma_desc_sw128(a0 + ks * 32), umma_desc_sw128(b0 + ks * 32), idesc, (g | ks) ? 1u : 0u);
+            umma_commit(a_empty + stage * 8);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          mbar_wait(syn_full + buf * 8, use);
+          tc_fence_after();
+          umma_tf32(d_tmem, umma_desc(smem_u32(s_asyn + buf * A_SYN), TM * 16, 128), bsyn_desc, idesc, 1u);
+          umma_commit(syn_empty + buf * 8);
+          umma_commit(acc_full + buf * 8);
+        }
+        umma_commit(b_empty);                                   // B may be replaced once these MMAs retire
+      }
+    }
+  } else if (warp == 2) {
+    // =========================== B: resident query block ===========================
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)G * B_GROUP;
+      for (int jb = 0; jb < p.col_blocks; ++jb) {
+        mbar_wait(b_empty, (jb & 1) ^ 1);
+        const unsigned char* src = p.image + (size_t)jb * (bytes + B_SYN);
+        mbar_expect_tx(b_full, bytes + B_SYN);
+        for (int g = 0; g < G; ++g) tma_bulk_g2s(smem_u32(s_b + (size_t)g * B_GROUP), src + (size_t)g * B_GROUP, B_GROUP, b_full);
+        tma_bulk_g2s(smem_u32(s_bsyn), src + bytes, B_SYN, b_full);
+      }
+    }
+  } else if (warp == 3) {
+    // =========================== synthetic A: (-|x|^2/2 hi, lo, 1, 1) per row ===========================
+    long long t = 0;
+    const uint32_t one = __float_as_uint(1.0f);
+    for (int jb = 0; jb < p.col_blocks; ++jb)
+      for (long long i = 0; i < my_tiles; ++i, ++t) {
+        const long long rt = blockIdx.x + i * gridDim.x;
+        const int buf = (int)(t & 1);
+        const uint32_t use = (uint32_t)((t >> 1) & 1);
+        mbar_wait(syn_empty + buf * 8, use ^ 1);
+        unsigned char* dst = s_asyn + buf * A_SYN;
+#pragma unroll
+        for (int j = 0; j < TM / 32; ++j) {
+          const int r = j * 32 + lane;
+          const long long row = rt * TM + r;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (row < p.n) {
+            const float a = -0.5f * __ldg(p.xn + row);
+            v.x = to_tf32(a);
+            v.y = to_tf32(a - __uint_as_float(v.x));
+            v.z = one;
+            v.w = one;
+          }
+          *reinterpret_cast<uint4*>(dst + r * 16) = v;                        // K chunk 0
+          *reinterpret_cast<uint4*>(dst + TM * 16 + r * 16) = make_uint4(0u, 0u, 0u, 0u);   // K chunk 1
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(syn_full + buf * 8);
+      }
+  } else {
+    // =========================== epilogue: sign test, survivors appended ===========================
+    const int ew = warp - 4;                                     // TMEM lane quadrant
+    long long t = 0;
+    for (int jb = 0; jb < p.col_blocks; ++jb)
+      for (long long i = 0; i < my_tiles; ++i, ++t) {
+        const long long rt = blockIdx.x + i * gridDim.x;
+        const int buf = (int)(t & 1);
+        const uint32_t use = (uint32_t)((t >> 1) & 1);
+        const long long row = rt * TM + ew * 32 + lane;
+        const bool rvalid = row < p.n;
+        mbar_wait(acc_full + buf * 8, use);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * QB);
+        const unsigned row_id = p.row_base + (unsigned)row;
+        const long long q0 = (long long)jb * QB;
+        uint32_t va[16], vb[16];                                  // ping-pong: no register copies
+        tmem_ld16(tbase, va);
+#pragma unroll 1
+        for (int g16 = 0; g16 < QB / 16; g16 += 2) {
+          tmem_ld16_nowait(tbase + (uint32_t)((g16 + 1) * 16), vb);
+          unsigned m = rvalid ? nonneg_mask16(va) : 0u;
+          if (m) SB_L2_APPEND(m, va, q0 + g16 * 16, row_id, p.tq, p.cand_buf, p.cand_cnt, p.cap);
+          tmem_ld_wait();
+          if (g16 + 2 < QB / 16) tmem_ld16_nowait(tbase + (uint32_t)((g16 + 2) * 16), va);
+          m = rvalid ? nonneg_mask16(vb) : 0u;
+          if (m) SB_L2_APPEND(m, vb, q0 + (g16 + 1) * 16, row_id, p.tq, p.cand_buf, p.cand_cnt, p.cap);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + buf * 8);
+      }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+size_t tma_smem_bytes(int G) {
+  return 1024 + (size_t)G * B_GROUP + (size_t)STAGES * A_STAGE + B_SYN + 2 * A_SYN + (2 * STAGES + 10) * 8 + 16;
+}
+
+// Queries -> per-block image: G groups of [256 rows x 128 B] in the SWIZZLE_128B K-major order
+// (16-byte chunk index XOR (row % 8) inside 1024-byte atoms), values rounded to TF32; columns
+// past Q are zero.  Also |q|^2.
+__global__ void query_image_sw128_kernel(const float* __restrict__ q, int Q, int D, long long ldq, int col_blocks,
+                                         unsigned char* __restrict__ img, float* __restrict__ qn) {
+  const int G = D / GK;
+  const size_t block_bytes = (size_t)G * B_GROUP + B_SYN;
+  const long long total = (long long)col_blocks * QB * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % D);
+    const long long col = i / D;
+    const int jb = (int)(col / QB), n = (int)(col % QB);
+    const float r = (col < Q) ? q[col * ldq + k] : 0.0f;
+    const int g = k / GK, kk = k % GK, chunk = kk / 4, e = kk & 3;
+    const size_t off = (size_t)jb * block_bytes + (size_t)g * B_GROUP + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 +
+                       (size_t)((chunk ^ (n & 7)) * 16) + e * 4;
+    *reinterpret_cast<uint32_t*>(img + off) = to_tf32(r);
+  }
+  for (long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x; col < (long long)col_blocks * QB;
+       col += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    if (col < Q)
+      for (int k = 0; k < D; ++k) acc += (double)q[col * ldq + k] * (double)q[col * ldq + k];
+    qn[col] = (float)acc;
+  }
+}
+
+// B_syn of every block: K chunk 0 of column n = (1, 1, -h hi, -h lo), chunk 1 = 0; padding columns
+// get a huge h so that they never pass.  Rewritten before every filter pass.
+__global__ void threshold_image_sw128_kernel(int Q, int cols, int D, const float* __restrict__ qn,
+                                             const float* __restrict__ tq, unsigned char* __restrict__ img) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cols) return;
+  const int G = D / GK;
+  const size_t block_bytes = (size_t)G * B_GROUP + B_SYN;
+  const int jb = col / QB, n = col % QB;
+  const float mh = (col < Q) ? -0.5f * (qn[col] - tq[col]) : -1.0e30f;
+  uint4 v;
+  v.x = __float_as_uint(1.0f);
+  v.y = v.x;
+  v.z = to_tf32(mh);
+  v.w = to_tf32(mh - __uint_as_float(v.z));
+  unsigned char* base = img + (size_t)jb * block_bytes + (size_t)G * B_GROUP;
+  *reinterpret_cast<uint4*>(base + n * 16) = v;
+  *reinterpret_cast<uint4*>(base + QB * 16 + n * 16) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+}  // namespace
+
+namespace sb {
+
+int tc_l2_tma_supported(int32_t D, int64_t ldd, const float* db) {
+  return D >= GK && D % GK == 0 && D <= 128 && ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(db) & 15u) == 0 &&
+         encode_tiled() != nullptr;
+}
+
+size_t tc_l2_tma_image_bytes(int32_t D, int col_blocks) { return (size_t)col_blocks * ((size_t)(D / GK) * B_GROUP + B_SYN); }
+
+int tc_l2_tma_query_image(const float* q, int Q, int D, long long ldq, int col_blocks, void* img, float* qn, cudaStream_t st) {
+  ProfScope prof("l2_query_image_kernel", st);
+  query_image_sw128_kernel<<<1184, 256, 0, st>>>(q, Q, D, ldq, col_blocks, static_cast<unsigned char*>(img), qn);
+  count_launch();
+  return check_launch("query_image_sw128_kernel");
+}
+
+int tc_l2_tma_threshold_image(int Q, int cols, int D, const float* qn, const float* tq, void* img, cudaStream_t st) {
+  threshold_image_sw128_kernel<<<(cols + 255) / 256, 256, 0, st>>>(Q, cols, D, qn, tq, static_cast<unsigned char*>(img));
+  count_launch();
+  return check_launch("threshold_image_sw128_kernel");
+}
+
+int tc_l2_filter_tma(const float* X, int64_t n, int32_t D, int64_t ldx, const void* image, int col_blocks, const float* xn,
+                     const float* tq, unsigned long long* cand_buf, int* cand_cnt, int cap, unsigned row_base,
+                     cudaStream_t st) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) {
+    set_error("tc_l2_filter_tma: cuTensorMapEncodeTiled is not available");
+    return SB_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)n};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ldx * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)GK, (cuuint32_t)TM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tc_l2_filter_tma: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SB_ERR_CUDA;
+  }
+  TmaL2Params p;
+  p.n = n; p.G = D / GK; p.col_blocks = col_blocks; p.image = static_cast<const unsigned char*>(image);
+  p.xn = xn; p.tq = tq; p.cand_buf = cand_buf; p.cand_cnt = cand_cnt; p.cap = cap; p.row_base = row_base;
+  const size_t smem_bytes = tma_smem_bytes(p.G);
+  const long long row_tiles = (n + TM - 1) / TM;
+  const int grid = (int)(row_tiles < sm_count() ? row_tiles : sm_count());
+  SB_CUDA_TRY(cudaFuncSetAttribute(l2_filter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  ProfScope prof("l2_filter_tc_kernel", st);
+  l2_filter_tma_kernel<<<grid, THREADS, smem_bytes, st>>>(tmap, p);
+  count_launch();
+  return check_launch("l2_filter_tma_kernel");
+}
+
+}  // namespace sb

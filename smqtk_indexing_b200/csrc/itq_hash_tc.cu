@@ -27,6 +27,7 @@
 //               prefetch), normalise/centre/split in registers, conflict-free STS
 //               into the UMMA layout, fence.proxy.async, mbarrier arrive.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace sb {
 int itq_hash_tc_supported(int64_t n, int32_t D, int64_t ldx, int32_t b, const float* X);
@@ -51,103 +52,7 @@ constexpr int PF = 4;                  // register prefetch depth of the A path 
 constexpr int A_PLANE = TILE_M * 16;   // bytes of one 16-byte K-chunk plane of A (all 256 rows)
 constexpr int A_PART = KCHUNKS * A_PLANE;             // A_hi (or A_lo) bytes per stage = 16 KB
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "TC_WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra TC_WAIT_DONE;\n"
-      "bra TC_WAIT_LOOP;\n"
-      "TC_WAIT_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// streaming 128-bit load: X is read exactly once, keep it out of L1
-__device__ __forceinline__ float4 ldg_stream(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-// Same rounding (nearest, ties away from zero) for FINITE inputs in two integer ops:
-// cvt.rna.tf32.f32 compiles to add + Inf/NaN test + select + mask on sm_100a.
-__device__ __forceinline__ uint32_t to_tf32_finite(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
-
-// K-major, no-swizzle shared-memory matrix descriptor (tcgen05 "SmemDescriptor"):
-// core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes;
-// LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = byte
-// distance between consecutive 8-row groups.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= 1ull << 46;  // descriptor version (sm_100)
-  return d;         // base_offset 0, layout_type 0 = SWIZZLE_NONE
-}
-
-// D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, issued by one thread.
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+using namespace tcptx;
 
 // ---- one-off: split R into the per-stage shared-memory image ------------------
 // image[kc][part][chunk][n][4] (part 0 = hi, 1 = lo): exactly the bytes a stage's R
@@ -455,31 +360,20 @@ __global__ void __launch_bounds__(THREADS, 1) itq_hash_tc_kernel(const TcParams 
           const long long row = rt * TILE_M + sub * UMMA_M + warp * 32 + lane;
           const bool rvalid = row < p.n;
           const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * b);
-          uint32_t cur[16], nxt[16];
-          tmem_ld16(tbase, cur);
+          const unsigned row_id = p.row_base + (unsigned)row;
+          const long long q0 = jb * 256;
+          uint32_t va[16], vb[16];                                // ping-pong: no register copies
+          tmem_ld16(tbase, va);
 #pragma unroll 1
-          for (int g16 = 0; g16 < 2 * nb; ++g16) {               // 16 accumulator columns per TMEM load
-            if (g16 + 1 < 2 * nb) tmem_ld16_nowait(tbase + (uint32_t)((g16 + 1) * 16), nxt);
-            unsigned pass = 0u;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pass |= (__uint_as_float(cur[j]) >= 0.0f) ? (1u << j) : 0u;
-            if (!rvalid) pass = 0u;
-            if (pass) {                                          // rare after the first chunk
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {                     // static register indices only
-                if (pass & (1u << j)) {
-                  const long long qg = jb * 256 + g16 * 16 + j;
-                  const float d2 = fmaxf(fmaf(-2.0f, __uint_as_float(cur[j]), __ldcg(p.tq + qg)), 0.0f);
-                  const int slot = atomicAdd(p.cand_cnt + qg, 1);
-                  if (slot < p.cap)
-                    p.cand_buf[qg * p.cap + slot] =
-                        ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(p.row_base + (unsigned)row);
-                }
-              }
-            }
+          for (int g16 = 0; g16 < 2 * nb; g16 += 2) {
+            tmem_ld16_nowait(tbase + (uint32_t)((g16 + 1) * 16), vb);
+            unsigned m = rvalid ? nonneg_mask16(va) : 0u;
+            if (m) SB_L2_APPEND(m, va, q0 + g16 * 16, row_id, p.tq, p.cand_buf, p.cand_cnt, p.cap);
             tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+            if (g16 + 2 < 2 * nb) tmem_ld16_nowait(tbase + (uint32_t)((g16 + 2) * 16), va);
+            m = rvalid ? nonneg_mask16(vb) : 0u;
+            if (m) SB_L2_APPEND(m, vb, q0 + (g16 + 1) * 16, row_id, p.tq, p.cand_buf, p.cand_cnt, p.cap);
+            tmem_ld_wait();
           }
         }
         tc_fence_before();

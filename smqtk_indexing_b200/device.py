@@ -302,6 +302,11 @@ def rerank_select(dist: torch.Tensor, cand_off: torch.Tensor, n: int):
 
 
 # --------------------------------------------------------------------- flat L2 index
+#: queries of the last ``l2_topk`` call that overflowed their survivor buffer and were redone by
+#: brute force (diagnostics / tests)
+LAST_L2_OVERFLOW = 0
+
+
 def l2_prepare(db: torch.Tensor):
     """(xn f32[N] = |row|^2, xn_max f32[1]) of a float32 table (once per table)."""
     require_cuda()
@@ -358,7 +363,9 @@ def l2_topk(db: torch.Tensor, q: torch.Tensor, k: int, prepared=None):
     with torch.cuda.device(db.device):
         _lib.check(lib.sb_l2_topk(_ptr(db), N, D, ldd, _ptr(xn), _ptr(xmax), _ptr(q), Q, max(q.stride(0), D), k,
                                   _ptr(idx), _ptr(dist), _ptr(overflow), _ptr(ws), ws_bytes, _stream()))
+    global LAST_L2_OVERFLOW
     bad = torch.nonzero(overflow).reshape(-1)
+    LAST_L2_OVERFLOW = int(bad.numel())
     if bad.numel():
         bi, bd = l2_brute_force(db, q[bad].contiguous(), k)
         idx[bad], dist[bad] = bi, bd
