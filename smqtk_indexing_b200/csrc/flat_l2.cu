@@ -32,7 +32,7 @@ int tc_l2_tma_query_image(const float* q, int Q, int D, long long ldq, int col_b
 int tc_l2_tma_threshold_image(int Q, int cols, int D, const float* qn, const float* tq, void* img, cudaStream_t st);
 int tc_l2_filter_tma(const float* X, int64_t n, int32_t D, int64_t ldx, const void* image, int col_blocks, const float* xn,
                      const float* tq, unsigned long long* cand_buf, int* cand_cnt, int cap, unsigned row_base,
-                     cudaStream_t st);
+                     int dense, cudaStream_t st);
 int tc_l2_filter(const float* X, int64_t n, int32_t D, int64_t ldx, const uint32_t* q_image, int col_blocks,
                  const float* xn, const float* tq, unsigned long long* cand_buf, int* cand_cnt, int cap,
                  unsigned row_base, int passes, cudaStream_t st);
@@ -147,6 +147,32 @@ __global__ void l2_threshold_image_kernel(int Q, int cols, int D, const float* _
     }
 }
 
+// The first chunk keeps every row (no threshold yet), so it does not go through the filter:
+// one CTA per query writes the keys of rows [0, m0) directly (direct-form FP32 d2, no atomics).
+__global__ void __launch_bounds__(256)
+l2_seed_kernel(const float* __restrict__ db, int m0, int D, long long ldd, const float* __restrict__ q, long long ldq,
+               unsigned long long* __restrict__ buf, int* __restrict__ cnt, int cap) {
+  extern __shared__ float s_q[];
+  const int qi = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) s_q[d] = q[(long long)qi * ldq + d];
+  __syncthreads();
+  for (int r = threadIdx.x; r < m0; r += blockDim.x) {
+    const float* x = db + (long long)r * ldd;
+    float acc = 0.0f;
+    for (int d = 0; d < D; ++d) {
+      const float t = x[d] - s_q[d];
+      acc = fmaf(t, t, acc);
+    }
+    buf[(long long)qi * cap + r] = ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned long long)r;
+  }
+  if (threadIdx.x == 0) cnt[qi] = m0;
+}
+
+__global__ void l2_set_count_kernel(int* __restrict__ cnt, int Q, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Q) cnt[i] = v;
+}
+
 // One CTA per query: sort the survivors by (approximate d2, row), tighten tau to the k-th
 // smallest, keep everything within the margin of it.  `final` also emits the candidate
 // rows in the layout sb_rerank / sb_rerank_select_rows consume.
@@ -156,7 +182,7 @@ __global__ void __launch_bounds__(CP_THREADS)
 l2_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt, int cap, int k, float* __restrict__ tau,
                   const float* __restrict__ margin, float* __restrict__ tq, int* __restrict__ overflow, int final,
                   long long* __restrict__ cand_idx, long long* __restrict__ cand_off, long long* __restrict__ cand_cnt,
-                  int Q) {
+                  int Q, int final_pitch) {
   extern __shared__ unsigned long long s_key[];   // P = next pow2 >= min(count, cap)
   const int qi = blockIdx.x, tid = threadIdx.x;
   const int raw = cnt[qi];
@@ -199,18 +225,20 @@ l2_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt, i
     tq[qi] = t + margin[qi];
   }
   if (final) {
-    long long* out = cand_idx + (size_t)qi * cap;
-    for (int i = tid; i < cap; i += CP_THREADS) out[i] = (i < keep) ? (long long)(s_key[i] & 0xffffffffull) : -1ll;
+    // the exact stage works on a tighter pitch than the survivor buffers: ~k + margin band rows remain
+    long long* out = cand_idx + (size_t)qi * final_pitch;
+    for (int i = tid; i < final_pitch; i += CP_THREADS) out[i] = (i < keep) ? (long long)(s_key[i] & 0xffffffffull) : -1ll;
     if (tid == 0) {
-      cand_cnt[qi] = keep;
-      cand_off[qi] = (long long)qi * cap;
-      if (qi == Q - 1) cand_off[Q] = (long long)Q * cap;
+      if (keep > final_pitch) overflow[qi] = 1;
+      cand_cnt[qi] = min(keep, final_pitch);
+      cand_off[qi] = (long long)qi * final_pitch;
+      if (qi == Q - 1) cand_off[Q] = (long long)Q * final_pitch;
     }
   }
 }
 
 struct L2Plan {
-  int col_blocks, cols, cap;
+  int col_blocks, cols, cap, final_pitch;
   size_t off_img, off_qn, off_tau, off_margin, off_tq, off_cnt, off_buf, off_cand_idx, off_cand_off, off_cand_cnt,
       off_dist, total;
 };
@@ -231,6 +259,9 @@ L2Plan make_l2_plan(int32_t D, int32_t Q, int32_t k) {
   p.col_blocks = (Q + QB - 1) / QB;
   p.cols = p.col_blocks * QB;
   p.cap = l2_cap(k);
+  p.final_pitch = 512;
+  while (p.final_pitch < 8 * k) p.final_pitch <<= 1;
+  if (p.final_pitch > p.cap) p.final_pitch = p.cap;
   size_t o = 0;
   p.off_img = o;      o += align256((size_t)p.cols * (D + KC) * 2 * sizeof(uint32_t));
   p.off_qn = o;       o += align256((size_t)p.cols * sizeof(float));
@@ -239,10 +270,10 @@ L2Plan make_l2_plan(int32_t D, int32_t Q, int32_t k) {
   p.off_tq = o;       o += align256((size_t)p.cols * sizeof(float));
   p.off_cnt = o;      o += align256((size_t)p.cols * sizeof(int));
   p.off_buf = o;      o += align256((size_t)p.cols * p.cap * sizeof(unsigned long long));
-  p.off_cand_idx = o; o += align256((size_t)Q * p.cap * sizeof(long long));
+  p.off_cand_idx = o; o += align256((size_t)Q * p.final_pitch * sizeof(long long));
   p.off_cand_off = o; o += align256((size_t)(Q + 1) * sizeof(long long));
   p.off_cand_cnt = o; o += align256((size_t)Q * sizeof(long long));
-  p.off_dist = o;     o += align256((size_t)Q * p.cap * sizeof(double));
+  p.off_dist = o;     o += align256((size_t)Q * p.final_pitch * sizeof(double));
   p.total = o;
   return p;
 }
@@ -333,10 +364,22 @@ int sb_l2_topk(const float* db, int64_t N, int32_t D, int64_t ldd, const float* 
     int64_t len = (done == 0) ? FIRST_CHUNK_MAX : done * (GROWTH - 1);
     if (done == 0 && len > p.cap) len = p.cap;
     if (len > N - done) len = N - done;
-    if (use_tma) {
+    if (done == 0 && use_tma) {
+      // seed chunk through the tensor cores in "dense" mode: every pair's key goes to buf[query][row]
+      if (int rc = sb::tc_l2_tma_threshold_image(Q, p.cols, D, qn, tq, img, st)) return rc;
+      if (int rc = sb::tc_l2_filter_tma(db, len, D, ldd, img, p.col_blocks, xn, tq, buf, cnt, p.cap, 0u, 1, st)) return rc;
+      l2_set_count_kernel<<<(Q + 255) / 256, 256, 0, st>>>(cnt, Q, (int)len);
+      sb::count_launch();
+      if (int rc = sb::check_launch("l2_set_count_kernel")) return rc;
+    } else if (done == 0) {
+      sb::ProfScope prof("l2_seed_kernel", st);
+      l2_seed_kernel<<<Q, 256, D * sizeof(float), st>>>(db, (int)len, D, ldd, q, ldq, buf, cnt, p.cap);
+      sb::count_launch();
+      if (int rc = sb::check_launch("l2_seed_kernel")) return rc;
+    } else if (use_tma) {
       if (int rc = sb::tc_l2_tma_threshold_image(Q, p.cols, D, qn, tq, img, st)) return rc;
       if (int rc = sb::tc_l2_filter_tma(db + done * ldd, len, D, ldd, img, p.col_blocks, xn + done, tq, buf, cnt, p.cap,
-                                        (unsigned)done, st))
+                                        (unsigned)done, 0, st))
         return rc;
     } else {
       l2_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, D, qn, tq, img);
@@ -351,13 +394,13 @@ int sb_l2_topk(const float* db, int64_t N, int32_t D, int64_t ldd, const float* 
     sb::ProfScope prof("l2_compact_kernel", st);
     l2_compact_kernel<<<Q, CP_THREADS, p.cap * sizeof(unsigned long long), st>>>(buf, cnt, p.cap, k, tau, margin, tq,
                                                                                  overflow_out, final, cand_idx, cand_off,
-                                                                                 cand_cnt, Q);
+                                                                                 cand_cnt, Q, p.final_pitch);
     sb::count_launch();
     if (int rc = sb::check_launch("l2_compact_kernel")) return rc;
   }
   // exact stage: direct-form distances of the survivors, (distance, row) selection
   if (int rc = sb_rerank_base(db, N, 0, D, ldd, q, Q, ldq, reinterpret_cast<const int64_t*>(cand_idx),
-                              reinterpret_cast<const int64_t*>(cand_off), (int64_t)Q * p.cap, SB_METRIC_EUCLIDEAN, dist,
+                              reinterpret_cast<const int64_t*>(cand_off), (int64_t)Q * p.final_pitch, SB_METRIC_EUCLIDEAN, dist,
                               stream))
     return rc;
   if (int rc = sb_rerank_select_rows(dist, reinterpret_cast<const int64_t*>(cand_off),

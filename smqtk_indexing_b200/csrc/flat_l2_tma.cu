@@ -36,6 +36,7 @@ constexpr int B_SYN = 2 * QB * 16;          // 8 KB  (no-swizzle, 2 K chunks)
 constexpr int A_SYN = 2 * TM * 16;          // 4 KB  (no-swizzle, 2 K chunks)
 constexpr int STAGES = 4;
 constexpr int PF_TILES = 4;                 // L2 prefetch distance of the A stream, in tiles
+constexpr int SQ_CAP = 96;                  // survivor queue entries per epilogue warp and tile
 constexpr int THREADS = 256;
 
 struct TmaL2Params {
@@ -49,6 +50,7 @@ struct TmaL2Params {
   int* cand_cnt;
   int cap;
   unsigned int row_base;
+  int dense;                   // first chunk: every (row, query) pair is kept -> key stored at buf[query][row], no atomics
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -69,6 +71,10 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
   const uint32_t acc_full = syn_empty + 16, acc_empty = acc_full + 16;
   const uint32_t b_full = acc_empty + 16, b_empty = b_full + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
+  // per-epilogue-warp survivor queues: [4][SQ_CAP] x (u64 key, i32 query) + a counter each
+  unsigned long long* sq_key = reinterpret_cast<unsigned long long*>(bars + 2 * STAGES + 12);
+  int* sq_q = reinterpret_cast<int*>(sq_key + 4 * SQ_CAP);
+  int* sq_cnt = sq_q + 4 * SQ_CAP;
 
   const long long row_tiles = (p.n + TM - 1) / TM;
   const long long my_tiles = (row_tiles > (long long)blockIdx.x) ? (row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -207,23 +213,51 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
         tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * QB);
         const unsigned row_id = p.row_base + (unsigned)row;
-        const long long q0 = (long long)jb * QB;
+        const int q0 = jb * QB;
+        unsigned long long* myq_key = sq_key + ew * SQ_CAP;
+        int* myq_q = sq_q + ew * SQ_CAP;
+        int* myq_cnt = sq_cnt + ew;
+        if (lane == 0) *myq_cnt = 0;
+        __syncwarp();
         uint32_t va[16], vb[16];                                  // ping-pong: no register copies
         tmem_ld16(tbase, va);
+        if (p.dense) {
+          // seed chunk: buf[query][row] = key for every pair (row < cap by construction)
+#pragma unroll 1
+          for (int g16 = 0; g16 < QB / 16; ++g16) {
+            if (rvalid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const long long qg = q0 + g16 * 16 + j;
+                const float d2 = fmaxf(fmaf(-2.0f, __uint_as_float(va[j]), __ldg(p.tq + qg)), 0.0f);
+                p.cand_buf[qg * p.cap + row] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)row_id;
+              }
+            }
+            if (g16 + 1 < QB / 16) tmem_ld16(tbase + (uint32_t)((g16 + 1) * 16), va);
+          }
+        } else
 #pragma unroll 1
         for (int g16 = 0; g16 < QB / 16; g16 += 2) {
           tmem_ld16_nowait(tbase + (uint32_t)((g16 + 1) * 16), vb);
           unsigned m = rvalid ? nonneg_mask16(va) : 0u;
-          if (m) SB_L2_APPEND(m, va, q0 + g16 * 16, row_id, p.tq, p.cand_buf, p.cand_cnt, p.cap);
+          if (m) SB_L2_QUEUE(m, va, q0 + g16 * 16, row_id, p.tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
           tmem_ld_wait();
           if (g16 + 2 < QB / 16) tmem_ld16_nowait(tbase + (uint32_t)((g16 + 2) * 16), va);
           m = rvalid ? nonneg_mask16(vb) : 0u;
-          if (m) SB_L2_APPEND(m, vb, q0 + (g16 + 1) * 16, row_id, p.tq, p.cand_buf, p.cand_cnt, p.cap);
+          if (m) SB_L2_QUEUE(m, vb, q0 + (g16 + 1) * 16, row_id, p.tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
           tmem_ld_wait();
         }
+        // the accumulator buffer is free: let the next tile's MMAs start, THEN pay for the appends
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + buf * 8);
+        const int nq = min(*myq_cnt, SQ_CAP);
+        for (int e = lane; e < nq; e += 32) {                      // 32 appends in flight per warp
+          const long long qg = myq_q[e];
+          const int slot = atomicAdd(p.cand_cnt + qg, 1);
+          if (slot < p.cap) p.cand_buf[qg * p.cap + slot] = myq_key[e];
+        }
+        __syncwarp();
       }
   }
 
@@ -254,7 +288,8 @@ EncodeTiledFn encode_tiled() {
 }
 
 size_t tma_smem_bytes(int G) {
-  return 1024 + (size_t)G * B_GROUP + (size_t)STAGES * A_STAGE + B_SYN + 2 * A_SYN + (2 * STAGES + 10) * 8 + 16;
+  return 1024 + (size_t)G * B_GROUP + (size_t)STAGES * A_STAGE + B_SYN + 2 * A_SYN + (2 * STAGES + 12) * 8 +
+         4 * SQ_CAP * 12 + 16;
 }
 
 // Queries -> per-block image: G groups of [256 rows x 128 B] in the SWIZZLE_128B K-major order
@@ -330,7 +365,7 @@ int tc_l2_tma_threshold_image(int Q, int cols, int D, const float* qn, const flo
 
 int tc_l2_filter_tma(const float* X, int64_t n, int32_t D, int64_t ldx, const void* image, int col_blocks, const float* xn,
                      const float* tq, unsigned long long* cand_buf, int* cand_cnt, int cap, unsigned row_base,
-                     cudaStream_t st) {
+                     int dense, cudaStream_t st) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) {
     set_error("tc_l2_filter_tma: cuTensorMapEncodeTiled is not available");
@@ -350,7 +385,7 @@ int tc_l2_filter_tma(const float* X, int64_t n, int32_t D, int64_t ldx, const vo
   }
   TmaL2Params p;
   p.n = n; p.G = D / GK; p.col_blocks = col_blocks; p.image = static_cast<const unsigned char*>(image);
-  p.xn = xn; p.tq = tq; p.cand_buf = cand_buf; p.cand_cnt = cand_cnt; p.cap = cap; p.row_base = row_base;
+  p.xn = xn; p.tq = tq; p.cand_buf = cand_buf; p.cand_cnt = cand_cnt; p.cap = cap; p.row_base = row_base; p.dense = dense;
   const size_t smem_bytes = tma_smem_bytes(p.G);
   const long long row_tiles = (n + TM - 1) / TM;
   const int grid = (int)(row_tiles < sm_count() ? row_tiles : sm_count());
