@@ -35,7 +35,6 @@ constexpr int B_GROUP = QB * 128;           // 32 KB
 constexpr int B_SYN = 2 * QB * 16;          // 8 KB  (no-swizzle, 2 K chunks)
 constexpr int A_SYN = 2 * TM * 16;          // 4 KB  (no-swizzle, 2 K chunks)
 constexpr int STAGES = 4;
-constexpr int PF_TILES = 4;                 // L2 prefetch distance of the A stream, in tiles
 constexpr int SQ_CAP = 96;                  // survivor queue entries per epilogue warp and tile
 constexpr int THREADS = 256;
 
@@ -106,12 +105,6 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
       for (int jb = 0; jb < p.col_blocks; ++jb)
         for (long long i = 0; i < my_tiles; ++i) {
           const long long rt = blockIdx.x + i * gridDim.x;
-          // The ring holds one tile (64 KB) -- too little to cover HBM latency on its own, so the
-          // tile PF_TILES ahead is pulled into L2 now and the ring is refilled from L2.
-          if (i + PF_TILES < my_tiles) {
-            const long long rp = rt + (long long)PF_TILES * gridDim.x;
-            for (int g = 0; g < G; ++g) tma_tensor_2d_prefetch_l2(&tmap, g * GK, (int)(rp * TM));
-          }
           for (int g = 0; g < G; ++g) {
             mbar_wait(a_empty + stage * 8, phase ^ 1);
             mbar_expect_tx(a_full + stage * 8, A_STAGE);
