@@ -555,3 +555,30 @@ def test_flat_l2_index_matrix_build_and_batch():
     orow, od = O.l2_topk(x, qs, 100)
     assert np.array_equal(rows, orow)
     np.testing.assert_allclose(dists, od, rtol=1e-9)
+
+
+def test_simple_rp_functor_bits_and_lsh_use():
+    """N4: random projections through the hash kernels; bits = (v - mean) . rps >= 0 for any
+    `normalize` (simple_rp.py:52-59 divides rows by a positive scalar)."""
+    from smqtk_indexing_b200.impls.lsh_functor.simple_rp import SimpleRPFunctor
+    rng = np.random.RandomState(6)
+    x = rng.rand(700, 48)
+    for normalize in (None, 2):
+        f = SimpleRPFunctor(bit_length=40, normalize=normalize, random_seed=5)
+        codes = f.fit(_descr(x))
+        np.random.seed(5)
+        rps = np.random.randn(48, 40)
+        assert np.array_equal(f.rps, rps)
+        z = (x - x.mean(0)).dot(rps)
+        far = np.abs(z) > 1e-4
+        assert codes.shape == (700, 40) and np.array_equal(codes[far], (z >= 0)[far])
+        with pytest.raises(RuntimeError):
+            f.fit(_descr(x))
+        q = rng.rand(48)
+        zq = (q - x.mean(0)).dot(rps)
+        assert np.array_equal(f.get_hash(q)[np.abs(zq) > 1e-4], (zq >= 0)[np.abs(zq) > 1e-4])
+    # drives the LSH index like ItqFunctor does
+    index = LSHNearestNeighborIndex(f, MemoryDescriptorSet(), MemoryKeyValueStore(), LinearHashIndex(), 'euclidean')
+    index.build_index(_descr(x))
+    r, d = index.nn(DescriptorMemoryElement(9999).set_vector(x[10]), 3)
+    assert r[0].uuid() == 10 and d[0] == 0.0

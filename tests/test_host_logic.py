@@ -325,3 +325,14 @@ def test_flat_l2_index_config_and_errors_need_no_device():
         ro.update_index([DescriptorMemoryElement(0).set_vector(np.zeros(4))])
     with pytest.raises(ReadOnlyError):
         ro.remove_from_index([0])
+
+
+def test_simple_rp_functor_config_and_errors():
+    from smqtk_indexing_b200.impls.lsh_functor.simple_rp import SimpleRPFunctor
+    assert SimpleRPFunctor in LshFunctor.get_impls()
+    f = SimpleRPFunctor(bit_length=16, normalize=2, random_seed=3)
+    assert f.get_config() == {"bit_length": 16, "normalize": 2, "random_seed": 3}
+    assert SimpleRPFunctor.from_config(f.get_config()).get_config() == f.get_config()
+    assert not f.has_model()
+    with pytest.raises(RuntimeError):
+        f.get_hash(np.zeros(4))
