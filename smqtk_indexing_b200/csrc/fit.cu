@@ -85,49 +85,77 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int p
   out[i] = acc * scale;
 }
 
-// ---- gram: C[Ma][Mb] = sum_r A[r][:]^T B[r][:] ---------------------------------------
-constexpr int GT = 64, GK = 16;
+// ---- FP64 register-tiled micro-kernel shared by the two GEMMs --------------------------------
+// CTA tile 128 x 128, 256 threads, 8 x 8 outputs per thread, K slab of 8 staged in shared memory.
+// A thread owns output rows {2*ty, 2*ty+1} + 32*m and columns {2*tx, 2*tx+1} + 32*m (m = 0..3):
+// every shared-memory read is a 128-bit LDS whose 16 lanes of a half-warp touch 256 contiguous
+// bytes (conflict-free), and one K step costs 8 LDS.128 for 64 DFMA -- the DFMA pipe (64 lanes/clk/SM)
+// and the shared-memory pipe finish together.
+constexpr int GT = 128, GK = 8;
 
+__device__ __forceinline__ void dgemm_slab(const double (&As)[GK][GT], const double (&Bs)[GK][GT], int ty, int tx,
+                                           double (&acc)[8][8]) {
+#pragma unroll
+  for (int kk = 0; kk < GK; ++kk) {
+    double a[8], b[8];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const double2 av = *reinterpret_cast<const double2*>(&As[kk][32 * m + 2 * ty]);
+      const double2 bv = *reinterpret_cast<const double2*>(&Bs[kk][32 * m + 2 * tx]);
+      a[2 * m] = av.x; a[2 * m + 1] = av.y;
+      b[2 * m] = bv.x; b[2 * m + 1] = bv.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+  }
+}
+// output index of accumulator slot i (rows) / j (columns) of thread coordinate t
+__device__ __forceinline__ int tile_index(int t, int i) { return 32 * (i >> 1) + 2 * t + (i & 1); }
+
+// ---- gram: C[Ma][Mb] = sum_r A[r][:]^T B[r][:] ---------------------------------------
 __global__ void __launch_bounds__(256)
 gram_partial_kernel(Operand A, Operand B, long long n, long long rows_per_block, double* __restrict__ partial) {
-  __shared__ double As[GK][GT + 1];
-  __shared__ double Bs[GK][GT + 1];
+  __shared__ __align__(16) double As[GK][GT];
+  __shared__ __align__(16) double Bs[GK][GT];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int a0 = blockIdx.x * GT, b0 = blockIdx.y * GT;
   const long long r0 = (long long)blockIdx.z * rows_per_block;
   const long long r1 = min(n, r0 + rows_per_block);
-  double acc[4][4] = {};
-  const int lk = tid >> 4;            // 0..15: row within the K slab
-  const int lc = (tid & 15) * 4;      // 4 consecutive columns
-  for (long long rr = r0; rr < r1; rr += GK) {
+  double acc[8][8] = {};
+  // staging: thread -> (slab row tid / 32, 4 columns (tid % 32) * 4 ..)
+  const int lk = tid >> 5;
+  const int lc = (tid & 31) * 4;
+  // register prefetch: the next slab's global loads are in flight while this slab is multiplied
+  double pa[4], pb[4];
+  auto load_slab = [&](long long rr) {
     const long long r = rr + lk;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int ca = a0 + lc + j, cb = b0 + lc + j;
-      As[lk][lc + j] = (r < r1 && ca < A.cols) ? fetch(A, r, ca) : 0.0;
-      Bs[lk][lc + j] = (r < r1 && cb < B.cols) ? fetch(B, r, cb) : 0.0;
+      pa[j] = (r < r1 && ca < A.cols) ? fetch(A, r, ca) : 0.0;
+      pb[j] = (r < r1 && cb < B.cols) ? fetch(B, r, cb) : 0.0;
+    }
+  };
+  if (r0 < r1) load_slab(r0);
+  for (long long rr = r0; rr < r1; rr += GK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      As[lk][lc + j] = pa[j];
+      Bs[lk][lc + j] = pb[j];
     }
     __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < GK; ++kk) {
-      double a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-    }
+    if (rr + GK < r1) load_slab(rr + GK);
+    dgemm_slab(As, Bs, ty, tx, acc);
     __syncthreads();
   }
   double* out = partial + (size_t)blockIdx.z * A.cols * B.cols;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int ra = a0 + ty * 4 + i, cb = b0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int ra = a0 + tile_index(ty, i), cb = b0 + tile_index(tx, j);
       if (ra < A.cols && cb < B.cols) out[(size_t)ra * B.cols + cb] = acc[i][j];
     }
 }
@@ -136,52 +164,50 @@ gram_partial_kernel(Operand A, Operand B, long long n, long long rows_per_block,
 __global__ void __launch_bounds__(256)
 project_kernel(Operand A, const double* __restrict__ Bm, int M, long long n, double* __restrict__ out_f64,
                uint32_t* __restrict__ out_codes, int Wc) {
-  __shared__ double As[GK][GT + 1];
-  __shared__ double Bs[GK][GT + 1];
-  __shared__ uint32_t s_bits[GT][3];
+  __shared__ __align__(16) double As[GK][GT];       // As[k][row]
+  __shared__ __align__(16) double Bs[GK][GT];       // Bs[k][col]
+  __shared__ uint32_t s_bits[GT][5];                // a 128-column tile touches at most 5 words
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const long long row0 = (long long)blockIdx.x * GT;
   const int col0 = blockIdx.y * GT;
   const int K = A.cols;
-  double acc[4][4] = {};
-  const int ar = tid >> 2, ak = (tid & 3) * 4;    // A tile: 64 rows x 16 k
-  const int bk = tid >> 4, bc = (tid & 15) * 4;   // B tile: 16 k x 64 cols
-  if (tid < GT * 3) (&s_bits[0][0])[tid] = 0u;
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  double acc[8][8] = {};
+  const int ar = tid >> 1, ak = (tid & 1) * 4;    // A tile: 128 rows x 8 k, 4 consecutive k per thread
+  const int bk = tid >> 5, bc = (tid & 31) * 4;   // B tile: 8 k x 128 cols
+  for (int i = tid; i < GT * 5; i += 256) (&s_bits[0][0])[i] = 0u;
+  double pa[4], pb[4];
+  auto load_slab = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int kk = k0 + ak + i;
-      As[ak + i][ar] = (row0 + ar < n && kk < K) ? fetch(A, row0 + ar, kk) : 0.0;
+      pa[i] = (row0 + ar < n && kk < K) ? fetch(A, row0 + ar, kk) : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int kk = k0 + bk, cc = col0 + bc + j;
-      Bs[bk][bc + j] = (kk < K && cc < M) ? Bm[(size_t)kk * M + cc] : 0.0;
+      pb[j] = (kk < K && cc < M) ? Bm[(size_t)kk * M + cc] : 0.0;
     }
+  };
+  load_slab(0);
+  for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[ak + i][ar] = pa[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Bs[bk][bc + j] = pb[j];
     __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < GK; ++kk) {
-      double a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-    }
+    if (k0 + GK < K) load_slab(k0 + GK);
+    dgemm_slab(As, Bs, ty, tx, acc);
     __syncthreads();
   }
   const int w_first = out_codes ? (Wc - 1 - (M - 1 - col0) / 32) : 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int r = tile_index(ty, i);
     const long long row = row0 + r;
     if (row >= n) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = col0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int col = col0 + tile_index(tx, j);
       if (col >= M) continue;
       const double z = acc[i][j];
       if (out_f64) out_f64[row * (long long)M + col] = z;
@@ -193,8 +219,8 @@ project_kernel(Operand A, const double* __restrict__ Bm, int M, long long n, dou
   }
   if (out_codes) {
     __syncthreads();
-    if (tid < GT * 3) {
-      const int r = tid / 3, wi = tid - r * 3;
+    for (int i = tid; i < GT * 5; i += 256) {
+      const int r = i / 5, wi = i - r * 5;
       const uint32_t v = s_bits[r][wi];
       if (row0 + r < n && v != 0u && w_first + wi < Wc) atomicOr(&out_codes[(row0 + r) * Wc + w_first + wi], v);
     }
