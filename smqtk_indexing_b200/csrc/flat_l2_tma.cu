@@ -74,6 +74,7 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
   unsigned long long* sq_key = reinterpret_cast<unsigned long long*>(bars + 2 * STAGES + 12);
   int* sq_q = reinterpret_cast<int*>(sq_key + 4 * SQ_CAP);
   int* sq_cnt = sq_q + 4 * SQ_CAP;
+  float* s_tq = reinterpret_cast<float*>(sq_cnt + 4);          // [4 warps][256]: this block's thresholds
 
   const long long row_tiles = (p.n + TM - 1) / TM;
   const long long my_tiles = (row_tiles > (long long)blockIdx.x) ? (row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -195,7 +196,12 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
     // =========================== epilogue: sign test, survivors appended ===========================
     const int ew = warp - 4;                                     // TMEM lane quadrant
     long long t = 0;
-    for (int jb = 0; jb < p.col_blocks; ++jb)
+    float* my_tq = s_tq + ew * QB;
+    for (int jb = 0; jb < p.col_blocks; ++jb) {
+      // thresholds of this query block, private copy per warp (a survivor's d2 = tq - 2 * accumulator)
+      __syncwarp();
+      for (int c = lane; c < QB; c += 32) my_tq[c] = __ldcg(p.tq + (long long)jb * QB + c);
+      __syncwarp();
       for (long long i = 0; i < my_tiles; ++i, ++t) {
         const long long rt = blockIdx.x + i * gridDim.x;
         const int buf = (int)(t & 1);
@@ -222,7 +228,7 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const long long qg = q0 + g16 * 16 + j;
-                const float d2 = fmaxf(fmaf(-2.0f, __uint_as_float(va[j]), __ldg(p.tq + qg)), 0.0f);
+                const float d2 = fmaxf(fmaf(-2.0f, __uint_as_float(va[j]), my_tq[g16 * 16 + j]), 0.0f);
                 p.cand_buf[qg * p.cap + row] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)row_id;
               }
             }
@@ -233,11 +239,11 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
         for (int g16 = 0; g16 < QB / 16; g16 += 2) {
           tmem_ld16_nowait(tbase + (uint32_t)((g16 + 1) * 16), vb);
           unsigned m = rvalid ? nonneg_mask16(va) : 0u;
-          if (m) SB_L2_QUEUE(m, va, q0 + g16 * 16, row_id, p.tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
+          if (m) SB_L2_QUEUE(m, va, q0, g16 * 16, row_id, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
           tmem_ld_wait();
           if (g16 + 2 < QB / 16) tmem_ld16_nowait(tbase + (uint32_t)((g16 + 2) * 16), va);
           m = rvalid ? nonneg_mask16(vb) : 0u;
-          if (m) SB_L2_QUEUE(m, vb, q0 + (g16 + 1) * 16, row_id, p.tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
+          if (m) SB_L2_QUEUE(m, vb, q0, (g16 + 1) * 16, row_id, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
           tmem_ld_wait();
         }
         // the accumulator buffer is free: let the next tile's MMAs start, THEN pay for the appends
@@ -252,6 +258,7 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
         }
         __syncwarp();
       }
+    }
   }
 
   tc_fence_before();
@@ -282,7 +289,7 @@ EncodeTiledFn encode_tiled() {
 
 size_t tma_smem_bytes(int G) {
   return 1024 + (size_t)G * B_GROUP + (size_t)STAGES * A_STAGE + B_SYN + 2 * A_SYN + (2 * STAGES + 12) * 8 +
-         4 * SQ_CAP * 12 + 16;
+         4 * SQ_CAP * 12 + 16 + 4 * QB * sizeof(float);
 }
 
 // Queries -> per-block image: G groups of [256 rows x 128 B] in the SWIZZLE_128B K-major order

@@ -161,17 +161,19 @@ static __device__ __noinline__ void l2_append_survivors(
 
 // Same cold path, but the survivors go to a per-warp shared-memory queue (drained after the
 // accumulator buffer has been released); when the queue is full they are appended directly.
+// Thresholds come from shared memory (`tq_local[col]`, this query block's 256 values): a dependent
+// global load per survivor would cost more than everything else on this path.
 static __device__ __noinline__ void l2_queue_survivors(
-    unsigned mask, int q0, unsigned row_id, const float* tq, unsigned long long* q_key, int* q_q, int* q_cnt, int q_cap,
-    unsigned long long* cand_buf, int* cand_cnt, int cap,
+    unsigned mask, int q0, int col0, unsigned row_id, const float* tq_local, unsigned long long* q_key, int* q_q, int* q_cnt,
+    int q_cap, unsigned long long* cand_buf, int* cand_cnt, int cap,
     uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t v4, uint32_t v5, uint32_t v6, uint32_t v7, uint32_t v8,
     uint32_t v9, uint32_t v10, uint32_t v11, uint32_t v12, uint32_t v13, uint32_t v14, uint32_t v15) {
   const uint32_t v[16] = {v0, v1, v2, v3, v4, v5, v6, v7, v8, v9, v10, v11, v12, v13, v14, v15};
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     if (mask & (0x8000u >> j)) {
-      const int qg = q0 + j;
-      const float d2 = fmaxf(fmaf(-2.0f, __uint_as_float(v[j]), __ldcg(tq + qg)), 0.0f);
+      const int qg = q0 + col0 + j;
+      const float d2 = fmaxf(fmaf(-2.0f, __uint_as_float(v[j]), tq_local[col0 + j]), 0.0f);
       const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)row_id;
       const int e = atomicAdd(q_cnt, 1);
       if (e < q_cap) {
@@ -184,9 +186,9 @@ static __device__ __noinline__ void l2_queue_survivors(
     }
   }
 }
-#define SB_L2_QUEUE(mask, v, q0, row_id, tq, qk, qq, qc, qcap, buf, cnt, cap)                                          \
-  tcptx::l2_queue_survivors(mask, q0, row_id, tq, qk, qq, qc, qcap, buf, cnt, cap, v[0], v[1], v[2], v[3], v[4], v[5], \
-                            v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15])
+#define SB_L2_QUEUE(mask, v, q0, col0, row_id, tql, qk, qq, qc, qcap, buf, cnt, cap)                                    \
+  tcptx::l2_queue_survivors(mask, q0, col0, row_id, tql, qk, qq, qc, qcap, buf, cnt, cap, v[0], v[1], v[2], v[3], v[4],  \
+                            v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15])
 
 // Ask the TMA unit to pull a tile into L2 only (no shared-memory destination, no barrier).
 __device__ __forceinline__ void tma_tensor_2d_prefetch_l2(const void* tmap, int c0, int c1) {

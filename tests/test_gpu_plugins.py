@@ -582,3 +582,17 @@ def test_simple_rp_functor_bits_and_lsh_use():
     index.build_index(_descr(x))
     r, d = index.nn(DescriptorMemoryElement(9999).set_vector(x[10]), 3)
     assert r[0].uuid() == 10 and d[0] == 0.0
+
+
+def test_itq_fit_streaming_equals_materialised():
+    """The V-free ITQ iteration (fit.itq_rotation_streaming) is the same algorithm up to FP64
+    re-association: same rotation to ~1e-9, same training codes except rounding-level projections."""
+    from smqtk_indexing_b200 import fit as fitops
+    rng = np.random.RandomState(8)
+    x = rng.rand(4000, 48).astype(np.float32)
+    for normalize in (None, 2):
+        c0, m0, r0 = fitops.itq_fit(x, 16, itq_iterations=8, normalize=normalize, random_seed=2, streaming=False)
+        c1, m1, r1 = fitops.itq_fit(x, 16, itq_iterations=8, normalize=normalize, random_seed=2, streaming=True)
+        np.testing.assert_array_equal(m0, m1)
+        np.testing.assert_allclose(r1, r0, rtol=0, atol=1e-8)
+        assert (c0 != c1).mean() < 1e-3

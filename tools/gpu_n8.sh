@@ -1,4 +1,9 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r1_bench_n8.json 2> gpurun_out/r1_bench_n8.err; echo "bench n8 rc=$?"
-tail -c 1800 gpurun_out/r1_bench_n8.json; tail -3 gpurun_out/r1_bench_n8.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 10 --warmup 3 > gpurun_out/r1_bench_n4.json 2> gpurun_out/r1_bench_n4.err; echo "bench n4 rc=$?"
-tail -c 600 gpurun_out/r1_bench_n4.json
+for n in 8 4 2; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29520+n)) bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/r1_bench_n$n.json 2> gpurun_out/r1_bench_n$n.err; echo "bench n$n rc=$?"
+done
+python - <<'PY'
+import json
+for n in (2,4,8):
+    d=json.loads(open('gpurun_out/r1_bench_n%d.json'%n).read().strip().splitlines()[-1])
+    print(n, round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value']), d['roofline']['kernel_ms'], d['clocks'])
+PY
