@@ -118,27 +118,39 @@ STREAMING_V_BYTES = 4 << 30
 
 
 def itq_rotation_streaming(xt: torch.Tensor, div, mean, pc_top: np.ndarray, n_iter: int,
-                           random_seed: Optional[int]) -> Tuple[torch.Tensor, np.ndarray]:
+                           random_seed: Optional[int], normalize=None) -> Tuple[torch.Tensor, np.ndarray]:
     """``_find_itq_rotation`` (itq.py:239-289) without the N x b matrix ``v = x . pc_top``:
     with P = pc_top, ``z = v.r = x.(P r)`` and ``c = ux^T v = (ux^T x) P``, so an iteration is one
     projection of X by the D x b matrix ``P r`` (sign bits only) and one b x D Gram
     ``ux^T x`` -- same arithmetic up to FP64 re-association, 4 N D b flop per iteration instead
     of 4 N b^2, and no 8 N b bytes of HBM (102 GB for 50M x 256 bits)."""
+    from . import device
     bit = pc_top.shape[1]
     if random_seed is not None:
         np.random.seed(random_seed)
     r = np.random.randn(bit, bit)
     u11, _, _ = np.linalg.svd(r)
     r = u11[:, :bit]
+    # float32 training data of an aligned shape: the sign step IS ItqFunctor.get_hash with the
+    # rotation P r, so it runs on the production tensor-core hash kernel (3xTF32; bits can differ
+    # from the FP64 projection only for |z| at rounding level -- the same bits queries will get)
+    mean32 = mean.to(torch.float32) if xt.dtype == torch.float32 else None
+    use_tc = mean32 is not None and device.itq_tc_supported(xt, bit)
+
+    def sign_codes(rot: np.ndarray) -> torch.Tensor:
+        pr = np.ascontiguousarray(pc_top @ rot)
+        if use_tc:
+            return device.itq_hash(xt, mean32, torch.from_numpy(pr.astype(np.float32)).to(xt.device),
+                                   normalize=normalize, variant=2)
+        prd = torch.from_numpy(pr).to(xt.device)
+        return project(xt, prd, a_div=div, a_mean=mean, want_values=False, want_codes=True)[1]
+
     for _ in range(n_iter):
-        pr = torch.from_numpy(np.ascontiguousarray(pc_top @ r)).to(xt.device)
-        _, ux = project(xt, pr, a_div=div, a_mean=mean, want_values=False, want_codes=True)   # sign(x . P r)
+        ux = sign_codes(r)                                                                  # sign(x . P r)
         g = gram(ux, xt, a_bits=bit, b_div=div, b_mean=mean).cpu().numpy()                  # ux^T . x   [b, D]
         ub, _, ua = np.linalg.svd(g @ pc_top)
         r = np.dot(ua, ub.transpose())
-    pr = torch.from_numpy(np.ascontiguousarray(pc_top @ r)).to(xt.device)
-    _, codes = project(xt, pr, a_div=div, a_mean=mean, want_values=False, want_codes=True)
-    return codes, r
+    return sign_codes(r), r
 
 
 def itq_fit(x, bit_length: int, itq_iterations: int = 50, normalize=None,
@@ -175,7 +187,7 @@ def itq_fit(x, bit_length: int, itq_iterations: int = 50, normalize=None,
         if streaming is None:
             streaming = n * bit_length * 8 > STREAMING_V_BYTES
         if streaming:
-            codes, r = itq_rotation_streaming(xt, div, mean, pc_top, itq_iterations, random_seed)
+            codes, r = itq_rotation_streaming(xt, div, mean, pc_top, itq_iterations, random_seed, normalize)
         else:
             v, _ = project(xt, pc_dev, a_div=div, a_mean=mean)
             codes, r = itq_rotation(v, itq_iterations, random_seed)

@@ -596,3 +596,17 @@ def test_itq_fit_streaming_equals_materialised():
         np.testing.assert_array_equal(m0, m1)
         np.testing.assert_allclose(r1, r0, rtol=0, atol=1e-8)
         assert (c0 != c1).mean() < 1e-3
+
+
+def test_itq_fit_streaming_on_tensor_core_hash():
+    """float32 data of an aligned shape: the streaming fit takes its sign bits from the production
+    tensor-core hash kernel; the model agrees with the FP64 fit up to rounding-level bit flips."""
+    from smqtk_indexing_b200 import fit as fitops
+    rng = np.random.RandomState(18)
+    x = rng.rand(6000, 64).astype(np.float32)
+    c0, m0, r0 = fitops.itq_fit(x, 32, itq_iterations=6, random_seed=4, streaming=False)
+    c1, m1, r1 = fitops.itq_fit(x, 32, itq_iterations=6, random_seed=4, streaming=True)
+    np.testing.assert_array_equal(m0, m1)
+    np.testing.assert_allclose(r1, r0, rtol=0, atol=1e-4)
+    np.testing.assert_allclose(r1.T @ r1, np.eye(32), atol=1e-9)
+    assert (c0 != c1).mean() < 1e-3

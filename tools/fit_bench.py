@@ -9,7 +9,9 @@ n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 b = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 5
-X = torch.rand((n, D), device="cuda")
+X = torch.empty((n, D), device="cuda")
+for s0 in range(0, n, 4_000_000):           # generate in slabs (keeps the RNG temporaries small)
+    X[s0:s0 + 4_000_000].uniform_()
 torch.cuda.synchronize()
 f = ItqFunctor(bit_length=b, itq_iterations=iters, random_seed=0)
 _lib.profile_fetch(); _lib.profile_enable(True)

@@ -1,1 +1,3 @@
-timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 99 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "heavy_ties or known_answer or variants_agree or empty_table or rejects_unaligned or rerank_known or select_order or expand_candidates or tensor_core_matches or duplicates_ties" > gpurun_out/r1_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -15 gpurun_out/r1_memcheck.log
+timeout 600 python -m pytest tests/test_gpu_plugins.py -m gpu -x -q -k "streaming or itq" 2>&1 | tail -3
+timeout 600 python tools/fit_bench.py 5e7 256 256 10 > gpurun_out/r1_c5_fit_build_b256.log 2>&1; tail -7 gpurun_out/r1_c5_fit_build_b256.log
+timeout 600 python tools/fit_bench.py 5e7 256 64 50 > gpurun_out/r1_c5_fit_build_b64.log 2>&1; tail -7 gpurun_out/r1_c5_fit_build_b64.log
