@@ -243,6 +243,20 @@ SB_API int sb_fit_project(const void* A, int32_t a_kind, int64_t lda, int32_t K,
                           const double* Bm, int32_t M, int64_t n,
                           double* out_f64, uint32_t* out_codes, int32_t Wc, void* stream);
 
+/* Tensor-core form of the ITQ iteration's row-scaled product (itq.py:274 in the V-free form of
+ * fit.py): out f64[b][D] = sum_r (bit_m(codes[r]) ? +1 : -1) * (X[r][d] / row_div[r] - mean[d]).
+ * codes u32[n][W] (layout above), X f32[n][ldx]; mean f32[D] / row_div f32[n] optional.
+ * `bound` >= max |X / row_div - mean| (any finite upper bound; a tight one keeps more bits): the
+ * centred values are split on fixed-point grids (2^-10 and 2^-21 of the bound's power of two), so
+ * the TF32 products and the FP32 accumulation in tensor memory are exact; windows of 8192 rows are
+ * flushed to FP64 and reduced in a fixed order (deterministic).  Error: the 2^-22 * bound rounding
+ * of each centred value, nothing else.  Needs D % 32 == 0, ldx % 4 == 0, b % 4 == 0, b <= 256. */
+SB_API int sb_fit_gram_bits_tc_supported(int64_t n, int32_t D, int64_t ldx, int32_t b);
+SB_API size_t sb_fit_gram_bits_tc_workspace_bytes(int64_t n, int32_t D, int32_t b);
+SB_API int sb_fit_gram_bits_tc(const uint32_t* codes, int32_t W, int32_t b, const float* X, int64_t n, int32_t D,
+                        int64_t ldx, const float* mean, const float* row_div, float bound, double* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

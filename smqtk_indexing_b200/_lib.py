@@ -61,6 +61,9 @@ SIGNATURES: Dict[str, tuple] = {
     "sb_fit_gram": (c_int32, [_P, c_int32, c_int64, c_int32, _P, _P, c_int32,
                               _P, c_int32, c_int64, c_int32, _P, _P, c_int32,
                               c_int64, c_double, _P, _P, c_size_t, _P]),
+    "sb_fit_gram_bits_tc_supported": (c_int32, [c_int64, c_int32, c_int64, c_int32]),
+    "sb_fit_gram_bits_tc_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "sb_fit_gram_bits_tc": (c_int32, [_P, c_int32, c_int32, _P, c_int64, c_int32, c_int64, _P, _P, c_float, _P, _P, c_size_t, _P]),
     "sb_fit_project": (c_int32, [_P, c_int32, c_int64, c_int32, _P, _P, _P, c_int32, c_int64, _P, _P, c_int32, _P]),
 }
 

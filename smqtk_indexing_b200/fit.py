@@ -64,6 +64,42 @@ def gram(a: torch.Tensor, b: torch.Tensor, scale: float = 1.0, a_div=None, a_mea
     return out
 
 
+def centred_bound(x: torch.Tensor, mean: Optional[torch.Tensor], div: Optional[torch.Tensor]) -> float:
+    """An upper bound on ``|x / div - mean|`` (column min / max reductions, no N x D temporary);
+    tight when there is no row normalisation."""
+    lo, hi = torch.aminmax(x, dim=0)
+    lo, hi = lo.double(), hi.double()
+    if div is None:
+        m = mean.double() if mean is not None else torch.zeros_like(lo)
+        b = float(torch.maximum((hi - m).abs(), (lo - m).abs()).max())
+    else:
+        b = float(torch.maximum(lo.abs(), hi.abs()).max()) / max(float(div.min()), 1e-30)
+        if mean is not None:
+            b += float(mean.abs().max())
+    return min(max(b * (1.0 + 1e-6), 1e-30), 1e29)
+
+
+def gram_bits_tc(codes: torch.Tensor, bits: int, x: torch.Tensor, mean32: Optional[torch.Tensor] = None,
+                 div32: Optional[torch.Tensor] = None, bound: Optional[float] = None) -> torch.Tensor:
+    """Tensor-core ``UX^T . (x / div - mean)`` -> float64[bits, D] (``sb_fit_gram_bits_tc``).
+    ``bound``: an upper bound on ``|x / div - mean|`` (computed when not given)."""
+    n, d = x.shape
+    if bound is None:
+        bound = centred_bound(x, mean32, div32)
+    lib = _lib.load()
+    nbytes = lib.sb_fit_gram_bits_tc_workspace_bytes(n, d, bits)
+    ws = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=x.device)
+    out = torch.empty((bits, d), dtype=torch.float64, device=x.device)
+    _lib.check(lib.sb_fit_gram_bits_tc(_ptr(codes), codes.shape[1], bits, _ptr(x), n, d, x.stride(0), _ptr(mean32),
+                                       _ptr(div32), float(bound), _ptr(out), _ptr(ws), nbytes, _stream()))
+    return out
+
+
+def gram_bits_tc_supported(x: torch.Tensor, bits: int) -> bool:
+    return (x.dtype == torch.float32 and x.data_ptr() % 16 == 0
+            and bool(_lib.load().sb_fit_gram_bits_tc_supported(x.shape[0], x.shape[1], x.stride(0), bits)))
+
+
 def project(a: torch.Tensor, bm: torch.Tensor, a_div=None, a_mean=None, want_values: bool = True,
             want_codes: bool = False):
     """opA . bm (f64[K, M]) -> values f64[n, M] and/or sign-bit codes int32[n, W]."""
@@ -115,10 +151,13 @@ def itq_rotation(v: torch.Tensor, n_iter: int, random_seed: Optional[int]) -> Tu
 #: Above this size the PCA-projected training matrix V (float64[N, b]) is not materialised:
 #: every ITQ iteration works from X directly (see ``itq_rotation_streaming``).
 STREAMING_V_BYTES = 4 << 30
+#: Below this many rows the FP64 Gram kernel is used even when the tensor-core one applies
+TC_GRAM_MIN_ROWS = 1 << 16
 
 
 def itq_rotation_streaming(xt: torch.Tensor, div, mean, pc_top: np.ndarray, n_iter: int,
-                           random_seed: Optional[int], normalize=None) -> Tuple[torch.Tensor, np.ndarray]:
+                           random_seed: Optional[int], normalize=None,
+                           tensor_cores: Optional[bool] = None) -> Tuple[torch.Tensor, np.ndarray]:
     """``_find_itq_rotation`` (itq.py:239-289) without the N x b matrix ``v = x . pc_top``:
     with P = pc_top, ``z = v.r = x.(P r)`` and ``c = ux^T v = (ux^T x) P``, so an iteration is one
     projection of X by the D x b matrix ``P r`` (sign bits only) and one b x D Gram
@@ -134,8 +173,12 @@ def itq_rotation_streaming(xt: torch.Tensor, div, mean, pc_top: np.ndarray, n_it
     # float32 training data of an aligned shape: the sign step IS ItqFunctor.get_hash with the
     # rotation P r, so it runs on the production tensor-core hash kernel (3xTF32; bits can differ
     # from the FP64 projection only for |z| at rounding level -- the same bits queries will get)
-    mean32 = mean.to(torch.float32) if xt.dtype == torch.float32 else None
+    mean32 = mean.to(torch.float32) if (xt.dtype == torch.float32 and tensor_cores is not False) else None
     use_tc = mean32 is not None and device.itq_tc_supported(xt, bit)
+    # ... and the +-1 Gram ux^T . x runs on the tensor cores too (fixed-point hi/lo split: exact accumulation)
+    use_tc_gram = mean32 is not None and gram_bits_tc_supported(xt, bit) and xt.shape[0] >= TC_GRAM_MIN_ROWS
+    div32 = div.to(torch.float32) if (use_tc_gram and div is not None) else None
+    bound = centred_bound(xt, mean32, div32) if use_tc_gram else None
 
     def sign_codes(rot: np.ndarray) -> torch.Tensor:
         pr = np.ascontiguousarray(pc_top @ rot)
@@ -147,18 +190,30 @@ def itq_rotation_streaming(xt: torch.Tensor, div, mean, pc_top: np.ndarray, n_it
 
     for _ in range(n_iter):
         ux = sign_codes(r)                                                                  # sign(x . P r)
-        g = gram(ux, xt, a_bits=bit, b_div=div, b_mean=mean).cpu().numpy()                  # ux^T . x   [b, D]
+        if use_tc_gram:
+            g = gram_bits_tc(ux, bit, xt, mean32, div32, bound).cpu().numpy()                      # ux^T . x   [b, D]
+        else:
+            g = gram(ux, xt, a_bits=bit, b_div=div, b_mean=mean).cpu().numpy()
         ub, _, ua = np.linalg.svd(g @ pc_top)
         r = np.dot(ua, ub.transpose())
     return sign_codes(r), r
 
 
 def itq_fit(x, bit_length: int, itq_iterations: int = 50, normalize=None,
-            random_seed: Optional[int] = None, dev=None, streaming: Optional[bool] = None):
+            random_seed: Optional[int] = None, dev=None, streaming: Optional[bool] = None,
+            tensor_cores: Optional[bool] = None, want_codes: bool = True):
     """Fit on ``x`` ([N, D] numpy array or CUDA tensor, float32 or float64).
 
     :param streaming: never materialise ``v`` (default: automatic, when it would exceed
         ``STREAMING_V_BYTES``).
+    :param tensor_cores: streaming fit only. ``False`` keeps every N-scaled product in FP64 (the
+        parity path: the rotation agrees with the numpy reference to 1e-8); ``None`` / ``True`` take
+        the sign bits from the 3xTF32 hash kernel and, from 65536 rows, ``ux^T x`` from the
+        fixed-point tensor-core Gram (the Gram is good to 1e-8, but a few rounding-level sign flips
+        per iteration make the rotation differ at the 1e-3 level -- an equally good ITQ model).
+    :param want_codes: ``False`` skips the device-to-host copy and the N x b bool expansion of the
+        training codes (the reference returns them; 12.8 GB of host memory for 50M x 256 bits) and
+        returns ``None`` in their place.
     :return: (codes bool[N, b], mean_vec [D] in x's dtype, rotation float64[D, b])
     """
     require_cuda()
@@ -187,10 +242,11 @@ def itq_fit(x, bit_length: int, itq_iterations: int = 50, normalize=None,
         if streaming is None:
             streaming = n * bit_length * 8 > STREAMING_V_BYTES
         if streaming:
-            codes, r = itq_rotation_streaming(xt, div, mean, pc_top, itq_iterations, random_seed, normalize)
+            codes, r = itq_rotation_streaming(xt, div, mean, pc_top, itq_iterations, random_seed, normalize,
+                                              tensor_cores)
         else:
             v, _ = project(xt, pc_dev, a_div=div, a_mean=mean)
             codes, r = itq_rotation(v, itq_iterations, random_seed)
-        codes_host = codes.cpu().numpy().view(np.uint32)
+        codes_host = codes.cpu().numpy().view(np.uint32) if want_codes else None
     mean_vec = mean.cpu().numpy().astype(out_dtype)
-    return unpack_bits(codes_host, bit_length), mean_vec, np.dot(pc_top, r)
+    return (unpack_bits(codes_host, bit_length) if want_codes else None), mean_vec, np.dot(pc_top, r)

@@ -229,8 +229,9 @@ class ItqFunctor(LshFunctor):
         ))
         return self.fit_matrix(x)
 
-    def fit_matrix(self, x) -> np.ndarray:
-        """``fit`` on an assembled ``[N, D]`` matrix (numpy or CUDA tensor)."""
+    def fit_matrix(self, x, want_codes: bool = True):
+        """``fit`` on an assembled ``[N, D]`` matrix (numpy or CUDA tensor).  ``want_codes=False``
+        skips the N x b bool matrix the reference's ``fit`` returns (returns ``None``)."""
         if self.has_model():
             raise RuntimeError("Model components have already been loaded.")
         from smqtk_indexing_b200 import fit as fitops
@@ -238,7 +239,7 @@ class ItqFunctor(LshFunctor):
             raise ValueError("Input descriptors have fewer features than "
                              "requested bit encoding.")
         codes, mean_vec, rotation = fitops.itq_fit(
-            x, self.bit_length, self.itq_iterations, self.normalize, self.random_seed)
+            x, self.bit_length, self.itq_iterations, self.normalize, self.random_seed, want_codes=want_codes)
         self.mean_vec = mean_vec
         self.rotation = rotation
         self.save_model()

@@ -610,3 +610,58 @@ def test_itq_fit_streaming_on_tensor_core_hash():
     np.testing.assert_allclose(r1, r0, rtol=0, atol=1e-4)
     np.testing.assert_allclose(r1.T @ r1, np.eye(32), atol=1e-9)
     assert (c0 != c1).mean() < 1e-3
+
+
+def test_itq_fit_streaming_on_tensor_core_gram():
+    """>= 65536 aligned float32 rows: the streaming fit also takes UX^T.X from the tensor cores."""
+    from smqtk_indexing_b200 import fit as fitops
+    rng = np.random.RandomState(19)
+    n = fitops.TC_GRAM_MIN_ROWS + 4321
+    # clustered descriptors with a decaying spectrum (on i.i.d. data every rotation is as good as any
+    # other and the ITQ iteration amplifies rounding-level differences into a different model)
+    centres = rng.randn(24, 64) * np.linspace(2.0, 0.2, 64)
+    x = (centres[rng.randint(0, 24, n)] + 0.15 * rng.randn(n, 64)).astype(np.float32)
+    c0, m0, r0 = fitops.itq_fit(x, 32, itq_iterations=5, random_seed=4, streaming=False)
+    c1, m1, r1 = fitops.itq_fit(x, 32, itq_iterations=5, random_seed=4, streaming=True)
+    c2, m2, r2 = fitops.itq_fit(x, 32, itq_iterations=5, random_seed=4, streaming=True, tensor_cores=False)
+    np.testing.assert_array_equal(m0, m1)
+    # FP64 streaming == FP64 with v materialised
+    np.testing.assert_allclose(r2, r0, rtol=0, atol=1e-8)
+    # tensor-core Gram: the Gram itself is good to 1e-8 (next test), but sign() makes the ITQ iteration
+    # discontinuous -- a handful of flipped rows per iteration moves the rotation at the 1e-3 level.
+    # Same model up to that: orthonormal, same quantisation loss, 99 % of the bits.
+    np.testing.assert_allclose(r1.T @ r1, np.eye(32), atol=1e-9)
+    np.testing.assert_allclose(r1, r0, rtol=0, atol=5e-2)
+    assert (c0 != c1).mean() < 1e-2
+    xc = x[:20000].astype(np.float64) - m0.astype(np.float64)
+    loss = [np.square(np.sign(xc @ r) - xc @ r).sum() for r in (r0, r1)]
+    assert abs(loss[1] - loss[0]) < 1e-3 * loss[0], loss
+
+
+@pytest.mark.parametrize("n,D,b,normalize", [(5000, 64, 32, None), (70000, 256, 256, None), (9000, 512, 128, 2),
+                                             (4100, 96, 64, None), (20000, 128, 100, None)])
+def test_gram_bits_tensor_core_matches_fp64(n, D, b, normalize):
+    """sb_fit_gram_bits_tc (MN-major TF32 operands on fixed-point grids, exact FP32 accumulation,
+    FP64 across 8192-row windows) vs the FP64 DFMA Gram on the same packed sign bits: the only
+    error is the rounding of each centred value to 2^-22 of the bound -- a random walk of
+    sqrt(n) * 2^-22 * bound, asserted here as 1e-7 of sum |x - mean|."""
+    import torch
+    from smqtk_indexing_b200 import device as dev, fit as fitops
+    from smqtk_indexing_b200.utils.bits import words_for_bits
+    rng = np.random.RandomState(n + b)
+    x = torch.from_numpy(rng.rand(n, D).astype(np.float32)).cuda()
+    W = words_for_bits(b)
+    bits = rng.rand(n, b) > 0.5
+    codes = dev.codes_to_device(O.pack_codes(bits, W))
+    div = fitops.row_div(x, normalize)
+    mean = fitops.col_mean(x, div)
+    ref = fitops.gram(codes, x, a_bits=b, b_div=div, b_mean=mean)
+    got = fitops.gram_bits_tc(codes, b, x, mean.to(torch.float32), None if div is None else div.to(torch.float32))
+    torch.cuda.synchronize()
+    xc = x.double() / (div[:, None] if div is not None else 1.0) - mean[None, :]
+    scale = xc.abs().sum(0)[None, :]                        # worst-case magnitude of each column sum
+    err = ((got - ref).abs() / scale).max().item()
+    assert err < 1e-7, err
+    # and against numpy on a small slice of the output
+    ux = np.where(bits[:, :4], 1.0, -1.0)
+    np.testing.assert_allclose(ref[:4].cpu().numpy(), ux.T @ xc.cpu().numpy(), rtol=1e-9, atol=1e-7)
