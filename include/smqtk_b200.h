@@ -129,6 +129,19 @@ SB_API int sb_hamming_scan_variant(const uint32_t* db, int64_t U, int32_t W,
                             uint64_t* keys_out, void* workspace, size_t workspace_bytes,
                             int32_t variant, void* stream);
 
+/* Batched scan on the tensor cores (hamming_tc.cu): bits -> +-1 FP8 E4M3, tcgen05.mma
+ * kind::f8f6f4, dot = 32 W - 2 * distance -- exact integers in the FP32 accumulator.  Same
+ * contract and the same keys as sb_hamming_scan, for W in {1, 2, 4, 8} and k <= 256; meant for
+ * large query batches, where the XOR/POPC scan is bound by the integer pipes instead of HBM.
+ * *overflow_out (device int32) becomes 1 if a per-query candidate buffer overflowed: the keys
+ * must then be discarded and sb_hamming_scan run instead. */
+SB_API int sb_hamming_scan_tc_supported(int64_t U, int32_t W, int32_t Q, int32_t k);
+SB_API size_t sb_hamming_scan_tc_workspace_bytes(int64_t U, int32_t W, int32_t Q, int32_t k);
+SB_API int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W,
+                       const uint32_t* q, int32_t Q, int32_t k, int64_t idx_base,
+                       uint64_t* keys_out, int32_t* overflow_out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* Merge `parts` sorted key lists per query (keys_in: u64[parts][Q][k], e.g. the
  * all-gathered per-GPU results) into the global top-k and decode:
  * out_dist i32[Q][k] (-1 = empty), out_idx i64[Q][k] (-1 = empty); either of

@@ -1,0 +1,654 @@
+// Batched Hamming scan / top-k on the tensor cores (reference: LinearHashIndex._nn,
+// smqtk_indexing/impls/hash_index/linear.py:232-240 + hamming_distance utils/metrics.py:155).
+//
+// Why: with thousands of queries per batch the XOR/POPC scan (hamming.cu) is bound by the integer
+// issue pipes, not by HBM -- every table word is reused from registers by 4096 queries (27 TB/s of
+// algorithmic bytes on a 6.6 TB/s HBM; profiles/r1_scan_full.md: ALU pipe 89 % busy).  The same
+// count is a dot product: with bits mapped to +-1, dot(a, b) = K - 2 * popcount(a xor b).  FP8
+// E4M3 holds +-1 exactly and the FP32 accumulator holds every integer up to 2^24, so
+// tcgen05.mma kind::f8f6f4 computes the distances EXACTLY at 8192 MAC/clk/SM instead of 64
+// LOP3 + 16 POPC lanes/clk/SM.  The single-query / small-batch scan stays on hamming.cu, where the
+// table really is streamed once per query and HBM is the bound.
+//
+// Data flow per CTA (persistent, one per SM):
+//   * B = 256 query codes, expanded once per batch to +-1 FP8 in the SWIZZLE_128B K-major layout
+//     (ham_query_image_kernel), RESIDENT in shared memory for a whole pass over the rows.
+//   * A = 128 table rows per tile.  Producer warps read the PACKED codes (32 bytes per 256-bit
+//     row: HBM traffic stays at U * b / 8 per pass) and expand them to FP8 straight into the
+//     swizzled layout -- the table is never stored expanded.
+//   * The threshold rides in one extra K step: A_syn = 32 x (+1), B_syn = 32 slots that sum to
+//     2 * tq - K + 1, so the accumulator is 2 * (tq - d) + 1 and "d <= tq" is a sign test (odd,
+//     never zero).  Survivors are decoded (d = tq - floor(acc / 2)) and appended to their query's
+//     candidate buffer as canonical keys d << 40 | row.
+//   * Accumulators double-buffered in TMEM (2 x 256 columns): the epilogue of tile t overlaps the
+//     MMAs of tile t + 1.
+// Thresholds tighten between chunks (ham_compact_kernel keeps the best k so far): chunk c is
+// GROWTH x the rows seen before it, and rows are visited in a golden-ratio permutation of 32-row
+// granules, so every chunk is a uniform sample of the table whatever its order -- a chunk then
+// yields ~GROWTH * (k + ties) survivors per query for ANY data distribution (the table is sorted,
+// near-duplicate clusters are contiguous).  A query whose buffer still overflows raises a flag and
+// the caller re-runs the batch on hamming.cu.
+// Warp roles (14 warps): 0-7 epilogue (TMEM lane quadrant = warp % 4, column half = warp / 4: the
+// epilogue is a chain of dependent integer ops per warp, so it wants warps, not instructions),
+// 8 MMA issue + TMEM alloc, 9 B loader, 10-13 producers (one table row per thread and tile).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+using namespace tcptx;
+
+namespace {
+
+constexpr int TM = 128;                     // rows per tile (UMMA M)
+constexpr int QB = 256;                     // query columns per block (UMMA N)
+constexpr int A_GROUP = TM * 128;           // 16 KB: 128 rows x 128 FP8 (4 code words)
+constexpr int B_GROUP = QB * 128;           // 32 KB
+constexpr int B_SYN = 2 * QB * 16;          // 8 KB  (no-swizzle, 2 K chunks of 16 bytes)
+constexpr int A_SYN = 2 * TM * 16;          // 4 KB
+constexpr int MAX_STAGES = 4;
+constexpr int SQ_CAP = 96;                  // survivor queue entries per epilogue warp and tile
+constexpr int GRAN = 32;                    // rows per granule of the visiting order
+constexpr int EPI_WARPS = 8, MMA_WARP = 8, B_WARP = 9, PROD_WARP0 = 10, PROD_WARPS = 4;
+constexpr int EPI_COLS = QB / 2;            // columns per epilogue warp
+constexpr int THREADS = (PROD_WARP0 + PROD_WARPS) * 32;   // 448
+constexpr int GROWTH = 8;
+constexpr int CP_THREADS = 1024;
+
+struct HamTcParams {
+  const uint32_t* db;          // u32[U][W]
+  long long U;
+  int W, G, ksteps;            // G = 128-byte K groups per row, ksteps = MMAs per group
+  long long vg0, vg1;          // virtual granules of this chunk
+  long long NG, P;             // physical granule = (virtual * P) mod NG
+  int col_blocks, cb_per;      // query blocks in total / per blockIdx.y
+  const unsigned char* image;  // per block: G x B_GROUP (SW128) then B_SYN
+  const int* tq;               // thresholds (Hamming distance) per query column
+  unsigned long long* cand_buf;
+  int* cand_cnt;
+  int cap;
+  long long idx_base;
+  int dense;                   // first chunk: every pair is kept -> key stored at buf[query][virtual row]
+  int stages;
+};
+
+// 4 code bits -> 4 FP8 E4M3 bytes: bit = 0 -> +1.0 (0x38), bit = 1 -> -1.0 (0xB8); bit i -> byte i
+__device__ __forceinline__ uint32_t expand_nibble(uint32_t x) { return ((x * 0x10204080u) & 0x80808080u) | 0x38383838u; }
+__device__ __forceinline__ void expand_word(uint32_t w, uint4& lo, uint4& hi) {
+  lo.x = expand_nibble(w & 15u);
+  lo.y = expand_nibble((w >> 4) & 15u);
+  lo.z = expand_nibble((w >> 8) & 15u);
+  lo.w = expand_nibble((w >> 12) & 15u);
+  hi.x = expand_nibble((w >> 16) & 15u);
+  hi.y = expand_nibble((w >> 20) & 15u);
+  hi.z = expand_nibble((w >> 24) & 15u);
+  hi.w = expand_nibble(w >> 28);
+}
+// byte offset of 16-byte chunk c of row r inside a [rows x 128 B] SWIZZLE_128B K-major group
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+  return (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::f8f6f4 (E4M3 x E4M3 -> F32), issued by one thread.
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Cold path, out of line, accumulators by value (see tc_ptx.cuh::l2_queue_survivors): decode the
+// pairs flagged in `mask` (bit 15 - j <-> column col0 + j) and queue their keys.
+static __device__ __noinline__ void ham_queue_survivors(
+    unsigned mask, int q0, int col0, unsigned long long row_key, const int* tq_local, unsigned long long* q_key, int* q_q,
+    int* q_cnt, int q_cap, unsigned long long* cand_buf, int* cand_cnt, int cap,
+    uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t v4, uint32_t v5, uint32_t v6, uint32_t v7, uint32_t v8,
+    uint32_t v9, uint32_t v10, uint32_t v11, uint32_t v12, uint32_t v13, uint32_t v14, uint32_t v15) {
+  const uint32_t v[16] = {v0, v1, v2, v3, v4, v5, v6, v7, v8, v9, v10, v11, v12, v13, v14, v15};
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (mask & (0x8000u >> j)) {
+      const int qg = q0 + col0 + j;
+      const int d = tq_local[col0 + j] - (int)(__uint_as_float(v[j]) * 0.5f);     // acc = 2 (tq - d) + 1
+      const unsigned long long key = ((unsigned long long)(unsigned)d << 40) | row_key;
+      const int e = atomicAdd(q_cnt, 1);
+      if (e < q_cap) {
+        q_key[e] = key;
+        q_q[e] = qg;
+      } else {
+        const int slot = atomicAdd(cand_cnt + qg, 1);
+        if (slot < cap) cand_buf[(long long)qg * cap + slot] = key;
+      }
+    }
+  }
+}
+#define SB_HAM_QUEUE(mask, v, q0, col0, row_key, tql, qk, qq, qc, qcap, buf, cnt, cap)                                 \
+  ham_queue_survivors(mask, q0, col0, row_key, tql, qk, qq, qc, qcap, buf, cnt, cap, v[0], v[1], v[2], v[3], v[4], v[5], \
+                      v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15])
+
+__global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms: align by hand
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = p.G;
+  const uint32_t a_stage = (uint32_t)G * A_GROUP;
+  // layout (offsets are multiples of 1024): [B data G x 32 KB][B_syn][A_syn][A ring][barriers, queues, thresholds]
+  unsigned char* s_b = smem;
+  unsigned char* s_bsyn = s_b + (size_t)G * B_GROUP;
+  unsigned char* s_asyn = s_bsyn + B_SYN;
+  unsigned char* s_a = s_asyn + A_SYN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + (size_t)p.stages * a_stage);
+  const uint32_t a_full = smem_u32(bars), a_empty = a_full + MAX_STAGES * 8;
+  const uint32_t acc_full = a_empty + MAX_STAGES * 8, acc_empty = acc_full + 16;
+  const uint32_t b_full = acc_empty + 16, b_empty = b_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
+  unsigned long long* sq_key = reinterpret_cast<unsigned long long*>(bars + 2 * MAX_STAGES + 8);
+  int* sq_q = reinterpret_cast<int*>(sq_key + EPI_WARPS * SQ_CAP);
+  int* sq_cnt = sq_q + EPI_WARPS * SQ_CAP;
+  int* s_tq = sq_cnt + EPI_WARPS;                                // [8 warps][128]: this block's thresholds
+
+  const long long n_gran = p.vg1 - p.vg0;
+  const long long n_tiles = (n_gran + 3) / 4;
+  const long long my_tiles = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int jb0 = blockIdx.y * p.cb_per;
+  const int jb1 = min(p.col_blocks, jb0 + p.cb_per);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(a_full + s * 8, PROD_WARPS); mbar_init(a_empty + s * 8, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b * 8, 1); mbar_init(acc_empty + b * 8, EPI_WARPS); }
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // A_syn = +1.0 everywhere; codes narrower than 128 bits leave K chunks of the A ring untouched: zero them once
+  for (int i = threadIdx.x; i < A_SYN / 4; i += THREADS) reinterpret_cast<uint32_t*>(s_asyn)[i] = 0x38383838u;
+  if (p.W < 4)
+    for (int i = threadIdx.x; i < (int)(p.stages * a_stage / 16); i += THREADS)
+      reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == B_WARP) {
+    // =========================== B: resident query block ===========================
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)G * B_GROUP + B_SYN;        // B data and B_syn are contiguous in both places
+      for (int jb = jb0; jb < jb1; ++jb) {
+        const int it = jb - jb0;
+        mbar_wait(b_empty, (it & 1) ^ 1);
+        const unsigned char* src = p.image + (size_t)jb * bytes;
+        mbar_expect_tx(b_full, bytes);
+        for (uint32_t o = 0; o < bytes; o += 8192) tma_bulk_g2s(smem_u32(s_b + o), src + o, 8192, b_full);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // =========================== MMA issue ===========================
+    if (lane == 0) {
+      // D = F32 (bit 4), A = B = E4M3 (format 0), both K-major, N = 256, M = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(QB >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      const uint64_t asyn_desc = umma_desc(smem_u32(s_asyn), TM * 16, 128);
+      const uint64_t bsyn_desc = umma_desc(smem_u32(s_bsyn), QB * 16, 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      long long t = 0;
+      for (int jb = jb0; jb < jb1; ++jb) {
+        mbar_wait(b_full, (jb - jb0) & 1);
+        tc_fence_after();
+        for (long long i = 0; i < my_tiles; ++i, ++t) {
+          const int buf = (int)(t & 1);
+          const uint32_t use = (uint32_t)((t >> 1) & 1);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * QB);
+          mbar_wait(acc_empty + buf * 8, use ^ 1);
+          mbar_wait(a_full + stage * 8, phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(s_a) + (uint32_t)stage * a_stage, b0 = smem_u32(s_b);
+          for (int g = 0; g < G; ++g)
+            for (int ks = 0; ks < p.ksteps; ++ks)
+              umma_f8(d_tmem, umma_desc_sw128(a0 + g * A_GROUP + ks * 32), umma_desc_sw128(b0 + g * B_GROUP + ks * 32), idesc,
+                      (g | ks) ? 1u : 0u);
+          umma_f8(d_tmem, asyn_desc, bsyn_desc, idesc, 1u);
+          umma_commit(a_empty + stage * 8);
+          umma_commit(acc_full + buf * 8);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(b_empty);                                   // B may be replaced once these MMAs retire
+      }
+    }
+  } else if (warp >= PROD_WARP0) {
+    // =========================== A: packed codes -> +-1 FP8, swizzled ===========================
+    const int r = threadIdx.x - PROD_WARP0 * 32;                 // row of the tile
+    const int W = p.W;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t cw[8], cn[8];
+    // granule of tile i for this thread: vg = vg_first + i * 4 * gridDim.x, physical pg = vg * P mod NG, kept incrementally
+    const long long vg_first = p.vg0 + (long long)blockIdx.x * 4 + (r >> 5);
+    const long long pg_first = (long long)(((unsigned long long)vg_first * (unsigned long long)p.P) % (unsigned long long)p.NG);
+    const long long pg_step = (long long)(((unsigned long long)(4 * gridDim.x) * (unsigned long long)p.P) % (unsigned long long)p.NG);
+    long long vg_ld = vg_first, pg_ld = pg_first;
+    auto load = [&](uint32_t (&w)[8]) {                        // loads the NEXT tile in sequence
+      const bool in_chunk = vg_ld < p.vg1;
+      const long long row = pg_ld * GRAN + lane;
+      const bool valid = in_chunk && row < p.U;
+      vg_ld += 4 * gridDim.x;
+      pg_ld += pg_step;
+      if (pg_ld >= p.NG) pg_ld -= p.NG;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = 0u;
+      // bit = 0 everywhere would still expand to +1: invalid rows are flagged through w[] = 0 AND `valid`
+      if (valid) {
+        const uint32_t* src = p.db + row * W;
+        if (W == 8) {
+          const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(src)), x1 = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+          w[0] = x0.x; w[1] = x0.y; w[2] = x0.z; w[3] = x0.w; w[4] = x1.x; w[5] = x1.y; w[6] = x1.z; w[7] = x1.w;
+        } else if (W == 4) {
+          const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(src));
+          w[0] = x0.x; w[1] = x0.y; w[2] = x0.z; w[3] = x0.w;
+        } else if (W == 2) {
+          const uint2 x0 = __ldg(reinterpret_cast<const uint2*>(src));
+          w[0] = x0.x; w[1] = x0.y;
+        } else {
+          w[0] = __ldg(src);
+        }
+      }
+      return valid;
+    };
+    for (int jb = jb0; jb < jb1; ++jb) {
+      vg_ld = vg_first;
+      pg_ld = pg_first;
+      bool vcur = (my_tiles > 0) ? load(cw) : false;
+      for (long long i = 0; i < my_tiles; ++i) {
+        bool vnext = false;
+        if (i + 1 < my_tiles) vnext = load(cn);
+        mbar_wait(a_empty + stage * 8, phase ^ 1);
+        unsigned char* dst = s_a + (size_t)stage * a_stage;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < W) {
+            uint4 lo, hi;
+            expand_word(cw[j], lo, hi);
+            if (!vcur) { lo = make_uint4(0u, 0u, 0u, 0u); hi = lo; }   // rows past the table: all-zero operand
+            unsigned char* grp = dst + (j >> 2) * A_GROUP;
+            *reinterpret_cast<uint4*>(grp + sw128_off(r, 2 * (j & 3))) = lo;
+            *reinterpret_cast<uint4*>(grp + sw128_off(r, 2 * (j & 3) + 1)) = hi;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + stage * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cw[j] = cn[j];
+        vcur = vnext;
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp < EPI_WARPS) {
+    // =========================== epilogue: sign test, survivors queued ===========================
+    const int ew = warp & 3;                                     // TMEM lane quadrant = granule of the tile
+    const int half = warp >> 2;                                  // which 128 of the 256 query columns
+    long long t = 0;
+    int* my_tq = s_tq + warp * EPI_COLS;
+    unsigned long long* myq_key = sq_key + warp * SQ_CAP;
+    int* myq_q = sq_q + warp * SQ_CAP;
+    int* myq_cnt = sq_cnt + warp;
+    const long long vg_first = p.vg0 + (long long)blockIdx.x * 4 + ew;
+    const long long pg_first = (long long)(((unsigned long long)vg_first * (unsigned long long)p.P) % (unsigned long long)p.NG);
+    const long long pg_step = (long long)(((unsigned long long)(4 * gridDim.x) * (unsigned long long)p.P) % (unsigned long long)p.NG);
+    for (int jb = jb0; jb < jb1; ++jb) {
+      __syncwarp();
+      for (int c = lane; c < EPI_COLS; c += 32) my_tq[c] = __ldcg(p.tq + (long long)jb * QB + half * EPI_COLS + c);
+      __syncwarp();
+      const int q0 = jb * QB + half * EPI_COLS;
+      long long vg = vg_first, pg = pg_first;
+      for (long long i = 0; i < my_tiles; ++i, ++t) {
+        const long long vt = blockIdx.x + i * gridDim.x;
+        const int buf = (int)(t & 1);
+        const uint32_t use = (uint32_t)((t >> 1) & 1);
+        const long long row = pg * GRAN + lane;
+        const bool rvalid = (vg < p.vg1) && (row < p.U);
+        vg += 4 * gridDim.x;
+        pg += pg_step;
+        if (pg >= p.NG) pg -= p.NG;
+        const unsigned long long row_key = (unsigned long long)(p.idx_base + row);
+        mbar_wait(acc_full + buf * 8, use);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * QB + half * EPI_COLS);
+        if (lane == 0) *myq_cnt = 0;
+        __syncwarp();
+        if (p.dense) {
+          // seed chunk: buf[query][virtual row] = key for every pair (virtual row < cap by construction)
+          const long long vrow = vt * TM + ew * 32 + lane;
+          uint32_t va[16];
+#pragma unroll 1
+          for (int g16 = 0; g16 < EPI_COLS / 16; ++g16) {
+            tmem_ld16(tbase + (uint32_t)(g16 * 16), va);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const long long qg = q0 + g16 * 16 + j;
+              const int d = my_tq[g16 * 16 + j] - (int)(__uint_as_float(va[j]) * 0.5f);
+              p.cand_buf[qg * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)d << 40) | row_key) : ~0ull;
+            }
+          }
+        } else {
+          // 32 accumulators per load, two loads in flight; the common case (no survivor among the 32)
+          // is an AND tree over the sign bits -- depth 4, no per-element work
+          uint32_t va[32], vb[32];
+          tmem_ld32_nowait(tbase, va);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c32 = 0; c32 < EPI_COLS / 32; c32 += 2) {
+            tmem_ld32_nowait(tbase + (uint32_t)((c32 + 1) * 32), vb);
+            {
+              uint32_t a = 0xffffffffu;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a &= va[j];
+              if (rvalid && !(a >> 31)) {
+                const uint32_t(&lo)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&va[0]);
+                const uint32_t(&hi)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&va[16]);
+                unsigned m = nonneg_mask16(lo);
+                if (m) SB_HAM_QUEUE(m, lo, q0, c32 * 32, row_key, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
+                m = nonneg_mask16(hi);
+                if (m) SB_HAM_QUEUE(m, hi, q0, c32 * 32 + 16, row_key, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
+              }
+            }
+            tmem_ld_wait();
+            if (c32 + 2 < EPI_COLS / 32) tmem_ld32_nowait(tbase + (uint32_t)((c32 + 2) * 32), va);
+            {
+              uint32_t a = 0xffffffffu;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a &= vb[j];
+              if (rvalid && !(a >> 31)) {
+                const uint32_t(&lo)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&vb[0]);
+                const uint32_t(&hi)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&vb[16]);
+                unsigned m = nonneg_mask16(lo);
+                if (m) SB_HAM_QUEUE(m, lo, q0, (c32 + 1) * 32, row_key, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
+                m = nonneg_mask16(hi);
+                if (m) SB_HAM_QUEUE(m, hi, q0, (c32 + 1) * 32 + 16, row_key, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
+              }
+            }
+            tmem_ld_wait();
+          }
+        }
+        // the accumulator buffer is free: let the next tile's MMAs start, THEN pay for the appends
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + buf * 8);
+        const int nq = min(*myq_cnt, SQ_CAP);
+        for (int e = lane; e < nq; e += 32) {                      // 32 appends in flight per warp
+          const long long qg = myq_q[e];
+          const int slot = atomicAdd(p.cand_cnt + qg, 1);
+          if (slot < p.cap) p.cand_buf[qg * p.cap + slot] = myq_key[e];
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// Query codes -> per-block image: G groups of [256 rows x 128 B] in the SWIZZLE_128B K-major order,
+// same bit -> byte expansion as the table rows; columns past Q and K chunks past the code are zero
+// (the image is cleared first).  One thread per (column, word).
+__global__ void ham_query_image_kernel(const uint32_t* __restrict__ q, int Q, int W, int G, unsigned char* __restrict__ img) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Q * W) return;
+  const int col = (int)(i / W), j = (int)(i % W);
+  const int jb = col / QB, n = col % QB;
+  uint4 lo, hi;
+  expand_word(q[(long long)col * W + j], lo, hi);
+  unsigned char* grp = img + (size_t)jb * ((size_t)G * B_GROUP + B_SYN) + (size_t)(j >> 2) * B_GROUP;
+  *reinterpret_cast<uint4*>(grp + sw128_off(n, 2 * (j & 3))) = lo;
+  *reinterpret_cast<uint4*>(grp + sw128_off(n, 2 * (j & 3) + 1)) = hi;
+}
+
+// B_syn of every block: 32 E4M3 slots per column that sum to s = 2 * tq - K + 1 (|s| <= 16 * 32);
+// padding columns get -512 (their data bytes are zero: the accumulator is negative).
+__global__ void ham_threshold_image_kernel(int Q, int cols, int G, int K, const int* __restrict__ tq,
+                                           unsigned char* __restrict__ img) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cols) return;
+  const int jb = col / QB, n = col % QB;
+  const int s = (col < Q) ? (2 * min(tq[col], K) - K + 1) : -512;
+  const uint32_t sign = s < 0 ? 0x80u : 0u;
+  const int mag = s < 0 ? -s : s;
+  const int n16 = mag >> 4, rem = mag & 15;
+  // E4M3 codes of the integers 0..15 (16 = 0x58)
+  const unsigned char e4m3[16] = {0x00, 0x38, 0x40, 0x44, 0x48, 0x4A, 0x4C, 0x4E, 0x50, 0x51, 0x52, 0x53, 0x54, 0x55, 0x56, 0x57};
+  uint32_t words[8];
+#pragma unroll
+  for (int wd = 0; wd < 8; ++wd) {
+    uint32_t v = 0u;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int slot = wd * 4 + b;
+      uint32_t byte = 0u;
+      if (slot < n16) byte = 0x58u | sign;
+      else if (slot == n16 && rem) byte = (uint32_t)e4m3[rem] | sign;
+      v |= byte << (8 * b);
+    }
+    words[wd] = v;
+  }
+  unsigned char* base = img + (size_t)jb * ((size_t)G * B_GROUP + B_SYN) + (size_t)G * B_GROUP;
+  *reinterpret_cast<uint4*>(base + n * 16) = make_uint4(words[0], words[1], words[2], words[3]);
+  *reinterpret_cast<uint4*>(base + QB * 16 + n * 16) = make_uint4(words[4], words[5], words[6], words[7]);
+}
+
+__global__ void ham_init_kernel(int cols, int K, int* __restrict__ tq, int* __restrict__ cnt, int* __restrict__ overflow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *overflow = 0;
+  if (i >= cols) return;
+  tq[i] = K;
+  cnt[i] = 0;
+}
+
+__global__ void ham_set_count_kernel(int* __restrict__ cnt, int Q, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Q) cnt[i] = v;
+}
+
+// One CTA per query: sort the survivors (canonical keys: distance, row), keep the best k, tighten
+// the threshold to the k-th distance (later rows may still tie with it at a smaller row index, so
+// the test stays "<="); `final` writes keys_out.
+__global__ void __launch_bounds__(CP_THREADS)
+ham_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt, int cap, int k, int K, int* __restrict__ tq,
+                   int* __restrict__ overflow, int final, unsigned long long* __restrict__ keys_out) {
+  extern __shared__ unsigned long long s_key[];   // P = next pow2 >= min(count, cap)
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  const int raw = cnt[qi];
+  const int m = min(raw, cap);
+  if (raw > cap && tid == 0) *overflow = 1;
+  unsigned long long* mine = buf + (size_t)qi * cap;
+  int P = 1;
+  while (P < m) P <<= 1;
+  for (int i = tid; i < P; i += CP_THREADS) s_key[i] = (i < m) ? mine[i] : ~0ull;
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < P / 2; i += CP_THREADS) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long a = s_key[lo], b = s_key[hi];
+        if ((a > b) == up) { s_key[lo] = b; s_key[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  // rows past the table were stored as empty keys by the dense chunk: they sort last
+  int keep = min(m, k);
+  {
+    int lo = 0, hi = keep;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_key[mid] != ~0ull) lo = mid + 1; else hi = mid;
+    }
+    keep = lo;
+  }
+  for (int i = tid; i < keep; i += CP_THREADS) mine[i] = s_key[i];
+  if (tid == 0) {
+    cnt[qi] = keep;
+    tq[qi] = (keep >= k) ? (int)(s_key[k - 1] >> 40) : K;
+  }
+  if (final)
+    for (int i = tid; i < k; i += CP_THREADS) keys_out[(size_t)qi * k + i] = (i < keep) ? s_key[i] : ~0ull;
+}
+
+struct HamTcPlan {
+  int G, ksteps, K, col_blocks, cols, cap, first_rows, stages;
+  size_t block_bytes, smem_bytes;
+  size_t off_img, off_tq, off_cnt, off_flag, off_buf, total;
+};
+
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+HamTcPlan make_plan(int32_t W, int32_t Q, int32_t k) {
+  HamTcPlan p;
+  p.G = W <= 4 ? 1 : W / 4;
+  p.ksteps = W < 4 ? W : 4;
+  p.K = 32 * W;
+  p.col_blocks = (Q + QB - 1) / QB;
+  p.cols = p.col_blocks * QB;
+  p.cap = 4096;
+  while (p.cap < 4 * (GROWTH + 1) * k) p.cap <<= 1;
+  p.first_rows = 1024;
+  while (p.first_rows < 4 * k) p.first_rows <<= 1;
+  if (p.first_rows > p.cap) p.first_rows = p.cap;
+  p.stages = MAX_STAGES;
+  p.block_bytes = (size_t)p.G * B_GROUP + B_SYN;
+  p.smem_bytes = 1024 + p.block_bytes + A_SYN + (size_t)p.stages * p.G * A_GROUP + (2 * MAX_STAGES + 8) * 8 +
+                 EPI_WARPS * SQ_CAP * 12 + EPI_WARPS * 4 + EPI_WARPS * EPI_COLS * sizeof(int);
+  size_t o = 0;
+  p.off_img = o;  o += align256((size_t)p.col_blocks * p.block_bytes);
+  p.off_tq = o;   o += align256((size_t)p.cols * sizeof(int));
+  p.off_cnt = o;  o += align256((size_t)p.cols * sizeof(int));
+  p.off_flag = o; o += 256;
+  p.off_buf = o;  o += align256((size_t)p.cols * p.cap * sizeof(unsigned long long));
+  p.total = o;
+  return p;
+}
+
+long long gcd_ll(long long a, long long b) {
+  while (b) { const long long t = a % b; a = b; b = t; }
+  return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_hamming_scan_tc_supported(int64_t U, int32_t W, int32_t Q, int32_t k) {
+  return U >= 1 && (W == 1 || W == 2 || W == 4 || W == 8) && Q >= 1 && k >= 1 && k <= 256 && U < (1ll << 38);
+}
+
+size_t sb_hamming_scan_tc_workspace_bytes(int64_t U, int32_t W, int32_t Q, int32_t k) {
+  if (!sb_hamming_scan_tc_supported(U, W, Q, k)) return 0;
+  return make_plan(W, Q, k).total;
+}
+
+// Same contract as sb_hamming_scan; *overflow_out (device int) is set to 1 when a candidate buffer
+// overflowed -- the keys are then NOT trustworthy and the caller must re-run sb_hamming_scan.
+int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q, int32_t Q, int32_t k, int64_t idx_base,
+                       uint64_t* keys_out, int32_t* overflow_out, void* workspace, size_t workspace_bytes, void* stream) {
+  SB_REQUIRE(db && q && keys_out && overflow_out, "sb_hamming_scan_tc: NULL pointer");
+  if (!sb_hamming_scan_tc_supported(U, W, Q, k) || idx_base < 0 || idx_base + U >= (1ll << 40) ||
+      (reinterpret_cast<uintptr_t>(db) & 15u)) {
+    sb::set_error("sb_hamming_scan_tc: needs W in {1, 2, 4, 8}, 1 <= k <= 256, U < 2^38, 16-byte aligned table");
+    return SB_ERR_UNSUPPORTED;
+  }
+  const HamTcPlan p = make_plan(W, Q, k);
+  if (workspace == nullptr || workspace_bytes < p.total) {
+    sb::set_error("sb_hamming_scan_tc: workspace too small (%zu < %zu bytes)", workspace_bytes, p.total);
+    return SB_ERR_WORKSPACE;
+  }
+  SB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sb_hamming_scan_tc: workspace must be 256-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  unsigned char* img = ws + p.off_img;
+  int* tq = reinterpret_cast<int*>(ws + p.off_tq);
+  int* cnt = reinterpret_cast<int*>(ws + p.off_cnt);
+  int* flag = reinterpret_cast<int*>(ws + p.off_flag);
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(ws + p.off_buf);
+
+  SB_CUDA_TRY(cudaMemsetAsync(img, 0, (size_t)p.col_blocks * p.block_bytes, st));
+  {
+    sb::ProfScope prof("ham_query_image_kernel", st);
+    const long long items = (long long)Q * W;
+    ham_query_image_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(q, Q, W, p.G, img);
+    sb::count_launch();
+    if (int rc = sb::check_launch("ham_query_image_kernel")) return rc;
+  }
+  ham_init_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(p.cols, p.K, tq, cnt, flag);
+  sb::count_launch();
+  if (int rc = sb::check_launch("ham_init_kernel")) return rc;
+
+  // visiting order: 32-row granules in a golden-ratio stride permutation (any prefix is spread evenly over the table)
+  const long long NG = (U + GRAN - 1) / GRAN;
+  long long P = 1;
+  if (NG > 2) {
+    P = (long long)(0.6180339887498949 * (double)NG);
+    if (P < 1) P = 1;
+    while (gcd_ll(P, NG) != 1) ++P;
+    if (P >= NG) P = 1;
+  }
+
+  SB_CUDA_TRY(cudaFuncSetAttribute(ham_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+  SB_CUDA_TRY(cudaFuncSetAttribute(ham_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(p.cap * sizeof(unsigned long long))));
+  const int sms = sb::sm_count();
+  long long done = 0;                                         // granules
+  while (done < NG) {
+    long long len = (done == 0) ? p.first_rows / GRAN : done * (GROWTH - 1);
+    if (len > NG - done) len = NG - done;
+    const int dense = (done == 0) ? 1 : 0;
+    ham_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.G, p.K, tq, img);
+    sb::count_launch();
+    if (int rc = sb::check_launch("ham_threshold_image_kernel")) return rc;
+    HamTcParams hp;
+    hp.db = db; hp.U = U; hp.W = W; hp.G = p.G; hp.ksteps = p.ksteps; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
+    hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
+    hp.idx_base = idx_base; hp.dense = dense; hp.stages = p.stages;
+    const long long n_tiles = (len + 3) / 4;
+    const int gx = (int)(n_tiles < sms ? n_tiles : sms);
+    int gy = sms / gx;
+    if (gy < 1) gy = 1;
+    if (gy > p.col_blocks) gy = p.col_blocks;
+    hp.cb_per = (p.col_blocks + gy - 1) / gy;
+    gy = (p.col_blocks + hp.cb_per - 1) / hp.cb_per;
+    {
+      sb::ProfScope prof("ham_filter_tc_kernel", st);
+      ham_filter_tc_kernel<<<dim3(gx, gy), THREADS, p.smem_bytes, st>>>(hp);
+      sb::count_launch();
+      if (int rc = sb::check_launch("ham_filter_tc_kernel")) return rc;
+    }
+    if (dense) {
+      ham_set_count_kernel<<<(Q + 255) / 256, 256, 0, st>>>(cnt, Q, (int)(len * GRAN));
+      sb::count_launch();
+      if (int rc = sb::check_launch("ham_set_count_kernel")) return rc;
+    }
+    done += len;
+    const int final = (done >= NG) ? 1 : 0;
+    sb::ProfScope prof("ham_compact_kernel", st);
+    ham_compact_kernel<<<Q, CP_THREADS, p.cap * sizeof(unsigned long long), st>>>(buf, cnt, p.cap, k, p.K, tq, flag, final,
+                                                                                  reinterpret_cast<unsigned long long*>(keys_out));
+    sb::count_launch();
+    if (int rc = sb::check_launch("ham_compact_kernel")) return rc;
+  }
+  SB_CUDA_TRY(cudaMemcpyAsync(overflow_out, flag, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return SB_OK;
+}
+
+}  // extern "C"

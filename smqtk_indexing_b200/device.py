@@ -153,10 +153,40 @@ def itq_hash(X: torch.Tensor, mean: Optional[torch.Tensor], R: torch.Tensor, nor
 
 
 # --------------------------------------------------------------------- stage 2
+#: the tensor-core scan takes over from this many queries / table rows (below, the XOR/POPC scan
+#: streams the table once per handful of queries and is bound by HBM, which is the better regime)
+TC_SCAN_MIN_QUERIES = 128
+TC_SCAN_MIN_ROWS = 1 << 16
+#: set by hamming_scan_keys: how many batches overflowed a candidate buffer and were re-run
+TC_SCAN_OVERFLOWS = 0
+SCAN_VARIANT_TC = 3
+
+
+def hamming_scan_tc_supported(U: int, W: int, Q: int, k: int) -> bool:
+    return bool(_lib.load().sb_hamming_scan_tc_supported(U, W, Q, k))
+
+
+def hamming_scan_keys_tc(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0):
+    """Tensor-core scan (``sb_hamming_scan_tc``) -> (keys int64[Q, k], overflow int32[1])."""
+    U, W = db.shape
+    Q = q.shape[0]
+    lib = _lib.load()
+    ws_bytes = lib.sb_hamming_scan_tc_workspace_bytes(U, W, Q, k)
+    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=db.device)
+    keys = torch.empty((Q, k), dtype=torch.int64, device=db.device)
+    flag = torch.empty((1,), dtype=torch.int32, device=db.device)
+    with torch.cuda.device(db.device):
+        _lib.check(lib.sb_hamming_scan_tc(_ptr(db), U, W, _ptr(q), Q, k, idx_base, _ptr(keys), _ptr(flag),
+                                          _ptr(ws), ws_bytes, _stream()))
+    return keys, flag
+
+
 def hamming_scan_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0,
                       variant: int = 0) -> torch.Tensor:
     """Local top-k as packed keys int64[Q, k] (uint64 bit pattern, ascending,
-    SB_KEY_EMPTY padded)."""
+    SB_KEY_EMPTY padded).  ``variant`` 0 picks the kernel: the tensor-core scan for large batches
+    over large tables, the XOR/POPC scan otherwise (1, 2: POPC formulations, 3: tensor cores)."""
+    global TC_SCAN_OVERFLOWS
     require_cuda()
     _chk(db, torch.int32, "db")
     _chk(q, torch.int32, "q")
@@ -164,6 +194,17 @@ def hamming_scan_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int =
     Q = q.shape[0]
     if q.shape[1] != W:
         raise ValueError("query codes have %d words, table has %d" % (q.shape[1], W))
+    if variant == SCAN_VARIANT_TC and not hamming_scan_tc_supported(U, W, Q, k):
+        raise ValueError("tensor-core scan does not support U=%d W=%d Q=%d k=%d" % (U, W, Q, k))
+    if variant == SCAN_VARIANT_TC or (variant == 0 and Q >= TC_SCAN_MIN_QUERIES and U >= TC_SCAN_MIN_ROWS
+                                      and hamming_scan_tc_supported(U, W, Q, k)):
+        keys, flag = hamming_scan_keys_tc(db, q, k, idx_base)
+        if int(flag.item()) == 0:
+            return keys
+        TC_SCAN_OVERFLOWS += 1          # a candidate buffer overflowed: the exact XOR/POPC scan decides
+        variant = 0
+    elif variant == SCAN_VARIANT_TC:
+        variant = 0
     lib = _lib.load()
     ws_bytes = lib.sb_hamming_scan_workspace_bytes(U, W, Q, k)
     ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=db.device)

@@ -99,6 +99,83 @@ def test_sharded_scan_merge_equals_single(dev):
     assert np.array_equal(d.cpu().numpy(), od) and np.array_equal(i.cpu().numpy(), oi)
 
 
+def _tc_keys(dev, table, q, k, idx_base=0):
+    dt, dq = dev.codes_to_device(table), dev.codes_to_device(q)
+    keys, flag = dev.hamming_scan_keys_tc(dt, dq, k, idx_base)
+    d, i = dev.topk_merge(keys.unsqueeze(0).contiguous())
+    torch.cuda.synchronize()
+    return d.cpu().numpy(), i.cpu().numpy(), int(flag.item())
+
+
+@pytest.mark.parametrize("b,W", [(1, 1), (5, 1), (32, 1), (33, 2), (64, 2), (100, 4), (128, 4), (200, 8), (256, 8)])
+def test_hamming_tensor_core_scan_bit_exact(dev, b, W):
+    """sb_hamming_scan_tc (FP8 +-1 dot products on tcgen05) returns the oracle's keys exactly:
+    ragged table sizes (partial granules / tiles / chunks), Q across query-block boundaries, k up to
+    256, idx_base, a query equal to a table row."""
+    rng = np.random.RandomState(100 + b)
+    for U, Q, k in [(1, 1, 1), (7, 3, 10), (1000, 5, 10), (4097, 257, 10), (20000, 130, 7), (3000, 2, 100),
+                    (70001, 300, 33), (9000, 20, 256)]:
+        table = _rand_table(rng, U, b, W)
+        q = O.pack_codes(rng.rand(Q, b) > 0.5, W)
+        q[0] = table[U // 2]
+        od, oi = O.hamming_topk(table, q, k, idx_base=5)
+        d, i, flag = _tc_keys(dev, table, q, k, idx_base=5)
+        if flag:
+            # only the tie-saturated toy widths may overflow (a 5-bit table is thousands of copies of 32
+            # codes; real tables hold unique codes): the dispatcher then takes the XOR/POPC scan
+            assert b <= 5
+            dt, dq = dev.codes_to_device(table), dev.codes_to_device(q)
+            keys = dev.hamming_scan_keys(dt, dq, k, idx_base=5, variant=dev.SCAN_VARIANT_TC)
+            d, i = (t.cpu().numpy() for t in dev.topk_merge(keys.unsqueeze(0).contiguous()))
+        kk = od.shape[1]
+        assert np.array_equal(d[:, :kk], od), (b, U, Q, k)
+        assert np.array_equal(i[:, :kk], oi), (b, U, Q, k)
+        assert (d[:, kk:] == -1).all() and (i[:, kk:] == -1).all()
+
+
+def test_hamming_tensor_core_scan_ties_and_clusters(dev):
+    """Tie-heavy tables, and a sorted table with large near-duplicate clusters (the order real ITQ
+    codes arrive in): the golden-ratio visiting order keeps every chunk a uniform sample."""
+    rng = np.random.RandomState(23)
+    for b, W in [(8, 1), (32, 1), (256, 8)]:
+        table = _rand_table(rng, 50000, b, W, dup=True)
+        q = O.pack_codes(rng.rand(16, b) > 0.9, W)
+        od, oi = O.hamming_topk(table, q, 25)
+        # thousands of copies of a few codes: candidate buffers may overflow (-> XOR/POPC scan); exact either way
+        keys = dev.hamming_scan_keys(dev.codes_to_device(table), dev.codes_to_device(q), 25, variant=dev.SCAN_VARIANT_TC)
+        d, i = (t.cpu().numpy() for t in dev.topk_merge(keys.unsqueeze(0).contiguous()))
+        assert np.array_equal(d, od) and np.array_equal(i, oi)
+    centres = rng.rand(40, 256) > 0.5
+    bits = centres[rng.randint(0, 40, 200000)] ^ (rng.rand(200000, 256) < 0.03)
+    table = O.pack_codes(bits, 8)
+    order = np.lexsort(tuple(table[:, w] for w in range(7, -1, -1)))
+    table = np.ascontiguousarray(table[order])
+    q = O.pack_codes(centres[rng.randint(0, 40, 300)] ^ (rng.rand(300, 256) < 0.03), 8)
+    od, oi = O.hamming_topk(table, q, 10)
+    d, i, flag = _tc_keys(dev, table, q, 10)
+    assert flag == 0 and np.array_equal(d, od) and np.array_equal(i, oi)
+
+
+def test_hamming_scan_dispatch_and_overflow_fallback(dev):
+    """hamming_scan_keys picks the tensor-core scan for large batches; identical keys either way.
+    A table of identical rows overflows the candidate buffers (every row ties): the flag is raised
+    and the XOR/POPC scan decides."""
+    rng = np.random.RandomState(29)
+    table = _rand_table(rng, 100000, 256, 8)
+    q = O.pack_codes(rng.rand(200, 256) > 0.5, 8)
+    dt, dq = dev.codes_to_device(table), dev.codes_to_device(q)
+    k_auto = dev.hamming_scan_keys(dt, dq, 10)
+    k_tc = dev.hamming_scan_keys(dt, dq, 10, variant=dev.SCAN_VARIANT_TC)
+    k_popc = dev.hamming_scan_keys(dt, dq, 10, variant=1)
+    assert torch.equal(k_auto, k_popc) and torch.equal(k_tc, k_popc)
+    same = np.repeat(table[:1], 100000, axis=0)
+    ds = dev.codes_to_device(same)
+    before = dev.TC_SCAN_OVERFLOWS
+    keys = dev.hamming_scan_keys(ds, dq, 10, variant=dev.SCAN_VARIANT_TC)
+    assert dev.TC_SCAN_OVERFLOWS == before + 1
+    assert torch.equal(keys, dev.hamming_scan_keys(ds, dq, 10, variant=1))
+
+
 def test_hamming_empty_table(dev):
     q = dev.codes_to_device(np.zeros((2, 8), np.uint32))
     db = torch.empty((0, 8), dtype=torch.int32, device=q.device)
