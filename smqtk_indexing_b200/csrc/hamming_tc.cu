@@ -28,9 +28,14 @@
 // yields ~GROWTH * (k + ties) survivors per query for ANY data distribution (the table is sorted,
 // near-duplicate clusters are contiguous).  A query whose buffer still overflows raises a flag and
 // the caller re-runs the batch on hamming.cu.
-// Warp roles (14 warps): 0-7 epilogue (TMEM lane quadrant = warp % 4, column half = warp / 4: the
-// epilogue is a chain of dependent integer ops per warp, so it wants warps, not instructions),
-// 8 MMA issue + TMEM alloc, 9 B loader, 10-13 producers (one table row per thread and tile).
+// Measured on B200 (profiles/): the bit -> FP8 expansion in the producers is the most expensive
+// stage per tile, so TWO query blocks are resident and every expanded tile feeds both (the two
+// accumulator buffers are the two blocks), and the producers get 8 of the 14 warps.
+// Warp roles: 0-3 epilogue (TMEM lane quadrants), 4 MMA issue + TMEM alloc, 5 B loader,
+// 6-13 producers (half a table row per thread and tile).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -45,10 +50,9 @@ constexpr int B_GROUP = QB * 128;           // 32 KB
 constexpr int B_SYN = 2 * QB * 16;          // 8 KB  (no-swizzle, 2 K chunks of 16 bytes)
 constexpr int A_SYN = 2 * TM * 16;          // 4 KB
 constexpr int MAX_STAGES = 4;
-constexpr int SQ_CAP = 96;                  // survivor queue entries per epilogue warp and tile
+constexpr int NB = 2;                       // query blocks resident per pass: every expanded A tile feeds 2 x 256 queries
 constexpr int GRAN = 32;                    // rows per granule of the visiting order
-constexpr int EPI_WARPS = 8, MMA_WARP = 8, B_WARP = 9, PROD_WARP0 = 10, PROD_WARPS = 4;
-constexpr int EPI_COLS = QB / 2;            // columns per epilogue warp
+constexpr int EPI_WARPS = 4, MMA_WARP = 4, B_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 8;
 constexpr int THREADS = (PROD_WARP0 + PROD_WARPS) * 32;   // 448
 constexpr int GROWTH = 8;
 constexpr int CP_THREADS = 1024;
@@ -62,12 +66,15 @@ struct HamTcParams {
   int col_blocks, cb_per;      // query blocks in total / per blockIdx.y
   const unsigned char* image;  // per block: G x B_GROUP (SW128) then B_SYN
   const int* tq;               // thresholds (Hamming distance) per query column
+  const uint32_t* qcodes;      // u32[Q][W] packed query codes (survivor re-check)
+  int Q;
   unsigned long long* cand_buf;
   int* cand_cnt;
   int cap;
   long long idx_base;
   int dense;                   // first chunk: every pair is kept -> key stored at buf[query][virtual row]
   int stages;
+  int debug;
 };
 
 // 4 code bits -> 4 FP8 E4M3 bytes: bit = 0 -> +1.0 (0x38), bit = 1 -> -1.0 (0xB8); bit i -> byte i
@@ -98,65 +105,62 @@ __device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_
       : "memory");
 }
 
-// Cold path, out of line, accumulators by value (see tc_ptx.cuh::l2_queue_survivors): decode the
-// pairs flagged in `mask` (bit 15 - j <-> column col0 + j) and queue their keys.
-static __device__ __noinline__ void ham_queue_survivors(
-    unsigned mask, int q0, int col0, unsigned long long row_key, const int* tq_local, unsigned long long* q_key, int* q_q,
-    int* q_cnt, int q_cap, unsigned long long* cand_buf, int* cand_cnt, int cap,
-    uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t v4, uint32_t v5, uint32_t v6, uint32_t v7, uint32_t v8,
-    uint32_t v9, uint32_t v10, uint32_t v11, uint32_t v12, uint32_t v13, uint32_t v14, uint32_t v15) {
-  const uint32_t v[16] = {v0, v1, v2, v3, v4, v5, v6, v7, v8, v9, v10, v11, v12, v13, v14, v15};
+// Survivors are rare (~GROWTH * k per query and chunk among millions of pairs), so the epilogue does
+// not decode them from the accumulator registers (a divergent, register-indexed walk: ~400
+// instructions per survivor, measured at 40 % of the kernel).  It only learns, per lane, WHICH
+// 64-column group holds one; the warp then recomputes that row against the group's 64 queries with
+// XOR/POPC from the packed codes -- two queries per lane, no divergence, ~50 instructions per group.
+template <int W>
+__device__ __forceinline__ void ham_recheck_group(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qcodes, int Q,
+                                                  long long row, unsigned long long row_key, int qg0, const int* tq_grp,
+                                                  unsigned long long* cand_buf, int* cand_cnt, int cap, int lane) {
+  uint32_t x[W];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    if (mask & (0x8000u >> j)) {
-      const int qg = q0 + col0 + j;
-      const int d = tq_local[col0 + j] - (int)(__uint_as_float(v[j]) * 0.5f);     // acc = 2 (tq - d) + 1
-      const unsigned long long key = ((unsigned long long)(unsigned)d << 40) | row_key;
-      const int e = atomicAdd(q_cnt, 1);
-      if (e < q_cap) {
-        q_key[e] = key;
-        q_q[e] = qg;
-      } else {
+  for (int w = 0; w < W; ++w) x[w] = __ldg(db + row * W + w);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int col = lane + 32 * h;
+    const int qg = qg0 + col;
+    if (qg < Q) {
+      int d = 0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) d += __popc(x[w] ^ __ldg(qcodes + (long long)qg * W + w));
+      if (d <= tq_grp[col]) {
         const int slot = atomicAdd(cand_cnt + qg, 1);
-        if (slot < cap) cand_buf[(long long)qg * cap + slot] = key;
+        if (slot < cap) cand_buf[(long long)qg * cap + slot] = ((unsigned long long)(unsigned)d << 40) | row_key;
       }
     }
   }
 }
-#define SB_HAM_QUEUE(mask, v, q0, col0, row_key, tql, qk, qq, qc, qcap, buf, cnt, cap)                                 \
-  ham_queue_survivors(mask, q0, col0, row_key, tql, qk, qq, qc, qcap, buf, cnt, cap, v[0], v[1], v[2], v[3], v[4], v[5], \
-                      v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15])
 
+template <int G, int KSTEPS>
 __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms: align by hand
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = p.G;
-  const uint32_t a_stage = (uint32_t)G * A_GROUP;
-  // layout (offsets are multiples of 1024): [B data G x 32 KB][B_syn][A_syn][A ring][barriers, queues, thresholds]
+  constexpr int W = (G == 2) ? 8 : KSTEPS;                        // code words per row
+  constexpr uint32_t a_stage = (uint32_t)G * A_GROUP;
+  constexpr uint32_t b_block = (uint32_t)G * B_GROUP + B_SYN;      // one query block: data groups, then its B_syn
+  // layout (offsets are multiples of 1024): [B block 0][B block 1][A_syn][A ring][barriers, queues, thresholds]
   unsigned char* s_b = smem;
-  unsigned char* s_bsyn = s_b + (size_t)G * B_GROUP;
-  unsigned char* s_asyn = s_bsyn + B_SYN;
+  unsigned char* s_asyn = s_b + NB * b_block;
   unsigned char* s_a = s_asyn + A_SYN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + (size_t)p.stages * a_stage);
   const uint32_t a_full = smem_u32(bars), a_empty = a_full + MAX_STAGES * 8;
   const uint32_t acc_full = a_empty + MAX_STAGES * 8, acc_empty = acc_full + 16;
   const uint32_t b_full = acc_empty + 16, b_empty = b_full + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
-  unsigned long long* sq_key = reinterpret_cast<unsigned long long*>(bars + 2 * MAX_STAGES + 8);
-  int* sq_q = reinterpret_cast<int*>(sq_key + EPI_WARPS * SQ_CAP);
-  int* sq_cnt = sq_q + EPI_WARPS * SQ_CAP;
-  int* s_tq = sq_cnt + EPI_WARPS;                                // [8 warps][128]: this block's thresholds
+  int* s_tq = reinterpret_cast<int*>(bars + 2 * MAX_STAGES + 8);  // [4 warps][2 blocks x 256]: thresholds
 
   const long long n_gran = p.vg1 - p.vg0;
   const long long n_tiles = (n_gran + 3) / 4;
   const long long my_tiles = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int jb0 = blockIdx.y * p.cb_per;
+  const int jb0 = blockIdx.y * p.cb_per;                         // cb_per is a multiple of NB
   const int jb1 = min(p.col_blocks, jb0 + p.cb_per);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(a_full + s * 8, PROD_WARPS); mbar_init(a_empty + s * 8, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b * 8, 1); mbar_init(acc_empty + b * 8, EPI_WARPS); }
+    for (int b = 0; b < NB; ++b) { mbar_init(acc_full + b * 8, 1); mbar_init(acc_empty + b * 8, EPI_WARPS); }
     mbar_init(b_full, 1);
     mbar_init(b_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
   }
   // A_syn = +1.0 everywhere; codes narrower than 128 bits leave K chunks of the A ring untouched: zero them once
   for (int i = threadIdx.x; i < A_SYN / 4; i += THREADS) reinterpret_cast<uint32_t*>(s_asyn)[i] = 0x38383838u;
-  if (p.W < 4)
+  if (KSTEPS < 4)
     for (int i = threadIdx.x; i < (int)(p.stages * a_stage / 16); i += THREADS)
       reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
@@ -178,13 +182,14 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == B_WARP) {
-    // =========================== B: resident query block ===========================
+    // =========================== B: NB resident query blocks ===========================
     if (lane == 0) {
-      const uint32_t bytes = (uint32_t)G * B_GROUP + B_SYN;        // B data and B_syn are contiguous in both places
-      for (int jb = jb0; jb < jb1; ++jb) {
-        const int it = jb - jb0;
+      int it = 0;
+      for (int jb = jb0; jb < jb1; jb += NB, ++it) {
+        const int nb = min(NB, jb1 - jb);
         mbar_wait(b_empty, (it & 1) ^ 1);
-        const unsigned char* src = p.image + (size_t)jb * bytes;
+        const unsigned char* src = p.image + (size_t)jb * b_block;   // blocks are contiguous in the image too
+        const uint32_t bytes = (uint32_t)nb * b_block;
         mbar_expect_tx(b_full, bytes);
         for (uint32_t o = 0; o < bytes; o += 8192) tma_bulk_g2s(smem_u32(s_b + o), src + o, 8192, b_full);
       }
@@ -192,31 +197,46 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
   } else if (warp == MMA_WARP) {
     // =========================== MMA issue ===========================
     if (lane == 0) {
-      // D = F32 (bit 4), A = B = E4M3 (format 0), both K-major, N = 256, M = 128
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(QB >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      // D = F16 (format 0: every partial sum is an integer below 2048, exact in half precision),
+      // A = B = E4M3 (format 0), both K-major, N = 256, M = 128
+      const uint32_t idesc = ((uint32_t)(QB >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       const uint64_t asyn_desc = umma_desc(smem_u32(s_asyn), TM * 16, 128);
-      const uint64_t bsyn_desc = umma_desc(smem_u32(s_bsyn), QB * 16, 128);
-      int stage = 0;
+      // descriptors differ only in the 14-bit start-address field (shared window < 256 KB: no carry out of it):
+      // one 64-bit add per operand and MMA instead of rebuilding them
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(s_a));
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(s_b));
+      const uint64_t bsyn_desc0 = umma_desc(smem_u32(s_b) + G * B_GROUP, QB * 16, 128);
+      int stage = 0, it = 0;
       uint32_t phase = 0;
-      long long t = 0;
-      for (int jb = jb0; jb < jb1; ++jb) {
-        mbar_wait(b_full, (jb - jb0) & 1);
+      long long t[NB] = {0, 0};                                  // tiles issued per accumulator buffer
+      for (int jb = jb0; jb < jb1; jb += NB, ++it) {
+        const int nb = min(NB, jb1 - jb);
+        mbar_wait(b_full, it & 1);
         tc_fence_after();
-        for (long long i = 0; i < my_tiles; ++i, ++t) {
-          const int buf = (int)(t & 1);
-          const uint32_t use = (uint32_t)((t >> 1) & 1);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * QB);
-          mbar_wait(acc_empty + buf * 8, use ^ 1);
+        for (long long i = 0; i < my_tiles; ++i) {
           mbar_wait(a_full + stage * 8, phase);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(s_a) + (uint32_t)stage * a_stage, b0 = smem_u32(s_b);
-          for (int g = 0; g < G; ++g)
-            for (int ks = 0; ks < p.ksteps; ++ks)
-              umma_f8(d_tmem, umma_desc_sw128(a0 + g * A_GROUP + ks * 32), umma_desc_sw128(b0 + g * B_GROUP + ks * 32), idesc,
-                      (g | ks) ? 1u : 0u);
-          umma_f8(d_tmem, asyn_desc, bsyn_desc, idesc, 1u);
+          const uint64_t a_desc = a_desc0 + (uint64_t)(((uint32_t)stage * a_stage) >> 4);
+#pragma unroll
+          for (int blk = 0; blk < NB; ++blk) {
+            if (blk < nb) {
+              // one A tile, NB query blocks: accumulator buffer = block, so block 1's MMAs overlap block 0's epilogue
+              const uint32_t d_tmem = tmem_base + (uint32_t)(blk * QB);
+              mbar_wait(acc_empty + blk * 8, (uint32_t)(t[blk] & 1) ^ 1);
+              tc_fence_after();
+              const uint64_t b_desc = b_desc0 + (uint64_t)((blk * b_block) >> 4);
+#pragma unroll
+              for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks)
+                  if (!(p.debug & 4) || (g | ks) == 0)
+                  umma_f8(d_tmem, a_desc + (uint64_t)((g * A_GROUP + ks * 32) >> 4), b_desc + (uint64_t)((g * B_GROUP + ks * 32) >> 4),
+                          idesc, (g | ks) ? 1u : 0u);
+              umma_f8(d_tmem, asyn_desc, bsyn_desc0 + (uint64_t)((blk * b_block) >> 4), idesc, 1u);
+              umma_commit(acc_full + blk * 8);
+              ++t[blk];
+            }
+          }
           umma_commit(a_empty + stage * 8);
-          umma_commit(acc_full + buf * 8);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(b_empty);                                   // B may be replaced once these MMAs retire
@@ -224,17 +244,20 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
     }
   } else if (warp >= PROD_WARP0) {
     // =========================== A: packed codes -> +-1 FP8, swizzled ===========================
-    const int r = threadIdx.x - PROD_WARP0 * 32;                 // row of the tile
-    const int W = p.W;
+    // thread -> (row r of the tile, half h of its words)
+    constexpr int WH = (W >= 2) ? W / 2 : 1;                     // words per thread
+    const int pt = threadIdx.x - PROD_WARP0 * 32;
+    const int r = pt & (TM - 1), h = pt >> 7;
+    const bool worker = (W >= 2) || h == 0;
     int stage = 0;
     uint32_t phase = 0;
-    uint32_t cw[8], cn[8];
+    uint32_t cw[WH], cn[WH];
     // granule of tile i for this thread: vg = vg_first + i * 4 * gridDim.x, physical pg = vg * P mod NG, kept incrementally
     const long long vg_first = p.vg0 + (long long)blockIdx.x * 4 + (r >> 5);
     const long long pg_first = (long long)(((unsigned long long)vg_first * (unsigned long long)p.P) % (unsigned long long)p.NG);
     const long long pg_step = (long long)(((unsigned long long)(4 * gridDim.x) * (unsigned long long)p.P) % (unsigned long long)p.NG);
     long long vg_ld = vg_first, pg_ld = pg_first;
-    auto load = [&](uint32_t (&w)[8]) {                        // loads the NEXT tile in sequence
+    auto load = [&](uint32_t (&w)[WH]) {                        // loads the NEXT tile in sequence
       const bool in_chunk = vg_ld < p.vg1;
       const long long row = pg_ld * GRAN + lane;
       const bool valid = in_chunk && row < p.U;
@@ -242,26 +265,22 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
       pg_ld += pg_step;
       if (pg_ld >= p.NG) pg_ld -= p.NG;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) w[j] = 0u;
-      // bit = 0 everywhere would still expand to +1: invalid rows are flagged through w[] = 0 AND `valid`
-      if (valid) {
-        const uint32_t* src = p.db + row * W;
-        if (W == 8) {
-          const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(src)), x1 = __ldg(reinterpret_cast<const uint4*>(src) + 1);
-          w[0] = x0.x; w[1] = x0.y; w[2] = x0.z; w[3] = x0.w; w[4] = x1.x; w[5] = x1.y; w[6] = x1.z; w[7] = x1.w;
-        } else if (W == 4) {
+      for (int j = 0; j < WH; ++j) w[j] = 0u;
+      if (valid && worker) {
+        const uint32_t* src = p.db + row * W + h * WH;
+        if (WH == 4) {
           const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(src));
-          w[0] = x0.x; w[1] = x0.y; w[2] = x0.z; w[3] = x0.w;
-        } else if (W == 2) {
+          w[0] = x0.x; w[1] = x0.y; w[2 % WH] = x0.z; w[3 % WH] = x0.w;
+        } else if (WH == 2) {
           const uint2 x0 = __ldg(reinterpret_cast<const uint2*>(src));
-          w[0] = x0.x; w[1] = x0.y;
+          w[0] = x0.x; w[1 % WH] = x0.y;
         } else {
           w[0] = __ldg(src);
         }
       }
       return valid;
     };
-    for (int jb = jb0; jb < jb1; ++jb) {
+    for (int jb = jb0; jb < jb1; jb += NB) {
       vg_ld = vg_first;
       pg_ld = pg_first;
       bool vcur = (my_tiles > 0) ? load(cw) : false;
@@ -270,124 +289,105 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
         if (i + 1 < my_tiles) vnext = load(cn);
         mbar_wait(a_empty + stage * 8, phase ^ 1);
         unsigned char* dst = s_a + (size_t)stage * a_stage;
+        if (worker && !(p.debug & 2)) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < W) {
+          for (int j = 0; j < WH; ++j) {
+            const int wj = h * WH + j;                             // word of the row
             uint4 lo, hi;
             expand_word(cw[j], lo, hi);
             if (!vcur) { lo = make_uint4(0u, 0u, 0u, 0u); hi = lo; }   // rows past the table: all-zero operand
-            unsigned char* grp = dst + (j >> 2) * A_GROUP;
-            *reinterpret_cast<uint4*>(grp + sw128_off(r, 2 * (j & 3))) = lo;
-            *reinterpret_cast<uint4*>(grp + sw128_off(r, 2 * (j & 3) + 1)) = hi;
+            unsigned char* grp = dst + (wj >> 2) * A_GROUP;
+            *reinterpret_cast<uint4*>(grp + sw128_off(r, 2 * (wj & 3))) = lo;
+            *reinterpret_cast<uint4*>(grp + sw128_off(r, 2 * (wj & 3) + 1)) = hi;
           }
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full + stage * 8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cw[j] = cn[j];
+        for (int j = 0; j < WH; ++j) cw[j] = cn[j];
         vcur = vnext;
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp < EPI_WARPS) {
     // =========================== epilogue: sign test, survivors queued ===========================
-    const int ew = warp & 3;                                     // TMEM lane quadrant = granule of the tile
-    const int half = warp >> 2;                                  // which 128 of the 256 query columns
-    long long t = 0;
-    int* my_tq = s_tq + warp * EPI_COLS;
-    unsigned long long* myq_key = sq_key + warp * SQ_CAP;
-    int* myq_q = sq_q + warp * SQ_CAP;
-    int* myq_cnt = sq_cnt + warp;
+    const int ew = warp;                                         // TMEM lane quadrant = granule of the tile
+    long long t[NB] = {0, 0};
+    int* my_tq = s_tq + warp * (NB * QB);
     const long long vg_first = p.vg0 + (long long)blockIdx.x * 4 + ew;
     const long long pg_first = (long long)(((unsigned long long)vg_first * (unsigned long long)p.P) % (unsigned long long)p.NG);
     const long long pg_step = (long long)(((unsigned long long)(4 * gridDim.x) * (unsigned long long)p.P) % (unsigned long long)p.NG);
-    for (int jb = jb0; jb < jb1; ++jb) {
+    for (int jb = jb0; jb < jb1; jb += NB) {
+      const int nb = min(NB, jb1 - jb);
       __syncwarp();
-      for (int c = lane; c < EPI_COLS; c += 32) my_tq[c] = __ldcg(p.tq + (long long)jb * QB + half * EPI_COLS + c);
+      for (int c = lane; c < nb * QB; c += 32) my_tq[c] = __ldcg(p.tq + (long long)jb * QB + c);
       __syncwarp();
-      const int q0 = jb * QB + half * EPI_COLS;
       long long vg = vg_first, pg = pg_first;
-      for (long long i = 0; i < my_tiles; ++i, ++t) {
+      for (long long i = 0; i < my_tiles; ++i) {
         const long long vt = blockIdx.x + i * gridDim.x;
-        const int buf = (int)(t & 1);
-        const uint32_t use = (uint32_t)((t >> 1) & 1);
         const long long row = pg * GRAN + lane;
         const bool rvalid = (vg < p.vg1) && (row < p.U);
+        const long long row0 = pg * GRAN;                            // lane 0's row: the granule is contiguous
         vg += 4 * gridDim.x;
         pg += pg_step;
         if (pg >= p.NG) pg -= p.NG;
         const unsigned long long row_key = (unsigned long long)(p.idx_base + row);
-        mbar_wait(acc_full + buf * 8, use);
-        tc_fence_after();
-        const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * QB + half * EPI_COLS);
-        if (lane == 0) *myq_cnt = 0;
-        __syncwarp();
-        if (p.dense) {
-          // seed chunk: buf[query][virtual row] = key for every pair (virtual row < cap by construction)
-          const long long vrow = vt * TM + ew * 32 + lane;
-          uint32_t va[16];
 #pragma unroll 1
-          for (int g16 = 0; g16 < EPI_COLS / 16; ++g16) {
-            tmem_ld16(tbase + (uint32_t)(g16 * 16), va);
+        for (int blk = 0; blk < nb; ++blk) {
+          const int q0 = (jb + blk) * QB;
+          const int* tq_blk = my_tq + blk * QB;
+          mbar_wait(acc_full + blk * 8, (uint32_t)(t[blk] & 1));
+          ++t[blk];
+          tc_fence_after();
+          const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(blk * QB);
+          unsigned hit[QB / 64];                                     // lanes with a survivor in each 64-column group
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const long long qg = q0 + g16 * 16 + j;
-              const int d = my_tq[g16 * 16 + j] - (int)(__uint_as_float(va[j]) * 0.5f);
-              p.cand_buf[qg * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)d << 40) | row_key) : ~0ull;
+          for (int c128 = 0; c128 < QB; c128 += 128) {
+            uint32_t va[32], vb[32];                               // 2 x 64 columns of packed FP16 accumulators
+            tmem_ld32_pack16_nowait(tbase + (uint32_t)c128, va);
+            tmem_ld32_pack16_nowait(tbase + (uint32_t)(c128 + 64), vb);
+            tmem_ld_wait();
+            if (p.dense) {
+              // seed chunk: buf[query][virtual row] = key for every pair (virtual row < cap by construction)
+              const long long vrow = vt * TM + ew * 32 + lane;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) {
+                const uint32_t reg = (j < 32) ? va[j & 31] : vb[j & 31];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const int col = c128 + 2 * j + hh;
+                  const int d = tq_blk[col] - (int)(__half2float(__ushort_as_half((unsigned short)(reg >> (16 * hh)))) * 0.5f);
+                  p.cand_buf[(long long)(q0 + col) * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)d << 40) | row_key) : ~0ull;
+                }
+              }
+            } else {
+              // the common case (no survivor among 64 pairs) is an AND tree over the packed sign bits
+              uint32_t a = 0xffffffffu, b = 0xffffffffu;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { a &= va[j]; b &= vb[j]; }
+              hit[c128 / 64] = __ballot_sync(0xffffffffu, rvalid && (a & 0x80008000u) != 0x80008000u);
+              hit[c128 / 64 + 1] = __ballot_sync(0xffffffffu, rvalid && (b & 0x80008000u) != 0x80008000u);
             }
           }
-        } else {
-          // 32 accumulators per load, two loads in flight; the common case (no survivor among the 32)
-          // is an AND tree over the sign bits -- depth 4, no per-element work
-          uint32_t va[32], vb[32];
-          tmem_ld32_nowait(tbase, va);
-          tmem_ld_wait();
+          // the accumulator buffer is free: let the next tile's MMAs start, THEN pay for the appends
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + blk * 8);
+          if (!p.dense) {
 #pragma unroll
-          for (int c32 = 0; c32 < EPI_COLS / 32; c32 += 2) {
-            tmem_ld32_nowait(tbase + (uint32_t)((c32 + 1) * 32), vb);
-            {
-              uint32_t a = 0xffffffffu;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) a &= va[j];
-              if (rvalid && !(a >> 31)) {
-                const uint32_t(&lo)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&va[0]);
-                const uint32_t(&hi)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&va[16]);
-                unsigned m = nonneg_mask16(lo);
-                if (m) SB_HAM_QUEUE(m, lo, q0, c32 * 32, row_key, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
-                m = nonneg_mask16(hi);
-                if (m) SB_HAM_QUEUE(m, hi, q0, c32 * 32 + 16, row_key, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
+            for (int g64 = 0; g64 < QB / 64; ++g64) {
+              unsigned m = hit[g64];
+              while (m) {                                              // warp-uniform: one (row, 64 queries) re-check per set bit
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                ham_recheck_group<W>(p.db, p.qcodes, p.Q, row0 + l, (unsigned long long)(p.idx_base + row0 + l), q0 + g64 * 64,
+                                     tq_blk + g64 * 64, p.cand_buf, p.cand_cnt, p.cap, lane);
               }
             }
-            tmem_ld_wait();
-            if (c32 + 2 < EPI_COLS / 32) tmem_ld32_nowait(tbase + (uint32_t)((c32 + 2) * 32), va);
-            {
-              uint32_t a = 0xffffffffu;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) a &= vb[j];
-              if (rvalid && !(a >> 31)) {
-                const uint32_t(&lo)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&vb[0]);
-                const uint32_t(&hi)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&vb[16]);
-                unsigned m = nonneg_mask16(lo);
-                if (m) SB_HAM_QUEUE(m, lo, q0, (c32 + 1) * 32, row_key, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
-                m = nonneg_mask16(hi);
-                if (m) SB_HAM_QUEUE(m, hi, q0, (c32 + 1) * 32 + 16, row_key, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
-              }
-            }
-            tmem_ld_wait();
           }
+          __syncwarp();
         }
-        // the accumulator buffer is free: let the next tile's MMAs start, THEN pay for the appends
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty + buf * 8);
-        const int nq = min(*myq_cnt, SQ_CAP);
-        for (int e = lane; e < nq; e += 32) {                      // 32 appends in flight per warp
-          const long long qg = myq_q[e];
-          const int slot = atomicAdd(p.cand_cnt + qg, 1);
-          if (slot < p.cap) p.cand_buf[qg * p.cap + slot] = myq_key[e];
-        }
-        __syncwarp();
       }
     }
   }
@@ -527,10 +527,10 @@ HamTcPlan make_plan(int32_t W, int32_t Q, int32_t k) {
   p.first_rows = 1024;
   while (p.first_rows < 4 * k) p.first_rows <<= 1;
   if (p.first_rows > p.cap) p.first_rows = p.cap;
-  p.stages = MAX_STAGES;
+  p.stages = p.G == 2 ? 2 : MAX_STAGES;
   p.block_bytes = (size_t)p.G * B_GROUP + B_SYN;
-  p.smem_bytes = 1024 + p.block_bytes + A_SYN + (size_t)p.stages * p.G * A_GROUP + (2 * MAX_STAGES + 8) * 8 +
-                 EPI_WARPS * SQ_CAP * 12 + EPI_WARPS * 4 + EPI_WARPS * EPI_COLS * sizeof(int);
+  p.smem_bytes = 1024 + NB * p.block_bytes + A_SYN + (size_t)p.stages * p.G * A_GROUP + (2 * MAX_STAGES + 8) * 8 +
+                 EPI_WARPS * NB * QB * sizeof(int);
   size_t o = 0;
   p.off_img = o;  o += align256((size_t)p.col_blocks * p.block_bytes);
   p.off_tq = o;   o += align256((size_t)p.cols * sizeof(int));
@@ -605,7 +605,11 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
     if (P >= NG) P = 1;
   }
 
-  SB_CUDA_TRY(cudaFuncSetAttribute(ham_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+  void (*kernel)(const HamTcParams) = W == 8   ? ham_filter_tc_kernel<2, 4>
+                                      : W == 4 ? ham_filter_tc_kernel<1, 4>
+                                      : W == 2 ? ham_filter_tc_kernel<1, 2>
+                                               : ham_filter_tc_kernel<1, 1>;
+  SB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
   SB_CUDA_TRY(cudaFuncSetAttribute(ham_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(p.cap * sizeof(unsigned long long))));
   const int sms = sb::sm_count();
@@ -619,18 +623,20 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
     if (int rc = sb::check_launch("ham_threshold_image_kernel")) return rc;
     HamTcParams hp;
     hp.db = db; hp.U = U; hp.W = W; hp.G = p.G; hp.ksteps = p.ksteps; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
-    hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
+    hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.qcodes = q; hp.Q = Q; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
     hp.idx_base = idx_base; hp.dense = dense; hp.stages = p.stages;
+    { const char* e = getenv("SB_HAM_DEBUG"); hp.debug = e ? atoi(e) : 0; }
     const long long n_tiles = (len + 3) / 4;
     const int gx = (int)(n_tiles < sms ? n_tiles : sms);
     int gy = sms / gx;
     if (gy < 1) gy = 1;
     if (gy > p.col_blocks) gy = p.col_blocks;
     hp.cb_per = (p.col_blocks + gy - 1) / gy;
+    hp.cb_per = (hp.cb_per + NB - 1) / NB * NB;                 // whole groups of resident query blocks
     gy = (p.col_blocks + hp.cb_per - 1) / hp.cb_per;
     {
       sb::ProfScope prof("ham_filter_tc_kernel", st);
-      ham_filter_tc_kernel<<<dim3(gx, gy), THREADS, p.smem_bytes, st>>>(hp);
+      kernel<<<dim3(gx, gy), THREADS, p.smem_bytes, st>>>(hp);
       sb::count_launch();
       if (int rc = sb::check_launch("ham_filter_tc_kernel")) return rc;
     }
