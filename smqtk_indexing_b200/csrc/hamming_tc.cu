@@ -66,8 +66,9 @@ struct HamTcParams {
   int col_blocks, cb_per;      // query blocks in total / per blockIdx.y
   const unsigned char* image;  // per block: G x B_GROUP (SW128) then B_SYN
   const int* tq;               // thresholds (Hamming distance) per query column
-  const uint32_t* qcodes;      // u32[Q][W] packed query codes (survivor re-check)
-  int Q;
+  unsigned long long* recheck; // (row << 24 | 64-column group) entries
+  int* recheck_cnt;
+  int recheck_cap;
   unsigned long long* cand_buf;
   int* cand_cnt;
   int cap;
@@ -108,8 +109,10 @@ __device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_
 // Survivors are rare (~GROWTH * k per query and chunk among millions of pairs), so the epilogue does
 // not decode them from the accumulator registers (a divergent, register-indexed walk: ~400
 // instructions per survivor, measured at 40 % of the kernel).  It only learns, per lane, WHICH
-// 64-column group holds one; the warp then recomputes that row against the group's 64 queries with
-// XOR/POPC from the packed codes -- two queries per lane, no divergence, ~50 instructions per group.
+// 64-column group holds one and appends (row, group) to a global re-check list; ham_recheck_kernel
+// then recomputes each listed row against the group's 64 queries with XOR/POPC from the packed
+// codes -- one warp per entry, two queries per lane, the whole GPU hiding the load latency that a
+// re-check inside the epilogue would expose.
 template <int W>
 __device__ __forceinline__ void ham_recheck_group(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qcodes, int Q,
                                                   long long row, unsigned long long row_key, int qg0, const int* tq_grp,
@@ -375,14 +378,22 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty + blk * 8);
           if (!p.dense) {
+            int total = 0;
 #pragma unroll
-            for (int g64 = 0; g64 < QB / 64; ++g64) {
-              unsigned m = hit[g64];
-              while (m) {                                              // warp-uniform: one (row, 64 queries) re-check per set bit
-                const int l = __ffs(m) - 1;
-                m &= m - 1;
-                ham_recheck_group<W>(p.db, p.qcodes, p.Q, row0 + l, (unsigned long long)(p.idx_base + row0 + l), q0 + g64 * 64,
-                                     tq_blk + g64 * 64, p.cand_buf, p.cand_cnt, p.cap, lane);
+            for (int g64 = 0; g64 < QB / 64; ++g64) total += __popc(hit[g64]);
+            if (total) {                                               // rare: one atomic per (warp, tile, block) with survivors
+              int base = 0;
+              if (lane == 0) base = atomicAdd(p.recheck_cnt, total);
+              base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+              for (int g64 = 0; g64 < QB / 64; ++g64) {
+                const unsigned m = hit[g64];
+                if ((m >> lane) & 1u) {
+                  const int slot = base + __popc(m & ((1u << lane) - 1u));
+                  if (slot < p.recheck_cap)
+                    p.recheck[slot] = ((unsigned long long)row << 24) | (unsigned long long)((q0 >> 6) + g64);
+                }
+                base += __popc(m);
               }
             }
           }
@@ -397,6 +408,27 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
   if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// One warp per re-check entry (row, 64-query group): exact distances from the packed codes, survivors
+// appended to their query's candidate buffer.
+template <int W>
+__global__ void __launch_bounds__(256)
+ham_recheck_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qcodes, int Q, long long idx_base,
+                   const unsigned long long* __restrict__ list, const int* __restrict__ list_cnt, int list_cap,
+                   const int* __restrict__ tq, unsigned long long* __restrict__ cand_buf, int* __restrict__ cand_cnt, int cap,
+                   int* __restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const int raw = *list_cnt;
+  if (raw > list_cap && blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+  const int n = min(raw, list_cap);
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
+    const unsigned long long ent = list[e];
+    const long long row = (long long)(ent >> 24);
+    const int qg0 = (int)(ent & 0xffffffull) * 64;
+    ham_recheck_group<W>(db, qcodes, Q, row, (unsigned long long)(idx_base + row), qg0, tq + qg0, cand_buf, cand_cnt, cap, lane);
   }
 }
 
@@ -418,8 +450,9 @@ __global__ void ham_query_image_kernel(const uint32_t* __restrict__ q, int Q, in
 // B_syn of every block: 32 E4M3 slots per column that sum to s = 2 * tq - K + 1 (|s| <= 16 * 32);
 // padding columns get -512 (their data bytes are zero: the accumulator is negative).
 __global__ void ham_threshold_image_kernel(int Q, int cols, int G, int K, const int* __restrict__ tq,
-                                           unsigned char* __restrict__ img) {
+                                           unsigned char* __restrict__ img, int* __restrict__ list_cnt) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col == 0) *list_cnt = 0;                                   // the re-check list restarts with every chunk
   if (col >= cols) return;
   const int jb = col / QB, n = col % QB;
   const int s = (col < Q) ? (2 * min(tq[col], K) - K + 1) : -512;
@@ -510,7 +543,8 @@ ham_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt, 
 struct HamTcPlan {
   int G, ksteps, K, col_blocks, cols, cap, first_rows, stages;
   size_t block_bytes, smem_bytes;
-  size_t off_img, off_tq, off_cnt, off_flag, off_buf, total;
+  size_t off_img, off_tq, off_cnt, off_flag, off_list, off_buf, total;
+  int list_cap;
 };
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -535,7 +569,9 @@ HamTcPlan make_plan(int32_t W, int32_t Q, int32_t k) {
   p.off_img = o;  o += align256((size_t)p.col_blocks * p.block_bytes);
   p.off_tq = o;   o += align256((size_t)p.cols * sizeof(int));
   p.off_cnt = o;  o += align256((size_t)p.cols * sizeof(int));
-  p.off_flag = o; o += 256;
+  p.off_flag = o; o += 256;                                   // [0] overflow flag, [1] re-check list length
+  p.list_cap = 1 << 22;
+  p.off_list = o; o += align256((size_t)p.list_cap * sizeof(unsigned long long));
   p.off_buf = o;  o += align256((size_t)p.cols * p.cap * sizeof(unsigned long long));
   p.total = o;
   return p;
@@ -582,6 +618,7 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
   int* cnt = reinterpret_cast<int*>(ws + p.off_cnt);
   int* flag = reinterpret_cast<int*>(ws + p.off_flag);
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(ws + p.off_buf);
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(ws + p.off_list);
 
   SB_CUDA_TRY(cudaMemsetAsync(img, 0, (size_t)p.col_blocks * p.block_bytes, st));
   {
@@ -618,12 +655,12 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
     long long len = (done == 0) ? p.first_rows / GRAN : done * (GROWTH - 1);
     if (len > NG - done) len = NG - done;
     const int dense = (done == 0) ? 1 : 0;
-    ham_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.G, p.K, tq, img);
+    ham_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.G, p.K, tq, img, flag + 1);
     sb::count_launch();
     if (int rc = sb::check_launch("ham_threshold_image_kernel")) return rc;
     HamTcParams hp;
     hp.db = db; hp.U = U; hp.W = W; hp.G = p.G; hp.ksteps = p.ksteps; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
-    hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.qcodes = q; hp.Q = Q; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
+    hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.recheck = list; hp.recheck_cnt = flag + 1; hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
     hp.idx_base = idx_base; hp.dense = dense; hp.stages = p.stages;
     { const char* e = getenv("SB_HAM_DEBUG"); hp.debug = e ? atoi(e) : 0; }
     const long long n_tiles = (len + 3) / 4;
@@ -639,6 +676,16 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
       kernel<<<dim3(gx, gy), THREADS, p.smem_bytes, st>>>(hp);
       sb::count_launch();
       if (int rc = sb::check_launch("ham_filter_tc_kernel")) return rc;
+    }
+    if (!dense) {
+      sb::ProfScope prof("ham_recheck_kernel", st);
+      const int blocks = 4 * sms;
+      if (W == 8) ham_recheck_kernel<8><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
+      else if (W == 4) ham_recheck_kernel<4><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
+      else if (W == 2) ham_recheck_kernel<2><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
+      else ham_recheck_kernel<1><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
+      sb::count_launch();
+      if (int rc = sb::check_launch("ham_recheck_kernel")) return rc;
     }
     if (dense) {
       ham_set_count_kernel<<<(Q + 255) / 256, 256, 0, st>>>(cnt, Q, (int)(len * GRAN));
