@@ -238,6 +238,9 @@ def hamming_topk(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0):
     Q = q.shape[0]
     if q.shape[1] != W:
         raise ValueError("query codes have %d words, table has %d" % (q.shape[1], W))
+    if Q >= TC_SCAN_MIN_QUERIES and U >= TC_SCAN_MIN_ROWS and hamming_scan_tc_supported(U, W, Q, k):
+        # large batch over a large table: tensor-core scan (falls back to XOR/POPC on overflow), then decode
+        return topk_merge(hamming_scan_keys(db, q, k, idx_base).unsqueeze(0))
     lib = _lib.load()
     ws_bytes = lib.sb_hamming_scan_workspace_bytes(U, W, Q, k)
     ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=db.device)
