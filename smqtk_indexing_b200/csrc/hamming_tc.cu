@@ -5,36 +5,37 @@
 // issue pipes, not by HBM -- every table word is reused from registers by 4096 queries (27 TB/s of
 // algorithmic bytes on a 6.6 TB/s HBM; profiles/r1_scan_full.md: ALU pipe 89 % busy).  The same
 // count is a dot product: with bits mapped to +-1, dot(a, b) = K - 2 * popcount(a xor b).  FP8
-// E4M3 holds +-1 exactly and the FP32 accumulator holds every integer up to 2^24, so
-// tcgen05.mma kind::f8f6f4 computes the distances EXACTLY at 8192 MAC/clk/SM instead of 64
-// LOP3 + 16 POPC lanes/clk/SM.  The single-query / small-batch scan stays on hamming.cu, where the
-// table really is streamed once per query and HBM is the bound.
+// E4M3 holds +-1 exactly and every partial sum is an integer below 2048, exact even in an FP16
+// accumulator, so tcgen05.mma kind::f8f6f4 computes the distances EXACTLY at 8192 MAC/clk/SM
+// instead of 64 LOP3 + 16 POPC lanes/clk/SM.  The single-query / small-batch scan stays on
+// hamming.cu, where the table really is streamed once per query and HBM is the bound.
 //
 // Data flow per CTA (persistent, one per SM):
-//   * B = 256 query codes, expanded once per batch to +-1 FP8 in the SWIZZLE_128B K-major layout
-//     (ham_query_image_kernel), RESIDENT in shared memory for a whole pass over the rows.
+//   * B = TWO blocks of 256 query codes, expanded once per batch to +-1 FP8 in the SWIZZLE_128B
+//     K-major layout (ham_query_image_kernel), RESIDENT in shared memory for a whole pass over the
+//     rows.
 //   * A = 128 table rows per tile.  Producer warps read the PACKED codes (32 bytes per 256-bit
 //     row: HBM traffic stays at U * b / 8 per pass) and expand them to FP8 straight into the
-//     swizzled layout -- the table is never stored expanded.
+//     swizzled layout -- the table is never stored expanded.  The expansion is the most expensive
+//     stage per tile (measured), so every expanded tile feeds both resident query blocks and the
+//     producers get 8 of the 14 warps.
 //   * The threshold rides in one extra K step: A_syn = 32 x (+1), B_syn = 32 slots that sum to
 //     2 * tq - K + 1, so the accumulator is 2 * (tq - d) + 1 and "d <= tq" is a sign test (odd,
-//     never zero).  Survivors are decoded (d = tq - floor(acc / 2)) and appended to their query's
-//     candidate buffer as canonical keys d << 40 | row.
-//   * Accumulators double-buffered in TMEM (2 x 256 columns): the epilogue of tile t overlaps the
-//     MMAs of tile t + 1.
-// Thresholds tighten between chunks (ham_compact_kernel keeps the best k so far): chunk c is
-// GROWTH x the rows seen before it, and rows are visited in a golden-ratio permutation of 32-row
-// granules, so every chunk is a uniform sample of the table whatever its order -- a chunk then
-// yields ~GROWTH * (k + ties) survivors per query for ANY data distribution (the table is sorted,
-// near-duplicate clusters are contiguous).  A query whose buffer still overflows raises a flag and
-// the caller re-runs the batch on hamming.cu.
-// Measured on B200 (profiles/): the bit -> FP8 expansion in the producers is the most expensive
-// stage per tile, so TWO query blocks are resident and every expanded tile feeds both (the two
-// accumulator buffers are the two blocks), and the producers get 8 of the 14 warps.
+//     never zero).
+//   * Accumulators: FP16 in TMEM, one 256-column buffer per resident query block, so block 1's MMAs
+//     overlap block 0's epilogue.  The epilogue reads them packed (tcgen05.ld ... pack::16b, two
+//     columns per register) and ANDs the sign bits of 32 columns at a time: no survivor, no work.
+//   * Survivors are NOT decoded from registers: the lanes that saw one append (row, 32-query group)
+//     to a global list and ham_recheck_kernel recomputes those few pairs with XOR/POPC.
+// Thresholds tighten between chunks (ham_compact_kernel keeps the best k so far): a chunk is
+// (GROWTH - 1) x the rows seen before it, and rows are visited in a golden-ratio permutation of
+// 32-row granules, so every chunk is a uniform sample of the table whatever its order -- a chunk
+// then yields ~(GROWTH - 1) * (k + ties) survivors per query for ANY data distribution (the table
+// is sorted, near-duplicate clusters are contiguous).  A query whose buffer still overflows (a
+// table of massively tied codes) raises a flag and the caller re-runs the batch on hamming.cu.
 // Warp roles: 0-3 epilogue (TMEM lane quadrants), 4 MMA issue + TMEM alloc, 5 B loader,
 // 6-13 producers (half a table row per thread and tile).
 #include <cuda_fp16.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -54,8 +55,8 @@ constexpr int NB = 2;                       // query blocks resident per pass: e
 constexpr int GRAN = 32;                    // rows per granule of the visiting order
 constexpr int EPI_WARPS = 4, MMA_WARP = 4, B_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 8;
 constexpr int THREADS = (PROD_WARP0 + PROD_WARPS) * 32;   // 448
-constexpr int GROWTH = 8;
-constexpr int CP_THREADS = 1024;
+constexpr int GROWTH = 4;                   // rows of a chunk = 3 x the rows before it: ~3 (k + ties) survivors per query
+constexpr int CP_THREADS = 256;            // 7-8 compaction CTAs per SM: most queries hold a few hundred keys
 
 struct HamTcParams {
   const uint32_t* db;          // u32[U][W]
@@ -66,7 +67,7 @@ struct HamTcParams {
   int col_blocks, cb_per;      // query blocks in total / per blockIdx.y
   const unsigned char* image;  // per block: G x B_GROUP (SW128) then B_SYN
   const int* tq;               // thresholds (Hamming distance) per query column
-  unsigned long long* recheck; // (row << 24 | 64-column group) entries
+  unsigned long long* recheck; // (row << 24 | 32-column group) entries
   int* recheck_cnt;
   int recheck_cap;
   unsigned long long* cand_buf;
@@ -75,7 +76,6 @@ struct HamTcParams {
   long long idx_base;
   int dense;                   // first chunk: every pair is kept -> key stored at buf[query][virtual row]
   int stages;
-  int debug;
 };
 
 // 4 code bits -> 4 FP8 E4M3 bytes: bit = 0 -> +1.0 (0x38), bit = 1 -> -1.0 (0xB8); bit i -> byte i
@@ -109,9 +109,9 @@ __device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_
 // Survivors are rare (~GROWTH * k per query and chunk among millions of pairs), so the epilogue does
 // not decode them from the accumulator registers (a divergent, register-indexed walk: ~400
 // instructions per survivor, measured at 40 % of the kernel).  It only learns, per lane, WHICH
-// 64-column group holds one and appends (row, group) to a global re-check list; ham_recheck_kernel
-// then recomputes each listed row against the group's 64 queries with XOR/POPC from the packed
-// codes -- one warp per entry, two queries per lane, the whole GPU hiding the load latency that a
+// 32-column group holds one and appends (row, group) to a global re-check list; ham_recheck_kernel
+// then recomputes each listed row against the group's 32 queries with XOR/POPC from the packed
+// codes -- one warp per entry, one query per lane, the whole GPU hiding the load latency that a
 // re-check inside the epilogue would expose.
 template <int W>
 __device__ __forceinline__ void ham_recheck_group(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qcodes, int Q,
@@ -120,18 +120,14 @@ __device__ __forceinline__ void ham_recheck_group(const uint32_t* __restrict__ d
   uint32_t x[W];
 #pragma unroll
   for (int w = 0; w < W; ++w) x[w] = __ldg(db + row * W + w);
+  const int qg = qg0 + lane;
+  if (qg < Q) {
+    int d = 0;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int col = lane + 32 * h;
-    const int qg = qg0 + col;
-    if (qg < Q) {
-      int d = 0;
-#pragma unroll
-      for (int w = 0; w < W; ++w) d += __popc(x[w] ^ __ldg(qcodes + (long long)qg * W + w));
-      if (d <= tq_grp[col]) {
-        const int slot = atomicAdd(cand_cnt + qg, 1);
-        if (slot < cap) cand_buf[(long long)qg * cap + slot] = ((unsigned long long)(unsigned)d << 40) | row_key;
-      }
+    for (int w = 0; w < W; ++w) d += __popc(x[w] ^ __ldg(qcodes + (long long)qg * W + w));
+    if (d <= tq_grp[lane]) {
+      const int slot = atomicAdd(cand_cnt + qg, 1);
+      if (slot < cap) cand_buf[(long long)qg * cap + slot] = ((unsigned long long)(unsigned)d << 40) | row_key;
     }
   }
 }
@@ -231,7 +227,6 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
               for (int g = 0; g < G; ++g)
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ++ks)
-                  if (!(p.debug & 4) || (g | ks) == 0)
                   umma_f8(d_tmem, a_desc + (uint64_t)((g * A_GROUP + ks * 32) >> 4), b_desc + (uint64_t)((g * B_GROUP + ks * 32) >> 4),
                           idesc, (g | ks) ? 1u : 0u);
               umma_f8(d_tmem, asyn_desc, bsyn_desc0 + (uint64_t)((blk * b_block) >> 4), idesc, 1u);
@@ -292,7 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
         if (i + 1 < my_tiles) vnext = load(cn);
         mbar_wait(a_empty + stage * 8, phase ^ 1);
         unsigned char* dst = s_a + (size_t)stage * a_stage;
-        if (worker && !(p.debug & 2)) {
+        if (worker) {
 #pragma unroll
           for (int j = 0; j < WH; ++j) {
             const int wj = h * WH + j;                             // word of the row
@@ -344,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
           ++t[blk];
           tc_fence_after();
           const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(blk * QB);
-          unsigned hit[QB / 64];                                     // lanes with a survivor in each 64-column group
+          unsigned hit[QB / 32];                                     // lanes with a survivor in each 32-column group
 #pragma unroll
           for (int c128 = 0; c128 < QB; c128 += 128) {
             uint32_t va[32], vb[32];                               // 2 x 64 columns of packed FP16 accumulators
@@ -366,11 +361,13 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
               }
             } else {
               // the common case (no survivor among 64 pairs) is an AND tree over the packed sign bits
-              uint32_t a = 0xffffffffu, b = 0xffffffffu;
+              uint32_t a0 = 0xffffffffu, a1 = 0xffffffffu, b0 = 0xffffffffu, b1 = 0xffffffffu;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) { a &= va[j]; b &= vb[j]; }
-              hit[c128 / 64] = __ballot_sync(0xffffffffu, rvalid && (a & 0x80008000u) != 0x80008000u);
-              hit[c128 / 64 + 1] = __ballot_sync(0xffffffffu, rvalid && (b & 0x80008000u) != 0x80008000u);
+              for (int j = 0; j < 16; ++j) { a0 &= va[j]; a1 &= va[16 + j]; b0 &= vb[j]; b1 &= vb[16 + j]; }
+              hit[c128 / 32] = __ballot_sync(0xffffffffu, rvalid && (a0 & 0x80008000u) != 0x80008000u);
+              hit[c128 / 32 + 1] = __ballot_sync(0xffffffffu, rvalid && (a1 & 0x80008000u) != 0x80008000u);
+              hit[c128 / 32 + 2] = __ballot_sync(0xffffffffu, rvalid && (b0 & 0x80008000u) != 0x80008000u);
+              hit[c128 / 32 + 3] = __ballot_sync(0xffffffffu, rvalid && (b1 & 0x80008000u) != 0x80008000u);
             }
           }
           // the accumulator buffer is free: let the next tile's MMAs start, THEN pay for the appends
@@ -380,18 +377,18 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
           if (!p.dense) {
             int total = 0;
 #pragma unroll
-            for (int g64 = 0; g64 < QB / 64; ++g64) total += __popc(hit[g64]);
+            for (int g32 = 0; g32 < QB / 32; ++g32) total += __popc(hit[g32]);
             if (total) {                                               // rare: one atomic per (warp, tile, block) with survivors
               int base = 0;
               if (lane == 0) base = atomicAdd(p.recheck_cnt, total);
               base = __shfl_sync(0xffffffffu, base, 0);
 #pragma unroll
-              for (int g64 = 0; g64 < QB / 64; ++g64) {
-                const unsigned m = hit[g64];
+              for (int g32 = 0; g32 < QB / 32; ++g32) {
+                const unsigned m = hit[g32];
                 if ((m >> lane) & 1u) {
                   const int slot = base + __popc(m & ((1u << lane) - 1u));
                   if (slot < p.recheck_cap)
-                    p.recheck[slot] = ((unsigned long long)row << 24) | (unsigned long long)((q0 >> 6) + g64);
+                    p.recheck[slot] = ((unsigned long long)row << 24) | (unsigned long long)((q0 >> 5) + g32);
                 }
                 base += __popc(m);
               }
@@ -411,7 +408,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
   }
 }
 
-// One warp per re-check entry (row, 64-query group): exact distances from the packed codes, survivors
+// One warp per re-check entry (row, 32-query group): exact distances from the packed codes, survivors
 // appended to their query's candidate buffer.
 template <int W>
 __global__ void __launch_bounds__(256)
@@ -427,7 +424,7 @@ ham_recheck_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__
   for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
     const unsigned long long ent = list[e];
     const long long row = (long long)(ent >> 24);
-    const int qg0 = (int)(ent & 0xffffffull) * 64;
+    const int qg0 = (int)(ent & 0xffffffull) * 32;
     ham_recheck_group<W>(db, qcodes, Q, row, (unsigned long long)(idx_base + row), qg0, tq + qg0, cand_buf, cand_cnt, cap, lane);
   }
 }
@@ -662,7 +659,6 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
     hp.db = db; hp.U = U; hp.W = W; hp.G = p.G; hp.ksteps = p.ksteps; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
     hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.recheck = list; hp.recheck_cnt = flag + 1; hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
     hp.idx_base = idx_base; hp.dense = dense; hp.stages = p.stages;
-    { const char* e = getenv("SB_HAM_DEBUG"); hp.debug = e ? atoi(e) : 0; }
     const long long n_tiles = (len + 3) / 4;
     const int gx = (int)(n_tiles < sms ? n_tiles : sms);
     int gy = sms / gx;
@@ -679,7 +675,7 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
     }
     if (!dense) {
       sb::ProfScope prof("ham_recheck_kernel", st);
-      const int blocks = 4 * sms;
+      const int blocks = 8 * sms;                               // 64 warps per SM: the re-check is load-latency bound
       if (W == 8) ham_recheck_kernel<8><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
       else if (W == 4) ham_recheck_kernel<4><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
       else if (W == 2) ham_recheck_kernel<2><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
