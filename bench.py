@@ -89,54 +89,99 @@ def recorded_traffic(name="scan_traffic.json"):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.  NVML from a thread every 5 ms
+    (the timed region of a fast path lasts ~0.1 s: `nvidia-smi -lms` would catch one sample);
+    falls back to polling nvidia-smi when NVML cannot be loaded."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_id):
-        self.gpu_id = gpu_id
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
         self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
+                else nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
+                                               getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
+                                               getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap",
+                                        getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0))}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons",
+                              getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(mx)
+                if get_reasons is not None:
+                    r = int(get_reasons(h))
+                    for nm, bit in bits.items():
+                        if bit and (r & bit):
+                            self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
+            import pynvml as nv
+            import threading
+            nv.nvmlInit()
+            gid = str(self.gpu_index)
+            h = nv.nvmlDeviceGetHandleByUUID(gid) if gid.startswith("GPU-") else nv.nvmlDeviceGetHandleByIndex(int(gid))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu_id), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.splitlines():
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
-                continue
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+        elif self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in out.splitlines():
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    self.sm.append(float(parts[0]))
+                    self.mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         # the first samples can precede the first kernel: keep the busiest 80 %
-        sm_sorted = sorted(sm)
+        sm_sorted = sorted(self.sm)
         busy = sm_sorted[len(sm_sorted) // 5:] if len(sm_sorted) >= 5 else sm_sorted
         return {"sm_mhz": statistics.median(busy) if busy else None,
-                "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.thread is not None else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------- CPU legs (oracle = checker / baseline only)

@@ -155,7 +155,7 @@ def itq_hash(X: torch.Tensor, mean: Optional[torch.Tensor], R: torch.Tensor, nor
 # --------------------------------------------------------------------- stage 2
 #: the tensor-core scan takes over from this many queries / table rows (below, the XOR/POPC scan
 #: streams the table once per handful of queries and is bound by HBM, which is the better regime)
-TC_SCAN_MIN_QUERIES = 128
+TC_SCAN_MIN_QUERIES = 64
 TC_SCAN_MIN_ROWS = 1 << 16
 #: set by hamming_scan_keys: how many batches overflowed a candidate buffer and were re-run
 TC_SCAN_OVERFLOWS = 0
