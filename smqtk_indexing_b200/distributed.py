@@ -8,8 +8,13 @@ Sharding (DESIGN.md section "Multi-GPU"):
   * per-row codes are all-gathered once at build time (32 B per row at 256 bits)
     and every rank derives the SAME global sorted-unique code table and
     code -> rows CSR -- exactly the single-GPU structures;
-  * the Hamming scan is range-partitioned over that table: rank r scans table
-    rows [lo_r, hi_r) with ``idx_base = lo_r``, so its keys are already global.
+  * the Hamming scan is partitioned either over that table (``scan_partition="rows"``: rank r
+    scans table rows [lo_r, hi_r) with ``idx_base = lo_r``, so its keys are already global) or over
+    the QUERIES (``"queries"``: every rank holds the whole table anyway -- 32 B per code -- and scans
+    all of it for its slice of the batch; its keys are final, the all-gather assembles the batch and
+    nothing is merged).  Same keys either way.  The per-batch costs that do not shrink with the table
+    (threshold bookkeeping, survivor re-checks of the tensor-core scan) shrink with the query slice,
+    so ``"auto"`` partitions by queries once every rank gets at least 64 of them.
 
 Per query batch there are two small collectives:
   1. all-gather of the per-rank top-n keys (Q*n*8 bytes per rank) followed by
@@ -96,7 +101,14 @@ def partition_bounds(total: int, world: int, align: int = 4) -> List[int]:
 class ShardedLshIndex:
     """Row-sharded descriptors, range-partitioned Hamming scan, exact merge."""
 
-    def __init__(self, functor, distance_method: str = "euclidean", group=None, ops=None) -> None:
+    #: a rank's query slice must be at least this long for ``scan_partition="auto"`` to split the batch
+    MIN_QUERIES_PER_RANK = 64
+
+    def __init__(self, functor, distance_method: str = "euclidean", group=None, ops=None,
+                 scan_partition: str = "auto") -> None:
+        if scan_partition not in ("auto", "rows", "queries"):
+            raise ValueError("scan_partition must be 'auto', 'rows' or 'queries'")
+        self.scan_partition = scan_partition
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -130,6 +142,23 @@ class ShardedLshIndex:
 
     def near_codes(self, q_codes: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Global n nearest unique codes: local scan, all-gather, merge."""
+        Q = q_codes.shape[0]
+        by_queries = self.scan_partition == "queries" or (
+            self.scan_partition == "auto" and Q >= self.MIN_QUERIES_PER_RANK * self.world)
+        if by_queries and self.world > 1:
+            per = (Q + self.world - 1) // self.world              # equal slices (the last ones padded) for the collective
+            lo = min(Q, self.rank * per)
+            hi = min(Q, lo + per)
+            mine = q_codes[lo:hi]
+            if hi - lo < per:
+                mine = torch.cat([mine, torch.zeros((per - (hi - lo), q_codes.shape[1]), dtype=q_codes.dtype,
+                                                    device=q_codes.device)], dim=0)
+            with _stage("hamming_scan"):
+                keys = self.ops.scan_keys(self.table, mine.contiguous(), n, 0).contiguous()
+            with _stage("allgather_merge"):
+                gathered = torch.empty((self.world * per,) + tuple(keys.shape[1:]), dtype=keys.dtype, device=keys.device)
+                dist.all_gather_into_tensor(gathered, keys, group=self.group)  # rank-major = query order
+                return self.ops.merge_keys(gathered[:Q].contiguous().unsqueeze(0))   # one part: decode only
         with _stage("hamming_scan"):
             keys = self.ops.scan_keys(self.table[self.scan_lo:self.scan_hi], q_codes, n, self.scan_lo).contiguous()
         with _stage("allgather_merge"):

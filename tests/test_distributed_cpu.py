@@ -94,6 +94,11 @@ def _worker(rank, world, port, cuts, out_q):
         for n in (1, 5, 40):
             rows, d = idx.query(torch.from_numpy(q), n)
             res[n] = (rows.numpy(), d.numpy())
+            # the scan partitioned over the queries (9 queries over 2 / 3 ranks: ragged slices) gives the same answer
+            idx.scan_partition = "queries"
+            rows_q, d_q = idx.query(torch.from_numpy(q), n)
+            idx.scan_partition = "auto"
+            assert torch.equal(rows_q, rows) and torch.equal(d_q, d)
         out_q.put((rank, idx.num_rows, idx.num_codes, (idx.scan_lo, idx.scan_hi), res))
     finally:
         dist.destroy_process_group()
