@@ -102,6 +102,7 @@ class ClockSampler:
         self.thread = None
         self.stop_flag = False
         self.sm, self.mx, self.reasons = [], [], set()
+        self.errors, self.last_error, self.sample_now = 0, None, None
 
     def _nvml_loop(self, nv, h):
         bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
@@ -114,8 +115,13 @@ class ClockSampler:
                                         getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0))}
         get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons",
                               getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
-        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-        while not self.stop_flag:
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception as e:
+            sys.stderr.write("clock sampler: max clock query failed: %r\n" % (e,))
+            mx = float("nan")
+
+        def sample():
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 self.mx.append(mx)
@@ -124,9 +130,20 @@ class ClockSampler:
                     for nm, bit in bits.items():
                         if bit and (r & bit):
                             self.reasons.add(nm)
-            except Exception:
-                pass
-            time.sleep(0.005)
+            except Exception as e:
+                self.errors += 1
+                self.last_error = repr(e)
+
+        self.sample_now = sample
+        while not self.stop_flag:
+            sample()
+            time.sleep(0.004)
+
+    def sample_between_steps(self):
+        """Called by the timed loop right after a step's kernels were launched (the events bracket the
+        step, not this call): a guaranteed sample under load even when the polling thread is starved."""
+        if self.sample_now is not None:
+            self.sample_now()
 
     def start(self):
         try:
@@ -150,8 +167,12 @@ class ClockSampler:
 
     def stop(self):
         if self.thread is not None:
+            if self.sample_now is not None:
+                self.sample_now()            # at least one sample taken while the last timed kernels drain
             self.stop_flag = True
             self.thread.join(timeout=2)
+            if self.errors:
+                sys.stderr.write("clock sampler: %d failed NVML samples (%s)\n" % (self.errors, self.last_error))
         elif self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
@@ -388,9 +409,10 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, arg, steps):
+    def timed(fn, arg, steps, on_step=None):
         """EXACTLY `steps` steps; per-step CUDA events (the L2 flush between steps is
-        outside the events); returns the summed milliseconds."""
+        outside the events); returns the summed milliseconds.  `on_step` runs after each step has
+        been launched (the clock sampler's synchronous sample: the GPU is busy at that point)."""
         evs = []
         barrier()
         for _ in range(steps):
@@ -400,6 +422,8 @@ def run_b200(args):
             fn(arg)
             e1.record()
             evs.append((e0, e1))
+            if on_step is not None:
+                on_step()
         barrier()
         return sum(a.elapsed_time(b_) for a, b_ in evs)
 
@@ -415,7 +439,7 @@ def run_b200(args):
     launches0 = _lib.launch_count()
     _lib.profile_fetch()
     _lib.profile_enable(True)
-    ms_dev = timed(query_dev, q_dev, args.steps)
+    ms_dev = timed(query_dev, q_dev, args.steps, on_step=(sampler.sample_between_steps if rank == 0 else None))
     _lib.profile_enable(False)
     launches = _lib.launch_count() - launches0
     prof = _lib.profile_fetch()

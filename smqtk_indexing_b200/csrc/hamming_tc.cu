@@ -555,8 +555,8 @@ HamTcPlan make_plan(int32_t W, int32_t Q, int32_t k) {
   p.cols = p.col_blocks * QB;
   p.cap = 4096;
   while (p.cap < 4 * (GROWTH + 1) * k) p.cap <<= 1;
-  p.first_rows = 1024;
-  while (p.first_rows < 4 * k) p.first_rows <<= 1;
+  p.first_rows = 256;                                          // dense seed chunk: at least 8 k rows (its sort costs Q * rows)
+  while (p.first_rows < 8 * k) p.first_rows <<= 1;
   if (p.first_rows > p.cap) p.first_rows = p.cap;
   p.stages = p.G == 2 ? 2 : MAX_STAGES;
   p.block_bytes = (size_t)p.G * B_GROUP + B_SYN;

@@ -181,6 +181,55 @@ def hamming_scan_keys_tc(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: in
     return keys, flag
 
 
+class deferred_scan_check:
+    """Context manager for a pipeline of several stages: inside it the tensor-core scan does NOT
+    synchronise to read its overflow flag (the keys of an overflowed batch are still valid table
+    rows, only possibly not the nearest, so the later stages are safe to launch); the flags are
+    collected in ``self.flags`` and the caller asks ``overflowed()`` once, after the last stage,
+    and re-runs the batch with ``force_popc()`` if it says so."""
+    active = None
+
+    def __init__(self) -> None:
+        self.flags = []
+
+    def __enter__(self):
+        self._prev = deferred_scan_check.active
+        deferred_scan_check.active = self
+        return self
+
+    def __exit__(self, *exc):
+        deferred_scan_check.active = self._prev
+
+    def flag_tensor(self) -> Optional[torch.Tensor]:
+        """All collected flags folded into one int32[1] tensor (None if the scan never deferred)."""
+        if not self.flags:
+            return None
+        t = self.flags[0] if len(self.flags) == 1 else torch.stack(self.flags).max(dim=0).values
+        self.flags = [t]
+        return t
+
+    def overflowed(self) -> bool:
+        global TC_SCAN_OVERFLOWS
+        t = self.flag_tensor()
+        bad = t is not None and int(t.item()) != 0
+        self.flags = []
+        if bad:
+            TC_SCAN_OVERFLOWS += 1
+        return bad
+
+
+class force_popc:
+    """Context manager: ``hamming_scan_keys`` / ``hamming_topk`` stay on the XOR/POPC scan."""
+    active = False
+
+    def __enter__(self):
+        self._prev = force_popc.active
+        force_popc.active = True
+
+    def __exit__(self, *exc):
+        force_popc.active = self._prev
+
+
 def hamming_scan_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0,
                       variant: int = 0) -> torch.Tensor:
     """Local top-k as packed keys int64[Q, k] (uint64 bit pattern, ascending,
@@ -196,9 +245,12 @@ def hamming_scan_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int =
         raise ValueError("query codes have %d words, table has %d" % (q.shape[1], W))
     if variant == SCAN_VARIANT_TC and not hamming_scan_tc_supported(U, W, Q, k):
         raise ValueError("tensor-core scan does not support U=%d W=%d Q=%d k=%d" % (U, W, Q, k))
-    if variant == SCAN_VARIANT_TC or (variant == 0 and Q >= TC_SCAN_MIN_QUERIES and U >= TC_SCAN_MIN_ROWS
-                                      and hamming_scan_tc_supported(U, W, Q, k)):
+    if variant == SCAN_VARIANT_TC or (variant == 0 and not force_popc.active and Q >= TC_SCAN_MIN_QUERIES
+                                      and U >= TC_SCAN_MIN_ROWS and hamming_scan_tc_supported(U, W, Q, k)):
         keys, flag = hamming_scan_keys_tc(db, q, k, idx_base)
+        if deferred_scan_check.active is not None:
+            deferred_scan_check.active.flags.append(flag)       # checked once, at the end of the pipeline
+            return keys
         if int(flag.item()) == 0:
             return keys
         TC_SCAN_OVERFLOWS += 1          # a candidate buffer overflowed: the exact XOR/POPC scan decides
@@ -238,7 +290,8 @@ def hamming_topk(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0):
     Q = q.shape[0]
     if q.shape[1] != W:
         raise ValueError("query codes have %d words, table has %d" % (q.shape[1], W))
-    if Q >= TC_SCAN_MIN_QUERIES and U >= TC_SCAN_MIN_ROWS and hamming_scan_tc_supported(U, W, Q, k):
+    if (not force_popc.active and Q >= TC_SCAN_MIN_QUERIES and U >= TC_SCAN_MIN_ROWS
+            and hamming_scan_tc_supported(U, W, Q, k)):
         # large batch over a large table: tensor-core scan (falls back to XOR/POPC on overflow), then decode
         return topk_merge(hamming_scan_keys(db, q, k, idx_base).unsqueeze(0))
     lib = _lib.load()

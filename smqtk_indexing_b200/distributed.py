@@ -173,6 +173,23 @@ class ShardedLshIndex:
         from .engine import FIXED_PITCH_LIMIT
         with _stage("itq_hash"):
             q_codes = self.ops.hash(q)
+        from . import device
+        with device.deferred_scan_check() as chk:
+            out = self._query_hashed(q, q_codes, n)
+            # every rank must take the same branch afterwards: fold the flags (a rank that did not use the
+            # tensor-core scan contributes 0); still no host synchronisation
+            flag = chk.flag_tensor()
+            if flag is None:
+                flag = torch.zeros((1,), dtype=torch.int32, device=q.device)
+                chk.flags = [flag]
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        if chk.overflowed():
+            with device.force_popc():
+                out = self._query_hashed(q, q_codes, n)
+        return out
+
+    def _query_hashed(self, q: torch.Tensor, q_codes: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        from .engine import FIXED_PITCH_LIMIT
         _, code_rows = self.near_codes(q_codes, n)
         pitch = n * max(self.max_rows_per_code, 1)
         fixed = hasattr(self.ops, "expand") and n <= 2048 and q.shape[0] * pitch <= FIXED_PITCH_LIMIT

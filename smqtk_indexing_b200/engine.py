@@ -139,5 +139,12 @@ class DeviceLshIndex:
         """hash -> Hamming top-n unique codes -> candidates -> re-rank -> top-n."""
         with _stage("itq_hash"):
             q_codes = functor.get_hash_packed(q)
-        _, code_rows = self.near_codes(q_codes, n)
-        return self.rerank(q, code_rows, n, distance_method)
+        # the tensor-core scan's overflow flag is read once, after the last stage has been launched
+        with device.deferred_scan_check() as chk:
+            _, code_rows = self.near_codes(q_codes, n)
+            out = self.rerank(q, code_rows, n, distance_method)
+        if chk.overflowed():
+            with device.force_popc():
+                _, code_rows = self.near_codes(q_codes, n)
+                out = self.rerank(q, code_rows, n, distance_method)
+        return out

@@ -174,6 +174,17 @@ def test_hamming_scan_dispatch_and_overflow_fallback(dev):
     keys = dev.hamming_scan_keys(ds, dq, 10, variant=dev.SCAN_VARIANT_TC)
     assert dev.TC_SCAN_OVERFLOWS == before + 1
     assert torch.equal(keys, dev.hamming_scan_keys(ds, dq, 10, variant=1))
+    # pipeline form (engine.py / distributed.py): no sync inside the context, one check at the end, re-run forced
+    # onto the XOR/POPC scan
+    with dev.deferred_scan_check() as chk:
+        dev.hamming_scan_keys(ds, dq, 10)
+        assert len(chk.flags) == 1
+    assert chk.overflowed() and dev.TC_SCAN_OVERFLOWS == before + 2
+    with dev.force_popc():
+        assert torch.equal(dev.hamming_scan_keys(ds, dq, 10), keys)
+    with dev.deferred_scan_check() as chk:
+        k_ok = dev.hamming_scan_keys(dt, dq, 10)
+    assert not chk.overflowed() and torch.equal(k_ok, k_popc)
 
 
 def test_hamming_empty_table(dev):
