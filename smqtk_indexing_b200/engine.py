@@ -68,23 +68,40 @@ def expand_candidates(code_rows: torch.Tensor, csr_off: torch.Tensor, csr_rows: 
 
 
 class DeviceLshIndex:
-    """Descriptor rows + codes + unique-code table + CSR, all on one device."""
+    """Descriptor rows + codes + unique-code table + CSR, all on one device.
+
+    Ingest is incremental (reference lsh.py:331-450): rows are appended into
+    buffers that grow geometrically, removed rows become tombstones (their row numbers stay
+    valid for the layers that map rows to uuids) and ``reindex`` rebuilds the unique table and
+    the CSR over the live rows on the device (a radix sort of the codes: ~50 M rows/s)."""
+
+    #: buffers grow by this factor when an append does not fit
+    GROWTH = 1.5
 
     def __init__(self) -> None:
-        self.x: Optional[torch.Tensor] = None          # float32[N, D]
+        self.x: Optional[torch.Tensor] = None          # float32[N, D]   (view of the first N buffer rows)
         self.codes: Optional[torch.Tensor] = None      # int32[N, W]
-        self.table: Optional[torch.Tensor] = None      # int32[U, W] sorted unique
-        self.row_code: Optional[torch.Tensor] = None   # int64[N] row -> table row
+        self.alive: Optional[torch.Tensor] = None      # bool[N], None = every row is live
+        self.table: Optional[torch.Tensor] = None      # int32[U, W] sorted unique (live rows only)
+        self.row_code: Optional[torch.Tensor] = None   # int64[N] row -> table row (-1 = removed)
         self.csr_off: Optional[torch.Tensor] = None    # int64[U + 1]
-        self.csr_rows: Optional[torch.Tensor] = None   # int64[N]
+        self.csr_rows: Optional[torch.Tensor] = None   # int64[live rows]
         self.max_rows_per_code: int = 0
+        self._x_buf: Optional[torch.Tensor] = None
+        self._codes_buf: Optional[torch.Tensor] = None
+        self.num_dead: int = 0
 
     def clear(self) -> None:
         self.__init__()
 
     @property
     def num_rows(self) -> int:
+        """Physical rows (live + tombstones)."""
         return 0 if self.codes is None else int(self.codes.shape[0])
+
+    @property
+    def num_live(self) -> int:
+        return self.num_rows - self.num_dead
 
     @property
     def num_codes(self) -> int:
@@ -93,14 +110,82 @@ class DeviceLshIndex:
     def set_rows(self, x: Optional[torch.Tensor], codes: torch.Tensor) -> None:
         """Adopt descriptor rows (may be None for a codes-only index) and their codes."""
         self.x, self.codes = x, codes
+        self._x_buf, self._codes_buf = x, codes
+        self.alive, self.num_dead = None, 0
         self.reindex()
 
+    @staticmethod
+    def _grown(buf: Optional[torch.Tensor], used: int, new: torch.Tensor, growth: float) -> torch.Tensor:
+        """``buf`` (capacity rows) with ``new`` copied in at row ``used``; reallocated when too small."""
+        need = used + new.shape[0]
+        if buf is None or buf.shape[0] < need or buf.shape[1:] != new.shape[1:]:
+            cap = max(need, int(used * growth) + 1)
+            grown = torch.empty((cap,) + tuple(new.shape[1:]), dtype=new.dtype, device=new.device)
+            if used:
+                grown[:used] = buf[:used]
+            buf = grown
+        buf[used:need] = new
+        return buf
+
+    def append_rows(self, x: Optional[torch.Tensor], codes: torch.Tensor) -> int:
+        """Append rows (no re-index: call ``reindex`` after the batch).  Returns the first new row."""
+        n0 = self.num_rows
+        if n0 and codes.shape[1] != self.codes.shape[1]:
+            w = max(codes.shape[1], self.codes.shape[1])
+            codes = codeops.widen(codes, w)
+            if self.codes.shape[1] != w:
+                self._codes_buf = codeops.widen(self.codes, w)
+        self._codes_buf = self._grown(self._codes_buf, n0, codes, self.GROWTH)
+        self.codes = self._codes_buf[:n0 + codes.shape[0]]
+        if x is not None:
+            self._x_buf = self._grown(self._x_buf, n0, x, self.GROWTH)
+            self.x = self._x_buf[:n0 + x.shape[0]]
+        if self.alive is not None:
+            self.alive = torch.cat([self.alive, torch.ones(codes.shape[0], dtype=torch.bool, device=codes.device)])
+        return n0
+
+    def overwrite_rows(self, rows: torch.Tensor, x: Optional[torch.Tensor], codes: torch.Tensor) -> None:
+        """Replace the vectors / codes of existing rows (a uuid added again)."""
+        if codes.shape[1] != self.codes.shape[1]:
+            codes = codeops.widen(codes, self.codes.shape[1])
+        self.codes[rows] = codes
+        if x is not None and self.x is not None:
+            self.x[rows] = x
+
+    def remove_rows(self, rows: torch.Tensor) -> None:
+        """Tombstone rows (int64 tensor of live rows; no re-index)."""
+        if self.alive is None:
+            self.alive = torch.ones(self.num_rows, dtype=torch.bool, device=self.codes.device)
+        self.alive[rows] = False
+        self.num_dead = self.num_rows - int(self.alive.sum().item())
+
+    def compact(self) -> Optional[torch.Tensor]:
+        """Drop the tombstones physically.  Returns old-row -> new-row (int64, -1 = removed) or None
+        when nothing was dead; the caller re-maps whatever it keys by row."""
+        if self.alive is None or self.num_dead == 0:
+            self.alive, self.num_dead = None, 0
+            return None
+        live = torch.nonzero(self.alive).reshape(-1)
+        remap = torch.full((self.num_rows,), -1, dtype=torch.int64, device=live.device)
+        remap[live] = torch.arange(live.numel(), device=live.device)
+        x = self.x[live].contiguous() if self.x is not None else None
+        self.set_rows(x, self.codes[live].contiguous())
+        return remap
+
     def reindex(self) -> None:
-        """Recompute the unique table and the CSR from ``codes``."""
-        if self.codes is None or self.codes.shape[0] == 0:
+        """Recompute the unique table and the CSR from the codes of the live rows."""
+        if self.codes is None or self.num_live == 0:
             self.table = self.csr_off = self.csr_rows = self.row_code = None
+            self.max_rows_per_code = 0
             return
-        self.table, self.row_code, self.csr_off, self.csr_rows = codeops.build_table(self.codes)
+        if self.alive is None or self.num_dead == 0:
+            self.table, self.row_code, self.csr_off, self.csr_rows = codeops.build_table(self.codes)
+        else:
+            live = torch.nonzero(self.alive).reshape(-1)
+            self.table, rc, self.csr_off, rows_local = codeops.build_table(self.codes[live].contiguous())
+            self.csr_rows = live[rows_local]
+            self.row_code = torch.full((self.num_rows,), -1, dtype=torch.int64, device=live.device)
+            self.row_code[live] = rc
         # most rows sharing one code: sizes the fixed-pitch candidate segments (one sync per re-index)
         self.max_rows_per_code = int((self.csr_off[1:] - self.csr_off[:-1]).max().item())
 

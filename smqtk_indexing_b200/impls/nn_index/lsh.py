@@ -22,13 +22,17 @@ order, results in (distance, candidate position) order.
 """
 import logging
 import threading
-from typing import Any, Callable, Dict, Hashable, Iterable, List, Optional, Sequence, Set, Tuple, Type, TypeVar
+from typing import Any, Callable, Dict, Hashable, Iterable, Iterator, List, Optional, Sequence, Set, Tuple, Type, TypeVar
 
 import numpy
 
 from smqtk_core.configuration import from_config_dict, make_default_config, to_config_dict
 from smqtk_core.dict import merge_dict
 from smqtk_dataprovider import KeyValueStore
+try:                                     # the real package keeps the sentinel next to the interface
+    from smqtk_dataprovider.interfaces.key_value_store import NO_DEFAULT_VALUE
+except ImportError:                      # stand-in package
+    from smqtk_dataprovider import NO_DEFAULT_VALUE
 from smqtk_dataprovider.exceptions import ReadOnlyError
 from smqtk_descriptors import DescriptorElement, DescriptorSet
 
@@ -47,8 +51,8 @@ class _DeviceMirror(DeviceLshIndex):
 
     def __init__(self) -> None:
         super().__init__()
-        self.uuids: List[Hashable] = []     # row -> uuid
-        self.row_of: Dict[Hashable, int] = {}
+        self.uuids: List[Hashable] = []     # row -> uuid (a ``range`` for matrix-built indexes without uuids)
+        self.row_of: Optional[Dict[Hashable, int]] = {}   # uuid -> row; None = not built yet (matrix-built index)
 
     def count(self) -> int:
         return len(self.uuids)
@@ -201,11 +205,9 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
             codes, bits = self._hash_matrix(x)
             m = self._mirror
             import torch
-            m.x = torch.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32)).to(codes.device)
-            m.codes = codes
             m.uuids = [d.uuid() for d in elems]
             m.row_of = {u: i for i, u in enumerate(m.uuids)}
-            m.reindex()
+            m.set_rows(torch.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32)).to(codes.device), codes)
 
             # hash -> uuids map, one add_many (reference lsh.py:313-324)
             table_ints = bitutil.words_to_ints(device.codes_to_host(m.table))
@@ -243,28 +245,7 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
             # device mirror: append new uuids, overwrite re-added ones
             m = self._mirror
             xt = torch.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32)).to(codes.device)
-            if m.x is None:
-                m.x, m.codes = xt[:0], codes[:0]
-            if m.codes.shape[1] != codes.shape[1]:
-                from smqtk_indexing_b200 import codes as codeops
-                w = max(m.codes.shape[1], codes.shape[1])
-                m.codes, codes = codeops.widen(m.codes, w), codeops.widen(codes, w)
-            last = {d.uuid(): i for i, d in enumerate(new)}   # a uuid given twice keeps its last vector
-            app_rows = []
-            for u, i in last.items():
-                r = m.row_of.get(u)
-                if r is None:
-                    m.row_of[u] = len(m.uuids)
-                    m.uuids.append(u)
-                    app_rows.append(i)
-                else:
-                    m.x[r] = xt[i]
-                    m.codes[r] = codes[i]
-            if app_rows:
-                sel = torch.tensor(app_rows, dtype=torch.int64, device=codes.device)
-                m.x = torch.cat([m.x, xt[sel]], dim=0)
-                m.codes = torch.cat([m.codes, codes[sel]], dim=0)
-            m.reindex()
+            self._mirror_upsert(m, xt, codes, [d.uuid() for d in new])
 
             if self.hash_index is not None:
                 LOG.debug("Updating hash index structure.")
@@ -303,14 +284,17 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
             self.descriptor_set.remove_many_descriptors(uids)
 
             m = self._mirror
+            if m.row_of is None:                               # matrix-built mirror: build the lookup on first use
+                m.row_of = {u: i for i, u in enumerate(m.uuids)}
             gone = {m.row_of[u] for u in uids if u in m.row_of}
+            if m.alive is not None:                            # tombstones left by remove_from_index_matrix go too
+                gone |= set(torch.nonzero(~m.alive).reshape(-1).cpu().tolist())
             if gone:
                 keep = [r for r in range(len(m.uuids)) if r not in gone]
                 sel = torch.tensor(keep, dtype=torch.int64, device=m.codes.device)
-                m.x, m.codes = m.x[sel], m.codes[sel]
                 m.uuids = [m.uuids[r] for r in keep]
                 m.row_of = {u: i for i, u in enumerate(m.uuids)}
-                m.reindex()
+                m.set_rows(m.x[sel], m.codes[sel])
 
     # ------------------------------------------------------------------ queries
     def _nn(self, d: DescriptorElement, n: int = 1) -> Tuple[Tuple[DescriptorElement, ...], Tuple[float, ...]]:
@@ -384,14 +368,132 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
             m.clear()
             codes = self.lsh_functor.get_hash_packed(x)
             m.uuids = list(uuids) if uuids is not None else range(x.shape[0])  # type: ignore
-            m.row_of = {}
+            m.row_of = None                                      # uuid -> row lookup is built on first use
             m.set_rows(x, codes)
             if isinstance(self.hash_index, LinearHashIndex):
                 self.hash_index.set_code_table(m.table)
 
+    @staticmethod
+    def _mirror_upsert(m: "_DeviceMirror", xt, codes, uuids: Sequence[Hashable]) -> None:
+        """Device-mirror half of ``update_index`` (reference lsh.py:331-383): rows of new uuids are
+        appended, a uuid seen before gets its vector and code overwritten (the descriptor set
+        overwrites too); a uuid given twice in one batch keeps its last vector.  Re-indexes."""
+        import torch
+        if m.row_of is None:                                   # matrix-built mirror: build the lookup on first use
+            m.row_of = {u: i for i, u in enumerate(m.uuids)}
+        if not isinstance(m.uuids, list):
+            m.uuids = list(m.uuids)
+        last = {u: i for i, u in enumerate(uuids)}
+        app_src, ow_src, ow_dst = [], [], []
+        for u, i in last.items():
+            r = m.row_of.get(u)
+            if r is None:
+                m.row_of[u] = len(m.uuids)
+                m.uuids.append(u)
+                app_src.append(i)
+            else:
+                ow_src.append(i)
+                ow_dst.append(r)
+        dev = codes.device
+        if ow_src:
+            src = torch.tensor(ow_src, dtype=torch.int64, device=dev)
+            dst = torch.tensor(ow_dst, dtype=torch.int64, device=dev)
+            m.overwrite_rows(dst, xt[src], codes[src])
+            if m.alive is not None:                            # a removed uuid that comes back is live again
+                m.alive[dst] = True
+                m.num_dead = m.num_rows - int(m.alive.sum().item())
+        if app_src:
+            if len(app_src) == len(uuids):
+                m.append_rows(xt, codes)
+            else:
+                sel = torch.tensor(app_src, dtype=torch.int64, device=dev)
+                m.append_rows(xt[sel], codes[sel])
+        m.reindex()
+
+    def update_index_matrix(self, x, uuids: Optional[Sequence[Hashable]] = None) -> None:
+        """``update_index`` (reference lsh.py:331-383) for a ``[N, D]`` matrix, at device speed: hash,
+        append into the geometrically growing device buffers, re-index.  ``uuids[r]`` names row
+        ``r``; a uuid already present is overwritten in place.  Default uuids continue the row
+        numbering.  Like ``build_index_matrix`` this does not touch the ``descriptor_set`` /
+        ``hash2uuids_kvstore`` collaborators -- ``hash2uuids_view()`` serves their readers.
+
+        :raises ReadOnlyError: read-only index.  :raises ValueError: empty matrix."""
+        import torch
+        from smqtk_indexing_b200 import device
+        with self._model_lock:
+            if self.read_only:
+                raise ReadOnlyError("Cannot modify container attributes due to being in read-only mode.")
+            if x is None or len(x) == 0:
+                raise self._empty_iterable_exception()
+            m = self._mirror
+            if m.num_rows == 0:
+                return self.build_index_matrix(x, uuids)
+            if not isinstance(x, torch.Tensor):
+                x = torch.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32))
+            x = x.to(m.codes.device, torch.float32)
+            codes = self.lsh_functor.get_hash_packed(x)
+            if uuids is None and isinstance(m.uuids, range) and m.row_of is None:
+                m.append_rows(x, codes)                          # pure append, no per-row Python at all
+                m.uuids = range(m.num_rows)
+                m.reindex()
+            else:
+                if uuids is None:
+                    uuids = range(m.num_rows, m.num_rows + x.shape[0])
+                if len(uuids) != x.shape[0]:
+                    raise ValueError("uuids must name every row of x")
+                self._mirror_upsert(m, x, codes, uuids)
+            if isinstance(self.hash_index, LinearHashIndex):
+                self.hash_index.set_code_table(m.table)
+
+    def remove_from_index_matrix(self, uuids: Sequence[Hashable]) -> None:
+        """``remove_from_index`` (reference lsh.py:385-450) against the device-resident index: the rows
+        become tombstones (row numbers of the others do not move) and the unique table / CSR are
+        rebuilt over the live rows; buffers are compacted once half of them is dead.
+
+        :raises KeyError: a uuid is not in the index -- nothing is modified (lsh.py:407-416)."""
+        import torch
+        with self._model_lock:
+            if self.read_only:
+                raise ReadOnlyError("Cannot modify container attributes due to being in read-only mode.")
+            uuids = list(uuids)
+            if not uuids:
+                raise self._empty_iterable_exception()
+            m = self._mirror
+            if isinstance(m.uuids, range) and m.row_of is None:
+                rows = [int(u) if isinstance(u, (int, numpy.integer)) and 0 <= int(u) < m.num_rows else -1 for u in uuids]
+            else:
+                if m.row_of is None:
+                    m.row_of = {u: i for i, u in enumerate(m.uuids)}
+                rows = [m.row_of.get(u, -1) for u in uuids]
+            if m.num_rows == 0 or min(rows) < 0:
+                raise KeyError(uuids[rows.index(-1)] if -1 in rows else uuids[0])
+            sel = torch.tensor(rows, dtype=torch.int64, device=m.codes.device)
+            if m.alive is not None and not bool(m.alive[sel].all().item()):
+                raise KeyError(uuids[int((~m.alive[sel]).nonzero()[0].item())])
+            m.remove_rows(sel)
+            if m.row_of is not None:
+                for u in uuids:
+                    m.row_of.pop(u, None)
+            if m.num_dead * 2 > m.num_rows and not isinstance(m.uuids, range):
+                remap = m.compact()                              # re-indexes
+                if remap is not None:
+                    keep = torch.nonzero(remap >= 0).reshape(-1).cpu().tolist()
+                    m.uuids = [m.uuids[r] for r in keep]
+                    m.row_of = None
+            else:
+                m.reindex()
+            if isinstance(self.hash_index, LinearHashIndex):
+                self.hash_index.set_code_table(m.table)
+
+    def hash2uuids_view(self) -> "DeviceHashToUuids":
+        """Read-only ``KeyValueStore`` over the device index: ``{code int: set(uuid)}`` exactly as
+        ``build_index`` would have filled ``hash2uuids_kvstore`` (reference lsh.py:316-323), for
+        consumers of that store when the index was fed through the ``*_matrix`` methods."""
+        return DeviceHashToUuids(self)
+
     def count_rows(self) -> int:
-        """Descriptor rows in the device-resident index (see ``build_index_matrix``)."""
-        return self._mirror.num_rows
+        """Live descriptor rows in the device-resident index (see ``build_index_matrix``)."""
+        return self._mirror.num_live
 
     def nn_batch(self, queries, n: int = 1, return_device: bool = False):
         """Batched LSH query against the device-resident index.
@@ -425,3 +527,83 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
     def mirror_uuids(self) -> List[Hashable]:
         """row -> uuid for the rows returned by :meth:`nn_batch`."""
         return self._mirror.uuids
+
+
+class DeviceHashToUuids(KeyValueStore):
+    """Read-only ``KeyValueStore`` view ``{code int: set(uuid)}`` of a device-resident LSH index
+    (the shape ``LSHNearestNeighborIndex.build_index`` gives ``hash2uuids_kvstore``, reference
+    lsh.py:316-323).  Values are materialised from the code -> rows CSR on access; a snapshot of
+    the index at construction time is NOT taken -- the view follows later updates."""
+
+    def __init__(self, index: "LSHNearestNeighborIndex") -> None:
+        # no super().__init__(): Pluggable's constructor only enforces is_usable(), which is False on
+        # purpose (see below) -- instances are made by LSHNearestNeighborIndex.hash2uuids_view() only
+        self._index = index
+
+    @classmethod
+    def is_usable(cls) -> bool:
+        # a view bound to one index object, not something a config file can name: keep it out of
+        # ``KeyValueStore.get_impls()`` / default-config generation
+        return False
+
+    def get_config(self) -> Dict[str, Any]:
+        return {}
+
+    def __repr__(self) -> str:
+        return "<DeviceHashToUuids codes=%d>" % self.count()
+
+    def _state(self):
+        from smqtk_indexing_b200 import device
+        m = self._index._mirror
+        if m.table is None:
+            return [], None, None, m
+        ints = bitutil.words_to_ints(device.codes_to_host(m.table))
+        return ints, m.csr_off.cpu().numpy(), m.csr_rows.cpu().numpy(), m
+
+    def count(self) -> int:
+        return self._index._mirror.num_codes
+
+    def keys(self) -> Iterator[Hashable]:
+        return iter(self._state()[0])
+
+    def values(self) -> Iterator[Any]:
+        ints, off, rows, m = self._state()
+        for i in range(len(ints)):
+            yield {m.uuids[r] for r in rows[off[i]:off[i + 1]]}
+
+    def is_read_only(self) -> bool:
+        return True
+
+    def _find(self, key: Hashable):
+        ints, off, rows, m = self._state()
+        import bisect
+        i = bisect.bisect_left(ints, key) if isinstance(key, int) else len(ints)
+        if i < len(ints) and ints[i] == key:
+            return {m.uuids[r] for r in rows[off[i]:off[i + 1]]}
+        return None
+
+    def has(self, key: Hashable) -> bool:
+        return self._find(key) is not None
+
+    def get(self, key: Hashable, default: Any = NO_DEFAULT_VALUE) -> Any:
+        v = self._find(key)
+        if v is None:
+            if default is NO_DEFAULT_VALUE:
+                raise KeyError(key)
+            return default
+        return v
+
+    def add(self, key: Hashable, value: Any) -> "KeyValueStore":
+        raise ReadOnlyError("Cannot add to read-only instance %s." % self)
+
+    def add_many(self, d) -> "KeyValueStore":
+        raise ReadOnlyError("Cannot add to read-only instance %s." % self)
+
+    def remove(self, key: Hashable) -> "KeyValueStore":
+        raise ReadOnlyError("Cannot remove from read-only instance %s." % self)
+
+    def remove_many(self, keys) -> "KeyValueStore":
+        raise ReadOnlyError("Cannot remove from read-only instance %s." % self)
+
+    def clear(self) -> "KeyValueStore":
+        raise ReadOnlyError("Cannot clear a read-only %s instance." % type(self).__name__)

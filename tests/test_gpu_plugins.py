@@ -24,6 +24,7 @@ from smqtk_indexing_b200.interfaces import LshFunctor
 from smqtk_indexing_b200.impls.hash_index.linear import LinearHashIndex
 from smqtk_indexing_b200.impls.lsh_functor.itq import ItqFunctor
 from smqtk_indexing_b200.impls.nn_index.lsh import LSHNearestNeighborIndex
+from smqtk_indexing_b200.utils import bits as bitutil
 from smqtk_indexing_b200.utils import metrics
 
 pytestmark = pytest.mark.gpu
@@ -582,6 +583,101 @@ def test_simple_rp_functor_bits_and_lsh_use():
     index.build_index(_descr(x))
     r, d = index.nn(DescriptorMemoryElement(9999).set_vector(x[10]), 3)
     assert r[0].uuid() == 10 and d[0] == 0.0
+
+
+def _matrix_index(f):
+    return LSHNearestNeighborIndex(f, MemoryDescriptorSet(), MemoryKeyValueStore(), LinearHashIndex(), 'euclidean')
+
+
+def _same_neighbours(a, ua, b, ub, q, n):
+    """nn_batch of two indexes agrees once rows are translated to uuids (exact distances, same order)."""
+    ra, da = a.nn_batch(q, n)
+    rb, db = b.nn_batch(q, n)
+    np.testing.assert_array_equal(da, db)
+    ta = np.where(ra >= 0, np.asarray(ua, dtype=object)[np.clip(ra, 0, None)], None)
+    tb = np.where(rb >= 0, np.asarray(ub, dtype=object)[np.clip(rb, 0, None)], None)
+    assert (ta == tb).all()
+
+
+def test_matrix_update_remove_equal_fresh_build():
+    """update_index_matrix / remove_from_index_matrix (device-speed ingest: appended
+    buffers, tombstones, re-index over the live rows) leave the index in the state a fresh
+    build_index_matrix over the same rows gives -- reference semantics of lsh.py:331-450."""
+    import torch
+    rng = np.random.RandomState(31)
+    centres = rng.rand(60, 32)
+    x = (centres[rng.randint(0, 60, 6000)] + 0.05 * rng.randn(6000, 32)).astype(np.float32)
+    q = (centres[rng.randint(0, 60, 150)] + 0.05 * rng.randn(150, 32)).astype(np.float32)
+    f = ItqFunctor(bit_length=16, itq_iterations=10, random_seed=0)
+    f.fit_matrix(x)
+    x0, x1, x2 = x[:3000], x[3000:4500], x[4500:]
+
+    # pure appends with default uuids (= row numbers), two batches
+    a = _matrix_index(f)
+    a.update_index_matrix(x0)                       # empty index: same as build
+    a.update_index_matrix(x1)
+    a.update_index_matrix(x2)
+    fresh = _matrix_index(f)
+    fresh.build_index_matrix(x)
+    assert a.count_rows() == 6000 and a._mirror.num_codes == fresh._mirror.num_codes
+    _same_neighbours(a, range(6000), fresh, range(6000), q, 7)
+    assert torch.equal(a.hash_index.code_table, fresh.hash_index.code_table)
+
+    # removal: tombstones, rows keep their numbers; unknown / already removed uuid -> KeyError, nothing changes
+    gone = rng.choice(6000, 1700, replace=False)
+    a.remove_from_index_matrix([int(g) for g in gone])
+    keep = np.setdiff1d(np.arange(6000), gone)
+    fresh = _matrix_index(f)
+    fresh.build_index_matrix(x[keep], uuids=[int(k) for k in keep])
+    assert a.count_rows() == len(keep) and a._mirror.num_rows == 6000
+    _same_neighbours(a, range(6000), fresh, fresh.mirror_uuids(), q, 7)
+    for bad in ([int(gone[0])], [6000], [int(keep[0]), -5]):
+        with pytest.raises(KeyError):
+            a.remove_from_index_matrix(bad)
+    assert a.count_rows() == len(keep)
+    _same_neighbours(a, range(6000), fresh, fresh.mirror_uuids(), q, 7)
+    with pytest.raises(ValueError):
+        a.update_index_matrix(np.zeros((0, 32), np.float32))
+
+    # named uuids: overwrite in place, append the new ones, compaction once half the rows are dead
+    names = ["u%d" % i for i in range(6000)]
+    b = _matrix_index(f)
+    b.build_index_matrix(x0, uuids=names[:3000])
+    x_over = x[5000:5010]
+    b.update_index_matrix(np.concatenate([x_over, x1]), uuids=names[5:15] + names[3000:4500])
+    want = np.concatenate([x0, x1])
+    want[5:15] = x_over
+    fresh = _matrix_index(f)
+    fresh.build_index_matrix(want, uuids=names[:4500])
+    assert b.count_rows() == 4500
+    _same_neighbours(b, b.mirror_uuids(), fresh, names[:4500], q, 5)
+    b.remove_from_index_matrix(names[:2600])                   # > half dead: compacted
+    assert b._mirror.num_rows == b.count_rows() == 1900
+    fresh = _matrix_index(f)
+    fresh.build_index_matrix(want[2600:], uuids=names[2600:4500])
+    _same_neighbours(b, b.mirror_uuids(), fresh, names[2600:4500], q, 5)
+    b.update_index_matrix(x[:3], uuids=names[:3])              # removed uuids may come back
+    assert b.count_rows() == 1903
+
+    # the KeyValueStore view is what build_index would have put into hash2uuids_kvstore
+    view = b.hash2uuids_view()
+    ref = _matrix_index(f)
+    uu = b.mirror_uuids()
+    live = [r for r in range(b._mirror.num_rows)]
+    codes = f.get_hash_packed(b._mirror.x).cpu().numpy().view(np.uint32)
+    want_map = {}
+    for r in live:
+        want_map.setdefault(int(bitutil.words_to_ints(codes[r:r + 1])[0]), set()).add(uu[r])
+    assert view.count() == len(want_map) and set(view.keys()) == set(want_map)
+    assert {k: view.get(k) for k in view.keys()} == want_map
+    some = next(iter(want_map))
+    assert view.has(some) and not view.has(-1) and view.get(-1, None) is None
+    assert sum(len(v) for v in view.values()) == b.count_rows()
+    with pytest.raises(KeyError):
+        view.get(-1)
+    with pytest.raises(ReadOnlyError):
+        view.add(1, {2})
+    assert view.is_read_only() and ref.count_rows() == 0
 
 
 def test_itq_fit_streaming_equals_materialised():
