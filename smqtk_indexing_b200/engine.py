@@ -172,6 +172,32 @@ class DeviceLshIndex:
         self.set_rows(x, self.codes[live].contiguous())
         return remap
 
+    # ------------------------------------------------------------------ snapshot
+    def state_dict(self) -> dict:
+        """Host copy of what cannot be recomputed cheaply: descriptor rows, their codes, tombstones.
+        The unique table and the CSR are NOT stored -- ``load_state_dict`` re-derives them on the
+        device (a sort of the codes), which also keeps the format independent of their layout."""
+        return {
+            "format": "smqtk_indexing_b200.DeviceLshIndex/1",
+            "x": None if self.x is None else self.x.cpu(),
+            "codes": None if self.codes is None else self.codes.cpu(),
+            "alive": None if self.alive is None else self.alive.cpu(),
+        }
+
+    def load_state_dict(self, state: dict, dev) -> None:
+        if state.get("format") != "smqtk_indexing_b200.DeviceLshIndex/1":
+            raise ValueError("not a DeviceLshIndex snapshot: %r" % (state.get("format"),))
+        self.clear()
+        if state["codes"] is None:
+            return
+        x = None if state["x"] is None else state["x"].to(dev)
+        self.x, self.codes = x, state["codes"].to(dev)
+        self._x_buf, self._codes_buf = self.x, self.codes
+        if state["alive"] is not None:
+            self.alive = state["alive"].to(dev)
+            self.num_dead = self.num_rows - int(self.alive.sum().item())
+        self.reindex()
+
     def reindex(self) -> None:
         """Recompute the unique table and the CSR from the codes of the live rows."""
         if self.codes is None or self.num_live == 0:

@@ -491,6 +491,38 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
         consumers of that store when the index was fed through the ``*_matrix`` methods."""
         return DeviceHashToUuids(self)
 
+    def save_snapshot(self, path: str) -> None:
+        """Write the device-resident index (descriptor rows, codes, tombstones, row -> uuid) to
+        ``path`` (``torch.save``), so that a built index survives a restart without re-hashing:
+        ``load_snapshot`` re-derives the unique table and the CSR on the device.
+        The functor's model is NOT stored -- it has its own ``.npy`` caches (itq.py:212-237)."""
+        import torch
+        with self._model_lock:
+            m = self._mirror
+            state = m.state_dict()
+            state["uuids"] = ("range", len(m.uuids)) if isinstance(m.uuids, range) else ("list", list(m.uuids))
+            state["distance_method"] = self.distance_method
+            torch.save(state, path)
+
+    def load_snapshot(self, path: str) -> None:
+        """Replace the device-resident index by a snapshot written by ``save_snapshot``.
+
+        :raises ReadOnlyError: read-only index.  :raises ValueError: not a snapshot, or its codes
+            are wider than the functor's."""
+        import torch
+        from smqtk_indexing_b200 import device
+        with self._model_lock:
+            if self.read_only:
+                raise ReadOnlyError("Cannot modify container attributes due to being in read-only mode.")
+            state = torch.load(path, map_location="cpu", weights_only=False)
+            m = self._mirror
+            m.load_state_dict(state, device.device())
+            kind, val = state["uuids"]
+            m.uuids = range(val) if kind == "range" else list(val)     # type: ignore
+            m.row_of = None
+            if isinstance(self.hash_index, LinearHashIndex):
+                self.hash_index.set_code_table(m.table)
+
     def count_rows(self) -> int:
         """Live descriptor rows in the device-resident index (see ``build_index_matrix``)."""
         return self._mirror.num_live

@@ -659,6 +659,16 @@ def test_matrix_update_remove_equal_fresh_build():
     b.update_index_matrix(x[:3], uuids=names[:3])              # removed uuids may come back
     assert b.count_rows() == 1903
 
+    # snapshot: a restarted process reloads rows, codes, tombstones and uuids, re-derives table + CSR
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as td:
+        b.save_snapshot(os.path.join(td, "lsh.pt"))
+        c = _matrix_index(f)
+        c.load_snapshot(os.path.join(td, "lsh.pt"))
+    assert c.count_rows() == b.count_rows() and c.mirror_uuids() == b.mirror_uuids()
+    _same_neighbours(b, b.mirror_uuids(), c, c.mirror_uuids(), q, 5)
+    assert torch.equal(c.hash_index.code_table, b.hash_index.code_table)
+
     # the KeyValueStore view is what build_index would have put into hash2uuids_kvstore
     view = b.hash2uuids_view()
     ref = _matrix_index(f)

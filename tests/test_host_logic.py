@@ -300,6 +300,71 @@ def test_code_table_build_matches_oracle():
     assert e[0].shape == (0, 4) and e[2].tolist() == [0]
 
 
+def test_device_index_ingest_and_snapshot_logic_on_host_tensors(tmp_path):
+    """DeviceLshIndex bookkeeping (append into growing buffers, overwrite, tombstones, compaction,
+    snapshot round trip) is torch plumbing around codes.build_table: exercised here on CPU tensors
+    against the oracle's unique_code_table of the live rows."""
+    import torch
+    import np_oracle as O
+    from smqtk_indexing_b200.engine import DeviceLshIndex
+    rng = np.random.RandomState(3)
+
+    def rand_codes(n):
+        return torch.from_numpy(rng.randint(0, 40, size=(n, 2)).astype(np.uint32).view(np.int32))
+
+    def check(m, live_rows):
+        t, inv, off, rows = O.unique_code_table(m.codes.numpy().view(np.uint32)[live_rows])
+        assert np.array_equal(m.table.numpy().view(np.uint32), t)
+        assert np.array_equal(m.csr_off.numpy(), off)
+        assert np.array_equal(m.csr_rows.numpy(), np.asarray(live_rows)[rows])
+        assert np.array_equal(m.row_code.numpy()[live_rows], inv)
+        assert m.num_live == len(live_rows)
+
+    m = DeviceLshIndex()
+    c0, x0 = rand_codes(500), torch.rand(500, 8)
+    m.set_rows(x0, c0)
+    check(m, np.arange(500))
+    for n in (1, 300, 7):                                   # appends: buffers grow, views stay consistent
+        first = m.append_rows(torch.rand(n, 8), rand_codes(n))
+        assert first == m.num_rows - n
+        m.reindex()
+        check(m, np.arange(m.num_rows))
+    assert m._x_buf.shape[0] >= m.num_rows and torch.equal(m.x[:500], x0)
+    m.overwrite_rows(torch.tensor([3, 4]), torch.ones(2, 8), rand_codes(2))
+    m.reindex()
+    check(m, np.arange(m.num_rows))
+    assert torch.equal(m.x[3], torch.ones(8))
+    dead = rng.choice(m.num_rows, 200, replace=False)
+    m.remove_rows(torch.from_numpy(dead))
+    m.reindex()
+    live = np.setdiff1d(np.arange(m.num_rows), dead)
+    check(m, live)
+    assert (m.row_code.numpy()[dead] == -1).all() and m.num_dead == 200
+    # snapshot: same state after a round trip through torch.save (table / CSR re-derived)
+    path = str(tmp_path / "index.pt")
+    torch.save(m.state_dict(), path)
+    m2 = DeviceLshIndex()
+    m2.load_state_dict(torch.load(path, weights_only=False), "cpu")
+    check(m2, live)
+    assert torch.equal(m2.x, m.x) and m2.num_dead == 200
+    with pytest.raises(ValueError):
+        m2.load_state_dict({"format": "something else"}, "cpu")
+    # append after a removal keeps the tombstones; compaction drops them and returns the row map
+    m.append_rows(torch.rand(5, 8), rand_codes(5))
+    m.reindex()
+    live = np.concatenate([live, np.arange(m.num_rows - 5, m.num_rows)])
+    check(m, live)
+    codes_before = m.codes.numpy().copy()
+    remap = m.compact()
+    assert m.num_dead == 0 and m.num_rows == len(live)
+    assert np.array_equal(remap.numpy()[live], np.arange(len(live))) and (remap.numpy()[dead] == -1).all()
+    assert np.array_equal(m.codes.numpy(), codes_before[live])
+    check(m, np.arange(len(live)))
+    m.remove_rows(torch.arange(m.num_rows))
+    m.reindex()
+    assert m.table is None and m.num_live == 0
+
+
 def test_flat_l2_index_config_and_errors_need_no_device():
     from smqtk_descriptors.impls.descriptor_set.memory import MemoryDescriptorSet
     from smqtk_dataprovider.exceptions import ReadOnlyError
