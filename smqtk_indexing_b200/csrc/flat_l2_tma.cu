@@ -16,8 +16,11 @@
 //     x.q - |x|^2/2 - h and "d2 <= tq" is a sign test.
 //   * Tile = 128 rows x 256 queries, accumulators double-buffered in TMEM (2 x 256 columns):
 //     the epilogue of tile t overlaps the MMAs of tile t+1.
-// Warp roles (8 warps): 0 TMA producer (A ring), 1 MMA issue + TMEM alloc, 2 B loader,
-// 3 synthetic-A writer, 4-7 epilogue (TMEM lane quadrants).
+// Warp roles (12 warps): 0 TMA producer (A ring), 1 MMA issue + TMEM alloc, 2 B loader,
+// 3 synthetic-A writer, 4-11 epilogue (TMEM lane quadrant = (warp - 4) % 4, column half =
+// (warp - 4) / 4).  The epilogue is a chain of dependent integer ops per warp, so it wants warps:
+// it reads 32 accumulators per tcgen05.ld and ANDs their sign bits -- no survivor among the 32
+// (the common case), no per-element work.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -35,8 +38,10 @@ constexpr int B_GROUP = QB * 128;           // 32 KB
 constexpr int B_SYN = 2 * QB * 16;          // 8 KB  (no-swizzle, 2 K chunks)
 constexpr int A_SYN = 2 * TM * 16;          // 4 KB  (no-swizzle, 2 K chunks)
 constexpr int STAGES = 4;
-constexpr int SQ_CAP = 96;                  // survivor queue entries per epilogue warp and tile
-constexpr int THREADS = 256;
+constexpr int SQ_CAP = 64;                  // survivor queue entries per epilogue warp and tile
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_COLS = QB / 2;            // columns per epilogue warp
+constexpr int THREADS = (4 + EPI_WARPS) * 32;   // 384
 
 struct TmaL2Params {
   long long n;                 // rows in this chunk
@@ -70,11 +75,11 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
   const uint32_t acc_full = syn_empty + 16, acc_empty = acc_full + 16;
   const uint32_t b_full = acc_empty + 16, b_empty = b_full + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
-  // per-epilogue-warp survivor queues: [4][SQ_CAP] x (u64 key, i32 query) + a counter each
+  // per-epilogue-warp survivor queues: [8][SQ_CAP] x (u64 key, i32 query) + a counter each
   unsigned long long* sq_key = reinterpret_cast<unsigned long long*>(bars + 2 * STAGES + 12);
-  int* sq_q = reinterpret_cast<int*>(sq_key + 4 * SQ_CAP);
-  int* sq_cnt = sq_q + 4 * SQ_CAP;
-  float* s_tq = reinterpret_cast<float*>(sq_cnt + 4);          // [4 warps][256]: this block's thresholds
+  int* sq_q = reinterpret_cast<int*>(sq_key + EPI_WARPS * SQ_CAP);
+  int* sq_cnt = sq_q + EPI_WARPS * SQ_CAP;
+  float* s_tq = reinterpret_cast<float*>(sq_cnt + EPI_WARPS);  // [8 warps][128]: this block's thresholds
 
   const long long row_tiles = (p.n + TM - 1) / TM;
   const long long my_tiles = (row_tiles > (long long)blockIdx.x) ? (row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -83,7 +88,7 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
     for (int s = 0; s < STAGES; ++s) { mbar_init(a_full + s * 8, 1); mbar_init(a_empty + s * 8, 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(syn_full + b * 8, 1); mbar_init(syn_empty + b * 8, 1);
-      mbar_init(acc_full + b * 8, 1); mbar_init(acc_empty + b * 8, 4);
+      mbar_init(acc_full + b * 8, 1); mbar_init(acc_empty + b * 8, EPI_WARPS);
     }
     mbar_init(b_full, 1); mbar_init(b_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -119,6 +124,11 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(QB >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       const uint64_t bsyn_desc = umma_desc(smem_u32(s_bsyn), QB * 16, 128);
+      // descriptors differ only in the 14-bit start-address field (shared window < 256 KB: no carry out
+      // of it): one 64-bit add per operand and MMA instead of rebuilding them in the issuing thread
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(s_a));
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(s_b));
+      const uint64_t asyn_desc0 = umma_desc(smem_u32(s_asyn), TM * 16, 128);
       int stage = 0;
       uint32_t phase = 0;
       long long t = 0;
@@ -134,16 +144,17 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
           for (int g = 0; g < G; ++g) {
             mbar_wait(a_full + stage * 8, phase);
             tc_fence_after();
-            const uint32_t a0 = smem_u32(s_a + (size_t)stage * A_STAGE), b0 = smem_u32(s_b + (size_t)g * B_GROUP);
+            const uint64_t a_desc = a_desc0 + (uint64_t)((stage * A_STAGE) >> 4);
+            const uint64_t b_desc = b_desc0 + (uint64_t)((g * B_GROUP) >> 4);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_tf32(d_tmem, umma_desc_sw128(a0 + ks * 32), umma_desc_sw128(b0 + ks * 32), idesc, (g | ks) ? 1u : 0u);
+              umma_tf32(d_tmem, a_desc + (uint64_t)((ks * 32) >> 4), b_desc + (uint64_t)((ks * 32) >> 4), idesc, (g | ks) ? 1u : 0u);
             umma_commit(a_empty + stage * 8);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           mbar_wait(syn_full + buf * 8, use);
           tc_fence_after();
-          umma_tf32(d_tmem, umma_desc(smem_u32(s_asyn + buf * A_SYN), TM * 16, 128), bsyn_desc, idesc, 1u);
+          umma_tf32(d_tmem, asyn_desc0 + (uint64_t)((buf * A_SYN) >> 4), bsyn_desc, idesc, 1u);
           umma_commit(syn_empty + buf * 8);
           umma_commit(acc_full + buf * 8);
         }
@@ -194,14 +205,20 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
       }
   } else {
     // =========================== epilogue: sign test, survivors appended ===========================
-    const int ew = warp - 4;                                     // TMEM lane quadrant
+    const int ewi = warp - 4;                                    // epilogue warp index
+    const int ew = ewi & 3;                                      // TMEM lane quadrant
+    const int half = ewi >> 2;                                   // which 128 of the 256 query columns
     long long t = 0;
-    float* my_tq = s_tq + ew * QB;
+    float* my_tq = s_tq + ewi * EPI_COLS;
+    unsigned long long* myq_key = sq_key + ewi * SQ_CAP;
+    int* myq_q = sq_q + ewi * SQ_CAP;
+    int* myq_cnt = sq_cnt + ewi;
     for (int jb = 0; jb < p.col_blocks; ++jb) {
-      // thresholds of this query block, private copy per warp (a survivor's d2 = tq - 2 * accumulator)
+      // thresholds of this warp's columns, private copy (a survivor's d2 = tq - 2 * accumulator)
       __syncwarp();
-      for (int c = lane; c < QB; c += 32) my_tq[c] = __ldcg(p.tq + (long long)jb * QB + c);
+      for (int c = lane; c < EPI_COLS; c += 32) my_tq[c] = __ldcg(p.tq + (long long)jb * QB + half * EPI_COLS + c);
       __syncwarp();
+      const int q0 = jb * QB + half * EPI_COLS;
       for (long long i = 0; i < my_tiles; ++i, ++t) {
         const long long rt = blockIdx.x + i * gridDim.x;
         const int buf = (int)(t & 1);
@@ -210,20 +227,16 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
         const bool rvalid = row < p.n;
         mbar_wait(acc_full + buf * 8, use);
         tc_fence_after();
-        const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * QB);
+        const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * QB + half * EPI_COLS);
         const unsigned row_id = p.row_base + (unsigned)row;
-        const int q0 = jb * QB;
-        unsigned long long* myq_key = sq_key + ew * SQ_CAP;
-        int* myq_q = sq_q + ew * SQ_CAP;
-        int* myq_cnt = sq_cnt + ew;
         if (lane == 0) *myq_cnt = 0;
         __syncwarp();
-        uint32_t va[16], vb[16];                                  // ping-pong: no register copies
-        tmem_ld16(tbase, va);
         if (p.dense) {
           // seed chunk: buf[query][row] = key for every pair (row < cap by construction)
+          uint32_t va[16];
 #pragma unroll 1
-          for (int g16 = 0; g16 < QB / 16; ++g16) {
+          for (int g16 = 0; g16 < EPI_COLS / 16; ++g16) {
+            tmem_ld16(tbase + (uint32_t)(g16 * 16), va);
             if (rvalid) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -232,19 +245,44 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
                 p.cand_buf[qg * p.cap + row] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)row_id;
               }
             }
-            if (g16 + 1 < QB / 16) tmem_ld16(tbase + (uint32_t)((g16 + 1) * 16), va);
           }
-        } else
-#pragma unroll 1
-        for (int g16 = 0; g16 < QB / 16; g16 += 2) {
-          tmem_ld16_nowait(tbase + (uint32_t)((g16 + 1) * 16), vb);
-          unsigned m = rvalid ? nonneg_mask16(va) : 0u;
-          if (m) SB_L2_QUEUE(m, va, q0, g16 * 16, row_id, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
+        } else {
+          uint32_t va[32], vb[32];                                // ping-pong: one load in flight while the other is tested
+          tmem_ld32_nowait(tbase, va);
           tmem_ld_wait();
-          if (g16 + 2 < QB / 16) tmem_ld16_nowait(tbase + (uint32_t)((g16 + 2) * 16), va);
-          m = rvalid ? nonneg_mask16(vb) : 0u;
-          if (m) SB_L2_QUEUE(m, vb, q0, (g16 + 1) * 16, row_id, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
-          tmem_ld_wait();
+#pragma unroll
+          for (int c32 = 0; c32 < EPI_COLS / 32; c32 += 2) {
+            tmem_ld32_nowait(tbase + (uint32_t)((c32 + 1) * 32), vb);
+            {
+              uint32_t a = 0xffffffffu;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a &= va[j];
+              if (rvalid && !(a >> 31)) {                         // some accumulator is non-negative: a survivor
+                const uint32_t(&lo)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&va[0]);
+                const uint32_t(&hi)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&va[16]);
+                unsigned m = nonneg_mask16(lo);
+                if (m) SB_L2_QUEUE(m, lo, q0, c32 * 32, row_id, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
+                m = nonneg_mask16(hi);
+                if (m) SB_L2_QUEUE(m, hi, q0, c32 * 32 + 16, row_id, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
+              }
+            }
+            tmem_ld_wait();
+            if (c32 + 2 < EPI_COLS / 32) tmem_ld32_nowait(tbase + (uint32_t)((c32 + 2) * 32), va);
+            {
+              uint32_t a = 0xffffffffu;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a &= vb[j];
+              if (rvalid && !(a >> 31)) {
+                const uint32_t(&lo)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&vb[0]);
+                const uint32_t(&hi)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&vb[16]);
+                unsigned m = nonneg_mask16(lo);
+                if (m) SB_L2_QUEUE(m, lo, q0, (c32 + 1) * 32, row_id, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
+                m = nonneg_mask16(hi);
+                if (m) SB_L2_QUEUE(m, hi, q0, (c32 + 1) * 32 + 16, row_id, my_tq, myq_key, myq_q, myq_cnt, SQ_CAP, p.cand_buf, p.cand_cnt, p.cap);
+              }
+            }
+            tmem_ld_wait();
+          }
         }
         // the accumulator buffer is free: let the next tile's MMAs start, THEN pay for the appends
         tc_fence_before();
@@ -289,7 +327,7 @@ EncodeTiledFn encode_tiled() {
 
 size_t tma_smem_bytes(int G) {
   return 1024 + (size_t)G * B_GROUP + (size_t)STAGES * A_STAGE + B_SYN + 2 * A_SYN + (2 * STAGES + 12) * 8 +
-         4 * SQ_CAP * 12 + 16 + 4 * QB * sizeof(float);
+         EPI_WARPS * SQ_CAP * 12 + EPI_WARPS * 4 + EPI_WARPS * EPI_COLS * sizeof(float);
 }
 
 // Queries -> per-block image: G groups of [256 rows x 128 B] in the SWIZZLE_128B K-major order
