@@ -157,6 +157,14 @@ def itq_hash(X: torch.Tensor, mean: Optional[torch.Tensor], R: torch.Tensor, nor
 #: streams the table once per handful of queries and is bound by HBM, which is the better regime)
 TC_SCAN_MIN_QUERIES = 64
 TC_SCAN_MIN_ROWS = 1 << 16
+#: ... and this many (query, row) pairs: the tensor-core scan runs ~5.7e12 pairs/s plus ~0.25 ms of
+#: per-batch bookkeeping (8 chunks x 4 launches), the XOR/POPC scan ~0.9e12 pairs/s with none
+TC_SCAN_MIN_PAIRS = 1 << 28
+
+
+def _tc_scan_pays(U: int, W: int, Q: int, k: int) -> bool:
+    return (Q >= TC_SCAN_MIN_QUERIES and U >= TC_SCAN_MIN_ROWS and Q * U >= TC_SCAN_MIN_PAIRS
+            and hamming_scan_tc_supported(U, W, Q, k))
 #: set by hamming_scan_keys: how many batches overflowed a candidate buffer and were re-run
 TC_SCAN_OVERFLOWS = 0
 SCAN_VARIANT_TC = 3
@@ -245,8 +253,7 @@ def hamming_scan_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int =
         raise ValueError("query codes have %d words, table has %d" % (q.shape[1], W))
     if variant == SCAN_VARIANT_TC and not hamming_scan_tc_supported(U, W, Q, k):
         raise ValueError("tensor-core scan does not support U=%d W=%d Q=%d k=%d" % (U, W, Q, k))
-    if variant == SCAN_VARIANT_TC or (variant == 0 and not force_popc.active and Q >= TC_SCAN_MIN_QUERIES
-                                      and U >= TC_SCAN_MIN_ROWS and hamming_scan_tc_supported(U, W, Q, k)):
+    if variant == SCAN_VARIANT_TC or (variant == 0 and not force_popc.active and _tc_scan_pays(U, W, Q, k)):
         keys, flag = hamming_scan_keys_tc(db, q, k, idx_base)
         if deferred_scan_check.active is not None:
             deferred_scan_check.active.flags.append(flag)       # checked once, at the end of the pipeline
@@ -290,8 +297,7 @@ def hamming_topk(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0):
     Q = q.shape[0]
     if q.shape[1] != W:
         raise ValueError("query codes have %d words, table has %d" % (q.shape[1], W))
-    if (not force_popc.active and Q >= TC_SCAN_MIN_QUERIES and U >= TC_SCAN_MIN_ROWS
-            and hamming_scan_tc_supported(U, W, Q, k)):
+    if not force_popc.active and _tc_scan_pays(U, W, Q, k):
         # large batch over a large table: tensor-core scan (falls back to XOR/POPC on overflow), then decode
         return topk_merge(hamming_scan_keys(db, q, k, idx_base).unsqueeze(0))
     lib = _lib.load()

@@ -114,7 +114,7 @@ def test_hamming_tensor_core_scan_bit_exact(dev, b, W):
     256, idx_base, a query equal to a table row."""
     rng = np.random.RandomState(100 + b)
     for U, Q, k in [(1, 1, 1), (7, 3, 10), (1000, 5, 10), (4097, 257, 10), (20000, 130, 7), (3000, 2, 100),
-                    (70001, 300, 33), (9000, 20, 256)]:
+                    (70001, 300, 33), (9000, 20, 256), (5000, 600, 5), (3000, 1500, 3)]:
         table = _rand_table(rng, U, b, W)
         q = O.pack_codes(rng.rand(Q, b) > 0.5, W)
         q[0] = table[U // 2]
@@ -164,6 +164,8 @@ def test_hamming_scan_dispatch_and_overflow_fallback(dev):
     table = _rand_table(rng, 100000, 256, 8)
     q = O.pack_codes(rng.rand(200, 256) > 0.5, 8)
     dt, dq = dev.codes_to_device(table), dev.codes_to_device(q)
+    assert not dev._tc_scan_pays(100000, 8, 200, 10) and dev._tc_scan_pays(10_000_000, 8, 64, 10)
+    assert dev._tc_scan_pays(100000, 8, 4096, 10) and not dev._tc_scan_pays(10_000_000, 32, 4096, 10)
     k_auto = dev.hamming_scan_keys(dt, dq, 10)
     k_tc = dev.hamming_scan_keys(dt, dq, 10, variant=dev.SCAN_VARIANT_TC)
     k_popc = dev.hamming_scan_keys(dt, dq, 10, variant=1)
@@ -177,13 +179,13 @@ def test_hamming_scan_dispatch_and_overflow_fallback(dev):
     # pipeline form (engine.py / distributed.py): no sync inside the context, one check at the end, re-run forced
     # onto the XOR/POPC scan
     with dev.deferred_scan_check() as chk:
-        dev.hamming_scan_keys(ds, dq, 10)
+        dev.hamming_scan_keys(ds, dq, 10, variant=dev.SCAN_VARIANT_TC)
         assert len(chk.flags) == 1
     assert chk.overflowed() and dev.TC_SCAN_OVERFLOWS == before + 2
     with dev.force_popc():
         assert torch.equal(dev.hamming_scan_keys(ds, dq, 10), keys)
     with dev.deferred_scan_check() as chk:
-        k_ok = dev.hamming_scan_keys(dt, dq, 10)
+        k_ok = dev.hamming_scan_keys(dt, dq, 10, variant=dev.SCAN_VARIANT_TC)
     assert not chk.overflowed() and torch.equal(k_ok, k_popc)
 
 
