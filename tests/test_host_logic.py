@@ -45,6 +45,36 @@ def test_workspace_query_needs_no_device():
     assert lib.sb_hamming_scan_workspace_bytes(10, 3, 1, 1) == 0      # unsupported word count
 
 
+def test_tensor_core_entry_points_shape_rules_need_no_device():
+    """`*_supported` / `*_workspace_bytes` of the tcgen05 entry points are host-side arithmetic: the
+    shape rules stated in include/smqtk_b200.h, and the dispatcher's work threshold."""
+    from smqtk_indexing_b200 import _lib, device
+    lib = _lib.load()
+    for W in (1, 2, 4, 8):
+        assert lib.sb_hamming_scan_tc_supported(10_000_000, W, 4096, 10) == 1
+    for U, W, Q, k in [(10_000_000, 16, 4096, 10), (10_000_000, 3, 4096, 10), (10_000_000, 8, 4096, 257),
+                       (0, 8, 4096, 10), (10_000_000, 8, 0, 10), (1 << 38, 8, 1, 1)]:
+        assert lib.sb_hamming_scan_tc_supported(U, W, Q, k) == 0
+        assert lib.sb_hamming_scan_tc_workspace_bytes(U, W, Q, k) == 0
+    small = lib.sb_hamming_scan_tc_workspace_bytes(10_000_000, 8, 256, 10)
+    big = lib.sb_hamming_scan_tc_workspace_bytes(10_000_000, 8, 4096, 10)
+    assert 0 < small < big < (1 << 30)
+    # query image (72 KB per 256 queries) + candidate buffers (4096 keys per query) dominate
+    assert big >= 16 * 73728 + 4096 * 4096 * 8
+    assert lib.sb_hamming_scan_tc_workspace_bytes(10_000_000, 8, 4096, 256) > big
+    # dispatcher: large batches over large tables only
+    assert device._tc_scan_pays(10_000_000, 8, 4096, 10) and device._tc_scan_pays(1_250_000, 8, 512, 10)
+    assert not device._tc_scan_pays(10_000_000, 8, 1, 10) and not device._tc_scan_pays(50_000, 8, 4096, 10)
+    assert not device._tc_scan_pays(10_000_000, 16, 4096, 10)
+    # training Gram: D % 32, 16-byte rows, b % 4, b <= 256
+    assert lib.sb_fit_gram_bits_tc_supported(50_000_000, 256, 256, 256) == 1
+    assert lib.sb_fit_gram_bits_tc_supported(1000, 48, 48, 32) == 0          # D % 32
+    assert lib.sb_fit_gram_bits_tc_supported(1000, 64, 66, 32) == 0          # row pitch not 16-byte aligned
+    assert lib.sb_fit_gram_bits_tc_supported(1000, 64, 64, 30) == 0          # b % 4
+    assert lib.sb_fit_gram_bits_tc_supported(1000, 512, 512, 512) == 0       # b > 256
+    assert lib.sb_fit_gram_bits_tc_workspace_bytes(50_000_000, 256, 256) >= 256 * 256 * 8
+
+
 def test_no_silent_cpu_fallback():
     """Without a CUDA device every compute entry point must raise."""
     import torch
