@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
   } else if (warp < EPI_WARPS) {
     // =========================== epilogue: sign test, survivors queued ===========================
     const int ew = warp;                                         // TMEM lane quadrant = granule of the tile
-    long long t[NB] = {0, 0};
+    uint32_t par = 0u;                                           // bit blk: parity of accumulator buffer blk's next "full"
     int* my_tq = s_tq + warp * (NB * QB);
     const long long vg_first = p.vg0 + (long long)blockIdx.x * 4 + ew;
     const long long pg_first = (long long)(((unsigned long long)vg_first * (unsigned long long)p.P) % (unsigned long long)p.NG);
@@ -335,8 +335,8 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
         for (int blk = 0; blk < nb; ++blk) {
           const int q0 = (jb + blk) * QB;
           const int* tq_blk = my_tq + blk * QB;
-          mbar_wait(acc_full + blk * 8, (uint32_t)(t[blk] & 1));
-          ++t[blk];
+          mbar_wait(acc_full + blk * 8, (par >> blk) & 1u);
+          par ^= 1u << blk;
           tc_fence_after();
           const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(blk * QB);
           unsigned hit[QB / 32];                                     // lanes with a survivor in each 32-column group
