@@ -9,6 +9,7 @@ using, so raw bits are carried in signed tensors of the same width):
   codes  uint32[rows, W]  -> torch.int32
   keys   uint64[...]      -> torch.int64
 """
+import threading
 from typing import Optional, Tuple
 
 import numpy as np
@@ -189,24 +190,30 @@ def hamming_scan_keys_tc(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: in
     return keys, flag
 
 
+_scan_tls = threading.local()       # per-thread dispatch state: callers may drive several indexes from several threads
+
+
 class deferred_scan_check:
     """Context manager for a pipeline of several stages: inside it the tensor-core scan does NOT
     synchronise to read its overflow flag (the keys of an overflowed batch are still valid table
     rows, only possibly not the nearest, so the later stages are safe to launch); the flags are
     collected in ``self.flags`` and the caller asks ``overflowed()`` once, after the last stage,
     and re-runs the batch with ``force_popc()`` if it says so."""
-    active = None
 
     def __init__(self) -> None:
         self.flags = []
 
+    @staticmethod
+    def current() -> Optional["deferred_scan_check"]:
+        return getattr(_scan_tls, "deferred", None)
+
     def __enter__(self):
-        self._prev = deferred_scan_check.active
-        deferred_scan_check.active = self
+        self._prev = deferred_scan_check.current()
+        _scan_tls.deferred = self
         return self
 
     def __exit__(self, *exc):
-        deferred_scan_check.active = self._prev
+        _scan_tls.deferred = self._prev
 
     def flag_tensor(self) -> Optional[torch.Tensor]:
         """All collected flags folded into one int32[1] tensor (None if the scan never deferred)."""
@@ -228,14 +235,17 @@ class deferred_scan_check:
 
 class force_popc:
     """Context manager: ``hamming_scan_keys`` / ``hamming_topk`` stay on the XOR/POPC scan."""
-    active = False
+
+    @staticmethod
+    def on() -> bool:
+        return bool(getattr(_scan_tls, "force_popc", False))
 
     def __enter__(self):
-        self._prev = force_popc.active
-        force_popc.active = True
+        self._prev = force_popc.on()
+        _scan_tls.force_popc = True
 
     def __exit__(self, *exc):
-        force_popc.active = self._prev
+        _scan_tls.force_popc = self._prev
 
 
 def hamming_scan_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0,
@@ -253,10 +263,11 @@ def hamming_scan_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int =
         raise ValueError("query codes have %d words, table has %d" % (q.shape[1], W))
     if variant == SCAN_VARIANT_TC and not hamming_scan_tc_supported(U, W, Q, k):
         raise ValueError("tensor-core scan does not support U=%d W=%d Q=%d k=%d" % (U, W, Q, k))
-    if variant == SCAN_VARIANT_TC or (variant == 0 and not force_popc.active and _tc_scan_pays(U, W, Q, k)):
+    if variant == SCAN_VARIANT_TC or (variant == 0 and not force_popc.on() and _tc_scan_pays(U, W, Q, k)):
         keys, flag = hamming_scan_keys_tc(db, q, k, idx_base)
-        if deferred_scan_check.active is not None:
-            deferred_scan_check.active.flags.append(flag)       # checked once, at the end of the pipeline
+        pending = deferred_scan_check.current()
+        if pending is not None:
+            pending.flags.append(flag)                           # checked once, at the end of the pipeline
             return keys
         if int(flag.item()) == 0:
             return keys
@@ -297,7 +308,7 @@ def hamming_topk(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0):
     Q = q.shape[0]
     if q.shape[1] != W:
         raise ValueError("query codes have %d words, table has %d" % (q.shape[1], W))
-    if not force_popc.active and _tc_scan_pays(U, W, Q, k):
+    if not force_popc.on() and _tc_scan_pays(U, W, Q, k):
         # large batch over a large table: tensor-core scan (falls back to XOR/POPC on overflow), then decode
         return topk_merge(hamming_scan_keys(db, q, k, idx_base).unsqueeze(0))
     lib = _lib.load()
