@@ -29,6 +29,7 @@ import os
 import statistics
 import subprocess
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -104,9 +105,11 @@ class ClockSampler:
         self.sm, self.mx, self.reasons = [], [], set()
         self.errors, self.last_error, self.sample_now = 0, None, None
 
-    def _nvml_loop(self, nv, h):
-        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
-                else nv.nvmlClocksThrottleReasonHwSlowdown,
+    def _make_sampler(self, nv, h):
+        """The NVML queries of one sample, bound to a device handle (built in the calling thread so that
+        `sample_now` exists before the timed region starts, whatever the polling thread's scheduling)."""
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown",
+                                       getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0)),
                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
                                                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
@@ -120,23 +123,27 @@ class ClockSampler:
         except Exception as e:
             sys.stderr.write("clock sampler: max clock query failed: %r\n" % (e,))
             mx = float("nan")
+        lock = threading.Lock()
 
         def sample():
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                self.mx.append(mx)
-                if get_reasons is not None:
-                    r = int(get_reasons(h))
-                    for nm, bit in bits.items():
-                        if bit and (r & bit):
-                            self.reasons.add(nm)
-            except Exception as e:
-                self.errors += 1
-                self.last_error = repr(e)
+            with lock:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    self.mx.append(mx)
+                    if get_reasons is not None:
+                        r = int(get_reasons(h))
+                        for nm, bit in bits.items():
+                            if bit and (r & bit):
+                                self.reasons.add(nm)
+                except Exception as e:
+                    self.errors += 1
+                    self.last_error = repr(e)
 
-        self.sample_now = sample
+        return sample
+
+    def _nvml_loop(self):
         while not self.stop_flag:
-            sample()
+            self.sample_now()
             time.sleep(0.004)
 
     def sample_between_steps(self):
@@ -148,11 +155,11 @@ class ClockSampler:
     def start(self):
         try:
             import pynvml as nv
-            import threading
             nv.nvmlInit()
             gid = str(self.gpu_index)
             h = nv.nvmlDeviceGetHandleByUUID(gid) if gid.startswith("GPU-") else nv.nvmlDeviceGetHandleByIndex(int(gid))
-            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.sample_now = self._make_sampler(nv, h)
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
             self.thread.start()
             return
         except Exception:
