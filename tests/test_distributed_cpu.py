@@ -99,6 +99,14 @@ def _worker(rank, world, port, cuts, out_q):
             rows_q, d_q = idx.query(torch.from_numpy(q), n)
             idx.scan_partition = "auto"
             assert torch.equal(rows_q, rows) and torch.equal(d_q, d)
+        # fewer queries than ranks: the trailing ranks scan a padding row and contribute nothing
+        idx.scan_partition = "queries"
+        rows_1, d_1 = idx.query(torch.from_numpy(q[:1]), 5)
+        idx.scan_partition = "rows"
+        rows_r, d_r = idx.query(torch.from_numpy(q[:1]), 5)
+        idx.scan_partition = "auto"
+        assert torch.equal(rows_1, rows_r) and torch.equal(d_1, d_r)
+        assert torch.equal(rows_1[0], torch.from_numpy(res[5][0][0])) and torch.equal(d_1[0], torch.from_numpy(res[5][1][0]))
         out_q.put((rank, idx.num_rows, idx.num_codes, (idx.scan_lo, idx.scan_hi), res))
     finally:
         dist.destroy_process_group()
