@@ -1,3 +1,9 @@
 mkdir -p gpurun_out
-timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29701 tools/l2_sharded_bench.py 12.5e6 100 2>gpurun_out/l2s.err | tee gpurun_out/r1_flat_l2_sharded_n8.log
-tail -3 gpurun_out/l2s.err
+for n in 4 8; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2961$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/r1b_bench_n$n.json 2> gpurun_out/r1b_bench_n$n.err; echo "n=$n rc=$?"
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/r1b_bench_n$n.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','n_gpus','gpu_launches')}, d['e2e']['value'], d['kernel_ms_per_step'], d['clocks'])
+PY
+done
