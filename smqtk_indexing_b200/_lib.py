@@ -107,6 +107,30 @@ def load() -> ctypes.CDLL:
     return _lib
 
 
+ENV_ASSUME_USABLE = "SMQTK_B200_ASSUME_USABLE"
+_usable = None
+
+
+def usable() -> bool:
+    """``is_usable()`` of every plugin class: the C-ABI library is present AND a CUDA device is visible
+    (the reference's optional impls answer the same question about their imports, e.g.
+    smqtk_indexing/impls/hash_index/sklearn_balltree.py:43-45).  ``SMQTK_B200_ASSUME_USABLE=1`` skips the
+    device half only -- for host-logic tests and config generation in a container without a GPU; compute
+    entry points still raise there."""
+    global _usable
+    if not os.path.exists(LIB_PATH):
+        return False
+    if os.environ.get(ENV_ASSUME_USABLE, "") not in ("", "0"):
+        return True
+    if _usable is None:
+        try:
+            import torch
+            _usable = bool(torch.cuda.is_available())
+        except Exception:
+            _usable = False
+    return _usable
+
+
 def check(rc: int) -> None:
     if rc != SB_OK:
         msg = load().sb_last_error()

@@ -33,8 +33,9 @@ class LinearHashIndex(HashIndex):
 
     @classmethod
     def is_usable(cls) -> bool:
-        # Importable anywhere; compute entry points raise without a CUDA device.
-        return True
+        # library built and a CUDA device visible (no CPU implementation exists to fall back to)
+        from smqtk_indexing_b200 import _lib
+        return _lib.usable()
 
     @classmethod
     def get_default_config(cls) -> Dict[str, Any]:

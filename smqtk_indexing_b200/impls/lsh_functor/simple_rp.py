@@ -34,7 +34,9 @@ class SimpleRPFunctor(LshFunctor):
 
     @classmethod
     def is_usable(cls) -> bool:
-        return True
+        # library built and a CUDA device visible (no CPU implementation exists to fall back to)
+        from smqtk_indexing_b200 import _lib
+        return _lib.usable()
 
     def __init__(self, bit_length: int = 8, normalize: Optional[Union[int, float, str]] = None,
                  random_seed: Optional[int] = None):

@@ -37,7 +37,9 @@ class FlatL2NearestNeighborsIndex(NearestNeighborsIndex):
 
     @classmethod
     def is_usable(cls) -> bool:
-        return True
+        # library built and a CUDA device visible (no CPU implementation exists to fall back to)
+        from smqtk_indexing_b200 import _lib
+        return _lib.usable()
 
     @classmethod
     def get_default_config(cls) -> Dict[str, Any]:

@@ -142,6 +142,96 @@ def test_plugins_are_discoverable():
     assert LinearHashIndex.is_usable() and ItqFunctor.is_usable() and LSHNearestNeighborIndex.is_usable()
 
 
+def test_is_usable_needs_library_and_device(monkeypatch):
+    """is_usable() = C-ABI library present AND a CUDA device visible."""
+    import torch
+    monkeypatch.setattr(_lib, "_usable", None)
+    monkeypatch.delenv(_lib.ENV_ASSUME_USABLE, raising=False)
+    assert LinearHashIndex.is_usable() == torch.cuda.is_available()
+    assert ItqFunctor.is_usable() == torch.cuda.is_available()
+    assert LSHNearestNeighborIndex.is_usable() == torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        assert LinearHashIndex not in HashIndex.get_impls()
+        with pytest.raises(RuntimeError):                      # Pluggable.__init__ refuses unusable impls
+            LinearHashIndex()
+    monkeypatch.setenv(_lib.ENV_ASSUME_USABLE, "1")
+    assert LinearHashIndex.is_usable()
+    monkeypatch.setattr(_lib, "LIB_PATH", _lib.LIB_PATH + ".missing")
+    assert not LinearHashIndex.is_usable()                     # no library: never usable
+
+
+def test_entry_points_discover_plugins_from_a_fresh_interpreter(tmp_path):
+    """The package is INSTALLED (pip, offline) into a scratch directory and a fresh interpreter that
+    imports nothing but the interfaces must find every implementation through the `smqtk_plugins`
+    entry-point group -- the reference's registration mechanism (pyproject.toml:71-82), which is what
+    LSHNearestNeighborIndex.from_config relies on (impls/nn_index/lsh.py:88-97)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    target = str(tmp_path / "site")
+    src = str(tmp_path / "src")
+    import shutil
+    os.makedirs(src)
+    shutil.copy(os.path.join(root, "pyproject.toml"), src)
+    shutil.copy(os.path.join(root, "README.md"), src)
+    shutil.copytree(os.path.join(root, "smqtk_indexing_b200"), os.path.join(src, "smqtk_indexing_b200"),
+                    ignore=shutil.ignore_patterns("__pycache__", "obj", "*.o"))
+    r = subprocess.run([sys.executable, "-m", "pip", "install", "--no-index", "--no-build-isolation", "--no-deps",
+                        "--quiet", "--target", target, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    code = (
+        "import sys, json\n"
+        "from smqtk_indexing_b200.interfaces import HashIndex, LshFunctor, NearestNeighborsIndex\n"
+        "import smqtk_indexing_b200\n"
+        "assert smqtk_indexing_b200.__file__.startswith(%r), smqtk_indexing_b200.__file__\n"
+        "pre = [m for m in sys.modules if m.startswith('smqtk_indexing_b200.impls.')]\n"
+        "out = {'pre': pre}\n"
+        "for i in (HashIndex, LshFunctor, NearestNeighborsIndex):\n"
+        "    out[i.__name__] = sorted(c.__module__ + '.' + c.__name__ for c in i.get_impls())\n"
+        "print(json.dumps(out))\n" % target)
+    env = dict(os.environ, PYTHONPATH=target, SMQTK_B200_ASSUME_USABLE="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["pre"] == []                                    # nothing imported the implementations by hand
+    p = "smqtk_indexing_b200.impls."
+    assert {p + "hash_index.linear.LinearHashIndex",
+            p + "hash_index.sklearn_balltree.SkLearnBallTreeHashIndex"} <= set(out["HashIndex"])
+    assert {p + "lsh_functor.itq.ItqFunctor", p + "lsh_functor.simple_rp.SimpleRPFunctor"} <= set(out["LshFunctor"])
+    assert {p + "nn_index.lsh.LSHNearestNeighborIndex",
+            p + "nn_index.flat.FlatL2NearestNeighborsIndex"} <= set(out["NearestNeighborsIndex"])
+
+
+def test_balltree_named_alias_config_and_reference_cache():
+    """`SkLearnBallTreeHashIndex` by name (reference sklearn_balltree.py:112-151): same
+    constructor / config keys; reads the reference's .npz cache layout (:179-184)."""
+    from io import BytesIO
+    from smqtk_indexing_b200.impls.hash_index.sklearn_balltree import SkLearnBallTreeHashIndex
+    assert SkLearnBallTreeHashIndex in HashIndex.get_impls()
+    c = SkLearnBallTreeHashIndex.get_default_config()
+    assert c['leaf_size'] == 40 and c['random_seed'] is None and c['cache_element']['type'] is None
+    i = SkLearnBallTreeHashIndex.from_config(c)
+    assert i.get_config() == c and i.count() == 0
+    i = SkLearnBallTreeHashIndex(DataMemoryElement(), leaf_size=52, random_seed=42)
+    for inst in configuration_test_helper(i):
+        assert inst.leaf_size == 52 and inst.random_seed == 42 and isinstance(inst.cache_element, DataMemoryElement)
+    # a cache written by the reference: np.savez(data_arr=<0/1 matrix>, idx_array_arr, node_data_arr, node_bounds_arr, tail)
+    rng = np.random.RandomState(3)
+    bits = rng.rand(50, 70) > 0.5
+    bits[7] = bits[3]                                          # the tree stores duplicates happily
+    buff = BytesIO()
+    np.savez(buff, data_arr=bits.astype(np.float64), idx_array_arr=np.arange(50), node_data_arr=np.zeros(3),
+             node_bounds_arr=np.zeros((1, 3, 70)), tail=np.array([40, 1, 2, 0, 0, 0, 0, None], dtype=object))
+    i = SkLearnBallTreeHashIndex(DataMemoryElement(buff.getvalue()))
+    assert i.count() == 49
+    assert i.index == {B.bit_vector_to_int_large(v) for v in bits}
+    with pytest.raises(ValueError):
+        SkLearnBallTreeHashIndex().nn(bits[0], 1)             # empty index (interface check, hash_index.py:108-109)
+    ro = DataMemoryElement(readonly=True)
+    with pytest.raises(ValueError):
+        SkLearnBallTreeHashIndex(ro).save_model()
+
+
 def test_linear_config():
     c = LinearHashIndex.get_default_config()
     assert len(c) == 1 and c['cache_element']['type'] is None
