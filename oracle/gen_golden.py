@@ -200,6 +200,49 @@ def gen_lsh():
     save("lsh_nn", **out)
 
 
+# ---------------------------------------------------------------- LSH incremental ingest
+def gen_lsh_ingest():
+    """State the UNMODIFIED reference leaves after a build + update_index / remove_from_index
+    sequence (lsh.py:283-450): the hash2uuids KVS, the LinearHashIndex content, count(), and nn()
+    answers -- what the device-speed *_matrix ingest of the product must reproduce."""
+    N, D, b, seed = gi.INGEST_SHAPE
+    x, qs = gi.ingest_inputs()
+    f = ItqFunctor(bit_length=b, random_seed=seed, itq_iterations=20)
+    f.fit(_descr(x[:400]))
+    # the fixture is only meaningful if no projection sits at rounding level (fp32 device hashing)
+    z = np.dot(np.vstack([x, qs]).astype(np.float64) - f.mean_vec, f.rotation)
+    assert np.abs(z).min() > 5e-5, "pick another seed: a projection is within 5e-5 of zero"
+    idx = LSHNearestNeighborIndex(f, MemoryDescriptorSet(), MemoryKeyValueStore(),
+                                  hash_index=LinearHashIndex(), distance_method="euclidean")
+    out = {"mean": f.mean_vec, "rot": f.rotation}
+    live = set()
+    for si, step in enumerate(gi.INGEST_STEPS):
+        op, rows = gi.ingest_step_rows(step)
+        if op == "add":
+            (idx.build_index if si == 0 else idx.update_index)([DescriptorMemoryElement(r).set_vector(x[r]) for r in rows])
+            live |= set(rows)
+        else:
+            idx.remove_from_index(rows)
+            live -= set(rows)
+        kvs = idx.hash2uuids_kvstore
+        keys = sorted(kvs.keys())
+        off, uu = [0], []
+        for k in keys:
+            uu.extend(sorted(kvs.get(k)))
+            off.append(len(uu))
+        assert sorted(uu) == sorted(live)
+        out["s%d_keys_hex" % si] = np.array([int_to_hex(k) for k in keys])
+        out["s%d_off" % si] = np.array(off, np.int64)
+        out["s%d_uuids" % si] = np.array(uu, np.int64)
+        out["s%d_hash_index_hex" % si] = np.array(sorted(int_to_hex(k) for k in idx.hash_index.index))
+        out["s%d_count" % si] = np.array(idx.count())
+        for qi in range(len(qs)):
+            r, d = idx.nn(DescriptorMemoryElement(10 ** 6 + qi).set_vector(qs[qi]), gi.INGEST_N)
+            out["s%d_q%d_uuids" % (si, qi)] = np.array([e.uuid() for e in r], np.int64)
+            out["s%d_q%d_dists" % (si, qi)] = np.array(d, np.float64)
+    save("lsh_ingest", **out)
+
+
 if __name__ == "__main__":
     gen_bits()
     gen_hamming()
@@ -207,3 +250,4 @@ if __name__ == "__main__":
     gen_itq()
     gen_metrics()
     gen_lsh()
+    gen_lsh_ingest()

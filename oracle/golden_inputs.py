@@ -95,3 +95,37 @@ def lsh_inputs(ci):
     if method == "hik":
         qs = qs / qs.sum(axis=1, keepdims=True)
     return x, qs
+
+
+# ---- incremental ingest: one build + update / remove steps through the reference's
+# LSHNearestNeighborIndex.update_index / remove_from_index (lsh.py:331-450)
+INGEST_SHAPE = (900, 32, 16, 11)                # rows, D, bits, seed
+INGEST_N = 6                                    # neighbours asked per query
+#: (op, first row, one-past-last row, stride): rows double as uuids; "add" = update_index (build_index
+#: for the first step), "del" = remove_from_index.  Step 4 brings removed uuids back, step 6 re-adds
+#: live uuids with their unchanged vectors (a no-op in the reference's set semantics).
+INGEST_STEPS = [
+    ("add", 0, 400, 1),
+    ("add", 400, 650, 1),
+    ("del", 3, 600, 4),
+    ("add", 650, 900, 1),
+    ("add", 3, 200, 8),
+    ("del", 600, 900, 3),
+    ("add", 100, 140, 1),
+]
+
+
+def ingest_inputs():
+    """Clustered float32 descriptors (codes collide: several uuids per hash) and queries."""
+    N, D, b, seed = INGEST_SHAPE
+    rng = np.random.RandomState(seed)
+    centres = rng.rand(45, D)
+    x = (centres[rng.randint(0, 45, N)] + 0.04 * rng.randn(N, D)).astype(np.float32)
+    qs = (centres[rng.randint(0, 45, 12)] + 0.04 * rng.randn(12, D)).astype(np.float32)
+    qs[0] = x[1]
+    return x, qs
+
+
+def ingest_step_rows(step):
+    op, lo, hi, stride = step
+    return op, list(range(lo, hi, stride))

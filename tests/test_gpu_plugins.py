@@ -599,6 +599,71 @@ def _same_neighbours(a, ua, b, ub, q, n):
     assert (ta == tb).all()
 
 
+def test_matrix_ingest_matches_reference_state_and_oracle(golden):
+    """SURVEY 8f N3, pinned OUTSIDE the product: the same build / update / remove sequence the
+    UNMODIFIED reference ran through LSHNearestNeighborIndex.update_index / remove_from_index
+    (lsh.py:331-450; fixture tests/golden/lsh_ingest.npz, generator oracle/gen_golden.py::gen_lsh_ingest)
+    goes through update_index_matrix / remove_from_index_matrix.  After EVERY step:
+      * hash2uuids_view() == the reference's hash2uuids KVS (keys and uuid sets),
+      * the LinearHashIndex content == the reference's hash_index.index, count == reference count(),
+      * nn_batch == the reference's nn() answers (rtol 1e-5; order where the reference's tie order is defined),
+      * nn_batch == the oracle's LSH query over the live rows (canonical ties: exact rows)."""
+    g = golden("lsh_ingest")
+    N, D, b, seed = gi.INGEST_SHAPE
+    x, qs = gi.ingest_inputs()
+    f = ItqFunctor(bit_length=b)
+    f.mean_vec, f.rotation = g["mean"], g["rot"]
+    index = _matrix_index(f)
+    n = gi.INGEST_N
+    x64 = x.astype(np.float64)
+    mean, rot = np.real(g["mean"]), np.real(g["rot"])
+    all_codes = O.pack_codes(O.itq_hash(x64, mean, rot), 1)
+    q_codes = O.pack_codes(O.itq_hash(qs.astype(np.float64), mean, rot), 1)
+    live = set()
+    for si, step in enumerate(gi.INGEST_STEPS):
+        op, rows = gi.ingest_step_rows(step)
+        if op == "add":
+            index.update_index_matrix(x[rows], uuids=rows)
+            live |= set(rows)
+        else:
+            index.remove_from_index_matrix(rows)
+            live -= set(rows)
+        # --- state vs the reference's containers
+        keys = [int(h, 16) for h in g["s%d_keys_hex" % si]]
+        off, uu = g["s%d_off" % si], g["s%d_uuids" % si]
+        want = {k: set(int(u) for u in uu[off[i]:off[i + 1]]) for i, k in enumerate(keys)}
+        view = index.hash2uuids_view()
+        assert {k: view.get(k) for k in view.keys()} == want, "step %d" % si
+        assert sum(len(v) for v in view.values()) == int(g["s%d_count" % si]) == index.count_rows()
+        assert index.hash_index.index == {int(h, 16) for h in g["s%d_hash_index_hex" % si]}
+        # --- queries vs the reference's nn() and vs the oracle
+        rows_b, dists_b = index.nn_batch(qs, n)
+        uuids = index.mirror_uuids()
+        live_rows = np.array(sorted(live))
+        table = O.unique_code_table(all_codes[live_rows])[0]
+        ordered = 0
+        for qi in range(len(qs)):
+            keep = rows_b[qi] >= 0
+            got_u = [uuids[r] for r in rows_b[qi][keep]]
+            orow, od = O.lsh_nn(x64[live_rows], all_codes[live_rows], qs[qi].astype(np.float64), q_codes[qi:qi + 1], n, "euclidean")
+            np.testing.assert_allclose(dists_b[qi][keep], od, rtol=1e-5, atol=1e-9)
+            if len(od) < 2 or np.diff(od).min() > 1e-6 * od.max():
+                assert got_u == [int(live_rows[r]) for r in orow], "step %d query %d" % (si, qi)
+            srt = np.sort(O.hamming_distances(table, q_codes[qi]))
+            if n < len(table) and srt[n - 1] == srt[n]:
+                continue            # the reference's candidate pool depends on its unspecified tie order
+            ref_u, ref_d = g["s%d_q%d_uuids" % (si, qi)], g["s%d_q%d_dists" % (si, qi)]
+            np.testing.assert_allclose(dists_b[qi][keep], ref_d, rtol=1e-5, atol=5e-8)
+            if len(ref_d) < 2 or np.diff(ref_d).min() > 1e-4 * ref_d.max():
+                assert got_u == list(ref_u), "step %d query %d" % (si, qi)
+                ordered += 1
+        assert ordered >= 3, "step %d: too few queries with a defined order" % si
+    # KeyError before any mutation (lsh.py:407-416): uuid 3 is live again, 103 is not
+    with pytest.raises(KeyError):
+        index.remove_from_index_matrix([3, 103])
+    assert index.count_rows() == int(g["s%d_count" % (len(gi.INGEST_STEPS) - 1)])
+
+
 def test_matrix_update_remove_equal_fresh_build():
     """update_index_matrix / remove_from_index_matrix (device-speed ingest: appended
     buffers, tombstones, re-index over the live rows) leave the index in the state a fresh
