@@ -7,8 +7,10 @@ GPU parity at BASELINE.json's sizes and shapes.
   canonical ordering, exact agreement with an independent torch brute force on a
   sample of queries, shard-and-merge == single scan, few-queries kernel ==
   batched kernel) -- plus the oracle on the rows it can afford.
-* C1 (100k x 128-d, ITQ-64, euclidean, k=10) and a reduced C4 (hik, 4096-d, ITQ-256,
-  k=50) run the whole plugin pipeline against the oracle's array-form LSH query.
+* C1 (100k x 128-d, ITQ-64, euclidean, k=10) and C4 (hik, 1M x 4096-d, ITQ-256, k=50; plus a
+  reduced 20k-row variant) run the whole plugin pipeline against the oracle's array-form LSH query.
+* C5 (fit + build) runs at 10M x 256-d, where the streaming tensor-core fit engages.
+* The C2 scan tests FAIL unless the tcgen05 kernel produced the result (no silent fallback).
 """
 import numpy as np
 import pytest
@@ -38,6 +40,45 @@ def _popcount_rows(x_i32: torch.Tensor) -> torch.Tensor:
     return _LUT[b.long()].sum(dim=1, dtype=torch.int32)
 
 
+def _topk_on_tensor_cores(dev, db, q, k):
+    """hamming_topk that FAILS unless the tcgen05 scan produced the result: the dispatcher silently
+    re-runs an overflowed batch on the XOR/POPC scan (device.hamming_scan_keys), which would let a
+    full-size test pass without the headline kernel."""
+    from smqtk_indexing_b200 import _lib
+    overflows0 = dev.TC_SCAN_OVERFLOWS
+    _lib.profile_fetch()
+    _lib.profile_enable(True)
+    try:
+        dist, idx = dev.hamming_topk(db, q, k)
+        torch.cuda.synchronize()
+    finally:
+        _lib.profile_enable(False)
+    kernels = {name for name, _ in _lib.profile_fetch()}
+    assert "ham_filter_tc_kernel" in kernels, "the tensor-core scan did not run: %s" % sorted(kernels)
+    assert "hamming_scan_kernel" not in kernels, "the batch fell back to the XOR/POPC scan"
+    assert dev.TC_SCAN_OVERFLOWS == overflows0, "the tensor-core scan overflowed a candidate buffer"
+    return dist, idx
+
+
+def _check_topk_properties(db, q, k, dist, idx, sample):
+    """Size-independent checks of a top-k result + exact agreement with a torch brute force on `sample`."""
+    Q, U = q.shape[0], db.shape[0]
+    assert int(idx.min()) >= 0 and int(idx.max()) < U
+    rows = db[idx.reshape(-1)].reshape(Q, k, -1)
+    x = (rows ^ q[:, None, :]).reshape(Q * k, -1)
+    assert torch.equal(_popcount_rows(x).reshape(Q, k), dist)
+    key = dist.to(torch.int64) * (1 << 40) + idx
+    assert bool((key[:, 1:] > key[:, :-1]).all())
+    for qi in sample:
+        d_all = torch.zeros(U, dtype=torch.int32, device=db.device)
+        for s0 in range(0, U, 2_000_000):                      # bounded temporaries
+            d_all[s0:s0 + 2_000_000] = _popcount_rows(db[s0:s0 + 2_000_000] ^ q[qi][None, :])
+        kk = d_all.to(torch.int64) * (1 << 24) + torch.arange(U, device=db.device)
+        best = torch.topk(kk, k, largest=False, sorted=True).values
+        assert torch.equal(best >> 24, dist[qi].to(torch.int64))
+        assert torch.equal(best & ((1 << 24) - 1), idx[qi])
+
+
 @pytest.fixture(scope="module")
 def c2_scan(dev):
     U, W, Q, k = 10_000_000, 8, 4096, 10
@@ -53,8 +94,7 @@ def c2_scan(dev):
     near = q[1].clone()
     near[0] ^= 2
     db[5_000_001] = near
-    dist, idx = dev.hamming_topk(db, q, k)
-    torch.cuda.synchronize()
+    dist, idx = _topk_on_tensor_cores(dev, db, q, k)
     return db, q, k, dist, idx
 
 
@@ -134,6 +174,38 @@ def test_c2_hash_is_row_independent_and_matches_ffma(dev):
     assert (np.abs(z.cpu().numpy()[bad]) < 2e-5).all()
 
 
+def test_c2_scan_over_a_sorted_clustered_itq_table_10m(dev):
+    """C2 on the table REAL ITQ codes produce: 10M x 256-bit codes of clustered descriptors, hashed by a
+    fitted ITQ-256 model, sort-uniqued (near-duplicate codes are contiguous -- the case the golden-ratio
+    visiting order exists for).  Queries come from the same clusters, so every query has thousands of
+    codes at small distances.  The tcgen05 kernel must produce the result (no overflow fallback)."""
+    from smqtk_indexing_b200 import codes as codeops
+    from smqtk_indexing_b200.impls.lsh_functor.itq import ItqFunctor
+    N, D, b, Q, k, C = 10_000_000, 256, 256, 4096, 10, 3000
+    g = torch.Generator(device="cuda").manual_seed(77)
+    centres = torch.rand((C, D), generator=g, device="cuda")
+
+    def draw(n):
+        c = torch.randint(0, C, (n,), generator=g, device="cuda")
+        return centres[c] + 0.08 * torch.randn((n, D), generator=g, device="cuda")
+
+    f = ItqFunctor(bit_length=b, itq_iterations=5, random_seed=0)
+    f.fit_matrix(draw(200_000))
+    parts = [f.get_hash_packed(draw(1_000_000)) for _ in range(N // 1_000_000)]   # descriptors are not kept
+    table = codeops.sort_unique(torch.cat(parts))
+    del parts
+    U = table.shape[0]
+    assert U > 0.9 * N                                          # noise keeps most codes distinct
+    q = f.get_hash_packed(draw(Q))
+    dist, idx = _topk_on_tensor_cores(dev, table, q, k)
+    # clustered: the k-th neighbour is far below the 128 bits of random codes
+    assert float(dist[:, -1].float().mean()) < 90
+    _check_topk_properties(table, q, k, dist, idx, sample=(0, 1, 1234, 4095))
+    # the sorted table really is clustered: adjacent rows are much closer than random pairs
+    adj = _popcount_rows(table[1:200_001] ^ table[:200_000]).float().mean().item()
+    assert adj < 100
+
+
 # ------------------------------------------------------------------ config-shaped pipelines
 def _oracle_lsh(x64, table, off, rows, q_vec, q_words, n, method):
     """lsh.py:470-519 restated with a prebuilt unique-code table (np_oracle.lsh_nn rebuilds it per call)."""
@@ -193,6 +265,89 @@ def test_c4_pipeline_hik_4096d_itq256_k50():
     rows, dists = _pipeline_case(20_000, 4096, 256, 50, "hik", n_queries=64, n_check=12, seed=4,
                                  normalise_rows=True, fit_rows=5_000)
     assert rows[0][0] == 17 and abs(dists[0][0]) < 1e-6      # 1 - sum(fp32 row): not exactly 0
+
+
+def test_c4_full_size_1m_x_4096_hik_itq256_k50(dev):
+    """BASELINE configs[3] at its stated size: 1M x 4096-d L1-normalised histograms (16.4 GB fp32 on the
+    device), ITQ-256, histogram-intersection re-rank, k=50.  Descriptors are generated on the device;
+    the oracle sees the device codes (host copy, 32 MB) and float64 copies of only the candidate rows."""
+    from smqtk_dataprovider.impls.key_value_store.memory import MemoryKeyValueStore
+    from smqtk_descriptors.impls.descriptor_set.memory import MemoryDescriptorSet
+    from smqtk_indexing_b200.impls.hash_index.linear import LinearHashIndex
+    from smqtk_indexing_b200.impls.lsh_functor.itq import ItqFunctor
+    from smqtk_indexing_b200.impls.nn_index.lsh import LSHNearestNeighborIndex
+    N, D, b, k, Q, n_check = 1_000_000, 4096, 256, 50, 64, 10
+    g = torch.Generator(device="cuda").manual_seed(44)
+    x = torch.empty((N, D), dtype=torch.float32, device="cuda")
+    for s0 in range(0, N, 100_000):
+        blk = torch.rand((100_000, D), generator=g, device="cuda")
+        x[s0:s0 + 100_000] = blk / blk.sum(dim=1, keepdim=True)
+    qs = torch.rand((Q, D), generator=g, device="cuda")
+    qs[0] = x[17]
+    qs[1] = x[29] * (1 + 1e-3 * torch.rand(D, generator=g, device="cuda"))
+    qs = qs / qs.sum(dim=1, keepdim=True)
+    f = ItqFunctor(bit_length=b, itq_iterations=5, random_seed=0)
+    f.fit_matrix(x[:20_000])
+    index = LSHNearestNeighborIndex(f, MemoryDescriptorSet(), MemoryKeyValueStore(), LinearHashIndex(), "hik")
+    index.build_index_matrix(x)
+    rows, dists = index.nn_batch(qs, k)
+    assert rows[0][0] == 17 and abs(dists[0][0]) < 1e-6 and rows[1][0] == 29
+    codes = index._mirror.codes.cpu().numpy().view(np.uint32)
+    table, _, off, crow = O.unique_code_table(codes)
+    assert len(table) == index._mirror.num_codes
+    qcodes = f.get_hash_packed(qs).cpu().numpy().view(np.uint32)
+    qs64 = qs.cpu().numpy().astype(np.float64)
+    ordered = 0
+    for qi in range(n_check):
+        _, near = O.hamming_topk(table, qcodes[qi:qi + 1], k)
+        cand = np.concatenate([crow[off[c]:off[c + 1]] for c in near[0]])
+        xc = x[torch.from_numpy(cand).cuda()].cpu().numpy().astype(np.float64)
+        d = np.atleast_1d(O.DISTANCE_FUNCTIONS["hik"](qs64[qi], xc))
+        o = np.argsort(d, kind="stable")[:k]
+        np.testing.assert_allclose(dists[qi][:len(o)], d[o], rtol=1e-5, atol=1e-9)
+        if np.diff(d[o]).min() > 1e-6 * d[o].max():
+            assert list(rows[qi][:len(o)]) == list(cand[o])
+            ordered += 1
+    assert ordered >= n_check // 2
+
+
+def test_c5_fit_and_build_10m_x_256(dev):
+    """BASELINE configs[4] shape at 10M rows (the streaming tensor-core fit engages above 4 GiB of V):
+    ItqFunctor.fit_matrix over 10M x 256-d -> 64 bits, then hash + unique table + CSR over all rows.
+    The model must be orthonormal and as good as the FP64 fit of the same data (quantisation loss), the
+    build must cover every row exactly once and agree with re-hashing."""
+    from smqtk_indexing_b200 import engine, fit as fitops
+    from smqtk_indexing_b200.impls.lsh_functor.itq import ItqFunctor
+    n, D, b = 10_000_000, 256, 64
+    g = torch.Generator(device="cuda").manual_seed(55)
+    centres = torch.randn((64, D), generator=g, device="cuda") * torch.linspace(2.0, 0.2, D, device="cuda")
+    X = torch.empty((n, D), dtype=torch.float32, device="cuda")
+    for s0 in range(0, n, 1_000_000):
+        c = torch.randint(0, 64, (1_000_000,), generator=g, device="cuda")
+        X[s0:s0 + 1_000_000] = centres[c] + 0.15 * torch.randn((1_000_000, D), generator=g, device="cuda")
+    assert n * b * 8 > fitops.STREAMING_V_BYTES                 # the streaming path is the one under test
+    f = ItqFunctor(bit_length=b, itq_iterations=5, random_seed=0)
+    f.fit_matrix(X, want_codes=False)
+    r1 = np.asarray(f.rotation)
+    np.testing.assert_allclose(r1.T @ r1, np.eye(b), atol=1e-9)
+    # FP64 fit of the same rows (parity path), compared by quantisation loss on a sample
+    _, m0, r0 = fitops.itq_fit(X, b, itq_iterations=5, random_seed=0, streaming=True, tensor_cores=False,
+                               want_codes=False)
+    np.testing.assert_allclose(np.asarray(f.mean_vec, dtype=np.float64), m0.astype(np.float64), rtol=0, atol=1e-6)
+    xc = X[:50_000].double().cpu().numpy() - m0.astype(np.float64)
+    loss = [np.square(np.sign(xc @ r) - xc @ r).sum() for r in (r0, r1)]
+    assert abs(loss[1] - loss[0]) < 2e-3 * loss[0], loss
+    m = engine.DeviceLshIndex()
+    codes = f.get_hash_packed(X)
+    m.set_rows(X, codes)
+    assert m.num_rows == n and int((m.csr_off[1:] - m.csr_off[:-1]).sum()) == n
+    assert torch.equal(torch.sort(m.csr_rows).values, torch.arange(n, device="cuda"))
+    assert torch.equal(m.table[m.row_code], m.codes)
+    assert bool((m.csr_off[1:] > m.csr_off[:-1]).all())
+    t = m.table.to(torch.int64) & 0xFFFFFFFF
+    key = (t[:, 0] << 32) | t[:, 1]                             # 64-bit codes: table strictly ascending as integers
+    key = key ^ (-2 ** 63)
+    assert bool((key[1:] > key[:-1]).all())
 
 
 def test_c5_fit_and_build_throughput_shape():
