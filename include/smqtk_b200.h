@@ -208,6 +208,24 @@ SB_API int sb_expand_candidates(const int64_t* code_rows, int32_t Q, int32_t n,
                          const int64_t* csr_off, const int64_t* csr_rows, int64_t pitch,
                          int64_t* cand_idx, int64_t* cand_off, int64_t* cand_cnt, void* stream);
 
+/* ---- index build: sorted-unique code table + code -> rows CSR (replaces the Python set of ints of
+ * LinearHashIndex._build_index / _update_index / _remove_from_index, linear.py:148-204, and the
+ * {hash int: set(uuid)} loop of LSHNearestNeighborIndex._build_index, lsh.py:316-329).
+ *   codes u32[n_rows][W] per-row codes (layout above); rows_in i64[n] = the rows to index (live rows,
+ *   ascending) or NULL for all n = n_rows rows.
+ * Outputs (capacity n unless noted): table_out u32[U][W] ascending by integer value, distinct;
+ *   row_code_out i64[n_rows] row -> table row (-1 for rows not in rows_in); csr_off_out i64[U+1]
+ *   (capacity n+1), csr_rows_out i64[n]: rows of code c are csr_rows[csr_off[c] .. csr_off[c+1]) in
+ *   ascending row order; stats_out i64[2] = {U, most rows sharing one code} (device memory: the
+ *   caller reads it once to learn U).
+ * One stable LSD radix sort of a row permutation (8-bit digits, one kernel per pass with decoupled
+ * look-back; digits all rows agree on are skipped) + boundary flags + scan + scatter; no library
+ * sort.  n < 2^30, n_rows < 2^32, W in {1,2,4,8,16,32}. */
+SB_API size_t sb_unique_codes_workspace_bytes(int64_t n, int32_t W);
+SB_API int sb_unique_codes(const uint32_t* codes, int64_t n_rows, int32_t W, const int64_t* rows_in, int64_t n,
+                    uint32_t* table_out, int64_t* row_code_out, int64_t* csr_off_out, int64_t* csr_rows_out,
+                    int64_t* stats_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- flat index: exact L2 k-nearest rows (reference impls/nn_index/faiss.py:751-831
  * with 'IDMap,Flat' + metrics.py:73-86).  Tensor-core filter (3xTF32 |x|^2+|q|^2-2x.q against
  * per-query thresholds, chunked) + exact FP32 error-free re-rank of the survivors; result =

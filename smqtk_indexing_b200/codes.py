@@ -1,14 +1,14 @@
 """
-Device-side bookkeeping for tables of packed hash codes: lexicographic
-sort / unique / membership on ``int32[rows, W]`` tensors that carry uint32 bit
-patterns (word 0 most significant).
+Bookkeeping for tables of packed hash codes: sort / unique / union / difference on
+``int32[rows, W]`` tensors that carry uint32 bit patterns (word 0 most significant).
 
-These are index-maintenance steps (build / update / remove), not the query hot
-path; they are expressed with torch's device sort (plumbing) so that the table
-never leaves HBM.  Unsigned order is obtained by flipping the sign bit of every
-word before the signed lexicographic sort.
+CUDA tensors go through ``sb_unique_codes`` (csrc/unique_codes.cu: one radix-sort + flag + scan +
+scatter pipeline, no library sort) -- the index-build path of LinearHashIndex / LSHNearestNeighborIndex
+(reference linear.py:148-204, lsh.py:316-329).  HOST tensors (the world-size-2 gloo tests of the
+sharded index, which run the collective logic without a GPU) take a small torch restatement of the
+same contract; it is never used for CUDA tensors.
 """
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 
@@ -40,20 +40,34 @@ def lex_order(codes: torch.Tensor) -> torch.Tensor:
     return order
 
 
-def build_table(codes: torch.Tensor):
+def build_table(codes: torch.Tensor, rows: Optional[torch.Tensor] = None, with_max: bool = False):
     """Everything the index derives from per-row codes, in one pass:
 
-    :return: (table int32[U, W] sorted unique, row_code int64[rows] -> table row,
-              csr_off int64[U + 1], csr_rows int64[rows]) with the rows of each code in
-              ascending row order.
+    :param rows: int64 ascending row numbers to index (live rows); None = every row.
+    :return: (table int32[U, W] sorted unique, row_code int64[all rows] -> table row (-1 for rows
+              not in ``rows``), csr_off int64[U + 1], csr_rows int64[len(rows)]) with the rows of each
+              code in ascending row order (+ the largest number of rows on one code when ``with_max``).
     """
     if codes.dim() != 2 or codes.dtype != torch.int32:
         raise ValueError("codes must be int32[rows, W]")
-    n = codes.shape[0]
+    n = codes.shape[0] if rows is None else int(rows.numel())
     dev = codes.device
     if n == 0:
         e = torch.empty(0, dtype=torch.int64, device=dev)
-        return codes.clone(), e, torch.zeros(1, dtype=torch.int64, device=dev), e.clone()
+        rc = torch.full((codes.shape[0],), -1, dtype=torch.int64, device=dev)
+        out = (codes[:0].clone(), rc, torch.zeros(1, dtype=torch.int64, device=dev), e)
+        return out + (0,) if with_max else out
+    if codes.is_cuda:
+        from . import device
+        table, row_code, csr_off, csr_rows, mx = device.unique_codes(codes.contiguous(), rows)
+        return (table, row_code, csr_off, csr_rows, mx) if with_max else (table, row_code, csr_off, csr_rows)
+    # ---- host tensors only (gloo tests of the collective logic) ----
+    if rows is not None:
+        t, rc, off, cr = build_table(codes[rows].contiguous())
+        row_code = torch.full((codes.shape[0],), -1, dtype=torch.int64, device=dev)
+        row_code[rows] = rc
+        out = (t, row_code, off, rows[cr])
+        return out + (int((off[1:] - off[:-1]).max()),) if with_max else out
     order = lex_order(codes)
     s = codes[order]
     new = torch.ones(n, dtype=torch.bool, device=dev)
@@ -67,6 +81,8 @@ def build_table(codes: torch.Tensor):
     csr_off = torch.empty(first.numel() + 1, dtype=torch.int64, device=dev)
     csr_off[:-1] = first
     csr_off[-1] = n
+    if with_max:
+        return table, row_code, csr_off, order, int((csr_off[1:] - csr_off[:-1]).max())
     return table, row_code, csr_off, order
 
 

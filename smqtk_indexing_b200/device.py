@@ -153,6 +153,37 @@ def itq_hash(X: torch.Tensor, mean: Optional[torch.Tensor], R: torch.Tensor, nor
     return (codes, z) if want_z else codes
 
 
+# --------------------------------------------------------------------- index build
+def unique_codes(codes: torch.Tensor, rows: Optional[torch.Tensor] = None):
+    """``sb_unique_codes``: (table int32[U, W] sorted unique, row_code int64[n_rows] (-1 = row not in
+    ``rows``), csr_off int64[U + 1], csr_rows int64[n], max rows per code) of the codes of ``rows``
+    (int64 ascending; None = every row).  One host read (U and the max count) sizes the outputs."""
+    require_cuda()
+    _chk(codes, torch.int32, "codes")
+    n_rows, W = codes.shape
+    if rows is not None:
+        _chk(rows, torch.int64, "rows")
+    n = n_rows if rows is None else int(rows.numel())
+    lib = _lib.load()
+    ws_bytes = lib.sb_unique_codes_workspace_bytes(n, W)
+    if ws_bytes == 0:
+        raise ValueError("sb_unique_codes does not support n=%d W=%d" % (n, W))
+    dev = codes.device
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    table = torch.empty((n, W), dtype=torch.int32, device=dev)
+    row_code = torch.empty((n_rows,), dtype=torch.int64, device=dev)
+    csr_off = torch.empty((n + 1,), dtype=torch.int64, device=dev)
+    csr_rows = torch.empty((n,), dtype=torch.int64, device=dev)
+    stats = torch.empty((2,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sb_unique_codes(_ptr(codes), n_rows, W, _ptr(rows), n, _ptr(table), _ptr(row_code), _ptr(csr_off),
+                                       _ptr(csr_rows), _ptr(stats), _ptr(ws), ws_bytes, _stream()))
+    U, max_count = (int(v) for v in stats.cpu().tolist())
+    # the slices keep the full-capacity storage alive; the table is compacted when it is much smaller
+    table = table[:U] if 2 * U > n else table[:U].clone()
+    return table, row_code, csr_off[:U + 1], csr_rows, max_count
+
+
 # --------------------------------------------------------------------- stage 2
 #: the tensor-core scan takes over from this many queries / table rows (below, the XOR/POPC scan
 #: streams the table once per handful of queries and is bound by HBM, which is the better regime)

@@ -135,8 +135,7 @@ class ShardedLshIndex:
         self.row_bounds = [0]
         for s in sizes:
             self.row_bounds.append(self.row_bounds[-1] + s)
-        self.table, _, self.csr_off, self.csr_rows = codeops.build_table(codes_all)
-        self.max_rows_per_code = int((self.csr_off[1:] - self.csr_off[:-1]).max().item()) if len(self.table) else 0
+        self.table, _, self.csr_off, self.csr_rows, self.max_rows_per_code = codeops.build_table(codes_all, with_max=True)
         cuts = partition_bounds(int(self.table.shape[0]), self.world)
         self.scan_lo, self.scan_hi = cuts[self.rank], cuts[self.rank + 1]
 

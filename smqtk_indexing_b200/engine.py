@@ -73,7 +73,7 @@ class DeviceLshIndex:
     Ingest is incremental (reference lsh.py:331-450): rows are appended into
     buffers that grow geometrically, removed rows become tombstones (their row numbers stay
     valid for the layers that map rows to uuids) and ``reindex`` rebuilds the unique table and
-    the CSR over the live rows on the device (a radix sort of the codes: ~50 M rows/s)."""
+    the CSR over the live rows on the device (``sb_unique_codes``)."""
 
     #: buffers grow by this factor when an append does not fit
     GROWTH = 1.5
@@ -204,16 +204,12 @@ class DeviceLshIndex:
             self.table = self.csr_off = self.csr_rows = self.row_code = None
             self.max_rows_per_code = 0
             return
-        if self.alive is None or self.num_dead == 0:
-            self.table, self.row_code, self.csr_off, self.csr_rows = codeops.build_table(self.codes)
-        else:
-            live = torch.nonzero(self.alive).reshape(-1)
-            self.table, rc, self.csr_off, rows_local = codeops.build_table(self.codes[live].contiguous())
-            self.csr_rows = live[rows_local]
-            self.row_code = torch.full((self.num_rows,), -1, dtype=torch.int64, device=live.device)
-            self.row_code[live] = rc
-        # most rows sharing one code: sizes the fixed-pitch candidate segments (one sync per re-index)
-        self.max_rows_per_code = int((self.csr_off[1:] - self.csr_off[:-1]).max().item())
+        # sb_unique_codes: radix sort of a row permutation + boundaries + CSR in one device pipeline; the
+        # one host read per re-index returns U and the most rows sharing one code (sizes the fixed-pitch
+        # candidate segments)
+        live = None if (self.alive is None or self.num_dead == 0) else torch.nonzero(self.alive).reshape(-1)
+        self.table, self.row_code, self.csr_off, self.csr_rows, self.max_rows_per_code = codeops.build_table(
+            self.codes, rows=live, with_max=True)
 
     # ------------------------------------------------------------------ query stages
     def near_codes(self, q_codes: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:

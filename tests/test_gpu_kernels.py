@@ -189,6 +189,60 @@ def test_hamming_scan_dispatch_and_overflow_fallback(dev):
     assert not chk.overflowed() and torch.equal(k_ok, k_popc)
 
 
+# ------------------------------------------------------------------ index build: sb_unique_codes
+def _unique_case(dev, codes_np, rows_np=None):
+    import torch
+    codes = torch.from_numpy(np.ascontiguousarray(codes_np).view(np.int32)).cuda()
+    rows = None if rows_np is None else torch.from_numpy(rows_np.astype(np.int64)).cuda()
+    table, row_code, off, crow, mx = dev.unique_codes(codes, rows)
+    torch.cuda.synchronize()
+    sub = codes_np if rows_np is None else codes_np[rows_np]
+    ot, oinv, ooff, orow = O.unique_code_table(sub)
+    assert np.array_equal(table.cpu().numpy().view(np.uint32), ot)
+    assert np.array_equal(off.cpu().numpy(), ooff)
+    if rows_np is None:
+        assert np.array_equal(row_code.cpu().numpy(), oinv)
+        assert np.array_equal(crow.cpu().numpy(), orow)
+    else:
+        want = np.full(len(codes_np), -1, np.int64)
+        want[rows_np] = oinv
+        assert np.array_equal(row_code.cpu().numpy(), want)
+        assert np.array_equal(crow.cpu().numpy(), rows_np[orow])
+    assert mx == int(np.diff(ooff).max())
+
+
+@pytest.mark.parametrize("n,W,distinct", [(1, 1, 1), (2, 8, 1), (100, 2, 7), (8192, 8, 8192), (8193, 4, 500),
+                                          (100_003, 8, 100_003), (300_000, 1, 4000), (70_000, 32, 70_000),
+                                          (50_000, 16, 333)])
+def test_unique_codes_matches_oracle(dev, n, W, distinct):
+    """sb_unique_codes (radix sort of a row permutation + boundaries + CSR, csrc/unique_codes.cu) vs the
+    oracle's unique-code table (the array form of linear.py:163 / lsh.py:316-323): table, row -> code,
+    CSR offsets and rows (ascending rows per code: the sort is stable), max rows per code."""
+    rng = np.random.RandomState(n + W)
+    pool = rng.randint(0, 2 ** 32, size=(distinct, W), dtype=np.uint64).astype(np.uint32)
+    codes = pool[rng.randint(0, distinct, n)] if distinct < n else pool[rng.permutation(n)]
+    _unique_case(dev, codes)
+
+
+def test_unique_codes_zero_extended_clustered_and_subset(dev):
+    """Digits every row agrees on are skipped (zero-extended codes), near-duplicate clusters that
+    differ only in low words, all-equal codes, and an index over a subset of the rows (tombstones)."""
+    rng = np.random.RandomState(5)
+    n = 40_000
+    low = rng.randint(0, 2 ** 32, size=(n, 2), dtype=np.uint64).astype(np.uint32)
+    wide = np.zeros((n, 8), np.uint32)
+    wide[:, 6:] = low                                          # a 64-bit code widened to 256 bits
+    _unique_case(dev, wide)
+    clustered = np.repeat(rng.randint(0, 2 ** 32, size=(40, 8), dtype=np.uint64).astype(np.uint32), n // 40, axis=0)
+    clustered[:, 7] ^= rng.randint(0, 4, n).astype(np.uint32)  # clusters of 4 codes, differing in the last bits
+    clustered = clustered[rng.permutation(n)]
+    _unique_case(dev, clustered)
+    _unique_case(dev, np.full((5000, 4), 0xDEADBEEF, np.uint32))
+    live = np.sort(rng.choice(n, 17_001, replace=False))
+    _unique_case(dev, clustered, live)
+    _unique_case(dev, wide, np.array([n - 1]))
+
+
 def test_hamming_empty_table(dev):
     q = dev.codes_to_device(np.zeros((2, 8), np.uint32))
     db = torch.empty((0, 8), dtype=torch.int32, device=q.device)

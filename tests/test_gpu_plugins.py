@@ -658,9 +658,9 @@ def test_matrix_ingest_matches_reference_state_and_oracle(golden):
                 assert got_u == list(ref_u), "step %d query %d" % (si, qi)
                 ordered += 1
         assert ordered >= 3, "step %d: too few queries with a defined order" % si
-    # KeyError before any mutation (lsh.py:407-416): uuid 3 is live again, 103 is not
+    # KeyError before any mutation (lsh.py:407-416): uuid 3 is live again, 7 is not
     with pytest.raises(KeyError):
-        index.remove_from_index_matrix([3, 103])
+        index.remove_from_index_matrix([3, 7])
     assert index.count_rows() == int(g["s%d_count" % (len(gi.INGEST_STEPS) - 1)])
 
 
