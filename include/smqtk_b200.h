@@ -226,6 +226,24 @@ SB_API int sb_unique_codes(const uint32_t* codes, int64_t n_rows, int32_t W, con
                     uint32_t* table_out, int64_t* row_code_out, int64_t* csr_off_out, int64_t* csr_rows_out,
                     int64_t* stats_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Selection over LARGE candidate lists (reference: the O(m log m) `sorted(...)` of lsh.py:513-516):
+ * same contract as sb_rerank_select_rows (cand_cnt and cand_idx optional; cand_idx == NULL writes
+ * candidate positions), by ONE stable radix sort of (query, distance[, row]) keys over all M
+ * candidates instead of a per-query rank count.  NaN distances sort last.  tie_by_row needs
+ * candidate rows < 2^32.  M < 2^30. */
+SB_API size_t sb_rerank_select_sorted_workspace_bytes(int64_t M);
+SB_API int sb_rerank_select_sorted(const double* dist, const int64_t* cand_off, const int64_t* cand_cnt,
+                            const int64_t* cand_idx, int64_t M, int32_t Q, int32_t n, int32_t tie_by_row,
+                            int64_t* out_pos, double* out_dist, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Exhaustive Hamming top-k for ANY k (the reference's heapq.nsmallest takes any n, linear.py:232-240;
+ * the scan kernels keep lists of <= 2048): every (query, row) key is materialised and radix-sorted.
+ * keys_out u64[Q][k] packed keys ascending, SB_KEY_EMPTY padded when k > U.  Q * U < 2^30 per call
+ * (the caller loops over query chunks).  W in {1,2,4,8,16,32}. */
+SB_API size_t sb_hamming_topk_sorted_workspace_bytes(int64_t U, int32_t Q);
+SB_API int sb_hamming_topk_sorted(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q, int32_t Q, int32_t k,
+                           int64_t idx_base, uint64_t* keys_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- flat index: exact L2 k-nearest rows (reference impls/nn_index/faiss.py:751-831
  * with 'IDMap,Flat' + metrics.py:73-86).  Tensor-core filter (3xTF32 |x|^2+|q|^2-2x.q against
  * per-query thresholds, chunked) + exact FP32 error-free re-rank of the survivors; result =

@@ -55,6 +55,10 @@ SIGNATURES: Dict[str, tuple] = {
     "sb_expand_candidates": (c_int32, [_P, c_int32, c_int32, _P, _P, c_int64, _P, _P, _P, _P]),
     "sb_unique_codes_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "sb_unique_codes": (c_int32, [_P, c_int64, c_int32, _P, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "sb_rerank_select_sorted_workspace_bytes": (c_size_t, [c_int64]),
+    "sb_rerank_select_sorted": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, c_size_t, _P]),
+    "sb_hamming_topk_sorted_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "sb_hamming_topk_sorted": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P, c_size_t, _P]),
     "sb_l2_prepare": (c_int32, [_P, c_int64, c_int32, c_int64, _P, _P, _P]),
     "sb_l2_topk_supported": (c_int32, [c_int64, c_int32, c_int64, c_int32]),
     "sb_l2_topk_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),

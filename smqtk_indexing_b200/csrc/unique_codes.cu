@@ -353,6 +353,126 @@ bool uc_supported(int64_t n, int64_t n_rows, int32_t W) {
          (W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32);
 }
 
+// hist + plan + 4W radix passes: leaves the sorted permutation in perm_a / perm_b / the initial order (ctrl->final_src)
+int sort_rows_stage(const uint32_t* codes, int32_t W, const long long* rin, int64_t n, const UcPlan& p, unsigned char* ws,
+                    cudaStream_t st) {
+  uint32_t* hist = reinterpret_cast<uint32_t*>(ws + p.off_hist);
+  SortCtrl* ctrl = reinterpret_cast<SortCtrl*>(ws + p.off_ctrl);
+  uint32_t* state = reinterpret_cast<uint32_t*>(ws + p.off_state);
+  uint32_t* perm_a = reinterpret_cast<uint32_t*>(ws + p.off_perm_a);
+  uint32_t* perm_b = reinterpret_cast<uint32_t*>(ws + p.off_perm_b);
+  // hist, ctrl and both look-back buffers are contiguous at the start of the workspace
+  SB_CUDA_TRY(cudaMemsetAsync(ws, 0, p.off_perm_a, st));
+  {
+    sb::ProfScope prof("digit_hist_kernel", st);
+    const size_t smem = (size_t)p.passes * RADIX * sizeof(uint32_t);
+    if (smem > 48 * 1024)
+      SB_CUDA_TRY(cudaFuncSetAttribute(digit_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long blocks = (n * W + 255) / 256 / 8;
+    const long long cap = (long long)sb::sm_count() * (smem > 64 * 1024 ? 1 : 4);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    digit_hist_kernel<<<(unsigned)blocks, 256, smem, st>>>(codes, rin, n, W, hist);
+    sb::count_launch();
+    if (int rc = sb::check_launch("digit_hist_kernel")) return rc;
+  }
+  digit_plan_kernel<<<1, RADIX, 0, st>>>(hist, n, p.passes, ctrl);
+  sb::count_launch();
+  if (int rc = sb::check_launch("digit_plan_kernel")) return rc;
+  {
+    sb::ProfScope prof("radix_pass_kernel", st);            // the 4W passes as one profile record
+    for (int pass = 0; pass < p.passes; ++pass) {
+      radix_pass_kernel<<<p.tiles, RS_THREADS, 0, st>>>(codes, W, pass, n, rin, perm_a, perm_b, hist, ctrl, state, p.tiles);
+      sb::count_launch();
+    }
+    if (int rc = sb::check_launch("radix_pass_kernel")) return rc;
+  }
+  return SB_OK;
+}
+
+// ---- sorted selection (large candidate lists) and exhaustive Hamming top-k (large k) ----------
+__device__ __forceinline__ unsigned long long orderable(double d) {
+  // ascending unsigned order == ascending double order; every NaN sorts last
+  if (d != d) return ~0ull;
+  const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// key rows u32[M][4] = {segment, dist hi, dist lo, tie}: tie = candidate row (tie_by_row) or 0 (the sort is
+// stable: equal keys keep position order).  Entries past cand_cnt (fixed-pitch padding) sort last.
+__global__ void __launch_bounds__(256)
+select_keys_kernel(const double* __restrict__ dist, const long long* __restrict__ cand_off, const long long* __restrict__ cand_cnt,
+                   const long long* __restrict__ cand_idx, int Q, long long M, int tie_by_row, uint32_t* __restrict__ keys) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  int lo = 0, hi = Q;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (cand_off[mid] <= j) lo = mid; else hi = mid;
+  }
+  const bool real = cand_cnt == nullptr || (j - cand_off[lo]) < cand_cnt[lo];
+  const unsigned long long k = real ? orderable(dist[j]) : ~0ull;
+  uint4 row;
+  row.x = (uint32_t)lo;
+  row.y = (uint32_t)(k >> 32);
+  row.z = (uint32_t)k;
+  row.w = (tie_by_row && real) ? (uint32_t)cand_idx[j] : (real ? 0u : 0xffffffffu);
+  reinterpret_cast<uint4*>(keys)[j] = row;
+}
+
+__global__ void __launch_bounds__(256)
+select_emit_kernel(const double* __restrict__ dist, const long long* __restrict__ cand_off, const long long* __restrict__ cand_cnt,
+                   const long long* __restrict__ cand_idx, int Q, int n, const uint32_t* __restrict__ perm_a,
+                   const uint32_t* __restrict__ perm_b, const SortCtrl* __restrict__ ctrl, long long* __restrict__ out_pos,
+                   double* __restrict__ out_dist) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)Q * n) return;
+  const int q = (int)(t / n), i = (int)(t % n);
+  const long long beg = cand_off[q], m = cand_cnt ? min(cand_cnt[q], cand_off[q + 1] - beg) : cand_off[q + 1] - beg;
+  if (i < m) {
+    const long long j = (long long)load_perm(ctrl->final_src, perm_a, perm_b, nullptr, beg + i);
+    out_pos[t] = cand_idx ? cand_idx[j] : j;
+    out_dist[t] = dist[j];
+  } else {
+    out_pos[t] = -1;
+    out_dist[t] = nan("");
+  }
+}
+
+// key rows u32[Qc * U][4] = {query, (d << 40 | row) hi, lo, 0} for EVERY (query, row) pair
+template <int W>
+__global__ void __launch_bounds__(256)
+ham_all_keys_kernel(const uint32_t* __restrict__ db, long long U, const uint32_t* __restrict__ q, int Qc, long long idx_base,
+                    uint32_t* __restrict__ keys) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= U) return;
+  uint32_t x[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) x[w] = __ldg(db + r * W + w);
+  for (int qi = 0; qi < Qc; ++qi) {
+    int d = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) d += __popc(x[w] ^ __ldg(q + (long long)qi * W + w));
+    const unsigned long long k = ((unsigned long long)(unsigned)d << 40) | (unsigned long long)(idx_base + r);
+    reinterpret_cast<uint4*>(keys)[(long long)qi * U + r] = make_uint4((uint32_t)qi, (uint32_t)(k >> 32), (uint32_t)k, 0u);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ham_all_emit_kernel(const uint32_t* __restrict__ keys, long long U, int Qc, int k, const uint32_t* __restrict__ perm_a,
+                    const uint32_t* __restrict__ perm_b, const SortCtrl* __restrict__ ctrl, unsigned long long* __restrict__ keys_out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)Qc * k) return;
+  const int qi = (int)(t / k), i = (int)(t % k);
+  if (i < U) {
+    const long long j = (long long)load_perm(ctrl->final_src, perm_a, perm_b, nullptr, (long long)qi * U + i);
+    const uint4 row = reinterpret_cast<const uint4*>(keys)[j];
+    keys_out[t] = ((unsigned long long)row.y << 32) | row.z;
+  } else {
+    keys_out[t] = ~0ull;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -380,43 +500,16 @@ int sb_unique_codes(const uint32_t* codes, int64_t n_rows, int32_t W, const int6
   SB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sb_unique_codes: workspace must be 256-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(ws + p.off_hist);
   SortCtrl* ctrl = reinterpret_cast<SortCtrl*>(ws + p.off_ctrl);
-  uint32_t* state = reinterpret_cast<uint32_t*>(ws + p.off_state);
   uint32_t* perm_a = reinterpret_cast<uint32_t*>(ws + p.off_perm_a);
   uint32_t* perm_b = reinterpret_cast<uint32_t*>(ws + p.off_perm_b);
   unsigned char* flags = ws + p.off_flags;
   uint32_t* counts = reinterpret_cast<uint32_t*>(ws + p.off_counts);
   const long long* rin = reinterpret_cast<const long long*>(rows_in);
 
-  // hist, ctrl and both look-back buffers are contiguous at the start of the workspace
-  SB_CUDA_TRY(cudaMemsetAsync(ws, 0, p.off_perm_a, st));
   if (rows_in != nullptr)                                   // rows outside rows_in (tombstones) map to no code
     SB_CUDA_TRY(cudaMemsetAsync(row_code_out, 0xff, (size_t)n_rows * sizeof(int64_t), st));
-  {
-    sb::ProfScope prof("digit_hist_kernel", st);
-    const size_t smem = (size_t)p.passes * RADIX * sizeof(uint32_t);
-    if (smem > 48 * 1024)
-      SB_CUDA_TRY(cudaFuncSetAttribute(digit_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long blocks = (n * W + 255) / 256 / 8;
-    const long long cap = (long long)sb::sm_count() * (smem > 64 * 1024 ? 1 : 4);
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    digit_hist_kernel<<<(unsigned)blocks, 256, smem, st>>>(codes, rin, n, W, hist);
-    sb::count_launch();
-    if (int rc = sb::check_launch("digit_hist_kernel")) return rc;
-  }
-  digit_plan_kernel<<<1, RADIX, 0, st>>>(hist, n, p.passes, ctrl);
-  sb::count_launch();
-  if (int rc = sb::check_launch("digit_plan_kernel")) return rc;
-  {
-    sb::ProfScope prof("radix_pass_kernel", st);            // the 4W passes as one profile record
-    for (int pass = 0; pass < p.passes; ++pass) {
-      radix_pass_kernel<<<p.tiles, RS_THREADS, 0, st>>>(codes, W, pass, n, rin, perm_a, perm_b, hist, ctrl, state, p.tiles);
-      sb::count_launch();
-    }
-    if (int rc = sb::check_launch("radix_pass_kernel")) return rc;
-  }
+  if (int rc = sort_rows_stage(codes, W, rin, n, p, ws, st)) return rc;
   {
     sb::ProfScope prof("boundary_kernel", st);
     boundary_kernel<<<p.bd_blocks, BD_THREADS, 0, st>>>(codes, W, n, rin, perm_a, perm_b, ctrl, flags, counts);
@@ -443,6 +536,111 @@ int sb_unique_codes(const uint32_t* codes, int64_t n_rows, int32_t W, const int6
                                                        reinterpret_cast<long long*>(stats_out));
     sb::count_launch();
     if (int rc = sb::check_launch("max_count_kernel")) return rc;
+  }
+  return SB_OK;
+}
+
+/* Sorted selection for LARGE candidate lists: same contract as sb_rerank_select_rows (cand_cnt / cand_idx
+ * optional; cand_idx == NULL writes positions), but by one stable radix sort of (query, distance[, row])
+ * keys over all M candidates -- O(M) instead of the per-query O(m^2) rank count. */
+size_t sb_rerank_select_sorted_workspace_bytes(int64_t M) {
+  if (!uc_supported(M, M, 4)) return 0;
+  return al256((size_t)M * 16) + uc_plan(M, 4).total;
+}
+
+int sb_rerank_select_sorted(const double* dist, const int64_t* cand_off, const int64_t* cand_cnt, const int64_t* cand_idx,
+                            int64_t M, int32_t Q, int32_t n, int32_t tie_by_row, int64_t* out_pos, double* out_dist,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  SB_REQUIRE(Q >= 1 && n >= 1 && M >= 1, "sb_rerank_select_sorted: bad sizes");
+  SB_REQUIRE(dist && cand_off && out_pos && out_dist, "sb_rerank_select_sorted: NULL pointer");
+  SB_REQUIRE(!tie_by_row || cand_idx, "sb_rerank_select_sorted: tie_by_row needs cand_idx");
+  const size_t need = sb_rerank_select_sorted_workspace_bytes(M);
+  if (need == 0) {
+    sb::set_error("sb_rerank_select_sorted: M=%lld out of range", (long long)M);
+    return SB_ERR_UNSUPPORTED;
+  }
+  if (workspace == nullptr || workspace_bytes < need) {
+    sb::set_error("sb_rerank_select_sorted: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return SB_ERR_WORKSPACE;
+  }
+  SB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sb_rerank_select_sorted: workspace must be 256-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint32_t* keys = static_cast<uint32_t*>(workspace);
+  unsigned char* ws = static_cast<unsigned char*>(workspace) + al256((size_t)M * 16);
+  const UcPlan p = uc_plan(M, 4);
+  const long long* co = reinterpret_cast<const long long*>(cand_off);
+  const long long* cc = reinterpret_cast<const long long*>(cand_cnt);
+  const long long* ci = reinterpret_cast<const long long*>(cand_idx);
+  {
+    sb::ProfScope prof("select_keys_kernel", st);
+    select_keys_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(dist, co, cc, ci, Q, M, tie_by_row ? 1 : 0, keys);
+    sb::count_launch();
+    if (int rc = sb::check_launch("select_keys_kernel")) return rc;
+  }
+  if (int rc = sort_rows_stage(keys, 4, nullptr, M, p, ws, st)) return rc;
+  {
+    sb::ProfScope prof("select_emit_kernel", st);
+    const long long items = (long long)Q * n;
+    select_emit_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(
+        dist, co, cc, ci, Q, n, reinterpret_cast<uint32_t*>(ws + p.off_perm_a), reinterpret_cast<uint32_t*>(ws + p.off_perm_b),
+        reinterpret_cast<SortCtrl*>(ws + p.off_ctrl), reinterpret_cast<long long*>(out_pos), out_dist);
+    sb::count_launch();
+    if (int rc = sb::check_launch("select_emit_kernel")) return rc;
+  }
+  return SB_OK;
+}
+
+/* Exhaustive Hamming top-k for k beyond the scan kernels' list size (the reference takes any n,
+ * linear.py:232-240): every (query, row) key is materialised and sorted.  Q * U < 2^30 per call. */
+size_t sb_hamming_topk_sorted_workspace_bytes(int64_t U, int32_t Q) {
+  const int64_t M = U * (int64_t)Q;
+  if (U < 1 || Q < 1 || !uc_supported(M, M, 4)) return 0;
+  return al256((size_t)M * 16) + uc_plan(M, 4).total;
+}
+
+int sb_hamming_topk_sorted(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q, int32_t Q, int32_t k, int64_t idx_base,
+                           uint64_t* keys_out, void* workspace, size_t workspace_bytes, void* stream) {
+  SB_REQUIRE(db && q && keys_out, "sb_hamming_topk_sorted: NULL pointer");
+  SB_REQUIRE(k >= 1 && idx_base >= 0 && idx_base + U < (1ll << 40), "sb_hamming_topk_sorted: bad k / idx_base");
+  SB_REQUIRE(W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32, "sb_hamming_topk_sorted: W must be a power of two <= 32");
+  const size_t need = sb_hamming_topk_sorted_workspace_bytes(U, Q);
+  if (need == 0) {
+    sb::set_error("sb_hamming_topk_sorted: Q * U = %lld out of range (< 2^30)", (long long)(U * (int64_t)Q));
+    return SB_ERR_UNSUPPORTED;
+  }
+  if (workspace == nullptr || workspace_bytes < need) {
+    sb::set_error("sb_hamming_topk_sorted: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return SB_ERR_WORKSPACE;
+  }
+  SB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sb_hamming_topk_sorted: workspace must be 256-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t M = U * (int64_t)Q;
+  uint32_t* keys = static_cast<uint32_t*>(workspace);
+  unsigned char* ws = static_cast<unsigned char*>(workspace) + al256((size_t)M * 16);
+  const UcPlan p = uc_plan(M, 4);
+  {
+    sb::ProfScope prof("ham_all_keys_kernel", st);
+    const unsigned grid = (unsigned)((U + 255) / 256);
+    switch (W) {
+      case 1: ham_all_keys_kernel<1><<<grid, 256, 0, st>>>(db, U, q, Q, idx_base, keys); break;
+      case 2: ham_all_keys_kernel<2><<<grid, 256, 0, st>>>(db, U, q, Q, idx_base, keys); break;
+      case 4: ham_all_keys_kernel<4><<<grid, 256, 0, st>>>(db, U, q, Q, idx_base, keys); break;
+      case 8: ham_all_keys_kernel<8><<<grid, 256, 0, st>>>(db, U, q, Q, idx_base, keys); break;
+      case 16: ham_all_keys_kernel<16><<<grid, 256, 0, st>>>(db, U, q, Q, idx_base, keys); break;
+      default: ham_all_keys_kernel<32><<<grid, 256, 0, st>>>(db, U, q, Q, idx_base, keys); break;
+    }
+    sb::count_launch();
+    if (int rc = sb::check_launch("ham_all_keys_kernel")) return rc;
+  }
+  if (int rc = sort_rows_stage(keys, 4, nullptr, M, p, ws, st)) return rc;
+  {
+    sb::ProfScope prof("ham_all_emit_kernel", st);
+    const long long items = (long long)Q * k;
+    ham_all_emit_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(
+        keys, U, Q, k, reinterpret_cast<uint32_t*>(ws + p.off_perm_a), reinterpret_cast<uint32_t*>(ws + p.off_perm_b),
+        reinterpret_cast<SortCtrl*>(ws + p.off_ctrl), reinterpret_cast<unsigned long long*>(keys_out));
+    sb::count_launch();
+    if (int rc = sb::check_launch("ham_all_emit_kernel")) return rc;
   }
   return SB_OK;
 }

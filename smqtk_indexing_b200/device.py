@@ -279,6 +279,46 @@ class force_popc:
         _scan_tls.force_popc = self._prev
 
 
+#: longest per-query list the scan kernels keep; beyond it the exhaustive sorted path answers
+SCAN_MAX_K = 2048
+#: (query, row) keys materialised per call of the exhaustive path (16 bytes each + sort workspace)
+SORTED_TOPK_MAX_PAIRS = 1 << 26
+
+
+def hamming_topk_sorted_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0) -> torch.Tensor:
+    """Packed keys int64[Q, k] for ANY k (``sb_hamming_topk_sorted``: all (query, row) keys, one radix
+    sort) -- the reference's ``heapq.nsmallest`` takes any n (linear.py:232-240).  Queries are processed
+    in chunks of at most ``SORTED_TOPK_MAX_PAIRS`` (query, row) pairs."""
+    require_cuda()
+    U, W = db.shape
+    Q = q.shape[0]
+    keys = torch.empty((Q, k), dtype=torch.int64, device=db.device)
+    if U == 0:
+        return keys.fill_(-1)
+    if U > SORTED_TOPK_MAX_PAIRS * 8:
+        raise ValueError("n=%d neighbours over %d codes: the exhaustive path holds at most %d codes"
+                         % (k, U, SORTED_TOPK_MAX_PAIRS * 8))
+    lib = _lib.load()
+    per = max(1, SORTED_TOPK_MAX_PAIRS // U)
+    with torch.cuda.device(db.device):
+        for q0 in range(0, Q, per):
+            qc = min(per, Q - q0)
+            ws_bytes = lib.sb_hamming_topk_sorted_workspace_bytes(U, qc)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=db.device)
+            _lib.check(lib.sb_hamming_topk_sorted(_ptr(db), U, W, _ptr(q[q0:q0 + qc]), qc, k, idx_base,
+                                                  _ptr(keys[q0:q0 + qc]), _ptr(ws), ws_bytes, _stream()))
+    return keys
+
+
+def decode_keys(keys: torch.Tensor):
+    """Packed keys -> (dist int32, idx int64), -1 for empty slots (elementwise decode of the ABI's
+    key format; the merge kernel does the same for lists it has to merge)."""
+    empty = keys == -1
+    dist = torch.where(empty, torch.full_like(keys, -1), (keys >> _lib.KEY_ROW_BITS) & 0xFFFFFF).to(torch.int32)
+    idx = torch.where(empty, torch.full_like(keys, -1), keys & ((1 << _lib.KEY_ROW_BITS) - 1))
+    return dist, idx
+
+
 def hamming_scan_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0,
                       variant: int = 0) -> torch.Tensor:
     """Local top-k as packed keys int64[Q, k] (uint64 bit pattern, ascending,
@@ -294,6 +334,8 @@ def hamming_scan_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int =
         raise ValueError("query codes have %d words, table has %d" % (q.shape[1], W))
     if variant == SCAN_VARIANT_TC and not hamming_scan_tc_supported(U, W, Q, k):
         raise ValueError("tensor-core scan does not support U=%d W=%d Q=%d k=%d" % (U, W, Q, k))
+    if k > SCAN_MAX_K:
+        return hamming_topk_sorted_keys(db, q, k, idx_base)
     if variant == SCAN_VARIANT_TC or (variant == 0 and not force_popc.on() and _tc_scan_pays(U, W, Q, k)):
         keys, flag = hamming_scan_keys_tc(db, q, k, idx_base)
         pending = deferred_scan_check.current()
@@ -339,6 +381,8 @@ def hamming_topk(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0):
     Q = q.shape[0]
     if q.shape[1] != W:
         raise ValueError("query codes have %d words, table has %d" % (q.shape[1], W))
+    if k > SCAN_MAX_K:
+        return decode_keys(hamming_topk_sorted_keys(db, q, k, idx_base))
     if not force_popc.on() and _tc_scan_pays(U, W, Q, k):
         # large batch over a large table: tensor-core scan (falls back to XOR/POPC on overflow), then decode
         return topk_merge(hamming_scan_keys(db, q, k, idx_base).unsqueeze(0))
@@ -415,15 +459,42 @@ def expand_candidates(code_rows: torch.Tensor, csr_off: torch.Tensor, csr_rows: 
     return cand_idx, cand_off, cand_cnt
 
 
+#: longest candidate list of ONE query the rank-count selection kernel orders (it stages the list in
+#: shared memory and counts, O(m^2)); longer lists take the radix-sorted selection
+SELECT_RANK_MAX = 4096
+
+
+def _select_sorted(dist, cand_off, cand_cnt, cand_idx, n: int, tie_by_row: bool):
+    Q = cand_off.numel() - 1
+    M = dist.numel()
+    lib = _lib.load()
+    pos = torch.empty((Q, n), dtype=torch.int64, device=dist.device)
+    od = torch.empty((Q, n), dtype=torch.float64, device=dist.device)
+    if M == 0:
+        return pos.fill_(-1), od.fill_(float("nan"))
+    ws_bytes = lib.sb_rerank_select_sorted_workspace_bytes(M)
+    if ws_bytes == 0:
+        raise ValueError("candidate list of %d entries is beyond the selection's range" % M)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dist.device)
+    with torch.cuda.device(dist.device):
+        _lib.check(lib.sb_rerank_select_sorted(_ptr(dist), _ptr(cand_off), _ptr(cand_cnt), _ptr(cand_idx), M, Q, n,
+                                               1 if tie_by_row else 0, _ptr(pos), _ptr(od), _ptr(ws), ws_bytes, _stream()))
+    return pos, od
+
+
 def rerank_select_rows(dist: torch.Tensor, cand_off: torch.Tensor, cand_cnt: Optional[torch.Tensor],
-                       cand_idx: torch.Tensor, n: int, tie_by_row: bool = False):
+                       cand_idx: torch.Tensor, n: int, tie_by_row: bool = False, max_m: Optional[int] = None):
     """Per query the first ``n`` candidates by (distance, position), as candidate ROWS:
-    (rows int64[Q, n] or -1, dist float64[Q, n])."""
+    (rows int64[Q, n] or -1, dist float64[Q, n]).  ``max_m``: an upper bound on one query's list
+    length when the caller knows it (default: the total) -- lists beyond ``SELECT_RANK_MAX`` are
+    ordered by the radix-sorted selection."""
     require_cuda()
     _chk(dist, torch.float64, "dist")
     _chk(cand_off, torch.int64, "cand_off")
     _chk(cand_idx, torch.int64, "cand_idx")
     Q = cand_off.numel() - 1
+    if (dist.numel() if max_m is None else max_m) > SELECT_RANK_MAX:
+        return _select_sorted(dist, cand_off, cand_cnt, cand_idx, n, tie_by_row)
     rows = torch.empty((Q, n), dtype=torch.int64, device=dist.device)
     od = torch.empty((Q, n), dtype=torch.float64, device=dist.device)
     with torch.cuda.device(dist.device):
@@ -432,13 +503,15 @@ def rerank_select_rows(dist: torch.Tensor, cand_off: torch.Tensor, cand_cnt: Opt
     return rows, od
 
 
-def rerank_select(dist: torch.Tensor, cand_off: torch.Tensor, n: int):
+def rerank_select(dist: torch.Tensor, cand_off: torch.Tensor, n: int, max_m: Optional[int] = None):
     """Per query the first ``n`` candidates by (distance, position):
     (pos int64[Q, n] into the candidate list or -1, dist float64[Q, n])."""
     require_cuda()
     _chk(dist, torch.float64, "dist")
     _chk(cand_off, torch.int64, "cand_off")
     Q = cand_off.numel() - 1
+    if (dist.numel() if max_m is None else max_m) > SELECT_RANK_MAX:
+        return _select_sorted(dist, cand_off, None, None, n, False)
     pos = torch.empty((Q, n), dtype=torch.int64, device=dist.device)
     od = torch.empty((Q, n), dtype=torch.float64, device=dist.device)
     with torch.cuda.device(dist.device):
@@ -475,12 +548,15 @@ def l2_brute_force(db: torch.Tensor, q: torch.Tensor, k: int):
     dist = torch.full((Q, k), float("nan"), dtype=torch.float64, device=db.device)
     if N == 0:
         return idx, dist
-    all_rows = torch.arange(N, dtype=torch.int64, device=db.device)
-    off = torch.tensor([0, N], dtype=torch.int64, device=db.device)
-    for qi in range(Q):                      # one query at a time: N candidate slots each
-        d = rerank(db, q[qi:qi + 1], all_rows, off, "euclidean")
-        r, od = rerank_select_rows(d, off, None, all_rows, k, tie_by_row=True)
-        idx[qi], dist[qi] = r[0], od[0]
+    # query chunks of at most 2^25 (query, row) distances: candidate list of query j = every row
+    per = max(1, (1 << 25) // N)
+    for q0 in range(0, Q, per):
+        qc = min(per, Q - q0)
+        cand = torch.arange(N, dtype=torch.int64, device=db.device).repeat(qc)
+        off = torch.arange(qc + 1, dtype=torch.int64, device=db.device) * N
+        d = rerank(db, q[q0:q0 + qc], cand, off, "euclidean")
+        r, od = rerank_select_rows(d, off, None, cand, k, tie_by_row=True, max_m=N)
+        idx[q0:q0 + qc], dist[q0:q0 + qc] = r, od
     return idx, dist
 
 

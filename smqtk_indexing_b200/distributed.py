@@ -69,7 +69,9 @@ class DeviceOps:
 
     def rerank_select_rows(self, d, cand_off, cand_cnt, cand_idx, n):
         from . import device
-        return device.rerank_select_rows(d, cand_off, cand_cnt, cand_idx, n)
+        # fixed-pitch layout: every query owns numel / Q slots
+        return device.rerank_select_rows(d, cand_off, cand_cnt, cand_idx, n,
+                                         max_m=cand_idx.numel() // max(cand_off.numel() - 1, 1))
 
 
 def _all_gather_rows(t: torch.Tensor, group) -> Tuple[torch.Tensor, List[int]]:
@@ -239,7 +241,7 @@ class DeviceFlatOps:
         Q, m = dist_all.shape
         off = torch.arange(Q + 1, dtype=torch.int64, device=dist_all.device) * m
         return device.rerank_select_rows(dist_all.reshape(-1).contiguous(), off, None,
-                                         idx_all.reshape(-1).contiguous(), n, tie_by_row=True)
+                                         idx_all.reshape(-1).contiguous(), n, tie_by_row=True, max_m=m)
 
 
 class ShardedFlatL2Index:

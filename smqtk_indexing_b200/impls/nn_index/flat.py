@@ -65,7 +65,8 @@ class FlatL2NearestNeighborsIndex(NearestNeighborsIndex):
         self._x = None                               # float32[N, D] on the device
         self._prepared = None                        # (|row|^2, max) for sb_l2_topk
         self._uuids: List[Hashable] = []             # row -> uuid
-        self._row_of: Dict[Hashable, int] = {}
+        self._row_of: Optional[Dict[Hashable, int]] = {}   # uuid -> row; None = not built yet (matrix-built index)
+        self._adopted = False                        # self._x is the CALLER's tensor: copy before writing into it
 
     def get_config(self) -> Dict[str, Any]:
         return {
@@ -78,9 +79,10 @@ class FlatL2NearestNeighborsIndex(NearestNeighborsIndex):
             return len(self._uuids)
 
     # ------------------------------------------------------------------ device table
-    def _set_matrix(self, x, uuids: Sequence[Hashable]) -> None:
+    def _set_matrix(self, x, uuids: Sequence[Hashable], adopted: bool = False) -> None:
         from smqtk_indexing_b200 import device
         import torch
+        adopted = adopted and isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
         if not isinstance(x, torch.Tensor):
             x = torch.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32))
         if not x.is_cuda:
@@ -89,8 +91,15 @@ class FlatL2NearestNeighborsIndex(NearestNeighborsIndex):
             x = x.to(torch.float32)
         self._x = x.contiguous()
         self._uuids = list(uuids) if not isinstance(uuids, range) else uuids   # type: ignore
-        self._row_of = {} if isinstance(uuids, range) else {u: i for i, u in enumerate(self._uuids)}
+        # default (range) uuids: the uuid -> row lookup is built on first use (10M+ rows: not up front)
+        self._row_of = None if isinstance(uuids, range) else {u: i for i, u in enumerate(self._uuids)}
+        self._adopted = adopted
         self._prepared = device.l2_prepare(self._x) if len(self._x) else None
+
+    def _lookup(self) -> Dict[Hashable, int]:
+        if self._row_of is None:
+            self._row_of = {u: i for i, u in enumerate(self._uuids)}
+        return self._row_of
 
     @staticmethod
     def _vectors(descriptors: Sequence[DescriptorElement]) -> numpy.ndarray:
@@ -124,13 +133,17 @@ class FlatL2NearestNeighborsIndex(NearestNeighborsIndex):
             vec = torch.from_numpy(self._vectors(list(last.values()))).to(self._x.device)
             x = self._x
             uuids = list(self._uuids)
+            row_of = self._lookup()
             append = []
             for i, u in enumerate(last):
-                r = self._row_of.get(u)
+                r = row_of.get(u)
                 if r is None:
                     append.append(i)
                     uuids.append(u)
                 else:
+                    if self._adopted:                  # the matrix belongs to the caller: copy before the first write
+                        x = x.clone()
+                        self._adopted = False
                     x[r] = vec[i]                      # re-added uuid: overwrite in place
             if append:
                 sel = torch.tensor(append, dtype=torch.int64, device=x.device)
@@ -143,25 +156,28 @@ class FlatL2NearestNeighborsIndex(NearestNeighborsIndex):
             raise ReadOnlyError("Cannot modify read-only index.")
         with self._model_lock:
             uids = list(uids)
+            row_of = self._lookup()
             for uid in uids:                           # KeyError before any mutation (faiss.py:661-665)
-                if uid not in self._row_of:
+                if uid not in row_of:
                     raise KeyError(uid)
-            gone = {self._row_of[u] for u in uids}
+            gone = {row_of[u] for u in uids}
             keep = [r for r in range(len(self._uuids)) if r not in gone]
-            self._descriptor_set.remove_many_descriptors(uids)
+            if self._descriptor_set.count():           # matrix-built indexes never filled the descriptor set
+                self._descriptor_set.remove_many_descriptors([u for u in uids if self._descriptor_set.has_descriptor(u)])
             sel = torch.tensor(keep, dtype=torch.int64, device=self._x.device)
             self._set_matrix(self._x[sel], [self._uuids[r] for r in keep])
 
     def build_index_matrix(self, x, uuids: Optional[Sequence[Hashable]] = None) -> None:
         """Bulk build from a ``[N, D]`` matrix (numpy or float32 CUDA tensor, adopted without
-        a copy); ``uuids[r]`` names row ``r`` (default: the row number).  The
+        a copy -- the index never writes into it: a later ``update_index`` that overwrites a row
+        copies first); ``uuids[r]`` names row ``r`` (default: the row number).  The
         ``descriptor_set`` collaborator is not populated: use ``nn_batch``."""
         if self.read_only:
             raise ReadOnlyError("Cannot modify read-only index.")
         if x is None or len(x) == 0:
             raise self._empty_iterable_exception()
         with self._model_lock:
-            self._set_matrix(x, uuids if uuids is not None else range(len(x)))
+            self._set_matrix(x, uuids if uuids is not None else range(len(x)), adopted=True)
 
     # ------------------------------------------------------------------ queries
     def nn_batch(self, queries, n: int = 1, return_device: bool = False):

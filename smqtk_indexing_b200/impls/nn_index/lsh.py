@@ -53,6 +53,8 @@ class _DeviceMirror(DeviceLshIndex):
         super().__init__()
         self.uuids: List[Hashable] = []     # row -> uuid (a ``range`` for matrix-built indexes without uuids)
         self.row_of: Optional[Dict[Hashable, int]] = {}   # uuid -> row; None = not built yet (matrix-built index)
+        #: fed through the ``*_matrix`` methods / a snapshot: the collaborator containers are not its source of truth
+        self.matrix_built = False
 
     def count(self) -> int:
         return len(self.uuids)
@@ -228,6 +230,7 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
             if self.read_only:
                 raise ReadOnlyError("Cannot modify container attributes due to being in read-only mode.")
             new = list(descriptors)
+            stale = not self._mirror_in_sync()                   # collaborators were filled elsewhere (from_config over stores)
             LOG.debug("Updating descriptor index.")
             self.descriptor_set.add_many_descriptors(new)
 
@@ -246,8 +249,11 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
 
             # device mirror: append new uuids, overwrite re-added ones
             m = self._mirror
-            xt = torch.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32)).to(codes.device)
-            self._mirror_upsert(m, xt, codes, [d.uuid() for d in new])
+            if stale:
+                self._sync_mirror()                              # rebuilt from the descriptor set, new elements included
+            else:
+                xt = torch.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32)).to(codes.device)
+                self._mirror_upsert(m, xt, codes, [d.uuid() for d in new])
 
             if self.hash_index is not None:
                 LOG.debug("Updating hash index structure.")
@@ -260,6 +266,7 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
             if self.read_only:
                 raise ReadOnlyError("Cannot modify container attributes due to being in read-only mode.")
             uids = list(uids)
+            stale = not self._mirror_in_sync()
             # KeyError here (unknown uid) leaves everything untouched (lsh.py:407-416)
             descrs = list(self.descriptor_set.get_many_descriptors(uids))
             codes, bits = self._hash_matrix(self._vectors(descrs))
@@ -285,18 +292,10 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
 
             self.descriptor_set.remove_many_descriptors(uids)
 
-            m = self._mirror
-            if m.row_of is None:                               # matrix-built mirror: build the lookup on first use
-                m.row_of = {u: i for i, u in enumerate(m.uuids)}
-            gone = {m.row_of[u] for u in uids if u in m.row_of}
-            if m.alive is not None:                            # tombstones left by remove_from_index_matrix go too
-                gone |= set(torch.nonzero(~m.alive).reshape(-1).cpu().tolist())
-            if gone:
-                keep = [r for r in range(len(m.uuids)) if r not in gone]
-                sel = torch.tensor(keep, dtype=torch.int64, device=m.codes.device)
-                m.uuids = [m.uuids[r] for r in keep]
-                m.row_of = {u: i for i, u in enumerate(m.uuids)}
-                m.set_rows(m.x[sel], m.codes[sel])
+            if stale:
+                self._sync_mirror()
+            else:
+                self._mirror_remove([u for u in set(uids) if self._mirror_row(u) is not None])
 
     # ------------------------------------------------------------------ queries
     def _nn(self, d: DescriptorElement, n: int = 1) -> Tuple[Tuple[DescriptorElement, ...], Tuple[float, ...]]:
@@ -340,6 +339,59 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
         r_dists = tuple(float(v) for v, p in zip(od, pos) if p >= 0)
         return r_descrs, r_dists
 
+    # ------------------------------------------------------------------ device mirror upkeep
+    def _mirror_in_sync(self) -> bool:
+        """The reference keeps ALL index state in its collaborators (descriptor_set,
+        hash2uuids_kvstore, hash_index), so an instance made by ``from_config`` over persisted stores
+        is queryable at once (lsh.py:135-232).  The device mirror is private process state: it is in
+        sync when it was fed through the matrix API (its own source of truth) or holds exactly the
+        descriptor set's elements."""
+        m = self._mirror
+        return m.matrix_built or m.num_live == self.descriptor_set.count()
+
+    def _sync_mirror(self) -> None:
+        """Rebuild the device mirror from the descriptor set (vectors re-hashed on the device)."""
+        import torch
+        m = self._mirror
+        m.clear()
+        elems = list(self.descriptor_set)
+        if not elems:
+            return
+        x = self._vectors(elems)
+        codes, _ = self._hash_matrix(x)
+        m.uuids = [d.uuid() for d in elems]
+        m.row_of = {u: i for i, u in enumerate(m.uuids)}
+        m.set_rows(torch.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32)).to(codes.device), codes)
+
+    def _mirror_row(self, uuid: Hashable) -> Optional[int]:
+        m = self._mirror
+        if isinstance(m.uuids, range) and m.row_of is None:
+            return int(uuid) if isinstance(uuid, (int, numpy.integer)) and 0 <= int(uuid) < m.num_rows else None
+        if m.row_of is None:
+            m.row_of = {u: i for i, u in enumerate(m.uuids)}
+        return m.row_of.get(uuid)
+
+    def _mirror_remove(self, uuids: Sequence[Hashable]) -> None:
+        """Tombstone the rows of ``uuids`` (all present and live), re-index; compact once half the rows are dead."""
+        import torch
+        m = self._mirror
+        if not uuids:
+            return
+        rows = [self._mirror_row(u) for u in uuids]
+        sel = torch.tensor(rows, dtype=torch.int64, device=m.codes.device)
+        m.remove_rows(sel)
+        if m.row_of is not None:
+            for u in uuids:
+                m.row_of.pop(u, None)
+        if m.num_dead * 2 > m.num_rows and not isinstance(m.uuids, range):
+            remap = m.compact()                              # re-indexes
+            if remap is not None:
+                keep = torch.nonzero(remap >= 0).reshape(-1).cpu().tolist()
+                m.uuids = [m.uuids[r] for r in keep]
+                m.row_of = None
+        else:
+            m.reindex()
+
     def build_index_matrix(self, x, uuids: Optional[Sequence[Hashable]] = None) -> None:
         """Bulk build straight from a ``[N, D]`` matrix (numpy or float32 CUDA
         tensor, adopted without a copy): hash -> unique codes -> CSR, all on the
@@ -368,6 +420,7 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
                 x = x.to(torch.float32)
             m = self._mirror
             m.clear()
+            m.matrix_built = True
             codes = self.lsh_functor.get_hash_packed(x)
             m.uuids = list(uuids) if uuids is not None else range(x.shape[0])  # type: ignore
             m.row_of = None                                      # uuid -> row lookup is built on first use
@@ -461,29 +514,14 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
             if not uuids:
                 raise self._empty_iterable_exception()
             m = self._mirror
-            if isinstance(m.uuids, range) and m.row_of is None:
-                rows = [int(u) if isinstance(u, (int, numpy.integer)) and 0 <= int(u) < m.num_rows else -1 for u in uuids]
-            else:
-                if m.row_of is None:
-                    m.row_of = {u: i for i, u in enumerate(m.uuids)}
-                rows = [m.row_of.get(u, -1) for u in uuids]
+            rows = [self._mirror_row(u) for u in uuids]
+            rows = [-1 if r is None else r for r in rows]
             if m.num_rows == 0 or min(rows) < 0:
                 raise KeyError(uuids[rows.index(-1)] if -1 in rows else uuids[0])
             sel = torch.tensor(rows, dtype=torch.int64, device=m.codes.device)
             if m.alive is not None and not bool(m.alive[sel].all().item()):
                 raise KeyError(uuids[int((~m.alive[sel]).nonzero()[0].item())])
-            m.remove_rows(sel)
-            if m.row_of is not None:
-                for u in uuids:
-                    m.row_of.pop(u, None)
-            if m.num_dead * 2 > m.num_rows and not isinstance(m.uuids, range):
-                remap = m.compact()                              # re-indexes
-                if remap is not None:
-                    keep = torch.nonzero(remap >= 0).reshape(-1).cpu().tolist()
-                    m.uuids = [m.uuids[r] for r in keep]
-                    m.row_of = None
-            else:
-                m.reindex()
+            self._mirror_remove(uuids)
             if isinstance(self.hash_index, LinearHashIndex):
                 self.hash_index.set_code_table(m.table)
 
@@ -497,28 +535,71 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
         """Write the device-resident index (descriptor rows, codes, tombstones, row -> uuid) to
         ``path`` (``torch.save``), so that a built index survives a restart without re-hashing:
         ``load_snapshot`` re-derives the unique table and the CSR on the device.
-        The functor's model is NOT stored -- it has its own ``.npy`` caches (itq.py:212-237)."""
+        The functor's model is NOT stored -- it has its own ``.npy`` caches (itq.py:212-237); its
+        bit length, the descriptor dimension and the distance method are, and are checked on load.
+        uuids that are ints / strings (or the default row numbers) load without unpickling."""
         import torch
         with self._model_lock:
             m = self._mirror
             state = m.state_dict()
             state["uuids"] = ("range", len(m.uuids)) if isinstance(m.uuids, range) else ("list", list(m.uuids))
             state["distance_method"] = self.distance_method
+            state["bit_length"] = self._functor_bits()
+            state["dim"] = None if m.x is None else int(m.x.shape[1])
             torch.save(state, path)
 
-    def load_snapshot(self, path: str) -> None:
+    def _functor_bits(self) -> Optional[int]:
+        rot = getattr(self.lsh_functor, "rotation", None)
+        if rot is None:
+            rot = getattr(self.lsh_functor, "rps", None)
+        if rot is None:
+            return None
+        rot = numpy.asarray(rot)
+        return int(rot.reshape(rot.shape[0], -1).shape[1])
+
+    def load_snapshot(self, path: str, trust_pickle: bool = False) -> None:
         """Replace the device-resident index by a snapshot written by ``save_snapshot``.
 
-        :raises ReadOnlyError: read-only index.  :raises ValueError: not a snapshot, or its codes
-            are wider than the functor's."""
+        The file is read with ``torch.load(weights_only=True)`` (tensors, numbers, strings, lists /
+        tuples of those -- nothing is unpickled into code); a snapshot whose uuids are arbitrary
+        Python objects needs ``trust_pickle=True`` and must come from a trusted source.
+
+        :raises ReadOnlyError: read-only index.
+        :raises ValueError: not a snapshot; or it does not fit this index: its code width differs
+            from the functor's bit length, its descriptor dimension differs from the functor's, or it
+            was written for another ``distance_method``.  Nothing is modified in that case."""
+        import pickle
         import torch
         from smqtk_indexing_b200 import device
         with self._model_lock:
             if self.read_only:
                 raise ReadOnlyError("Cannot modify container attributes due to being in read-only mode.")
-            state = torch.load(path, map_location="cpu", weights_only=False)
+            try:
+                state = torch.load(path, map_location="cpu", weights_only=True)
+            except pickle.UnpicklingError as e:
+                if not trust_pickle:
+                    raise ValueError("snapshot %r holds objects that need unpickling (non-primitive uuids?): "
+                                     "pass trust_pickle=True if its source is trusted (%s)" % (path, str(e)[:80]))
+                state = torch.load(path, map_location="cpu", weights_only=False)
+            if not isinstance(state, dict) or state.get("format") != "smqtk_indexing_b200.DeviceLshIndex/1":
+                raise ValueError("not a DeviceLshIndex snapshot: %r" % (path,))
+            bits = self._functor_bits()
+            if state.get("codes") is not None and bits is not None:
+                if state.get("bit_length") not in (None, bits):
+                    raise ValueError("snapshot was hashed to %s bits, the functor produces %d" % (state["bit_length"], bits))
+                if int(state["codes"].shape[1]) != bitutil.words_for_bits(bits):
+                    raise ValueError("snapshot codes are %d words wide, the functor's %d-bit codes need %d"
+                                     % (state["codes"].shape[1], bits, bitutil.words_for_bits(bits)))
+            mean = getattr(self.lsh_functor, "mean_vec", None)
+            if state.get("x") is not None and mean is not None and int(state["x"].shape[1]) != int(numpy.asarray(mean).shape[0]):
+                raise ValueError("snapshot descriptors have %d dimensions, the functor's model %d"
+                                 % (state["x"].shape[1], numpy.asarray(mean).shape[0]))
+            if state.get("distance_method") not in (None, self.distance_method):
+                raise ValueError("snapshot was written for distance_method=%r, this index uses %r"
+                                 % (state["distance_method"], self.distance_method))
             m = self._mirror
             m.load_state_dict(state, device.device())
+            m.matrix_built = True
             kind, val = state["uuids"]
             m.uuids = range(val) if kind == "range" else list(val)     # type: ignore
             m.row_of = None
@@ -544,6 +625,10 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
         from smqtk_indexing_b200 import device
         with self._model_lock:
             m = self._mirror
+            if not self._mirror_in_sync():
+                # the collaborators were populated elsewhere (e.g. from_config over persisted stores) or
+                # changed behind this object: the mirror is rebuilt from the descriptor set, never queried partial
+                self._sync_mirror()
             if m.table is None:
                 raise ValueError("No index currently set to query from!")
             dev = m.x.device

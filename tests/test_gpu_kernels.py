@@ -85,6 +85,36 @@ def test_hamming_large_k(dev):
         assert np.array_equal(d, od) and np.array_equal(i, oi), k
 
 
+def test_hamming_any_k_beyond_the_scan_lists(dev):
+    """the reference takes any n (heapq.nsmallest, linear.py:232-240); k beyond the scan
+    kernels' 2048-entry lists goes through the exhaustive radix-sorted path, also in query chunks."""
+    rng = np.random.RandomState(14)
+    table = _rand_table(rng, 5000, 64, 2)
+    table[100:140] = table[99]                                 # ties
+    q = O.pack_codes(rng.rand(5, 64) > 0.5, 2)
+    for k in (2049, 4999, 5000):
+        od, oi = O.hamming_topk(table, q, k)
+        d, i = _run_topk(dev, table, q, k)
+        assert np.array_equal(d, od) and np.array_equal(i, oi), k
+    d, i = _run_topk(dev, table, q, 6000)                      # more than the table holds: padded
+    od, oi = O.hamming_topk(table, q, 5000)
+    assert np.array_equal(d[:, :5000], od) and np.array_equal(i[:, :5000], oi)
+    assert (d[:, 5000:] == -1).all() and (i[:, 5000:] == -1).all()
+    old = dev.SORTED_TOPK_MAX_PAIRS
+    dev.SORTED_TOPK_MAX_PAIRS = 2 * 5000                       # two queries per call
+    try:
+        d2, i2 = _run_topk(dev, table, q, 3000)
+    finally:
+        dev.SORTED_TOPK_MAX_PAIRS = old
+    od, oi = O.hamming_topk(table, q, 3000)
+    assert np.array_equal(d2, od) and np.array_equal(i2, oi)
+    keys = dev.hamming_scan_keys(torch.from_numpy(table.view(np.int32)).cuda(), torch.from_numpy(q.view(np.int32)).cuda(),
+                                 2500, idx_base=1 << 33)
+    kd, ki = dev.decode_keys(keys)
+    od, oi = O.hamming_topk(table, q, 2500)
+    assert np.array_equal(kd.cpu().numpy(), od) and np.array_equal(ki.cpu().numpy(), oi + (1 << 33))
+
+
 def test_sharded_scan_merge_equals_single(dev):
     """row-sharded table, per-shard top-k keys, sb_topk_merge == single scan."""
     rng = np.random.RandomState(17)
@@ -398,6 +428,40 @@ def test_rerank_known_answers(dev):
     assert one("hik", [1, 1], [0, 1]) == 0.0
     assert one("euclidean", [3, 4], [3, 4]) == 0.0
     assert one("cosine", [3, 4], [3, 4]) == 0.0
+
+
+@pytest.mark.parametrize("tie_by_row", [False, True])
+def test_rerank_select_large_lists_sorted_path(dev, tie_by_row):
+    """candidate lists far beyond the rank-count kernel's shared-memory stage (m up to 1e5,
+    fixed-pitch padding, ties, NaN) are ordered by the radix-sorted selection: (distance, position) or
+    (distance, row) order exactly as numpy's stable lexsort."""
+    rng = np.random.RandomState(23)
+    sizes = [100_000, 0, 3, 40_000, 7000]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    M = int(off[-1])
+    d = np.round(rng.rand(M), 3)                               # heavy ties
+    d[off[3] + 5] = np.nan
+    d[7] = -1.5                                                # negative values order before zero
+    rows = rng.permutation(M).astype(np.int64)
+    cnt = np.array([90_000, 0, 3, 40_000, 6500], np.int64)     # entries past cnt are padding
+    n = 300
+    t = lambda a: torch.from_numpy(a).cuda()
+    if tie_by_row:
+        got_r, got_d = dev.rerank_select_rows(t(d), t(off), t(cnt), t(rows), n, tie_by_row=True)
+    else:
+        got_r, got_d = dev.rerank_select(t(d), t(off), n)
+        cnt = np.array(sizes, np.int64)
+    got_r, got_d = got_r.cpu().numpy(), got_d.cpu().numpy()
+    for qi in range(len(sizes)):
+        m = int(cnt[qi])
+        seg = d[off[qi]:off[qi] + m]
+        key = np.where(np.isnan(seg), np.inf, seg)
+        tie = rows[off[qi]:off[qi] + m] if tie_by_row else np.arange(m)
+        o = np.lexsort((tie, key))[:n]
+        want = rows[off[qi] + o] if tie_by_row else o + off[qi]
+        assert np.array_equal(got_r[qi][:len(o)], want), qi
+        assert (got_r[qi][len(o):] == -1).all()
+        np.testing.assert_array_equal(got_d[qi][:len(o)], seg[o])
 
 
 def test_rerank_select_order(dev):

@@ -558,6 +558,53 @@ def test_flat_l2_index_matrix_build_and_batch():
     np.testing.assert_allclose(dists, od, rtol=1e-9)
 
 
+def test_flat_l2_matrix_built_index_supports_update_remove_without_touching_the_callers_tensor():
+    """A matrix-built index (default uuids = row numbers) takes the element API afterwards: remove by
+    row-number uuid, re-adding a uuid overwrites (no duplicate row), KeyError before mutation -- and the
+    caller's CUDA tensor, adopted without a copy, is never written (copy-on-write)."""
+    import torch
+    from smqtk_indexing_b200.impls.nn_index.flat import FlatL2NearestNeighborsIndex
+    rng = np.random.RandomState(13)
+    x = rng.rand(5000, 32).astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    keep_copy = xt.clone()
+    idx = FlatL2NearestNeighborsIndex(MemoryDescriptorSet())
+    idx.build_index_matrix(xt)
+    new_vec = rng.rand(32)
+    idx.update_index([DescriptorMemoryElement(7).set_vector(new_vec), DescriptorMemoryElement(5000).set_vector(x[0] + 1.0)])
+    assert idx.count() == 5001                                   # uuid 7 overwritten, uuid 5000 appended
+    assert torch.equal(xt, keep_copy)                            # the caller's matrix is untouched
+    rows, dists = idx.nn_batch(new_vec.astype(np.float32)[None, :], 1)
+    assert idx.row_uuids()[rows[0][0]] == 7 and dists[0][0] < 1e-6
+    idx.remove_from_index([3, 7])
+    assert idx.count() == 4999 and 7 not in idx.row_uuids() and 3 not in idx.row_uuids()
+    with pytest.raises(KeyError):
+        idx.remove_from_index([10, 3])
+    assert idx.count() == 4999
+    want = np.delete(np.vstack([x, x[:1] + 1.0]), [3, 7], axis=0)
+    qs = rng.rand(9, 32).astype(np.float32)
+    rows, dists = idx.nn_batch(qs, 5)
+    orow, od = O.l2_topk(want, qs, 5)
+    assert np.array_equal(rows, orow)
+    np.testing.assert_allclose(dists, od, rtol=1e-9)
+
+
+def test_flat_l2_unaligned_dimension_large_table():
+    """ADVICE r1: D % 16 != 0 takes the brute-force path (re-rank kernel over every row + selection);
+    at 1e5+ rows the selection must not be the O(m^2) rank count."""
+    from smqtk_indexing_b200.impls.nn_index.flat import FlatL2NearestNeighborsIndex
+    rng = np.random.RandomState(14)
+    x = rng.rand(120_000, 30).astype(np.float32)
+    idx = FlatL2NearestNeighborsIndex(MemoryDescriptorSet())
+    idx.build_index_matrix(x)
+    qs = rng.rand(6, 30).astype(np.float32)
+    qs[0] = x[77]
+    rows, dists = idx.nn_batch(qs, 20)
+    orow, od = O.l2_topk(x, qs, 20)
+    assert np.array_equal(rows, orow)
+    np.testing.assert_allclose(dists, od, rtol=1e-9)
+
+
 def test_simple_rp_functor_bits_and_lsh_use():
     """N4: random projections through the hash kernels; bits = (v - mean) . rps >= 0 for any
     `normalize` (simple_rp.py:52-59 divides rows by a positive scalar)."""
@@ -662,6 +709,118 @@ def test_matrix_ingest_matches_reference_state_and_oracle(golden):
     with pytest.raises(KeyError):
         index.remove_from_index_matrix([3, 7])
     assert index.count_rows() == int(g["s%d_count" % (len(gi.INGEST_STEPS) - 1)])
+
+
+def test_index_over_prepopulated_collaborators_is_queryable_and_never_partial():
+    """all reference state lives in the collaborators (lsh.py:160-232), so a second index
+    object over the SAME stores (what from_config over persisted stores gives) must answer nn_batch at
+    once -- and after one update_index it must see every row, not only the new one."""
+    rng = np.random.RandomState(41)
+    x = rng.rand(700, 24)
+    f = ItqFunctor(bit_length=12, itq_iterations=5, random_seed=1)
+    f.fit_matrix(x.astype(np.float32))
+    ds, kvs, hi = MemoryDescriptorSet(), MemoryKeyValueStore(), LinearHashIndex()
+    a = LSHNearestNeighborIndex(f, ds, kvs, hi, 'euclidean')
+    a.build_index(_descr(x[:600]))
+    qs = rng.rand(15, 24).astype(np.float32)
+    ra, da = a.nn_batch(qs, 5)
+    b = LSHNearestNeighborIndex(f, ds, kvs, hi, 'euclidean')     # empty mirror, populated collaborators
+    assert b.count() == 600 and b.count_rows() == 0
+    rb, db = b.nn_batch(qs, 5)                                    # mirror rebuilt from the descriptor set
+    np.testing.assert_array_equal(da, db)
+    ua, ub = a.mirror_uuids(), b.mirror_uuids()
+    assert [[ua[r] for r in row] for row in ra] == [[ub[r] for r in row] for row in rb]
+    c = LSHNearestNeighborIndex(f, ds, kvs, hi, 'euclidean')
+    c.update_index(_descr(x[600:], 600))                         # first call on a stale mirror is an update
+    assert c.count_rows() == 700 == c.count()
+    fresh = LSHNearestNeighborIndex(f, MemoryDescriptorSet(), MemoryKeyValueStore(), LinearHashIndex(), 'euclidean')
+    fresh.build_index(_descr(x))
+    rc, dc = c.nn_batch(qs, 5)
+    rf, df = fresh.nn_batch(qs, 5)
+    np.testing.assert_array_equal(dc, df)
+    # ... and a now sees a descriptor set that changed behind its back: never a partial answer
+    ra2, da2 = a.nn_batch(qs, 5)
+    np.testing.assert_array_equal(da2, df)
+    # element removal keeps row numbers (tombstones), KeyError leaves everything alone
+    c.remove_from_index([0, 1, 2, 650])
+    assert c.count_rows() == 696 == c.count()
+    with pytest.raises(KeyError):
+        c.remove_from_index([5, 0])
+    assert c.count_rows() == 696
+    keep = np.setdiff1d(np.arange(700), [0, 1, 2, 650])
+    fresh.build_index([DescriptorMemoryElement(int(i)).set_vector(x[i]) for i in keep])
+    rc, dc = c.nn_batch(qs, 5)
+    rf, df = fresh.nn_batch(qs, 5)
+    np.testing.assert_array_equal(dc, df)
+    uc, uf = c.mirror_uuids(), fresh.mirror_uuids()
+    assert [[uc[r] for r in row if r >= 0] for row in rc] == [[uf[r] for r in row if r >= 0] for row in rf]
+
+
+def test_any_n_through_the_plugin_api_and_heavy_collisions():
+    """n beyond the scan kernels' 2048-entry lists (LinearHashIndex.nn, LSH nn / nn_batch) and
+    the candidate pool of short codes (default bit_length=8: a handful of codes, thousands of rows each)."""
+    rng = np.random.RandomState(43)
+    bits = rng.rand(6000, 40) > 0.5
+    hi = LinearHashIndex()
+    hi.build_index(bits)
+    codes, dists = hi.nn(bits[0], 3000)
+    table = O.unique_code_table(O.pack_codes(bits, 2))[0]
+    od, oi = O.hamming_topk(table, O.pack_codes(bits[:1], 2), 3000)
+    assert codes.shape == (3000, 40) and np.array_equal(O.pack_codes(codes, 2), table[oi[0]])
+    np.testing.assert_allclose(dists, od[0] / 40.0)
+    # heavy collisions: 8-bit codes over 20k rows, n = 2500 -> every candidate list holds thousands of rows
+    x = rng.rand(20_000, 16).astype(np.float32)
+    f = ItqFunctor(bit_length=8, itq_iterations=5, random_seed=2)
+    f.fit_matrix(x)
+    index = _matrix_index(f)
+    index.build_index_matrix(x)
+    qs = rng.rand(3, 16).astype(np.float32)
+    n = 2500
+    rows, d = index.nn_batch(qs, n)
+    codes_dev = index._mirror.codes.cpu().numpy().view(np.uint32)
+    qc = f.get_hash_packed(qs).cpu().numpy().view(np.uint32)
+    x64 = x.astype(np.float64)
+    for qi in range(3):
+        orow, od = O.lsh_nn(x64, codes_dev, qs[qi].astype(np.float64), qc[qi:qi + 1], n, "euclidean")
+        np.testing.assert_allclose(d[qi][:len(od)], od, rtol=1e-5)
+        gaps = np.diff(od) > 1e-6 * od.max()
+        same = rows[qi][:len(od)] == orow
+        assert same[np.concatenate([[True], gaps]) & np.concatenate([gaps, [True]])].all()
+
+
+def test_snapshot_validation_and_safe_loading(tmp_path):
+    """load_snapshot reads with weights_only=True and refuses a snapshot that does not fit
+    the index (code width / dimension / distance method) without modifying anything."""
+    rng = np.random.RandomState(47)
+    x = rng.rand(500, 32).astype(np.float32)
+    f16 = ItqFunctor(bit_length=16, itq_iterations=3, random_seed=0)
+    f16.fit_matrix(x)
+    a = _matrix_index(f16)
+    a.build_index_matrix(x, uuids=["u%d" % i for i in range(500)])
+    p = str(tmp_path / "snap.pt")
+    a.save_snapshot(p)
+    ok = _matrix_index(f16)
+    ok.load_snapshot(p)
+    assert ok.count_rows() == 500 and ok.mirror_uuids()[7] == "u7"
+    f40 = ItqFunctor(bit_length=40, itq_iterations=3, random_seed=0)   # 2 words: does not fit 1-word codes
+    f40.fit_matrix(rng.rand(500, 64).astype(np.float32))
+    bad = _matrix_index(f40)
+    with pytest.raises(ValueError):
+        bad.load_snapshot(p)
+    assert bad.count_rows() == 0
+    other = LSHNearestNeighborIndex(f16, MemoryDescriptorSet(), MemoryKeyValueStore(), LinearHashIndex(), 'hik')
+    with pytest.raises(ValueError):
+        other.load_snapshot(p)
+    # uuids that need unpickling are refused unless the caller vouches for the file
+    b = _matrix_index(f16)
+    b.build_index_matrix(x[:10], uuids=[("t", i) if i else frozenset([1]) for i in range(10)])
+    p2 = str(tmp_path / "snap2.pt")
+    b.save_snapshot(p2)
+    c = _matrix_index(f16)
+    with pytest.raises(ValueError):
+        c.load_snapshot(p2)
+    c.load_snapshot(p2, trust_pickle=True)
+    assert c.count_rows() == 10
 
 
 def test_matrix_update_remove_equal_fresh_build():
