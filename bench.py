@@ -8,20 +8,29 @@ Headline benchmark: LSH kNN queries/s @k=10 over 10M x 256-bit ITQ codes
     python bench.py --impl reference --gpus N --steps K ...   # reference CPU path (rank 0 only)
 
 One "step" = one batch of Q queries through the whole query path
-(sb_itq_hash -> sb_hamming_topk over the unique-code table -> candidate
+(sb_itq_hash_tc -> sb_hamming_scan_tc over the unique-code table -> candidate
 expansion -> sb_rerank -> sb_rerank_select), i.e. LSHNearestNeighborIndex.nn
 (reference smqtk_indexing/impls/nn_index/lsh.py:452-519) for Q queries.
 
-  value   whole-job queries/s with the queries already resident in HBM
+  value   whole-job queries/s with the queries already resident in HBM, through the product's
+          default path (the pipeline replayed as one CUDA graph once the batch shape repeats)
   e2e     the same through the public plugin call LSHNearestNeighborIndex.nn_batch
           with pinned HOST query buffers in and host result arrays out
-  roofline  Hamming scan kernel: algorithmic bytes Q*U*(b/8) per launch over its
-          CUDA-event duration, against the measured HBM copy peak
+  roofline  the dominant kernel (ham_filter_tc_kernel, tcgen05 +-1 FP8 dot products): algorithmic
+          flops 2*Q*U*b per step over its CUDA-event duration -- measured in a second, kernel-by-kernel
+          pass of the same K steps --, against a cuBLASLt FP8 GEMM timed in this very run and 2 x the
+          measured bf16 figure; `rerank` and `single_query_scan` carry the HBM-bound kernels' GB/s
   cpu_baseline  the reference's algorithm (oracle/ref_port.py, literal port) on
           this box's host cores, bounded sample
+  parity_checked  8 queries of the timed batch re-derived with plain torch (float64 hash, byte-LUT
+          popcount top-k, CSR expansion, float64 distances) outside the timed region, at every N
 
-N > 1: one process per GPU (torchrun), database row-sharded, local top-k per GPU,
-NCCL all-gather + sb_topk_merge; total work is fixed (strong scaling).
+N > 1: one process per GPU (torchrun).  Descriptors are row-sharded; the 320 MB code table is
+replicated; the scan is partitioned over the QUERIES (each rank scans the whole table for its slice of
+the batch) and every rank finishes its slice alone, reading candidate rows from the owners' HBM over
+NVLink (CUDA IPC); one NCCL all-gather assembles the results.  `config.parallelism` states what ran;
+`--scan-partition rows` runs the row-partitioned scan (per-rank table slices, all-gather of the local
+top-k keys + merge) for comparison.  Total work is fixed (strong scaling).
 """
 import argparse
 import json
@@ -55,6 +64,11 @@ def parse_args():
     ap.add_argument("--fit-rows", type=int, default=100_000)
     ap.add_argument("--fit-iters", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scan-partition", default="auto", choices=["auto", "rows", "queries"],
+                    help="N > 1: how the Hamming scan is split over the ranks")
+    ap.add_argument("--rerank", default="auto", choices=["auto", "peer", "allreduce"],
+                    help="N > 1: candidate rows read from the owners' HBM (peer) or owner-computes + all-reduce")
+    ap.add_argument("--no-graph", action="store_true", help="never replay the pipeline as a CUDA graph")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU-baseline sample size (seconds of CPU work)")
     ap.add_argument("--ref-budget-s", type=float, default=100.0, help="--impl reference: seconds of CPU work in total")
     return ap.parse_args()
@@ -69,6 +83,32 @@ def fp8_peak():
             return 2.0 * float(json.load(f)["bf16_tflops"]), "2 x MEASURED_PEAKS.json bf16_tflops (burst)"
     except Exception:
         return 2.0 * 1590.0, "2 x B200_PROFILING.md bf16 fallback (1.59 PFLOP/s)"
+
+
+def measure_fp8_gemm(dev):
+    """cuBLASLt FP8 (E4M3 x E4M3 -> BF16) GEMM, 8192^3, best of 10 with CUDA events: the tensor-pipe
+    denominator measured in THIS run on THIS box (MEASURED_PEAKS.json has no FP8 figure).  None when the
+    library call is unavailable."""
+    import torch
+    try:
+        n = 8192
+        a = torch.randn((n, n), device=dev).to(torch.float8_e4m3fn)
+        b = torch.randn((n, n), device=dev).to(torch.float8_e4m3fn).t()          # column-major B as cuBLASLt wants
+        one = torch.ones((), device=dev)
+        for _ in range(3):
+            torch._scaled_mm(a, b, scale_a=one, scale_b=one, out_dtype=torch.bfloat16)
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._scaled_mm(a, b, scale_a=one, scale_b=one, out_dtype=torch.bfloat16)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception as e:                   # pragma: no cover - depends on the torch build
+        sys.stderr.write("fp8 GEMM measurement unavailable: %r\n" % (e,))
+        return None
 
 
 def hbm_peak():
@@ -313,14 +353,79 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(args, n_gpus):
+def workload_config(args, n_gpus, parallelism=None):
     return {
         "workload": "configs[1]: ITQ-%d hashing + LinearHashIndex Hamming top-k over %dx%d-d fp32 descriptors, "
                     "batch %d queries, k=%d, euclidean re-rank" % (args.bits, args.rows, args.dim, args.queries, args.k),
         "rows": args.rows, "dim": args.dim, "bits": args.bits, "queries_per_step": args.queries, "k": args.k,
-        "parallelism": "row-sharded x%d, all-gather top-k merge" % n_gpus if n_gpus > 1 else "single GPU",
+        "parallelism": parallelism or ("x%d" % n_gpus if n_gpus > 1 else "single GPU"),
         "l2": "L2 flushed between timed steps (512 MiB write + read-back); code table %d MB" % (args.rows * args.bits // 8 // 10 ** 6),
     }
+
+
+# --------------------------------------------------------------------------- parity (plain torch, outside the timed region)
+def parity_check(torch, dist, functor, state, x_local, row_lo, q_dev, k, result, n_check=8):
+    """Re-derive the answers of `n_check` queries of the timed batch WITHOUT any kernel of this repo:
+    float64 hash (itq.py:404-408), byte-LUT popcount over the whole unique-code table + torch.topk on
+    (distance, row) keys (linear.py:232-240 with the canonical tie order), CSR expansion (lsh.py:490-496),
+    float64 euclidean distances on the rank that owns each row (summed over ranks with one all-reduce when
+    N > 1), stable sort, first k (lsh.py:513-519).  Raises on a mismatch; returns the record for the JSON line."""
+    import numpy as np
+    rows_out, d_out = result
+    dev = q_dev.device
+    Q, D = q_dev.shape
+    table, csr_off, csr_rows = state.table, state.csr_off, state.csr_rows
+    U, W = table.shape
+    mean = torch.from_numpy(np.real(np.asarray(functor.mean_vec)).astype(np.float64)).to(dev)
+    rot = torch.from_numpy(np.ascontiguousarray(np.real(np.asarray(functor.rotation)), dtype=np.float64)).to(dev)
+    b = rot.shape[1]
+    z = (q_dev.double() - mean) @ rot
+    # a device bit may differ from the float64 bit only for |z| < 1e-5 |q - m| |r| (tests): take queries away from that
+    stable = z.abs().min(dim=1).values > 4e-5 * (q_dev.double() - mean).norm(dim=1)
+    picks = []
+    for c in range(n_check):                                    # spread over the batch: every rank's slice is covered at N = 8
+        for qi in range(c * Q // n_check, (c + 1) * Q // n_check):
+            if bool(stable[qi]):
+                picks.append(qi)
+                break
+    lut = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int32, device=dev)
+    n_local = x_local.shape[0]
+    worst = 0.0
+    for qi in picks:
+        bits = torch.zeros(W * 32, dtype=torch.int64, device=dev)
+        bits[W * 32 - b:] = (z[qi] >= 0).to(torch.int64)        # index 0 = most significant bit (bits.py:17-20)
+        words = (bits.view(W, 32) << torch.arange(31, -1, -1, device=dev)).sum(dim=1)
+        words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+        d_all = torch.empty(U, dtype=torch.int64, device=dev)
+        for s0 in range(0, U, 2_000_000):
+            x = (table[s0:s0 + 2_000_000] ^ words[None, :]).contiguous().view(torch.uint8)
+            d_all[s0:s0 + 2_000_000] = lut[x.long()].sum(dim=1)
+        keys = (d_all << 40) | torch.arange(U, device=dev)
+        near = (torch.topk(keys, min(k, U), largest=False, sorted=True).values & ((1 << 40) - 1)).tolist()
+        cand = torch.cat([csr_rows[int(csr_off[c]):int(csr_off[c + 1])] for c in near])
+        mine = (cand >= row_lo) & (cand < row_lo + n_local)
+        dd = torch.zeros(cand.numel(), dtype=torch.float64, device=dev)
+        if bool(mine.any()):
+            xr = x_local[(cand[mine] - row_lo)].double()
+            dd[mine] = ((xr - q_dev[qi].double()[None, :]) ** 2).sum(dim=1).sqrt()
+        if dist is not None:
+            dist.all_reduce(dd, op=dist.ReduceOp.SUM)
+        order = torch.sort(dd, stable=True).indices[:k]
+        want_rows, want_d = cand[order], dd[order]
+        m = want_rows.numel()
+        got_rows, got_d = rows_out[qi][:m], d_out[qi][:m]
+        rel = float(((got_d - want_d).abs() / want_d.clamp(min=1e-30)).max()) if m else 0.0
+        worst = max(worst, rel)
+        gaps_ok = m < 2 or float((want_d[1:] - want_d[:-1]).min()) > 1e-6 * float(want_d.max())
+        if rel > 1e-5 or (gaps_ok and not torch.equal(got_rows, want_rows)) or bool((rows_out[qi][m:] != -1).any()):
+            raise SystemExit("bench.py: PARITY FAILURE on query %d: got rows %s dists %s, torch reference rows %s dists %s"
+                             % (qi, got_rows.tolist(), got_d.tolist(), want_rows.tolist(), want_d.tolist()))
+    if len(picks) < n_check // 2:
+        raise SystemExit("bench.py: parity check found only %d stable queries" % len(picks))
+    return {"parity_checked": True, "queries": picks, "max_rel_dist_err": worst,
+            "how": "plain torch: float64 hash, byte-LUT popcount + topk over all %d codes, CSR expansion, float64 "
+                   "euclidean on the owning rank%s, stable sort; rows exact, distances rtol 1e-5" % (
+                       U, " + one SUM all-reduce" if dist is not None else "")}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -377,24 +482,46 @@ def run_b200(args):
         n_codes = index._mirror.num_codes
         scan_rows = n_codes
 
+        use_graph = [not args.no_graph]
+
         def query_dev(qd):
-            return index.nn_batch(qd, k, return_device=True)
+            return index.nn_batch(qd, k, return_device=True, graph=use_graph[0])
 
         def query_host(qh):
-            return index.nn_batch(qh, k)
+            return index.nn_batch(qh, k, graph=use_graph[0])
+        parallelism = "single GPU"
+        state = index._mirror
+        peers = None
     else:
         from smqtk_indexing_b200.distributed import ShardedLshIndex
-        index = ShardedLshIndex(functor, "euclidean")
+        index = ShardedLshIndex(functor, "euclidean", scan_partition=args.scan_partition, rerank=args.rerank,
+                                graph=not args.no_graph)
         index.build(x_local)
         n_codes = index.num_codes
-        scan_rows = index.scan_hi - index.scan_lo
+        by_q = index._by_queries(Q)
+        # rows of the code table each rank scans, and for how many of the batch's queries
+        scan_rows = n_codes if by_q else index.scan_hi - index.scan_lo
+        use_graph = [not args.no_graph]
 
         def query_dev(qd):
+            index.graph = use_graph[0]
             return index.query(qd, k)
 
         def query_host(qh):
+            index.graph = use_graph[0]
             rows, d = index.query(qh.to(dev, non_blocking=True), k)
             return rows.cpu().numpy(), d.cpu().numpy()
+        parallelism = ("x%d: descriptors row-sharded; %s; re-rank %s" % (
+            world,
+            "scan split over the QUERIES (code table replicated, each rank scans all %d codes for %d of the %d queries)"
+            % (n_codes, (Q + world - 1) // world, Q) if by_q else
+            "scan split over table ROWS (each rank scans %d of %d codes for all queries; all-gather of local top-k keys + merge)"
+            % (index.scan_hi - index.scan_lo, n_codes),
+            "per query slice with candidate rows read from the owners' HBM over NVLink (CUDA IPC), one all-gather of results"
+            if index.peers is not None else
+            "owner-computes + SUM all-reduce of candidate distances (peer access unavailable: %s)" % index.peer_error))
+        state = index
+        peers = index.peers
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t_build0
 
@@ -435,7 +562,12 @@ def run_b200(args):
         return sum(a.elapsed_time(b_) for a, b_ in evs)
 
     for _ in range(max(args.warmup, 3)):
-        query_dev(q_dev)
+        query_dev(q_dev)                       # (the 2nd batch of a shape captures the CUDA graph)
+    barrier()
+
+    # ---- parity, outside the timed region, at every N: 8 queries of the batch re-derived with plain torch ----
+    parity = parity_check(torch, dist if world > 1 else None, functor, state, x_local, bounds[rank], q_dev, k,
+                          query_dev(q_dev))
     barrier()
 
     gpu_id = "GPU-%s" % torch.cuda.get_device_properties(dev).uuid if hasattr(
@@ -443,14 +575,21 @@ def run_b200(args):
     sampler = ClockSampler(gpu_id)
     if rank == 0:
         sampler.start()
+    # timed region A (the reported value): the product's default path
+    ms_dev = timed(query_dev, q_dev, args.steps, on_step=(sampler.sample_between_steps if rank == 0 else None))
+    clocks = sampler.stop() if rank == 0 else None
+    # timed region B: the same K steps launched kernel by kernel with an event pair around every launch
+    # (a graph replay has no host-side launches to bracket): per-kernel durations, launch count
+    use_graph[0] = False
+    query_dev(q_dev)
     launches0 = _lib.launch_count()
     _lib.profile_fetch()
     _lib.profile_enable(True)
-    ms_dev = timed(query_dev, q_dev, args.steps, on_step=(sampler.sample_between_steps if rank == 0 else None))
+    ms_eager = timed(query_dev, q_dev, args.steps)
     _lib.profile_enable(False)
     launches = _lib.launch_count() - launches0
     prof = _lib.profile_fetch()
-    clocks = sampler.stop() if rank == 0 else None
+    use_graph[0] = not args.no_graph
 
     # ---- end to end: pinned host queries in, host results out, through the public call ----
     for _ in range(2):
@@ -459,7 +598,7 @@ def run_b200(args):
 
     # ---- single-query scan (the reference's per-call shape; HBM-bound) ----
     from smqtk_indexing_b200 import device as devops
-    table = index._mirror.table if world == 1 else index.table[index.scan_lo:index.scan_hi]
+    table = index._mirror.table if world == 1 else index.table
     one_q = functor.get_hash_packed(q_dev[:1])
     for _ in range(3):
         devops.hamming_scan_keys(table, one_q, k)
@@ -472,11 +611,12 @@ def run_b200(args):
     prof1 = [ms for name, ms in _lib.profile_fetch() if name == "hamming_scan_kernel"]
 
     # ---- max over ranks ----
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_dev, ms_e2e, ms_eager], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    ms_dev, ms_e2e, ms_eager = float(t[0]), float(t[1]), float(t[2])
 
+    fp8_meas = measure_fp8_gemm(dev) if rank == 0 else None
     if rank == 0:
         W = (b + 31) // 32
         per_kernel = {}
@@ -484,35 +624,42 @@ def run_b200(args):
             per_kernel.setdefault(name, []).append(ms)
         peak, peak_src = hbm_peak()
         ms_step = ms_dev / args.steps
+        ms_step_eager = ms_eager / args.steps
+        q_per_rank = (Q + world - 1) // world if (world > 1 and index._by_queries(Q)) else Q
         tc = per_kernel.get("ham_filter_tc_kernel", [])
         if tc:
             # batched path: +-1 FP8 dot products on tcgen05 (hamming_tc.cu); several launches per step (chunks)
             scan_ms = sum(tc) / args.steps
-            alg_flops = 2.0 * Q * scan_rows * (32 * W)
+            alg_flops = 2.0 * q_per_rank * scan_rows * (32 * W)           # this rank's share of 2*Q*U*b
             achieved = alg_flops / (scan_ms * 1e-3) / 1e12
-            tpeak, tpeak_src = fp8_peak()
+            proxy, proxy_src = fp8_peak()
+            tpeak, tpeak_src = (fp8_meas, "cuBLASLt FP8 E4M3 GEMM 8192^3 (torch._scaled_mm), best of 10, timed in this run") \
+                if fp8_meas else (proxy, proxy_src)
             traffic = recorded_traffic("scan_tc_traffic.json")
             roofline = {
                 "kernel": "ham_filter_tc_kernel", "bound": "tensor",
                 "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s", "frac": achieved / tpeak,
                 "traffic": traffic.get("dram_bytes_per_step") if traffic else None,
+                "traffic_source": "profiles/scan_tc_traffic.json (ncu dram__bytes_read+write of one batch, N=1 shape)"
+                                  if traffic else None,
                 "peak_source": tpeak_src,
+                "frac_of_2x_measured_bf16": achieved / proxy, "proxy_peak": proxy,
                 "nominal_fp8_peak": 4500.0, "frac_of_nominal": achieved / 4500.0,
                 "algorithmic_flops_per_step": alg_flops, "launches_per_step": len(tc) / args.steps,
-                "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / ms_step,
-                "note": "algorithmic flops = 2*Q*U*b: one multiply-add per (query, code, bit); the kernel issues "
-                        "b+32 per pair (the threshold rides in one extra K step).  peak = 2 x the MEASURED bf16 "
-                        "cuBLAS figure (no FP8 number in MEASURED_PEAKS.json); that GEMM ran power-limited at "
-                        "~1.37 GHz while these +-1 operands let the tensor pipe hold ~1.8 GHz, so frac near or "
-                        "above 1 is not a counting error -- frac_of_nominal uses the 4.5 PFLOP/s datasheet peak.  "
-                        "Equivalent algorithmic bytes (Q*U*b/8 per step): %.1f TB/s." % (
-                            float(Q) * scan_rows * W * 4 / (scan_ms * 1e-3) / 1e12),
+                "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / ms_step_eager,
+                "note": "per rank.  algorithmic flops = 2*Q*U*b: one multiply-add per (query, code, bit) of this rank's share; "
+                        "the kernel issues b+32 per pair (the threshold rides in one extra K step).  Durations come from "
+                        "the kernel-by-kernel pass (region B, %.3f ms/step); the reported value is the graph-replayed "
+                        "pass (region A).  A +-1 operand GEMM draws less power than cuBLAS's random-data GEMM and holds a "
+                        "higher clock, so frac can exceed 1 against a measured GEMM peak; frac_of_nominal uses the 4.5 "
+                        "PFLOP/s datasheet figure.  Equivalent algorithmic bytes (Q*U*b/8 per step): %.1f TB/s." % (
+                            ms_step_eager, float(q_per_rank) * scan_rows * W * 4 / (scan_ms * 1e-3) / 1e12),
             }
             int_pipe = None
         else:
             scan = per_kernel.get("hamming_scan_kernel", [])
-            scan_ms = sum(scan) / len(scan) if scan else float("nan")
-            alg_bytes = float(Q) * scan_rows * W * 4
+            scan_ms = sum(scan) / args.steps if scan else float("nan")
+            alg_bytes = float(q_per_rank) * scan_rows * W * 4
             achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
             traffic = recorded_traffic()
             roofline = {
@@ -521,34 +668,57 @@ def run_b200(args):
                 "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / ms_step if scan else None,
+                "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / ms_step_eager if scan else None,
                 "note": "algorithmic bytes = Q*U*(b/8): every query against every code; each loaded code word "
                         "is reused from registers for the CTA's whole query tile, so frac > 1 is expected and the "
                         "binding resources are the ALU (LOP3) and XU (POPC) pipes -- see int_pipe and profiles/",
             }
-            int_pipe = {"pairs_per_s": float(Q) * scan_rows / (scan_ms * 1e-3), "popc_per_pair": 4, "lop3_per_pair": 16}
+            int_pipe = {"pairs_per_s": float(q_per_rank) * scan_rows / (scan_ms * 1e-3), "popc_per_pair": 4, "lop3_per_pair": 16}
+        # stage 3 (HBM-bound gather): candidates x D x 4 bytes over the re-rank kernel's duration
+        rr = per_kernel.get("rerank_kernel", [])
+        rr_ms = sum(rr) / args.steps if rr else None
+        rerank_line = None
+        if rr_ms:
+            rr_bytes = float(q_per_rank) * k * max(state.max_rows_per_code, 1) * D * 4
+            rerank_line = {"kernel": "rerank_kernel<euclidean>", "bound": "hbm", "kernel_ms": rr_ms,
+                           "candidate_slots_per_step": int(q_per_rank * k * max(state.max_rows_per_code, 1)),
+                           "algorithmic_bytes_per_step": rr_bytes, "achieved_gbs": rr_bytes / (rr_ms * 1e-3) / 1e9,
+                           "frac_of_peak": rr_bytes / (rr_ms * 1e-3) / 1e9 / peak, "peak": peak, "peak_source": peak_src,
+                           "note": "one warp per candidate row (random 2 KB gathers%s); %d slots x %d B in %.1f us -- "
+                                   "latency-bound at this size, see profiles/ for the C4 shape (1M x 4096-d, k=50)" % (
+                                       ", peer rows over NVLink" if peers is not None else "",
+                                       int(q_per_rank * k * max(state.max_rows_per_code, 1)), D * 4, rr_ms * 1e3)}
         line = {
             "metric": METRIC, "value": Q * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "fp8 (+-1, exact integer distances)" if tc else "u32", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": workload_config(args, world, parallelism),
             "clocks": clocks,
             "e2e": {"value": Q * args.steps / (ms_e2e * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 16,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
+            "gpu_launches_note": "kernels of this repo per %d steps, counted in the kernel-by-kernel pass (region B); the "
+                                 "graph-replayed pass (region A) runs the same kernels from one cudaGraphLaunch per step%s"
+                                 % (args.steps, "" if not args.no_graph else " [graphs disabled: A == B]"),
+            "graph_replay": not args.no_graph,
+            "eager": {"ms_per_step": ms_step_eager, "value": Q * args.steps / (ms_eager * 1e-3)},
+            "parity_checked": bool(parity.get("parity_checked")), "parity": parity,
             "roofline": roofline,
+            "rerank": rerank_line,
             "int_pipe": int_pipe,
+            "fp8_gemm_tflops_measured": fp8_meas,
             "single_query_scan": {
-                "what": "sb_hamming_scan with Q=1 (LinearHashIndex.nn call shape): HBM-bound",
+                "what": "sb_hamming_scan with Q=1 (LinearHashIndex.nn call shape): HBM-bound, whole table",
                 "kernel_ms": statistics.median(prof1) if prof1 else None,
-                "achieved_gbs": (scan_rows * W * 4 / (statistics.median(prof1) * 1e-3) / 1e9) if prof1 else None,
-                "frac_of_peak": (scan_rows * W * 4 / (statistics.median(prof1) * 1e-3) / 1e9 / peak) if prof1 else None,
+                "achieved_gbs": (table.shape[0] * W * 4 / (statistics.median(prof1) * 1e-3) / 1e9) if prof1 else None,
+                "frac_of_peak": (table.shape[0] * W * 4 / (statistics.median(prof1) * 1e-3) / 1e9 / peak) if prof1 else None,
             },
             "kernel_ms_per_step": {n_: sum(v) / args.steps for n_, v in per_kernel.items()},
             "index": {"unique_codes": int(n_codes), "rows_local": int(n_local), "scan_rows_local": int(scan_rows),
-                      "build_s": build_s},
+                      "queries_scanned_per_rank": int(q_per_rank), "build_s": build_s,
+                      "peer_rerank": peers is not None},
         }
         if world == 1 and not args.no_cpu_baseline:
             leg = literal_cpu_leg(args, steps=3, warmup=1, budget_s=args.cpu_budget_s)

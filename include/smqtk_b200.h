@@ -128,6 +128,13 @@ SB_API int sb_hamming_scan_variant(const uint32_t* db, int64_t U, int32_t W,
                             const uint32_t* q, int32_t Q, int32_t k, int64_t idx_base,
                             uint64_t* keys_out, void* workspace, size_t workspace_bytes,
                             int32_t variant, void* stream);
+/* sb_hamming_scan, predicated on a DEVICE flag: every kernel returns at once unless *enable != 0,
+ * in which case keys_out is overwritten with the exact XOR/POPC result.  Launched right after
+ * sb_hamming_scan_tc with its overflow flag it makes the tensor-core scan exact for any table
+ * without a host round trip (workspace: sb_hamming_scan_workspace_bytes). */
+SB_API int sb_hamming_scan_if(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q, int32_t Q, int32_t k,
+                       int64_t idx_base, uint64_t* keys_out, const int32_t* enable, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* Batched scan on the tensor cores (hamming_tc.cu): bits -> +-1 FP8 E4M3, tcgen05.mma
  * kind::f8f6f4, dot = 32 W - 2 * distance -- exact integers in the FP32 accumulator.  Same
@@ -197,6 +204,18 @@ SB_API int sb_rerank_select(const double* dist, const int64_t* cand_off, int32_t
 SB_API int sb_rerank_select_rows(const double* dist, const int64_t* cand_off, const int64_t* cand_cnt,
                           const int64_t* cand_idx, int32_t Q, int32_t n, int32_t tie_by_row,
                           int64_t* out_rows, double* out_dist, void* stream);
+
+/* Re-rank against a ROW-SHARDED descriptor table spread over the GPUs of one box (BASELINE north_star:
+ * "database sharded by row across the 8 GPUs"): shards f32*[n_shards] is a DEVICE array of pointers valid
+ * in the calling process -- the local shard plus CUDA-IPC mappings of the peers' shards --, shard s holds
+ * global rows [shard_bounds[s], shard_bounds[s+1]) (i64[n_shards+1], device), all with leading dimension
+ * ldd.  Each candidate row is read where it lives (NVLink loads for peer shards): the distances of
+ * lsh.py:507-512 without any collective.  aligned16 != 0 promises 16-byte aligned shard bases.
+ * sb_enable_peer_access(peer): cudaDeviceEnablePeerAccess from the current device (idempotent). */
+SB_API int sb_rerank_peer(const float* const* shards, const int64_t* shard_bounds, int32_t n_shards, int32_t D,
+                   int64_t ldd, const float* q, int32_t Q, int64_t ldq, const int64_t* cand_idx,
+                   const int64_t* cand_off, int64_t M, int32_t metric, int32_t aligned16, double* out, void* stream);
+SB_API int sb_enable_peer_access(int32_t peer_device);
 
 /* Candidate expansion (lsh.py:490-496): the descriptor rows of each query's near codes,
  * in (code rank, row) order.  code_rows i64[Q][n] = rows of the unique-code table

@@ -43,11 +43,15 @@ SIGNATURES: Dict[str, tuple] = {
     "sb_hamming_scan": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P, c_size_t, _P]),
     "sb_hamming_scan_variant": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P,
                                           c_size_t, c_int32, _P]),
+    "sb_hamming_scan_if": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P, _P, c_size_t, _P]),
     "sb_topk_merge": (c_int32, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "sb_hamming_topk": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P, _P, c_size_t, _P]),
     "sb_rerank": (c_int32, [_P, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64, c_int32, _P, _P]),
     "sb_rerank_shard": (c_int32, [_P, c_int64, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64,
                                   c_int32, _P, _P]),
+    "sb_rerank_peer": (c_int32, [_P, _P, c_int32, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64, c_int32, c_int32,
+                                 _P, _P]),
+    "sb_enable_peer_access": (c_int32, [c_int32]),
     "sb_rerank_select": (c_int32, [_P, _P, c_int32, c_int32, _P, _P, _P]),
     "sb_rerank_select_rows": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
     "sb_rerank_base": (c_int32, [_P, c_int64, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64,

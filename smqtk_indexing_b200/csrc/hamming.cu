@@ -223,7 +223,9 @@ template <int W, int MODE>
 __global__ void __launch_bounds__(THREADS, 2)
 hamming_scan_kernel(const uint32_t* __restrict__ db, long long U, const uint32_t* __restrict__ qcodes, int Q, int QT,
                     int k, long long idx_base, long long codes_per_chunk, uint64_t* __restrict__ part, int P,
-                    int* __restrict__ tau_g, int* __restrict__ hist_g, int q_tma_ok, int one) {
+                    int* __restrict__ tau_g, int* __restrict__ hist_g, int q_tma_ok, int one,
+                    const int* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;       // predicated fallback (sb_hamming_scan_if): nothing to redo
   constexpr int C = ScanCfg<W>::C;
   constexpr int TILE = ScanCfg<W>::TILE;
   constexpr int MAXD = 32 * W;       // largest possible distance
@@ -385,7 +387,8 @@ template <int W>
 __global__ void __launch_bounds__(THREADS, 2)
 hamming_scan_few_kernel(const uint32_t* __restrict__ db, long long U, const uint32_t* __restrict__ qcodes, int Q, int k,
                         long long idx_base, long long codes_per_chunk, uint64_t* __restrict__ part, int P,
-                        int* __restrict__ tau_g) {
+                        int* __restrict__ tau_g, const int* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
   constexpr int C = ScanCfg<W>::C;
   constexpr int TILE = ScanCfg<W>::TILE;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -489,7 +492,8 @@ constexpr int SEED_WARPS = 4;
 template <int W>
 __global__ void __launch_bounds__(SEED_WARPS * 32)
 tau_seed_kernel(const uint32_t* __restrict__ db, int S, const uint32_t* __restrict__ qcodes, int Q, int k,
-                int* __restrict__ tau_g) {
+                int* __restrict__ tau_g, const int* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
   constexpr int MAXD = 32 * W;
   extern __shared__ int seed_hist[];  // [SEED_WARPS][MAXD + 1]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -531,7 +535,8 @@ tau_seed_kernel(const uint32_t* __restrict__ db, int S, const uint32_t* __restri
 template <int W>
 __global__ void __launch_bounds__(SEED_WARPS * 32)
 tau_seed_min_kernel(const uint32_t* __restrict__ db, int S, const uint32_t* __restrict__ qcodes, int Q, int k,
-                    int* __restrict__ tau_g) {
+                    int* __restrict__ tau_g, const int* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = blockIdx.x * SEED_WARPS + warp;
   if (q >= Q) return;
@@ -568,7 +573,8 @@ constexpr int MERGE_BINS = 1032;  // distances 0..1024 (+ padding)
 // u64[Q][P][k] when q_major == 1 (scan workspace).
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_kernel(const uint64_t* __restrict__ lists, int P, int Q, int k, int q_major, uint64_t* __restrict__ out_keys,
-             int32_t* __restrict__ out_dist, long long* __restrict__ out_idx) {
+             int32_t* __restrict__ out_dist, long long* __restrict__ out_idx, const int* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
   extern __shared__ __align__(8) unsigned char merge_dyn[];
   uint64_t* s_cand = reinterpret_cast<uint64_t*>(merge_dyn);          // [MERGE_CAP]
   uint64_t* s_out = s_cand + MERGE_CAP;                               // [k]
@@ -731,14 +737,14 @@ ScanPlan make_plan(long long U, int W, int Q, int k) {
 
 template <int W>
 int launch_scan(const ScanPlan& p, int mode, const uint32_t* db, long long U, const uint32_t* q, int Q, int k,
-                long long idx_base, uint64_t* part, int* tau_g, int* hist_g, cudaStream_t st) {
+                long long idx_base, uint64_t* part, int* tau_g, int* hist_g, const int* enable, cudaStream_t st) {
   if (k <= 32 && U >= 32) {
     // lane-minima seed over a table prefix (the prefix is part of the table, so any k of
     // its rows bound the k-th distance from above)
     long long S = min(U, 8192ll);
     if (const char* e = getenv("SB_SEED_ROWS")) S = min(U, max((long long)atoi(e), 32ll));   // tuning knob
     sb::ProfScope prof("tau_seed_kernel", st);
-    tau_seed_min_kernel<W><<<(Q + SEED_WARPS - 1) / SEED_WARPS, SEED_WARPS * 32, 0, st>>>(db, (int)S, q, Q, k, tau_g);
+    tau_seed_min_kernel<W><<<(Q + SEED_WARPS - 1) / SEED_WARPS, SEED_WARPS * 32, 0, st>>>(db, (int)S, q, Q, k, tau_g, enable);
     sb::count_launch();
     int rc = sb::check_launch("tau_seed_min_kernel");
     if (rc) return rc;
@@ -748,7 +754,7 @@ int launch_scan(const ScanPlan& p, int mode, const uint32_t* db, long long U, co
     if (S >= k) {
       const size_t sh = (size_t)SEED_WARPS * (32 * W + 1) * sizeof(int);
       sb::ProfScope prof("tau_seed_kernel", st);
-      tau_seed_kernel<W><<<(Q + SEED_WARPS - 1) / SEED_WARPS, SEED_WARPS * 32, sh, st>>>(db, (int)S, q, Q, k, tau_g);
+      tau_seed_kernel<W><<<(Q + SEED_WARPS - 1) / SEED_WARPS, SEED_WARPS * 32, sh, st>>>(db, (int)S, q, Q, k, tau_g, enable);
       sb::count_launch();
       int rc = sb::check_launch("tau_seed_kernel");
       if (rc) return rc;
@@ -759,7 +765,7 @@ int launch_scan(const ScanPlan& p, int mode, const uint32_t* db, long long U, co
     SB_CUDA_TRY(cudaFuncSetAttribute(hamming_scan_few_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     sb::ProfScope prof("hamming_scan_kernel", st);
     hamming_scan_few_kernel<W><<<p.chunks, THREADS, sh, st>>>(db, U, q, Q, k, idx_base, p.codes_per_chunk, part, p.P,
-                                                              tau_g);
+                                                              tau_g, enable);
     sb::count_launch();
     return sb::check_launch("hamming_scan_few_kernel");
   }
@@ -772,7 +778,7 @@ int launch_scan(const ScanPlan& p, int mode, const uint32_t* db, long long U, co
                                      (int)p.smem_bytes));                                                        \
     hamming_scan_kernel<W, M><<<grid, THREADS, p.smem_bytes, st>>>(db, U, q, Q, p.QT, k, idx_base,                \
                                                                      p.codes_per_chunk, part, p.P, tau_g, hist_g, \
-                                                                     q_tma_ok, /*one=*/1);                        \
+                                                                     q_tma_ok, /*one=*/1, enable);                \
   } while (0)
   if (mode == 0) SB_SCAN_LAUNCH(0);
   else if (mode == 1) SB_SCAN_LAUNCH(1);
@@ -783,19 +789,19 @@ int launch_scan(const ScanPlan& p, int mode, const uint32_t* db, long long U, co
 }
 
 int launch_merge(const uint64_t* lists, int P, int Q, int k, int q_major, uint64_t* out_keys, int32_t* out_dist,
-                 int64_t* out_idx, cudaStream_t st) {
+                 int64_t* out_idx, cudaStream_t st, const int* enable = nullptr) {
   const size_t dyn = merge_smem_bytes(k);
   SB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   sb::ProfScope prof("merge_kernel", st);
   merge_kernel<<<Q, MERGE_THREADS, dyn, st>>>(lists, P, Q, k, q_major, out_keys, out_dist,
-                                              reinterpret_cast<long long*>(out_idx));
+                                              reinterpret_cast<long long*>(out_idx), enable);
   sb::count_launch();
   return sb::check_launch("merge_kernel");
 }
 
 int scan_impl(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q, int32_t Q, int32_t k, int64_t idx_base,
               uint64_t* keys_out, int32_t* out_dist, int64_t* out_idx, void* workspace, size_t workspace_bytes,
-              int variant, void* stream) {
+              int variant, void* stream, const int* enable = nullptr) {
   SB_REQUIRE(W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32, "sb_hamming_scan: W=%d not in {1,2,4,8,16,32}", W);
   SB_REQUIRE(Q >= 1 && k >= 1 && U >= 0, "sb_hamming_scan: need Q>=1, k>=1, U>=0 (Q=%d k=%d U=%lld)", Q, k, (long long)U);
   SB_REQUIRE(k <= 2048, "sb_hamming_scan: k=%d exceeds the supported maximum of 2048", k);
@@ -821,15 +827,15 @@ int scan_impl(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q, int32
   const int mode = (variant == 1) ? 0 : (variant == 2 ? 1 : 2);
   int rc;
   switch (W) {
-    case 1: rc = launch_scan<1>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, st); break;
-    case 2: rc = launch_scan<2>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, st); break;
-    case 4: rc = launch_scan<4>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, st); break;
-    case 8: rc = launch_scan<8>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, st); break;
-    case 16: rc = launch_scan<16>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, st); break;
-    default: rc = launch_scan<32>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, st); break;
+    case 1: rc = launch_scan<1>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, enable, st); break;
+    case 2: rc = launch_scan<2>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, enable, st); break;
+    case 4: rc = launch_scan<4>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, enable, st); break;
+    case 8: rc = launch_scan<8>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, enable, st); break;
+    case 16: rc = launch_scan<16>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, enable, st); break;
+    default: rc = launch_scan<32>(p, mode, db, U, q, Q, k, idx_base, part, tau_g, hist_g, enable, st); break;
   }
   if (rc) return rc;
-  return launch_merge(part, p.P, Q, k, /*q_major=*/1, keys_out, out_dist, out_idx, st);
+  return launch_merge(part, p.P, Q, k, /*q_major=*/1, keys_out, out_dist, out_idx, st, enable);
 }
 
 }  // namespace
@@ -845,6 +851,16 @@ int sb_hamming_scan(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q,
                     int64_t idx_base, uint64_t* keys_out, void* workspace, size_t workspace_bytes, void* stream) {
   SB_REQUIRE(keys_out != nullptr, "sb_hamming_scan: keys_out is NULL");
   return scan_impl(db, U, W, q, Q, k, idx_base, keys_out, nullptr, nullptr, workspace, workspace_bytes, 0, stream);
+}
+
+/* Predicated form: every kernel of the scan returns at once unless *enable (device int) != 0, in which
+ * case keys_out is overwritten with the exact result.  Launched right after sb_hamming_scan_tc with its
+ * overflow flag, it makes the tensor-core path exact WITHOUT a host round trip for the flag. */
+int sb_hamming_scan_if(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q, int32_t Q, int32_t k,
+                       int64_t idx_base, uint64_t* keys_out, const int32_t* enable, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  SB_REQUIRE(keys_out != nullptr && enable != nullptr, "sb_hamming_scan_if: NULL pointer");
+  return scan_impl(db, U, W, q, Q, k, idx_base, keys_out, nullptr, nullptr, workspace, workspace_bytes, 0, stream, enable);
 }
 
 int sb_hamming_scan_variant(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q, int32_t Q, int32_t k,

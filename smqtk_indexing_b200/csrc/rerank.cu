@@ -69,7 +69,8 @@ template <int METRIC>
 __global__ void __launch_bounds__(RR_WARPS * 32)
 rerank_kernel(const float* __restrict__ db, long long N, int D, long long ldd, const float* __restrict__ q, int Q,
               long long ldq, const long long* __restrict__ cand_idx, const long long* __restrict__ cand_off,
-              long long M, double* __restrict__ out, int vec_ok, long long row_base, double miss_value) {
+              long long M, double* __restrict__ out, int vec_ok, long long row_base, double miss_value,
+              const float* const* __restrict__ shards, const long long* __restrict__ shard_bounds, int n_shards) {
   const int lane = threadIdx.x & 31;
   const long long j = (long long)blockIdx.x * RR_WARPS + (threadIdx.x >> 5);
   if (j >= M) return;
@@ -79,13 +80,28 @@ rerank_kernel(const float* __restrict__ db, long long N, int D, long long ldd, c
     int mid = (lo + hi) >> 1;
     if (cand_off[mid] <= j) lo = mid; else hi = mid;
   }
-  const long long row = cand_idx[j] - row_base;              // db holds global rows [row_base, row_base + N)
-  if (row < 0 || row >= N) {
-    if (lane == 0) out[j] = miss_value;
-    return;
+  long long row = cand_idx[j] - row_base;                    // db holds global rows [row_base, row_base + N)
+  const float* b;
+  if (shards != nullptr) {
+    // row-sharded table: shard s holds global rows [bounds[s], bounds[s+1]); the other shards are peer
+    // GPUs' HBM mapped into this process (CUDA IPC) and read over NVLink -- no collective in the re-rank
+    int sh = -1;
+    if (row >= 0)
+      for (int t = 0; t < n_shards; ++t)
+        if (row >= shard_bounds[t] && row < shard_bounds[t + 1]) sh = t;
+    if (sh < 0) {
+      if (lane == 0) out[j] = miss_value;
+      return;
+    }
+    b = shards[sh] + (row - shard_bounds[sh]) * ldd;
+  } else {
+    if (row < 0 || row >= N) {
+      if (lane == 0) out[j] = miss_value;
+      return;
+    }
+    b = db + row * ldd;
   }
   const float* a = q + (long long)lo * ldq;
-  const float* b = db + row * ldd;
   F2 s0{0.f, 0.f}, s1{0.f, 0.f}, s2{0.f, 0.f};
   if (vec_ok) {
     const float4* a4 = reinterpret_cast<const float4*>(a);
@@ -242,15 +258,18 @@ extern "C" {
 
 static int rerank_impl(const float* db, int64_t N, int32_t D, int64_t ldd, const float* q, int32_t Q, int64_t ldq,
                        const int64_t* cand_idx, const int64_t* cand_off, int64_t M, int32_t metric, double* out,
-                       int64_t row_base, double miss_value, void* stream) {
+                       int64_t row_base, double miss_value, void* stream, const float* const* shards = nullptr,
+                       const int64_t* shard_bounds = nullptr, int n_shards = 0) {
   SB_REQUIRE(D >= 1 && Q >= 1 && M >= 0 && N >= 0, "sb_rerank: bad sizes");
   SB_REQUIRE(ldd >= D && ldq >= D, "sb_rerank: leading dimension smaller than D");
   SB_REQUIRE(metric >= SB_METRIC_EUCLIDEAN && metric <= SB_METRIC_HIK, "sb_rerank: bad metric %d", metric);
   if (M == 0) return SB_OK;
-  SB_REQUIRE(db && q && cand_idx && cand_off && out, "sb_rerank: NULL pointer");
+  SB_REQUIRE((db || shards) && q && cand_idx && cand_off && out, "sb_rerank: NULL pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // peer shards: the caller guarantees 16-byte aligned shard bases (checked in sb_rerank_peer)
   const int vec_ok = ((reinterpret_cast<uintptr_t>(db) | reinterpret_cast<uintptr_t>(q)) % 16 == 0 && ldd % 4 == 0 &&
                       ldq % 4 == 0) ? 1 : 0;
+  const long long* sbnd = reinterpret_cast<const long long*>(shard_bounds);
   const unsigned grid = (unsigned)((M + RR_WARPS - 1) / RR_WARPS);
   const long long* ci = reinterpret_cast<const long long*>(cand_idx);
   const long long* co = reinterpret_cast<const long long*>(cand_off);
@@ -258,15 +277,15 @@ static int rerank_impl(const float* db, int64_t N, int32_t D, int64_t ldd, const
   switch (metric) {
     case SB_METRIC_EUCLIDEAN:
       rerank_kernel<SB_METRIC_EUCLIDEAN><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok,
-                                                                         row_base, miss_value);
+                                                                         row_base, miss_value, shards, sbnd, n_shards);
       break;
     case SB_METRIC_COSINE:
       rerank_kernel<SB_METRIC_COSINE><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok,
-                                                                      row_base, miss_value);
+                                                                      row_base, miss_value, shards, sbnd, n_shards);
       break;
     default:
       rerank_kernel<SB_METRIC_HIK><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok,
-                                                                   row_base, miss_value);
+                                                                   row_base, miss_value, shards, sbnd, n_shards);
       break;
   }
   sb::count_launch();
@@ -289,6 +308,45 @@ int sb_rerank_shard(const float* db, int64_t N, int64_t row_base, int32_t D, int
                     int64_t ldq, const int64_t* cand_idx, const int64_t* cand_off, int64_t M, int32_t metric,
                     double* out, void* stream) {
   return rerank_impl(db, N, D, ldd, q, Q, ldq, cand_idx, cand_off, M, metric, out, row_base, 0.0, stream);
+}
+
+/* Re-rank against a ROW-SHARDED table whose shards live on several GPUs of one box: shards[s] (device
+ * array of n_shards pointers, valid in THIS process: the local shard and CUDA-IPC mappings of the peers')
+ * holds global rows [shard_bounds[s], shard_bounds[s+1]).  Candidate rows are read where they live, over
+ * NVLink for peer shards -- the re-rank needs no collective.  Rows outside every shard give NaN. */
+int sb_rerank_peer(const float* const* shards, const int64_t* shard_bounds, int32_t n_shards, int32_t D, int64_t ldd,
+                   const float* q, int32_t Q, int64_t ldq, const int64_t* cand_idx, const int64_t* cand_off, int64_t M,
+                   int32_t metric, int32_t aligned16, double* out, void* stream) {
+  SB_REQUIRE(shards && shard_bounds && n_shards >= 1, "sb_rerank_peer: NULL shard table");
+  // `aligned16`: every shard base is 16-byte aligned (the host knows the pointers; the device array is not read here)
+  const float* fake_db = aligned16 ? reinterpret_cast<const float*>(uintptr_t(16)) : reinterpret_cast<const float*>(uintptr_t(4));
+  return rerank_impl(fake_db, 0, D, ldd, q, Q, ldq, cand_idx, cand_off, M, metric, out, 0, nan(""), stream, shards,
+                     shard_bounds, n_shards);
+}
+
+/* Peer access from the CURRENT device to `peer_device` (needed before kernels read CUDA-IPC mappings of a
+ * peer's memory).  Returns SB_OK when access is (already) enabled, SB_ERR_UNSUPPORTED when the devices
+ * cannot reach each other. */
+int sb_enable_peer_access(int32_t peer_device) {
+  int cur = 0;
+  SB_CUDA_TRY(cudaGetDevice(&cur));
+  if (cur == peer_device) return SB_OK;
+  int can = 0;
+  SB_CUDA_TRY(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+  if (!can) {
+    sb::set_error("sb_enable_peer_access: device %d cannot access device %d", cur, peer_device);
+    return SB_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return SB_OK;
+  }
+  if (e != cudaSuccess) {
+    sb::set_error("cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+    return SB_ERR_CUDA;
+  }
+  return SB_OK;
 }
 
 int sb_rerank_select(const double* dist, const int64_t* cand_off, int32_t Q, int32_t n, int64_t* out_pos,

@@ -197,9 +197,18 @@ TC_SCAN_MIN_PAIRS = 1 << 28
 def _tc_scan_pays(U: int, W: int, Q: int, k: int) -> bool:
     return (Q >= TC_SCAN_MIN_QUERIES and U >= TC_SCAN_MIN_ROWS and Q * U >= TC_SCAN_MIN_PAIRS
             and hamming_scan_tc_supported(U, W, Q, k))
-#: set by hamming_scan_keys: how many batches overflowed a candidate buffer and were re-run
-TC_SCAN_OVERFLOWS = 0
 SCAN_VARIANT_TC = 3
+#: per-device int32[1] accumulators of the tensor-core scan's overflow flags (device memory: the
+#: dispatcher never reads a flag on the host -- the predicated XOR/POPC scan redoes an overflowed batch)
+_overflow_acc = {}
+
+
+def tc_scan_overflows(dev: Optional[object] = None) -> int:
+    """How many tensor-core scan batches overflowed a candidate buffer and were redone by the
+    predicated XOR/POPC scan on ``dev`` (diagnostics / tests; synchronises)."""
+    d = device(dev)
+    acc = _overflow_acc.get(d.index if d.index is not None else torch.cuda.current_device())
+    return 0 if acc is None else int(acc.item())
 
 
 def hamming_scan_tc_supported(U: int, W: int, Q: int, k: int) -> bool:
@@ -222,46 +231,6 @@ def hamming_scan_keys_tc(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: in
 
 
 _scan_tls = threading.local()       # per-thread dispatch state: callers may drive several indexes from several threads
-
-
-class deferred_scan_check:
-    """Context manager for a pipeline of several stages: inside it the tensor-core scan does NOT
-    synchronise to read its overflow flag (the keys of an overflowed batch are still valid table
-    rows, only possibly not the nearest, so the later stages are safe to launch); the flags are
-    collected in ``self.flags`` and the caller asks ``overflowed()`` once, after the last stage,
-    and re-runs the batch with ``force_popc()`` if it says so."""
-
-    def __init__(self) -> None:
-        self.flags = []
-
-    @staticmethod
-    def current() -> Optional["deferred_scan_check"]:
-        return getattr(_scan_tls, "deferred", None)
-
-    def __enter__(self):
-        self._prev = deferred_scan_check.current()
-        _scan_tls.deferred = self
-        return self
-
-    def __exit__(self, *exc):
-        _scan_tls.deferred = self._prev
-
-    def flag_tensor(self) -> Optional[torch.Tensor]:
-        """All collected flags folded into one int32[1] tensor (None if the scan never deferred)."""
-        if not self.flags:
-            return None
-        t = self.flags[0] if len(self.flags) == 1 else torch.stack(self.flags).max(dim=0).values
-        self.flags = [t]
-        return t
-
-    def overflowed(self) -> bool:
-        global TC_SCAN_OVERFLOWS
-        t = self.flag_tensor()
-        bad = t is not None and int(t.item()) != 0
-        self.flags = []
-        if bad:
-            TC_SCAN_OVERFLOWS += 1
-        return bad
 
 
 class force_popc:
@@ -324,7 +293,6 @@ def hamming_scan_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int =
     """Local top-k as packed keys int64[Q, k] (uint64 bit pattern, ascending,
     SB_KEY_EMPTY padded).  ``variant`` 0 picks the kernel: the tensor-core scan for large batches
     over large tables, the XOR/POPC scan otherwise (1, 2: POPC formulations, 3: tensor cores)."""
-    global TC_SCAN_OVERFLOWS
     require_cuda()
     _chk(db, torch.int32, "db")
     _chk(q, torch.int32, "q")
@@ -337,16 +305,23 @@ def hamming_scan_keys(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int =
     if k > SCAN_MAX_K:
         return hamming_topk_sorted_keys(db, q, k, idx_base)
     if variant == SCAN_VARIANT_TC or (variant == 0 and not force_popc.on() and _tc_scan_pays(U, W, Q, k)):
+        # tensor-core scan, then the XOR/POPC scan PREDICATED on its overflow flag: every kernel of the second
+        # scan returns at once unless a candidate buffer overflowed (tables of massively tied codes), in which
+        # case it overwrites the keys with the exact result.  No host round trip, same keys either way.
         keys, flag = hamming_scan_keys_tc(db, q, k, idx_base)
-        pending = deferred_scan_check.current()
-        if pending is not None:
-            pending.flags.append(flag)                           # checked once, at the end of the pipeline
-            return keys
-        if int(flag.item()) == 0:
-            return keys
-        TC_SCAN_OVERFLOWS += 1          # a candidate buffer overflowed: the exact XOR/POPC scan decides
-        variant = 0
-    elif variant == SCAN_VARIANT_TC:
+        lib = _lib.load()
+        ws_bytes = lib.sb_hamming_scan_workspace_bytes(U, W, Q, k)
+        ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=db.device)
+        with torch.cuda.device(db.device):
+            _lib.check(lib.sb_hamming_scan_if(_ptr(db), U, W, _ptr(q), Q, k, idx_base, _ptr(keys), _ptr(flag),
+                                              _ptr(ws), ws_bytes, _stream()))
+        if not torch.cuda.is_current_stream_capturing():
+            acc = _overflow_acc.get(db.device.index)
+            if acc is None:
+                acc = _overflow_acc[db.device.index] = torch.zeros((1,), dtype=torch.int32, device=db.device)
+            acc.add_(flag)
+        return keys
+    if variant == SCAN_VARIANT_TC:
         variant = 0
     lib = _lib.load()
     ws_bytes = lib.sb_hamming_scan_workspace_bytes(U, W, Q, k)
@@ -439,6 +414,29 @@ def rerank_shard(db: torch.Tensor, row_base: int, q: torch.Tensor, cand_idx: tor
         _lib.check(_lib.load().sb_rerank_shard(_ptr(db), N, row_base, D, max(db.stride(0), D), _ptr(q), Q,
                                                max(q.stride(0), D), _ptr(cand_idx), _ptr(cand_off), M,
                                                _lib.METRICS[metric], _ptr(out), _stream()))
+    return out
+
+
+def rerank_peer(shards, q: torch.Tensor, cand_idx: torch.Tensor, cand_off: torch.Tensor, metric: str) -> torch.Tensor:
+    """float64[M] distances of candidate GLOBAL rows against a row-sharded table whose shards live on
+    several GPUs (``peer.PeerShards``): each row is loaded from the GPU that holds it (NVLink)."""
+    require_cuda()
+    if q.dtype != torch.float32 or q.stride(1) != 1:
+        raise ValueError("q must be float32 with unit column stride")
+    _chk(cand_idx, torch.int64, "cand_idx")
+    _chk(cand_off, torch.int64, "cand_off")
+    if metric not in _lib.METRICS:
+        raise ValueError("Invalid distance method label. Must be one of "
+                         "['euclidean' | 'cosine' | 'hik']")
+    Q, D = q.shape
+    if D != shards.dim or cand_off.numel() != Q + 1:
+        raise ValueError("shape mismatch between the shards, q and cand_off")
+    M = cand_idx.numel()
+    out = torch.empty((M,), dtype=torch.float64, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().sb_rerank_peer(_ptr(shards.ptr_table), _ptr(shards.bound_table), shards.n_shards, D,
+                                              shards.ld, _ptr(q), Q, max(q.stride(0), D), _ptr(cand_idx), _ptr(cand_off), M,
+                                              _lib.METRICS[metric], 1 if shards.aligned16 else 0, _ptr(out), _stream()))
     return out
 
 

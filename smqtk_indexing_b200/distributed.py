@@ -9,18 +9,23 @@ Sharding (DESIGN.md section "Multi-GPU"):
     and every rank derives the SAME global sorted-unique code table and
     code -> rows CSR -- exactly the single-GPU structures;
   * the Hamming scan is partitioned either over that table (``scan_partition="rows"``: rank r
-    scans table rows [lo_r, hi_r) with ``idx_base = lo_r``, so its keys are already global) or over
+    scans table rows [lo_r, hi_r) with ``idx_base = lo_r``, so its keys are already global; one
+    all-gather of the per-rank top-n keys + ``sb_topk_merge`` gives the global n nearest codes) or over
     the QUERIES (``"queries"``: every rank holds the whole table anyway -- 32 B per code -- and scans
-    all of it for its slice of the batch; its keys are final, the all-gather assembles the batch and
-    nothing is merged).  Same keys either way.  The per-batch costs that do not shrink with the table
-    (threshold bookkeeping, survivor re-checks of the tensor-core scan) shrink with the query slice,
-    so ``"auto"`` partitions by queries once every rank gets at least 64 of them.
+    all of it for its slice of the batch; its keys are final).  Same keys either way.  The per-batch
+    costs that do not shrink with the table (threshold bookkeeping, survivor re-checks of the
+    tensor-core scan) shrink with the query slice, so ``"auto"`` partitions by queries once every
+    rank gets at least 64 of them.
 
-Per query batch there are two small collectives:
-  1. all-gather of the per-rank top-n keys (Q*n*8 bytes per rank) followed by
-     ``sb_topk_merge`` -> the global n nearest unique codes, identical on all ranks;
-  2. all-reduce (SUM) of candidate distances: every rank re-ranks the candidate rows
-     that live in its descriptor shard and contributes an exact 0.0 for the others.
+Re-rank, two modes with identical results:
+  * ``rerank="peer"`` (default on CUDA when the GPUs can reach each other): every rank finishes ITS
+    slice of the batch alone -- candidate expansion, distances, selection -- loading each candidate
+    row from the GPU that owns it through CUDA-IPC mappings (``peer.py``, ``sb_rerank_peer``: NVLink
+    loads, no collective), then ONE all-gather assembles the (row, distance) results of all slices.
+    Per batch: 1 collective with the scan partitioned over queries, 2 (keys, results) over rows; no
+    host synchronisation anywhere (an overflowed tensor-core scan is redone by a predicated kernel).
+  * ``rerank="allreduce"`` (any backend, the gloo tests): every rank expands ALL candidates, computes the
+    distances of the rows it owns (exact 0.0 elsewhere) and a SUM all-reduce assembles the vector.
 Because keys and candidate order are global, the result is bit-identical to the
 single-GPU index, ties included.
 """
@@ -63,6 +68,10 @@ class DeviceOps:
         from . import device
         return device.rerank_shard(x, row_base, q, cand_idx, cand_off, self.distance_method)
 
+    def rerank_peer(self, shards, q, cand_idx, cand_off) -> torch.Tensor:
+        from . import device
+        return device.rerank_peer(shards, q, cand_idx, cand_off, self.distance_method)
+
     def expand(self, code_rows, csr_off, csr_rows, pitch):
         from . import device
         return device.expand_candidates(code_rows.contiguous(), csr_off, csr_rows, pitch)
@@ -101,16 +110,22 @@ def partition_bounds(total: int, world: int, align: int = 4) -> List[int]:
 
 
 class ShardedLshIndex:
-    """Row-sharded descriptors, range-partitioned Hamming scan, exact merge."""
+    """Row-sharded descriptors, partitioned Hamming scan, exact merge."""
 
     #: a rank's query slice must be at least this long for ``scan_partition="auto"`` to split the batch
     MIN_QUERIES_PER_RANK = 64
+    #: capture the pipeline of a (Q, n) shape into a CUDA graph once it has been asked for this often
+    GRAPH_AFTER = 2
 
     def __init__(self, functor, distance_method: str = "euclidean", group=None, ops=None,
-                 scan_partition: str = "auto") -> None:
+                 scan_partition: str = "auto", rerank: str = "auto", graph: bool = True) -> None:
         if scan_partition not in ("auto", "rows", "queries"):
             raise ValueError("scan_partition must be 'auto', 'rows' or 'queries'")
+        if rerank not in ("auto", "peer", "allreduce"):
+            raise ValueError("rerank must be 'auto', 'peer' or 'allreduce'")
         self.scan_partition = scan_partition
+        self.rerank_mode = rerank
+        self.graph = graph
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -120,6 +135,9 @@ class ShardedLshIndex:
         self.table = self.csr_off = self.csr_rows = None
         self.max_rows_per_code = 0
         self.scan_lo = self.scan_hi = 0
+        self.peers = None                 # peer.PeerShards when the re-rank reads the owners' HBM directly
+        self.peer_error: Optional[str] = None
+        self._graphs: dict = {}
 
     @property
     def num_rows(self) -> int:
@@ -132,6 +150,7 @@ class ShardedLshIndex:
     def build(self, x_local: torch.Tensor) -> None:
         """Collective: every rank passes the descriptor rows it owns."""
         self.x_local = x_local
+        self._graphs = {}
         codes_local = self.ops.hash(x_local)
         codes_all, sizes = _all_gather_rows(codes_local, self.group)
         self.row_bounds = [0]
@@ -140,60 +159,127 @@ class ShardedLshIndex:
         self.table, _, self.csr_off, self.csr_rows, self.max_rows_per_code = codeops.build_table(codes_all, with_max=True)
         cuts = partition_bounds(int(self.table.shape[0]), self.world)
         self.scan_lo, self.scan_hi = cuts[self.rank], cuts[self.rank + 1]
+        self.peers, self.peer_error = None, None
+        if self.rerank_mode != "allreduce" and x_local.is_cuda and self.world > 1 and hasattr(self.ops, "rerank_peer"):
+            # map every peer's shard into this process (CUDA IPC); all ranks must agree on the outcome
+            try:
+                from . import peer
+                self.peers = peer.share_rows(x_local, self.row_bounds, self.group)
+            except Exception as e:                               # no P2P path between the devices, IPC refused, ...
+                self.peer_error = "%s: %s" % (type(e).__name__, str(e)[:200])
+            ok = torch.tensor([1 if self.peers is not None else 0], dtype=torch.int32, device=x_local.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                self.peers = None
+                if self.rerank_mode == "peer":
+                    raise RuntimeError("rerank='peer' needs CUDA IPC + peer access between all ranks' GPUs (%s)"
+                                       % (self.peer_error or "a peer rank failed"))
+
+    # ------------------------------------------------------------------ partitions
+    def _by_queries(self, Q: int) -> bool:
+        return self.world > 1 and (self.scan_partition == "queries" or (
+            self.scan_partition == "auto" and Q >= self.MIN_QUERIES_PER_RANK * self.world))
+
+    def _slice(self, Q: int) -> Tuple[int, int, int]:
+        per = (Q + self.world - 1) // self.world                 # equal slices (the last ones padded) for the collectives
+        lo = min(Q, self.rank * per)
+        return per, lo, min(Q, lo + per)
+
+    @staticmethod
+    def _padded(t: torch.Tensor, lo: int, hi: int, per: int, fill=0) -> torch.Tensor:
+        mine = t[lo:hi]
+        if hi - lo < per:
+            pad = torch.full((per - (hi - lo),) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
+            mine = torch.cat([mine, pad], dim=0)
+        return mine.contiguous()
+
+    def _gather(self, t: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)      # rank-major concatenation
+        return out
 
     def near_codes(self, q_codes: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Global n nearest unique codes: local scan, all-gather, merge."""
+        """Global n nearest unique codes of ALL queries on every rank: local scan, all-gather, merge."""
         Q = q_codes.shape[0]
-        by_queries = self.scan_partition == "queries" or (
-            self.scan_partition == "auto" and Q >= self.MIN_QUERIES_PER_RANK * self.world)
-        if by_queries and self.world > 1:
-            per = (Q + self.world - 1) // self.world              # equal slices (the last ones padded) for the collective
-            lo = min(Q, self.rank * per)
-            hi = min(Q, lo + per)
-            mine = q_codes[lo:hi]
-            if hi - lo < per:
-                mine = torch.cat([mine, torch.zeros((per - (hi - lo), q_codes.shape[1]), dtype=q_codes.dtype,
-                                                    device=q_codes.device)], dim=0)
+        if self._by_queries(Q):
+            per, lo, hi = self._slice(Q)
             with _stage("hamming_scan"):
-                keys = self.ops.scan_keys(self.table, mine.contiguous(), n, 0).contiguous()
+                keys = self.ops.scan_keys(self.table, self._padded(q_codes, lo, hi, per), n, 0).contiguous()
             with _stage("allgather_merge"):
-                gathered = torch.empty((self.world * per,) + tuple(keys.shape[1:]), dtype=keys.dtype, device=keys.device)
-                dist.all_gather_into_tensor(gathered, keys, group=self.group)  # rank-major = query order
-                return self.ops.merge_keys(gathered[:Q].contiguous().unsqueeze(0))   # one part: decode only
+                return self.ops.merge_keys(self._gather(keys)[:Q].contiguous().unsqueeze(0))   # one part: decode only
         with _stage("hamming_scan"):
             keys = self.ops.scan_keys(self.table[self.scan_lo:self.scan_hi], q_codes, n, self.scan_lo).contiguous()
         with _stage("allgather_merge"):
-            Q = keys.shape[0]
-            gathered = torch.empty((self.world * Q,) + tuple(keys.shape[1:]), dtype=keys.dtype, device=keys.device)
-            dist.all_gather_into_tensor(gathered, keys, group=self.group)      # rank-major concatenation
-            return self.ops.merge_keys(gathered.view((self.world, Q) + tuple(keys.shape[1:])))
+            return self.ops.merge_keys(self._gather(keys).view((self.world, Q) + tuple(keys.shape[1:])))
 
+    # ------------------------------------------------------------------ queries
     def query(self, q: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Collective: all ranks pass the SAME queries; all get the full result
         (global rows int64[Q, n], dists f64[Q, n])."""
+        from . import engine
+        if not (self.graph and q.is_cuda and self.peers is not None) or engine.STAGE_EVENTS is not None:
+            return self._query(q, n)
+        key = (int(q.shape[0]), int(q.shape[1]), int(n), q.dtype, self.scan_partition)
+        ent = self._graphs.get(key)
+        if isinstance(ent, engine.GraphedCall):
+            return ent(q)
+        seen = (ent or 0) + 1
+        if seen >= self.GRAPH_AFTER and self._fixed_pitch(q.shape[0], n):
+            self._graphs[key] = g = engine.GraphedCall(lambda qq: self._query(qq, n), q.contiguous())
+            return g(q)
+        self._graphs[key] = seen
+        return self._query(q, n)
+
+    def _fixed_pitch(self, Q: int, n: int) -> bool:
         from .engine import FIXED_PITCH_LIMIT
+        return hasattr(self.ops, "expand") and n <= 2048 and Q * n * max(self.max_rows_per_code, 1) <= FIXED_PITCH_LIMIT
+
+    def _query(self, q: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.peers is not None:
+            return self._query_peer(q, n)
         with _stage("itq_hash"):
             q_codes = self.ops.hash(q)
-        from . import device
-        with device.deferred_scan_check() as chk:
-            out = self._query_hashed(q, q_codes, n)
-            # every rank must take the same branch afterwards: fold the flags (a rank that did not use the
-            # tensor-core scan contributes 0); still no host synchronisation
-            flag = chk.flag_tensor()
-            if flag is None:
-                flag = torch.zeros((1,), dtype=torch.int32, device=q.device)
-                chk.flags = [flag]
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
-        if chk.overflowed():
-            with device.force_popc():
-                out = self._query_hashed(q, q_codes, n)
-        return out
+        return self._query_allreduce(q, q_codes, n)
 
-    def _query_hashed(self, q: torch.Tensor, q_codes: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        from .engine import FIXED_PITCH_LIMIT
+    def _query_peer(self, q: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Every rank answers ITS slice of the batch; one all-gather assembles the batch."""
+        Q = q.shape[0]
+        per, lo, hi = self._slice(Q)
+        q_mine = self._padded(q, lo, hi, per)
+        if self._by_queries(Q):
+            with _stage("itq_hash"):
+                codes_mine = self.ops.hash(q_mine)
+            with _stage("hamming_scan"):
+                keys = self.ops.scan_keys(self.table, codes_mine, n, 0).contiguous()
+                _, code_rows = self.ops.merge_keys(keys.unsqueeze(0))                 # one part: decode only
+        else:
+            with _stage("itq_hash"):
+                q_codes = self.ops.hash(q)
+            _, code_rows_all = self.near_codes(q_codes, n)
+            code_rows = self._padded(code_rows_all, lo, hi, per, fill=-1)
+        pitch = n * max(self.max_rows_per_code, 1)
+        with _stage("expand"):
+            if self._fixed_pitch(per, n):                      # device-only, fixed-pitch segments padded with -1
+                cand_idx, cand_off, cand_cnt = self.ops.expand(code_rows, self.csr_off, self.csr_rows, pitch)
+            else:
+                cand_idx, cand_off = expand_candidates(code_rows, self.csr_off, self.csr_rows)
+                cand_cnt = None
+        with _stage("rerank"):
+            d = self.ops.rerank_peer(self.peers, q_mine, cand_idx, cand_off)
+            if cand_cnt is not None:
+                rows, od = self.ops.rerank_select_rows(d, cand_off, cand_cnt, cand_idx, n)
+            else:
+                pos, od = self.ops.rerank_select(d, cand_off, n)
+                rows = torch.where(pos >= 0, cand_idx[pos.clamp(min=0)], pos) if cand_idx.numel() else pos
+        with _stage("allgather_results"):
+            packed = torch.cat([rows, od.view(torch.int64)], dim=1)                   # (row | distance bits)[per, 2n]
+            full = self._gather(packed)[:Q]
+            return full[:, :n].contiguous(), full[:, n:].contiguous().view(torch.float64)
+
+    def _query_allreduce(self, q: torch.Tensor, q_codes: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
         _, code_rows = self.near_codes(q_codes, n)
         pitch = n * max(self.max_rows_per_code, 1)
-        fixed = hasattr(self.ops, "expand") and n <= 2048 and q.shape[0] * pitch <= FIXED_PITCH_LIMIT
+        fixed = self._fixed_pitch(q.shape[0], n)
         cand_cnt = None
         with _stage("expand"):
             if fixed:       # device-only, fixed-pitch segments padded with -1 (no host round trip)

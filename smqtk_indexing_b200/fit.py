@@ -126,8 +126,18 @@ def _eig_descending(c: np.ndarray, bit_length: int) -> np.ndarray:
     return np.array([pc[:, i] for i in order[:bit_length]]).transpose()
 
 
-def itq_rotation(v: torch.Tensor, n_iter: int, random_seed: Optional[int]) -> Tuple[torch.Tensor, np.ndarray]:
-    """``_find_itq_rotation`` (itq.py:239-289) on a device-resident ``v`` f64[n, b].
+def _allreduce_sum(t: torch.Tensor, group) -> torch.Tensor:
+    """SUM over the ranks that hold row shards (the fit is data-parallel over rows; only the
+    [D], [D, D] and [b, D] / [b, b] partial sums cross NVLink).  No-op for a single process."""
+    if group is not None:
+        import torch.distributed as dist
+        if dist.get_world_size(group) > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def itq_rotation(v: torch.Tensor, n_iter: int, random_seed: Optional[int], group=None) -> Tuple[torch.Tensor, np.ndarray]:
+    """``_find_itq_rotation`` (itq.py:239-289) on a device-resident ``v`` f64[n, b] (this rank's rows).
 
     :return: (codes int32[n, W] of the final rotation, rotation f64[b, b] on host)
     """
@@ -140,7 +150,7 @@ def itq_rotation(v: torch.Tensor, n_iter: int, random_seed: Optional[int]) -> Tu
     for _ in range(n_iter):
         r_dev = torch.from_numpy(np.ascontiguousarray(r)).to(v.device)
         _, ux = project(v, r_dev, want_values=False, want_codes=True)      # sign(v . r)
-        c = gram(ux, v, a_bits=bit).cpu().numpy()                           # ux^T . v
+        c = _allreduce_sum(gram(ux, v, a_bits=bit), group).cpu().numpy()    # ux^T . v
         ub, _, ua = np.linalg.svd(c)
         r = np.dot(ua, ub.transpose())
     r_dev = torch.from_numpy(np.ascontiguousarray(r)).to(v.device)
@@ -157,7 +167,7 @@ TC_GRAM_MIN_ROWS = 1 << 16
 
 def itq_rotation_streaming(xt: torch.Tensor, div, mean, pc_top: np.ndarray, n_iter: int,
                            random_seed: Optional[int], normalize=None,
-                           tensor_cores: Optional[bool] = None) -> Tuple[torch.Tensor, np.ndarray]:
+                           tensor_cores: Optional[bool] = None, group=None) -> Tuple[torch.Tensor, np.ndarray]:
     """``_find_itq_rotation`` (itq.py:239-289) without the N x b matrix ``v = x . pc_top``:
     with P = pc_top, ``z = v.r = x.(P r)`` and ``c = ux^T v = (ux^T x) P``, so an iteration is one
     projection of X by the D x b matrix ``P r`` (sign bits only) and one b x D Gram
@@ -191,9 +201,10 @@ def itq_rotation_streaming(xt: torch.Tensor, div, mean, pc_top: np.ndarray, n_it
     for _ in range(n_iter):
         ux = sign_codes(r)                                                                  # sign(x . P r)
         if use_tc_gram:
-            g = gram_bits_tc(ux, bit, xt, mean32, div32, bound).cpu().numpy()                      # ux^T . x   [b, D]
+            g = gram_bits_tc(ux, bit, xt, mean32, div32, bound)                                     # ux^T . x   [b, D]
         else:
-            g = gram(ux, xt, a_bits=bit, b_div=div, b_mean=mean).cpu().numpy()
+            g = gram(ux, xt, a_bits=bit, b_div=div, b_mean=mean)
+        g = _allreduce_sum(g, group).cpu().numpy()
         ub, _, ua = np.linalg.svd(g @ pc_top)
         r = np.dot(ua, ub.transpose())
     return sign_codes(r), r
@@ -201,8 +212,14 @@ def itq_rotation_streaming(xt: torch.Tensor, div, mean, pc_top: np.ndarray, n_it
 
 def itq_fit(x, bit_length: int, itq_iterations: int = 50, normalize=None,
             random_seed: Optional[int] = None, dev=None, streaming: Optional[bool] = None,
-            tensor_cores: Optional[bool] = None, want_codes: bool = True):
+            tensor_cores: Optional[bool] = None, want_codes: bool = True, group=None):
     """Fit on ``x`` ([N, D] numpy array or CUDA tensor, float32 or float64).
+
+    :param group: a ``torch.distributed`` process group whose ranks each pass THEIR row shard of the
+        training matrix (collective call): column sums, the covariance and every iteration's
+        ``ux^T v`` are summed over the ranks with all-reduces of [D], [D, D] and [b, D] values
+        (itq.py:338-383 is a sum over rows throughout); every rank ends with the same model and the
+        training codes of its own rows.
 
     :param streaming: never materialise ``v`` (default: automatic, when it would exceed
         ``STREAMING_V_BYTES``).
@@ -235,18 +252,30 @@ def itq_fit(x, bit_length: int, itq_iterations: int = 50, normalize=None,
         raise ValueError("Input descriptors have fewer features than requested bit encoding.")
     with torch.cuda.device(xt.device):
         div = row_div(xt, normalize)
-        mean = col_mean(xt, div)
-        cov = gram(xt, xt, scale=1.0 / max(n - 1, 1), a_div=div, a_mean=mean, b_div=div, b_mean=mean)
+        n_total = n
+        if group is not None:
+            cnt = _allreduce_sum(torch.tensor([n], dtype=torch.float64, device=xt.device), group)
+            n_total = int(cnt.item())
+            mean = _allreduce_sum(col_mean(xt, div) * float(n), group) / float(n_total)
+        else:
+            mean = col_mean(xt, div)
+        cov = _allreduce_sum(gram(xt, xt, scale=1.0, a_div=div, a_mean=mean, b_div=div, b_mean=mean), group) \
+            if group is not None else gram(xt, xt, scale=1.0 / max(n - 1, 1), a_div=div, a_mean=mean, b_div=div, b_mean=mean)
+        if group is not None:
+            cov = cov / float(max(n_total - 1, 1))
         pc_top = _eig_descending(np.atleast_2d(cov.cpu().numpy()), bit_length)
         pc_dev = torch.from_numpy(np.ascontiguousarray(pc_top)).to(xt.device)
         if streaming is None:
             streaming = n * bit_length * 8 > STREAMING_V_BYTES
+        if group is not None:                                       # every rank must take the same branch
+            flag = _allreduce_sum(torch.tensor([1.0 if streaming else 0.0], dtype=torch.float64, device=xt.device), group)
+            streaming = bool(flag.item() > 0)
         if streaming:
             codes, r = itq_rotation_streaming(xt, div, mean, pc_top, itq_iterations, random_seed, normalize,
-                                              tensor_cores)
+                                              tensor_cores, group)
         else:
             v, _ = project(xt, pc_dev, a_div=div, a_mean=mean)
-            codes, r = itq_rotation(v, itq_iterations, random_seed)
+            codes, r = itq_rotation(v, itq_iterations, random_seed, group)
         codes_host = codes.cpu().numpy().view(np.uint32) if want_codes else None
     mean_vec = mean.cpu().numpy().astype(out_dtype)
     return (unpack_bits(codes_host, bit_length) if want_codes else None), mean_vec, np.dot(pc_top, r)

@@ -231,9 +231,11 @@ class ItqFunctor(LshFunctor):
         ))
         return self.fit_matrix(x)
 
-    def fit_matrix(self, x, want_codes: bool = True):
+    def fit_matrix(self, x, want_codes: bool = True, group=None):
         """``fit`` on an assembled ``[N, D]`` matrix (numpy or CUDA tensor).  ``want_codes=False``
-        skips the N x b bool matrix the reference's ``fit`` returns (returns ``None``)."""
+        skips the N x b bool matrix the reference's ``fit`` returns (returns ``None``).
+        ``group``: a ``torch.distributed`` group whose ranks each pass their ROW SHARD of the training
+        matrix (collective): the partial sums are all-reduced, every rank gets the same model."""
         if self.has_model():
             raise RuntimeError("Model components have already been loaded.")
         from smqtk_indexing_b200 import fit as fitops
@@ -241,7 +243,8 @@ class ItqFunctor(LshFunctor):
             raise ValueError("Input descriptors have fewer features than "
                              "requested bit encoding.")
         codes, mean_vec, rotation = fitops.itq_fit(
-            x, self.bit_length, self.itq_iterations, self.normalize, self.random_seed, want_codes=want_codes)
+            x, self.bit_length, self.itq_iterations, self.normalize, self.random_seed, want_codes=want_codes,
+            group=group)
         self.mean_vec = mean_vec
         self.rotation = rotation
         self.save_model()

@@ -610,12 +610,14 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
         """Live descriptor rows in the device-resident index (see ``build_index_matrix``)."""
         return self._mirror.num_live
 
-    def nn_batch(self, queries, n: int = 1, return_device: bool = False):
+    def nn_batch(self, queries, n: int = 1, return_device: bool = False, graph: bool = True):
         """Batched LSH query against the device-resident index.
 
         :param queries: ``[Q, D]`` float array (host) or float32 CUDA tensor.
         :param n: neighbours per query (also the number of nearest unique codes
             whose descriptors form the candidate pool, as in the reference).
+        :param graph: replay the pipeline as one CUDA graph once the same batch shape repeats
+            (``False``: always launch kernel by kernel).
         :return: ``(rows int64[Q, n], dists float64[Q, n])`` -- rows index
             :meth:`mirror_uuids`; -1 / NaN pad queries with fewer than ``n``
             candidates.  Device tensors when ``return_device``.
@@ -638,7 +640,10 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
                 q = torch.from_numpy(numpy.ascontiguousarray(queries, dtype=numpy.float32)).to(dev, non_blocking=True)
             if q.dim() == 1:
                 q = q.unsqueeze(0)
-            rows, dists = m.query(self.lsh_functor, q, n, self.distance_method)
+            if graph and q.dtype == torch.float32 and hasattr(self.lsh_functor, "get_hash_packed"):
+                rows, dists = m.query_graphed(self.lsh_functor, q.contiguous(), n, self.distance_method)
+            else:
+                rows, dists = m.query(self.lsh_functor, q, n, self.distance_method)
         if return_device:
             return rows, dists
         return rows.cpu().numpy(), dists.cpu().numpy()

@@ -41,11 +41,11 @@ def _popcount_rows(x_i32: torch.Tensor) -> torch.Tensor:
 
 
 def _topk_on_tensor_cores(dev, db, q, k):
-    """hamming_topk that FAILS unless the tcgen05 scan produced the result: the dispatcher silently
-    re-runs an overflowed batch on the XOR/POPC scan (device.hamming_scan_keys), which would let a
+    """hamming_topk that FAILS unless the tcgen05 scan produced the result: an overflowed batch is
+    redone by the predicated XOR/POPC scan (device.hamming_scan_keys), which would let a
     full-size test pass without the headline kernel."""
     from smqtk_indexing_b200 import _lib
-    overflows0 = dev.TC_SCAN_OVERFLOWS
+    overflows0 = dev.tc_scan_overflows()
     _lib.profile_fetch()
     _lib.profile_enable(True)
     try:
@@ -55,8 +55,8 @@ def _topk_on_tensor_cores(dev, db, q, k):
         _lib.profile_enable(False)
     kernels = {name for name, _ in _lib.profile_fetch()}
     assert "ham_filter_tc_kernel" in kernels, "the tensor-core scan did not run: %s" % sorted(kernels)
-    assert "hamming_scan_kernel" not in kernels, "the batch fell back to the XOR/POPC scan"
-    assert dev.TC_SCAN_OVERFLOWS == overflows0, "the tensor-core scan overflowed a candidate buffer"
+    # (the predicated fallback kernels are always launched and return at once: their names prove nothing)
+    assert dev.tc_scan_overflows() == overflows0, "the tensor-core scan overflowed a candidate buffer: fallback result"
     return dist, idx
 
 

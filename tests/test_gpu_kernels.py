@@ -202,21 +202,24 @@ def test_hamming_scan_dispatch_and_overflow_fallback(dev):
     assert torch.equal(k_auto, k_popc) and torch.equal(k_tc, k_popc)
     same = np.repeat(table[:1], 100000, axis=0)
     ds = dev.codes_to_device(same)
-    before = dev.TC_SCAN_OVERFLOWS
+    before = dev.tc_scan_overflows()
+    _lib = __import__("smqtk_indexing_b200._lib", fromlist=["x"])
+    _lib.profile_fetch()
+    _lib.profile_enable(True)
     keys = dev.hamming_scan_keys(ds, dq, 10, variant=dev.SCAN_VARIANT_TC)
-    assert dev.TC_SCAN_OVERFLOWS == before + 1
+    torch.cuda.synchronize()
+    _lib.profile_enable(False)
+    ran = [name for name, _ in _lib.profile_fetch()]
+    # the overflow is handled ON THE DEVICE: the predicated XOR/POPC scan (sb_hamming_scan_if) ran after the
+    # tensor-core scan and replaced the keys; the host never read the flag
+    assert "ham_filter_tc_kernel" in ran and "hamming_scan_kernel" in ran
+    assert dev.tc_scan_overflows() == before + 1
     assert torch.equal(keys, dev.hamming_scan_keys(ds, dq, 10, variant=1))
-    # pipeline form (engine.py / distributed.py): no sync inside the context, one check at the end, re-run forced
-    # onto the XOR/POPC scan
-    with dev.deferred_scan_check() as chk:
-        dev.hamming_scan_keys(ds, dq, 10, variant=dev.SCAN_VARIANT_TC)
-        assert len(chk.flags) == 1
-    assert chk.overflowed() and dev.TC_SCAN_OVERFLOWS == before + 2
     with dev.force_popc():
         assert torch.equal(dev.hamming_scan_keys(ds, dq, 10), keys)
-    with dev.deferred_scan_check() as chk:
-        k_ok = dev.hamming_scan_keys(dt, dq, 10, variant=dev.SCAN_VARIANT_TC)
-    assert not chk.overflowed() and torch.equal(k_ok, k_popc)
+    # no overflow: the predicated kernels return at once and leave the tensor-core keys alone
+    k_ok = dev.hamming_scan_keys(dt, dq, 10, variant=dev.SCAN_VARIANT_TC)
+    assert dev.tc_scan_overflows() == before + 1 and torch.equal(k_ok, k_popc)
 
 
 # ------------------------------------------------------------------ index build: sb_unique_codes

@@ -1,0 +1,100 @@
+"""
+Multi-GPU parity ON HARDWARE (NCCL, one process per GPU): the sharded index in every
+(scan partition x re-rank mode) combination returns exactly what the single-GPU index returns
+for the same descriptors -- rows, distances, ties -- and what the oracle's array-form LSH query
+gives.  Needs >= 2 CUDA devices (skipped on the 1-GPU test box; run with `gpurun --gpus 2`).
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _data():
+    rng = np.random.RandomState(7)
+    N, D = 120_000, 64
+    centres = rng.rand(300, D)
+    x = (centres[rng.randint(0, 300, N)] + 0.05 * rng.randn(N, D)).astype(np.float32)
+    x[5000:5040] = x[77]                                        # duplicate descriptors across shards: ties
+    q = (centres[rng.randint(0, 300, 1024)] + 0.05 * rng.randn(1024, D)).astype(np.float32)
+    q[0] = x[77]
+    return x, q
+
+
+def _worker(rank, world, port, out_q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from smqtk_indexing_b200.distributed import ShardedLshIndex
+        from smqtk_indexing_b200.impls.lsh_functor.itq import ItqFunctor
+        x, q = _data()
+        f = ItqFunctor(bit_length=32, itq_iterations=5, random_seed=0)
+        f.fit_matrix(x[:20_000])                                # same data, same seed: same model on every rank
+        cuts = [len(x) * r // world for r in range(world + 1)]
+        cuts[1] += 13                                           # uneven shards
+        xl = torch.from_numpy(x[cuts[rank]:cuts[rank + 1]]).to(dev)
+        qd = torch.from_numpy(q).to(dev)
+        res = {}
+        for rerank in ("peer", "allreduce"):
+            for part in ("queries", "rows"):
+                idx = ShardedLshIndex(f, "euclidean", scan_partition=part, rerank=rerank)
+                idx.build(xl)
+                assert (idx.peers is not None) == (rerank == "peer"), idx.peer_error
+                for n, nq in ((10, 1024), (3, 5), (10, 1024), (10, 1024)):   # repeats: the 2nd+ batch replays a CUDA graph
+                    rows, d = idx.query(qd[:nq], n)
+                    torch.cuda.synchronize()
+                    res[(rerank, part, n, nq)] = (rows.cpu().numpy(), d.cpu().numpy())
+        if rank == 0:
+            codes = f.get_hash_packed(torch.from_numpy(x).to(dev)).cpu().numpy().view(np.uint32)
+            qc = f.get_hash_packed(qd).cpu().numpy().view(np.uint32)
+            out_q.put((res, codes, qc))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 CUDA devices")
+def test_sharded_lsh_index_on_nccl_equals_oracle_in_every_mode():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out_q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res, codes, qc = out_q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    x, q = _data()
+    x64 = x.astype(np.float64)
+    base = res[("peer", "queries", 10, 1024)]
+    for key, (rows, d) in res.items():
+        ref = res[("peer", "queries", key[2], key[3])]
+        assert np.array_equal(rows, ref[0]), key                # every mode: identical rows and distance bits
+        assert np.array_equal(d.view(np.int64), ref[1].view(np.int64)), key
+    for qi in list(range(12)) + [1023]:
+        orow, od = O.lsh_nn(x64, codes, q[qi].astype(np.float64), qc[qi:qi + 1], 10, "euclidean")
+        np.testing.assert_allclose(base[1][qi][:len(od)], od, rtol=1e-5, atol=1e-9)
+        if len(od) > 1 and np.diff(od).min() > 1e-6 * od.max():
+            assert list(base[0][qi][:len(od)]) == list(orow)
+    assert base[0][0][0] in (77,) + tuple(range(5000, 5040)) and base[1][0][0] == 0.0
