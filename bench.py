@@ -456,19 +456,16 @@ def run_b200(args):
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     x_local = torch.rand((n_local, D), generator=g, device=dev, dtype=torch.float32)
     functor = ItqFunctor(bit_length=b, itq_iterations=args.fit_iters, random_seed=0)
-    if rank == 0:
-        functor.fit_matrix(x_local[:min(args.fit_rows, n_local)])
-        mean_t = torch.from_numpy(np.ascontiguousarray(functor.mean_vec, dtype=np.float64)).to(dev)
-        rot_t = torch.from_numpy(np.ascontiguousarray(functor.rotation, dtype=np.float64)).to(dev)
+    t_fit0 = time.perf_counter()
+    if world == 1:
+        functor.fit_matrix(x_local[:min(args.fit_rows, n_local)], want_codes=False)
     else:
-        mean_t = torch.empty(D, dtype=torch.float64, device=dev)
-        rot_t = torch.empty((D, b), dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.broadcast(mean_t, 0)
-        dist.broadcast(rot_t, 0)
-        if rank != 0:
-            functor.mean_vec = mean_t.cpu().numpy().astype(np.float32)
-            functor.rotation = rot_t.cpu().numpy()
+        # row-sharded fit: every rank passes 1/N of the training rows, the partial sums are all-reduced
+        # (fit.py: [D], [D, D] and [b, D] values per step), every rank ends with the same model
+        functor.fit_matrix(x_local[:min((args.fit_rows + world - 1) // world, n_local)], want_codes=False,
+                           group=dist.group.WORLD)
+    torch.cuda.synchronize()
+    fit_s = time.perf_counter() - t_fit0
 
     t_build0 = time.perf_counter()
     if world == 1:
@@ -717,7 +714,7 @@ def run_b200(args):
             },
             "kernel_ms_per_step": {n_: sum(v) / args.steps for n_, v in per_kernel.items()},
             "index": {"unique_codes": int(n_codes), "rows_local": int(n_local), "scan_rows_local": int(scan_rows),
-                      "queries_scanned_per_rank": int(q_per_rank), "build_s": build_s,
+                      "queries_scanned_per_rank": int(q_per_rank), "build_s": build_s, "fit_s": fit_s,
                       "peer_rerank": peers is not None},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -62,6 +62,18 @@ def _worker(rank, world, port, out_q):
                     rows, d = idx.query(qd[:nq], n)
                     torch.cuda.synchronize()
                     res[(rerank, part, n, nq)] = (rows.cpu().numpy(), d.cpu().numpy())
+        # row-sharded fit (all-reduce of the [D], [D, D], [b, D] partial sums): same model as the
+        # single-process fit of all rows, on every rank
+        fs = ItqFunctor(bit_length=32, itq_iterations=5, random_seed=0)
+        fs.fit_matrix(x[cuts[rank] // 6:cuts[rank + 1] // 6], want_codes=False, group=dist.group.WORLD)
+        res["fit"] = (np.asarray(fs.mean_vec), np.asarray(fs.rotation))
+        if rank == 0:
+            one = ItqFunctor(bit_length=32, itq_iterations=5, random_seed=0)
+            one.fit_matrix(x[:cuts[-1] // 6], want_codes=False)
+            res["fit_single"] = (np.asarray(one.mean_vec), np.asarray(one.rotation))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, res["fit"][1].tobytes())
+        assert all(g == gathered[0] for g in gathered), "ranks ended with different models"
         if rank == 0:
             codes = f.get_hash_packed(torch.from_numpy(x).to(dev)).cpu().numpy().view(np.uint32)
             qc = f.get_hash_packed(qd).cpu().numpy().view(np.uint32)
@@ -88,6 +100,10 @@ def test_sharded_lsh_index_on_nccl_equals_oracle_in_every_mode():
     x, q = _data()
     x64 = x.astype(np.float64)
     base = res[("peer", "queries", 10, 1024)]
+    (m_sh, r_sh), (m_one, r_one) = res.pop("fit"), res.pop("fit_single")
+    np.testing.assert_allclose(m_sh, m_one, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(r_sh.T @ r_sh, np.eye(32), atol=1e-9)
+    np.testing.assert_allclose(r_sh, r_one, rtol=0, atol=1e-6)           # summation order differs, nothing else
     for key, (rows, d) in res.items():
         ref = res[("peer", "queries", key[2], key[3])]
         assert np.array_equal(rows, ref[0]), key                # every mode: identical rows and distance bits
