@@ -214,7 +214,13 @@ SB_API int sb_rerank_select_rows(const double* dist, const int64_t* cand_off, co
  * sb_enable_peer_access(peer): cudaDeviceEnablePeerAccess from the current device (idempotent). */
 SB_API int sb_rerank_peer(const float* const* shards, const int64_t* shard_bounds, int32_t n_shards, int32_t D,
                    int64_t ldd, const float* q, int32_t Q, int64_t ldq, const int64_t* cand_idx,
-                   const int64_t* cand_off, int64_t M, int32_t metric, int32_t aligned16, double* out, void* stream);
+                   const int64_t* cand_off, int64_t M, int64_t pitch, int32_t metric, int32_t aligned16, double* out,
+                   void* stream);
+/* sb_rerank for the fixed-pitch candidate layout of sb_expand_candidates (M = Q * pitch; the query of slot j
+ * is j / pitch, no search); `pitch` in sb_rerank_peer means the same (0 = ragged lists, cand_off is searched). */
+SB_API int sb_rerank_pitched(const float* db, int64_t N, int32_t D, int64_t ldd, const float* q, int32_t Q, int64_t ldq,
+                      const int64_t* cand_idx, const int64_t* cand_off, int64_t pitch, int32_t metric, double* out,
+                      void* stream);
 SB_API int sb_enable_peer_access(int32_t peer_device);
 
 /* Candidate expansion (lsh.py:490-496): the descriptor rows of each query's near codes,

@@ -49,8 +49,9 @@ SIGNATURES: Dict[str, tuple] = {
     "sb_rerank": (c_int32, [_P, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64, c_int32, _P, _P]),
     "sb_rerank_shard": (c_int32, [_P, c_int64, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64,
                                   c_int32, _P, _P]),
-    "sb_rerank_peer": (c_int32, [_P, _P, c_int32, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64, c_int32, c_int32,
-                                 _P, _P]),
+    "sb_rerank_peer": (c_int32, [_P, _P, c_int32, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64, c_int64, c_int32,
+                                 c_int32, _P, _P]),
+    "sb_rerank_pitched": (c_int32, [_P, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64, c_int32, _P, _P]),
     "sb_enable_peer_access": (c_int32, [c_int32]),
     "sb_rerank_select": (c_int32, [_P, _P, c_int32, c_int32, _P, _P, _P]),
     "sb_rerank_select_rows": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),

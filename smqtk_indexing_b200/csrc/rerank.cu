@@ -66,19 +66,43 @@ __device__ __forceinline__ void accumulate(F2& s0, F2& s1, F2& s2, float a, floa
 }
 
 template <int METRIC>
+__device__ __forceinline__ void accumulate4(F2& s0, F2& s1, F2& s2, const float4& x, const float4& y) {
+  accumulate<METRIC>(s0, s1, s2, x.x, y.x);
+  accumulate<METRIC>(s0, s1, s2, x.y, y.y);
+  accumulate<METRIC>(s0, s1, s2, x.z, y.z);
+  accumulate<METRIC>(s0, s1, s2, x.w, y.w);
+}
+
+// candidate rows are read exactly once: keep them out of L1 (the query row, shared by the query's candidates, stays)
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+template <int METRIC>
 __global__ void __launch_bounds__(RR_WARPS * 32)
 rerank_kernel(const float* __restrict__ db, long long N, int D, long long ldd, const float* __restrict__ q, int Q,
               long long ldq, const long long* __restrict__ cand_idx, const long long* __restrict__ cand_off,
               long long M, double* __restrict__ out, int vec_ok, long long row_base, double miss_value,
-              const float* const* __restrict__ shards, const long long* __restrict__ shard_bounds, int n_shards) {
+              const float* const* __restrict__ shards, const long long* __restrict__ shard_bounds, int n_shards,
+              long long pitch) {
   const int lane = threadIdx.x & 31;
   const long long j = (long long)blockIdx.x * RR_WARPS + (threadIdx.x >> 5);
   if (j >= M) return;
-  // owning query: last qi with cand_off[qi] <= j
-  int lo = 0, hi = Q;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (cand_off[mid] <= j) lo = mid; else hi = mid;
+  // owning query: fixed-pitch segments (sb_expand_candidates) need one division; ragged lists a binary
+  // search for the last qi with cand_off[qi] <= j (12 dependent L2 loads at Q = 4096: as long as the row itself)
+  int lo = 0;
+  if (pitch > 0) {
+    lo = (int)(j / pitch);
+  } else {
+    int hi = Q;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (cand_off[mid] <= j) lo = mid; else hi = mid;
+    }
   }
   long long row = cand_idx[j] - row_base;                    // db holds global rows [row_base, row_base + N)
   const float* b;
@@ -106,12 +130,21 @@ rerank_kernel(const float* __restrict__ db, long long N, int D, long long ldd, c
   if (vec_ok) {
     const float4* a4 = reinterpret_cast<const float4*>(a);
     const float4* b4 = reinterpret_cast<const float4*>(b);
-    for (int i = lane; i < D / 4; i += 32) {
-      float4 x = __ldg(a4 + i), y = __ldg(b4 + i);
-      accumulate<METRIC>(s0, s1, s2, x.x, y.x);
-      accumulate<METRIC>(s0, s1, s2, x.y, y.y);
-      accumulate<METRIC>(s0, s1, s2, x.z, y.z);
-      accumulate<METRIC>(s0, s1, s2, x.w, y.w);
+    const int n4 = D / 4;
+    int i = lane;
+    // a gathered row is read once, by one warp: what bounds this kernel is memory LATENCY, so four 128-bit
+    // loads per operand are issued before any of them is consumed (a 2 KB row = 4 loads per lane in flight)
+    for (; i + 96 < n4; i += 128) {
+      float4 y0 = ldg_stream4(b4 + i), y1 = ldg_stream4(b4 + i + 32), y2 = ldg_stream4(b4 + i + 64), y3 = ldg_stream4(b4 + i + 96);
+      float4 x0 = __ldg(a4 + i), x1 = __ldg(a4 + i + 32), x2 = __ldg(a4 + i + 64), x3 = __ldg(a4 + i + 96);
+      accumulate4<METRIC>(s0, s1, s2, x0, y0);
+      accumulate4<METRIC>(s0, s1, s2, x1, y1);
+      accumulate4<METRIC>(s0, s1, s2, x2, y2);
+      accumulate4<METRIC>(s0, s1, s2, x3, y3);
+    }
+    for (; i < n4; i += 32) {
+      float4 x = __ldg(a4 + i), y = ldg_stream4(b4 + i);
+      accumulate4<METRIC>(s0, s1, s2, x, y);
     }
     for (int i = (D / 4) * 4 + lane; i < D; i += 32) accumulate<METRIC>(s0, s1, s2, __ldg(a + i), __ldg(b + i));
   } else {
@@ -259,7 +292,7 @@ extern "C" {
 static int rerank_impl(const float* db, int64_t N, int32_t D, int64_t ldd, const float* q, int32_t Q, int64_t ldq,
                        const int64_t* cand_idx, const int64_t* cand_off, int64_t M, int32_t metric, double* out,
                        int64_t row_base, double miss_value, void* stream, const float* const* shards = nullptr,
-                       const int64_t* shard_bounds = nullptr, int n_shards = 0) {
+                       const int64_t* shard_bounds = nullptr, int n_shards = 0, int64_t pitch = 0) {
   SB_REQUIRE(D >= 1 && Q >= 1 && M >= 0 && N >= 0, "sb_rerank: bad sizes");
   SB_REQUIRE(ldd >= D && ldq >= D, "sb_rerank: leading dimension smaller than D");
   SB_REQUIRE(metric >= SB_METRIC_EUCLIDEAN && metric <= SB_METRIC_HIK, "sb_rerank: bad metric %d", metric);
@@ -277,15 +310,15 @@ static int rerank_impl(const float* db, int64_t N, int32_t D, int64_t ldd, const
   switch (metric) {
     case SB_METRIC_EUCLIDEAN:
       rerank_kernel<SB_METRIC_EUCLIDEAN><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok,
-                                                                         row_base, miss_value, shards, sbnd, n_shards);
+                                                                         row_base, miss_value, shards, sbnd, n_shards, (long long)pitch);
       break;
     case SB_METRIC_COSINE:
       rerank_kernel<SB_METRIC_COSINE><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok,
-                                                                      row_base, miss_value, shards, sbnd, n_shards);
+                                                                      row_base, miss_value, shards, sbnd, n_shards, (long long)pitch);
       break;
     default:
       rerank_kernel<SB_METRIC_HIK><<<grid, RR_WARPS * 32, 0, st>>>(db, N, D, ldd, q, Q, ldq, ci, co, M, out, vec_ok,
-                                                                   row_base, miss_value, shards, sbnd, n_shards);
+                                                                   row_base, miss_value, shards, sbnd, n_shards, (long long)pitch);
       break;
   }
   sb::count_launch();
@@ -316,12 +349,23 @@ int sb_rerank_shard(const float* db, int64_t N, int64_t row_base, int32_t D, int
  * NVLink for peer shards -- the re-rank needs no collective.  Rows outside every shard give NaN. */
 int sb_rerank_peer(const float* const* shards, const int64_t* shard_bounds, int32_t n_shards, int32_t D, int64_t ldd,
                    const float* q, int32_t Q, int64_t ldq, const int64_t* cand_idx, const int64_t* cand_off, int64_t M,
-                   int32_t metric, int32_t aligned16, double* out, void* stream) {
+                   int64_t pitch, int32_t metric, int32_t aligned16, double* out, void* stream) {
   SB_REQUIRE(shards && shard_bounds && n_shards >= 1, "sb_rerank_peer: NULL shard table");
+  SB_REQUIRE(pitch == 0 || M == (int64_t)Q * pitch, "sb_rerank_peer: fixed-pitch layout needs M == Q * pitch");
   // `aligned16`: every shard base is 16-byte aligned (the host knows the pointers; the device array is not read here)
   const float* fake_db = aligned16 ? reinterpret_cast<const float*>(uintptr_t(16)) : reinterpret_cast<const float*>(uintptr_t(4));
   return rerank_impl(fake_db, 0, D, ldd, q, Q, ldq, cand_idx, cand_off, M, metric, out, 0, nan(""), stream, shards,
-                     shard_bounds, n_shards);
+                     shard_bounds, n_shards, pitch);
+}
+
+/* sb_rerank for the FIXED-PITCH candidate layout of sb_expand_candidates (query of slot j = j / pitch: no
+ * search for the owning query); padding slots (-1) give NaN. */
+int sb_rerank_pitched(const float* db, int64_t N, int32_t D, int64_t ldd, const float* q, int32_t Q, int64_t ldq,
+                      const int64_t* cand_idx, const int64_t* cand_off, int64_t pitch, int32_t metric, double* out,
+                      void* stream) {
+  SB_REQUIRE(pitch >= 1, "sb_rerank_pitched: pitch must be positive");
+  return rerank_impl(db, N, D, ldd, q, Q, ldq, cand_idx, cand_off, (int64_t)Q * pitch, metric, out, 0, nan(""), stream,
+                     nullptr, nullptr, 0, pitch);
 }
 
 /* Peer access from the CURRENT device to `peer_device` (needed before kernels read CUDA-IPC mappings of a

@@ -374,8 +374,9 @@ def hamming_topk(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0):
 
 # --------------------------------------------------------------------- stage 3
 def rerank(db: torch.Tensor, q: torch.Tensor, cand_idx: torch.Tensor, cand_off: torch.Tensor,
-           metric: str) -> torch.Tensor:
-    """float64[M] distances of each candidate row to its query."""
+           metric: str, pitch: int = 0) -> torch.Tensor:
+    """float64[M] distances of each candidate row to its query.  ``pitch`` > 0: the candidates are in
+    the fixed-pitch layout of ``expand_candidates`` (M = Q * pitch)."""
     require_cuda()
     if db.dtype != torch.float32 or q.dtype != torch.float32 or db.stride(1) != 1 or q.stride(1) != 1:
         raise ValueError("db and q must be float32 with unit column stride")
@@ -391,9 +392,16 @@ def rerank(db: torch.Tensor, q: torch.Tensor, cand_idx: torch.Tensor, cand_off: 
     M = cand_idx.numel()
     out = torch.empty((M,), dtype=torch.float64, device=db.device)
     with torch.cuda.device(db.device):
-        _lib.check(_lib.load().sb_rerank(_ptr(db), N, D, max(db.stride(0), D), _ptr(q), Q, max(q.stride(0), D),
-                                         _ptr(cand_idx), _ptr(cand_off), M, _lib.METRICS[metric], _ptr(out),
-                                         _stream()))
+        if pitch > 0:
+            if M != Q * pitch:
+                raise ValueError("fixed-pitch candidates: %d slots for %d queries x pitch %d" % (M, Q, pitch))
+            _lib.check(_lib.load().sb_rerank_pitched(_ptr(db), N, D, max(db.stride(0), D), _ptr(q), Q, max(q.stride(0), D),
+                                                     _ptr(cand_idx), _ptr(cand_off), pitch, _lib.METRICS[metric], _ptr(out),
+                                                     _stream()))
+        else:
+            _lib.check(_lib.load().sb_rerank(_ptr(db), N, D, max(db.stride(0), D), _ptr(q), Q, max(q.stride(0), D),
+                                             _ptr(cand_idx), _ptr(cand_off), M, _lib.METRICS[metric], _ptr(out),
+                                             _stream()))
     return out
 
 
@@ -417,7 +425,8 @@ def rerank_shard(db: torch.Tensor, row_base: int, q: torch.Tensor, cand_idx: tor
     return out
 
 
-def rerank_peer(shards, q: torch.Tensor, cand_idx: torch.Tensor, cand_off: torch.Tensor, metric: str) -> torch.Tensor:
+def rerank_peer(shards, q: torch.Tensor, cand_idx: torch.Tensor, cand_off: torch.Tensor, metric: str,
+                pitch: int = 0) -> torch.Tensor:
     """float64[M] distances of candidate GLOBAL rows against a row-sharded table whose shards live on
     several GPUs (``peer.PeerShards``): each row is loaded from the GPU that holds it (NVLink)."""
     require_cuda()
@@ -436,7 +445,7 @@ def rerank_peer(shards, q: torch.Tensor, cand_idx: torch.Tensor, cand_off: torch
     with torch.cuda.device(q.device):
         _lib.check(_lib.load().sb_rerank_peer(_ptr(shards.ptr_table), _ptr(shards.bound_table), shards.n_shards, D,
                                               shards.ld, _ptr(q), Q, max(q.stride(0), D), _ptr(cand_idx), _ptr(cand_off), M,
-                                              _lib.METRICS[metric], 1 if shards.aligned16 else 0, _ptr(out), _stream()))
+                                              pitch, _lib.METRICS[metric], 1 if shards.aligned16 else 0, _ptr(out), _stream()))
     return out
 
 

@@ -68,9 +68,9 @@ class DeviceOps:
         from . import device
         return device.rerank_shard(x, row_base, q, cand_idx, cand_off, self.distance_method)
 
-    def rerank_peer(self, shards, q, cand_idx, cand_off) -> torch.Tensor:
+    def rerank_peer(self, shards, q, cand_idx, cand_off, pitch: int = 0) -> torch.Tensor:
         from . import device
-        return device.rerank_peer(shards, q, cand_idx, cand_off, self.distance_method)
+        return device.rerank_peer(shards, q, cand_idx, cand_off, self.distance_method, pitch)
 
     def expand(self, code_rows, csr_off, csr_rows, pitch):
         from . import device
@@ -265,7 +265,7 @@ class ShardedLshIndex:
                 cand_idx, cand_off = expand_candidates(code_rows, self.csr_off, self.csr_rows)
                 cand_cnt = None
         with _stage("rerank"):
-            d = self.ops.rerank_peer(self.peers, q_mine, cand_idx, cand_off)
+            d = self.ops.rerank_peer(self.peers, q_mine, cand_idx, cand_off, pitch if cand_cnt is not None else 0)
             if cand_cnt is not None:
                 rows, od = self.ops.rerank_select_rows(d, cand_off, cand_cnt, cand_idx, n)
             else:

@@ -262,7 +262,7 @@ class DeviceLshIndex:
                 cand_idx, cand_off, cand_cnt = device.expand_candidates(code_rows.contiguous(), self.csr_off,
                                                                         self.csr_rows, pitch)
             with _stage("rerank"):
-                dist = device.rerank(self.x, q, cand_idx, cand_off, distance_method)
+                dist = device.rerank(self.x, q, cand_idx, cand_off, distance_method, pitch=pitch)
                 return device.rerank_select_rows(dist, cand_off, cand_cnt, cand_idx, n, max_m=pitch)
         # heavy code collisions: exact-size ragged expansion (needs the total on the host)
         with _stage("expand"):
