@@ -726,8 +726,16 @@ def run_b200(args):
                 line["cpu_baseline_compiled"] = {"unavailable": str(e)[:120]}
         print(json.dumps(line))
     if world > 1:
+        # orderly teardown, then a hard exit: captured graphs that hold NCCL work and CUDA-IPC mappings of
+        # exited peers can stall interpreter shutdown; nothing is left to flush but stdout
+        sys.stdout.flush()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        index.close()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -222,6 +222,13 @@ SB_API int sb_rerank_pitched(const float* db, int64_t N, int32_t D, int64_t ldd,
                       const int64_t* cand_idx, const int64_t* cand_off, int64_t pitch, int32_t metric, double* out,
                       void* stream);
 SB_API int sb_enable_peer_access(int32_t peer_device);
+/* CUDA IPC plumbing for the shard table of sb_rerank_peer (one process per GPU).  sb_ipc_export: the 64-byte
+ * handle (host memory) of the cudaMalloc allocation that contains dev_ptr + dev_ptr's offset in it.
+ * sb_ipc_import: opens a peer's handle under the CURRENT device with lazy peer access, so that this device's
+ * kernels can load from it; returns the allocation base in this process.  sb_ipc_release closes it. */
+SB_API int sb_ipc_export(const void* dev_ptr, void* handle_out, int64_t* offset_out);
+SB_API int sb_ipc_import(const void* handle, void** base_out);
+SB_API int sb_ipc_release(void* base);
 
 /* Candidate expansion (lsh.py:490-496): the descriptor rows of each query's near codes,
  * in (code rank, row) order.  code_rows i64[Q][n] = rows of the unique-code table

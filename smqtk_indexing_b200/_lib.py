@@ -53,6 +53,9 @@ SIGNATURES: Dict[str, tuple] = {
                                  c_int32, _P, _P]),
     "sb_rerank_pitched": (c_int32, [_P, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64, c_int32, _P, _P]),
     "sb_enable_peer_access": (c_int32, [c_int32]),
+    "sb_ipc_export": (c_int32, [_P, _P, _P]),
+    "sb_ipc_import": (c_int32, [_P, _P]),
+    "sb_ipc_release": (c_int32, [_P]),
     "sb_rerank_select": (c_int32, [_P, _P, c_int32, c_int32, _P, _P, _P]),
     "sb_rerank_select_rows": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
     "sb_rerank_base": (c_int32, [_P, c_int64, c_int64, c_int32, c_int64, _P, c_int32, c_int64, _P, _P, c_int64,

@@ -175,6 +175,14 @@ class ShardedLshIndex:
                     raise RuntimeError("rerank='peer' needs CUDA IPC + peer access between all ranks' GPUs (%s)"
                                        % (self.peer_error or "a peer rank failed"))
 
+    def close(self) -> None:
+        """Drop the captured CUDA graphs (they hold NCCL work) and the peer mappings.  Call on every rank
+        before ``destroy_process_group``."""
+        self._graphs = {}
+        if self.peers is not None:
+            self.peers.release()
+            self.peers = None
+
     # ------------------------------------------------------------------ partitions
     def _by_queries(self, Q: int) -> bool:
         return self.world > 1 and (self.scan_partition == "queries" or (

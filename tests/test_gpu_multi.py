@@ -62,6 +62,7 @@ def _worker(rank, world, port, out_q):
                     rows, d = idx.query(qd[:nq], n)
                     torch.cuda.synchronize()
                     res[(rerank, part, n, nq)] = (rows.cpu().numpy(), d.cpu().numpy())
+                idx.close()
         # row-sharded fit (all-reduce of the [D], [D, D], [b, D] partial sums): same model as the
         # single-process fit of all rows, on every rank
         fs = ItqFunctor(bit_length=32, itq_iterations=5, random_seed=0)
@@ -78,9 +79,15 @@ def _worker(rank, world, port, out_q):
             codes = f.get_hash_packed(torch.from_numpy(x).to(dev)).cpu().numpy().view(np.uint32)
             qc = f.get_hash_packed(qd).cpu().numpy().view(np.uint32)
             out_q.put((res, codes, qc))
+            out_q.close()
+            out_q.join_thread()
+        torch.cuda.synchronize()
         dist.barrier()
-    finally:
-        dist.destroy_process_group()
+        os._exit(0)                      # captured graphs hold NCCL work: skip interpreter teardown
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        os._exit(1)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 CUDA devices")
@@ -93,10 +100,21 @@ def test_sharded_lsh_index_on_nccl_equals_oracle_in_every_mode():
     procs = [ctx.Process(target=_worker, args=(r, world, port, out_q)) for r in range(world)]
     for p in procs:
         p.start()
-    res, codes, qc = out_q.get(timeout=600)
+    import queue
+    got = None
+    for _ in range(300):                                        # a dead worker must fail the test at once, not after a timeout
+        try:
+            got = out_q.get(timeout=2)
+            break
+        except queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
     for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+        p.join(timeout=60)
+        if p.is_alive():
+            p.kill()
+    assert got is not None and all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    res, codes, qc = got
     x, q = _data()
     x64 = x.astype(np.float64)
     base = res[("peer", "queries", 10, 1024)]
