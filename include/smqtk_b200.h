@@ -148,6 +148,14 @@ SB_API int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W,
                        const uint32_t* q, int32_t Q, int32_t k, int64_t idx_base,
                        uint64_t* keys_out, int32_t* overflow_out,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* The same scan with PACKED FP4 operands (hamming_tc4.cu): bits -> +-1 E2M1, tcgen05.mma kind::mxf4.block_scale
+ * (every block scale 2^0), K = 64 per MMA at the cycle count of kind::f8f6f4's K = 32 -- half the tensor-pipe
+ * time, the same exact integer distances and the same keys.  Same contract as sb_hamming_scan_tc. */
+SB_API int sb_hamming_scan_tc4_supported(int64_t U, int32_t W, int32_t Q, int32_t k);
+SB_API size_t sb_hamming_scan_tc4_workspace_bytes(int64_t U, int32_t W, int32_t Q, int32_t k);
+SB_API int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q, int32_t Q, int32_t k,
+                        int64_t idx_base, uint64_t* keys_out, int32_t* overflow_out, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* Merge `parts` sorted key lists per query (keys_in: u64[parts][Q][k], e.g. the
  * all-gathered per-GPU results) into the global top-k and decode:

@@ -40,6 +40,9 @@ SIGNATURES: Dict[str, tuple] = {
     "sb_hamming_scan_tc_supported": (c_int32, [c_int64, c_int32, c_int32, c_int32]),
     "sb_hamming_scan_tc_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "sb_hamming_scan_tc": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P, _P, c_size_t, _P]),
+    "sb_hamming_scan_tc4_supported": (c_int32, [c_int64, c_int32, c_int32, c_int32]),
+    "sb_hamming_scan_tc4_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
+    "sb_hamming_scan_tc4": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P, _P, c_size_t, _P]),
     "sb_hamming_scan": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P, c_size_t, _P]),
     "sb_hamming_scan_variant": (c_int32, [_P, c_int64, c_int32, _P, c_int32, c_int32, c_int64, _P, _P,
                                           c_size_t, c_int32, _P]),

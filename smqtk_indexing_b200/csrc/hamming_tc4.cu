@@ -1,0 +1,697 @@
+// Batched Hamming scan / top-k on the tensor cores, PACKED FP4 operands (reference: LinearHashIndex._nn,
+// smqtk_indexing/impls/hash_index/linear.py:232-240 + hamming_distance utils/metrics.py:155).
+//
+// Same algorithm, data flow and bookkeeping as hamming_tc.cu (read its header first); what changes is the
+// operand format: bits are mapped to +-1 in E2M1 (4 bits per element: +1.0 = 0x2, -1.0 = 0xA) and multiplied
+// with tcgen05.mma kind::mxf4.block_scale -- K = 64 elements per MMA at the cycle count of kind::f8f6f4's K = 32
+// (measured, tools/experiments/mxf4_probe2.cu: 137.6 cycles for 128 x 256 x 64 vs 137.6 for 128 x 256 x 32), i.e.
+// HALF the tensor-pipe time for the same dot products, still exact: every product is +-1 and the FP32
+// accumulator holds the integers.  A 256-bit code is ONE 128-byte SWIZZLE_128B row (4 MMAs, start address
+// advancing 32 bytes), so a tile has one K group instead of two.
+//   * Block scaling cannot be switched off: every UE8M0 block scale is 2^0.  The scale factors live in tensor
+//     memory; the whole 16-column SF window is filled with 0x7F in every lane with tcgen05.st once per CTA, so
+//     the (sub-partition replicated) SF layout never matters.  Instruction descriptor: a/b format = 1
+//     (MXF4Format::E2M1; 5 is the kind::mxf8f6f4 code and raises "illegal instruction"), scale format UE8M0.
+//   * Accumulators are FP32 only, and the SF window needs columns too: query blocks are 240 columns
+//     (accumulator 0 = TMEM columns [0, 240), SF window [240, 256), accumulator 1 = [256, 496)).
+//   * Bit -> nibble expansion is two instructions per 8 elements: out = ((w << s) & 0x88888888) | 0x22222222
+//     for s = 3, 2, 1, 0 takes every 4th bit of a code word as the sign of 8 consecutive elements.  This permutes
+//     the elements inside a row, identically for table rows and query rows -- a dot product does not care.
+//   * The threshold still rides in one extra K step: A_syn = 64 x (+1), B_syn = up to 44 E2M1 slots (values 6, 4,
+//     3, 2, 1) that sum to 2 * tq - K + 1; "d <= tq" stays a sign test on the accumulator.
+//   * Survivor groups are 32 columns of a 240-column block: the re-check list stores the group's first query in
+//     units of 16 (240 = 15 * 16) and a flag for the last, half-width group of a block.
+// Warp roles: 0-3 epilogue (TMEM lane quadrants), 4 MMA issue + TMEM alloc, 5 B loader,
+// 6-13 producers (half a table row per thread and tile).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+using namespace tcptx;
+
+namespace {
+
+constexpr int TM = 128;                     // rows per tile (UMMA M)
+constexpr int QB = 240;                     // query columns per block (UMMA N): 2 x 240 FP32 accumulators + SF columns <= 512
+constexpr int A_GROUP = TM * 128;           // 16 KB: 128 rows x 256 E2M1 (8 code words)
+constexpr int B_GROUP = QB * 128;           // 30 KB
+constexpr int B_SYN = 2 * QB * 16;          // 7.5 KB  (no-swizzle, 2 K chunks of 16 bytes = 64 E2M1)
+constexpr int B_BLOCK = 38 * 1024;          // B_GROUP + B_SYN rounded up to the 1024-byte swizzle atom
+constexpr int A_SYN = 2 * TM * 16;          // 4 KB
+constexpr int SF_COL = QB;                  // TMEM columns [240, 256): scale factors (all 2^0)
+constexpr int ACC1_COL = 256;               // second accumulator
+constexpr int MAX_STAGES = 4;
+constexpr int NB = 2;                       // query blocks resident per pass: every expanded A tile feeds 2 x 256 queries
+constexpr int GRAN = 32;                    // rows per granule of the visiting order
+constexpr int EPI_WARPS = 4, MMA_WARP = 4, B_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 8;
+constexpr int THREADS = (PROD_WARP0 + PROD_WARPS) * 32;   // 448
+constexpr int GROWTH = 4;                   // rows of a chunk = 3 x the rows before it: ~3 (k + ties) survivors per query
+constexpr int CP_THREADS = 256;            // 7-8 compaction CTAs per SM: most queries hold a few hundred keys
+
+struct HamTc4Params {
+  const uint32_t* db;          // u32[U][W]
+  long long U;
+  int W, G, ksteps;            // G = 128-byte K groups per row, ksteps = MMAs per group
+  long long vg0, vg1;          // virtual granules of this chunk
+  long long NG, P;             // physical granule = (virtual * P) mod NG
+  int col_blocks, cb_per;      // query blocks in total / per blockIdx.y
+  const unsigned char* image;  // per block: G x B_GROUP (SW128) then B_SYN
+  const int* tq;               // thresholds (Hamming distance) per query column
+  unsigned long long* recheck; // (row << 24 | half-width flag << 23 | first query of the 32-column group / 16) entries
+  int* recheck_cnt;
+  int recheck_cap;
+  unsigned long long* cand_buf;
+  int* cand_cnt;
+  int cap;
+  long long idx_base;
+  int dense;                   // first chunk: every pair is kept -> key stored at buf[query][virtual row]
+  int stages;
+};
+
+// 32 code bits -> 32 E2M1 elements (16 bytes): +1.0 = 0x2, -1.0 = 0xA.  Output word s holds the bits
+// s, s + 4, s + 8, ... of the code word as the signs of 8 consecutive elements (an element permutation inside
+// the row, the same for every row of both operands).
+__device__ __forceinline__ uint4 expand_word4(uint32_t w) {
+  uint4 o;
+  o.x = ((w << 3) & 0x88888888u) | 0x22222222u;
+  o.y = ((w << 2) & 0x88888888u) | 0x22222222u;
+  o.z = ((w << 1) & 0x88888888u) | 0x22222222u;
+  o.w = (w & 0x88888888u) | 0x22222222u;
+  return o;
+}
+// byte offset of 16-byte chunk c of row r inside a [rows x 128 B] SWIZZLE_128B K-major group
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+  return (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::mxf4 block-scaled (E2M1 x E2M1 -> F32, K = 64), issued by one thread.
+__device__ __forceinline__ void umma_fp4(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                         uint32_t tsfa, uint32_t tsfb) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
+      : "memory");
+}
+
+// One re-check entry = (row, group of up to 32 queries starting at `qg0`): exact distances from the packed codes
+// (see hamming_tc.cu for why survivors are not decoded from the accumulator registers).
+template <int W>
+__device__ __forceinline__ void ham4_recheck_group(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qcodes, int Q,
+                                                   long long row, unsigned long long row_key, int qg0, int width,
+                                                   const int* __restrict__ tq, unsigned long long* cand_buf, int* cand_cnt,
+                                                   int cap, int lane) {
+  uint32_t x[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) x[w] = __ldg(db + row * W + w);
+  const int qg = qg0 + lane;
+  if (lane < width && qg < Q) {
+    int d = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) d += __popc(x[w] ^ __ldg(qcodes + (long long)qg * W + w));
+    if (d <= tq[qg]) {
+      const int slot = atomicAdd(cand_cnt + qg, 1);
+      if (slot < cap) cand_buf[(long long)qg * cap + slot] = ((unsigned long long)(unsigned)d << 40) | row_key;
+    }
+  }
+}
+
+// W = code words per row (1, 2, 4, 8); KSTEPS = MMAs of K = 64 elements per tile and block
+template <int W>
+__global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4Params p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms: align by hand
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int KSTEPS = (W >= 2) ? W / 2 : 1;                    // 64 elements = 2 code words per MMA
+  constexpr uint32_t a_stage = (uint32_t)A_GROUP;
+  // layout (offsets are multiples of 1024): [B block 0][B block 1][A_syn][A ring][barriers, thresholds]
+  unsigned char* s_b = smem;
+  unsigned char* s_asyn = s_b + NB * B_BLOCK;
+  unsigned char* s_a = s_asyn + A_SYN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + (size_t)MAX_STAGES * a_stage);
+  const uint32_t a_full = smem_u32(bars), a_empty = a_full + MAX_STAGES * 8;
+  const uint32_t acc_full = a_empty + MAX_STAGES * 8, acc_empty = acc_full + 16;
+  const uint32_t b_full = acc_empty + 16, b_empty = b_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
+  int* s_tq = reinterpret_cast<int*>(bars + 2 * MAX_STAGES + 8);  // [4 warps][2 blocks x 240]: thresholds
+
+  const long long n_gran = p.vg1 - p.vg0;
+  const long long n_tiles = (n_gran + 3) / 4;
+  const long long my_tiles = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int jb0 = blockIdx.y * p.cb_per;                         // cb_per is a multiple of NB
+  const int jb1 = min(p.col_blocks, jb0 + p.cb_per);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(a_full + s * 8, PROD_WARPS); mbar_init(a_empty + s * 8, 1); }
+    for (int b = 0; b < NB; ++b) { mbar_init(acc_full + b * 8, 1); mbar_init(acc_empty + b * 8, EPI_WARPS); }
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // A_syn = +1.0 in every E2M1 element; codes narrower than 256 bits leave K chunks of the A ring untouched: zero
+  // the ring once (a zero nibble is +0.0)
+  for (int i = threadIdx.x; i < A_SYN / 4; i += THREADS) reinterpret_cast<uint32_t*>(s_asyn)[i] = 0x22222222u;
+  if (W < 8)
+    for (int i = threadIdx.x; i < (int)(MAX_STAGES * a_stage / 16); i += THREADS)
+      reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // every UE8M0 block scale = 2^0: 0x7F in every byte of every lane of the SF window (whatever layout the MMA reads)
+  if (warp < 4) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(SF_COL + c);
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(0x7F7F7F7Fu) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == B_WARP) {
+    // =========================== B: NB resident query blocks ===========================
+    if (lane == 0) {
+      int it = 0;
+      for (int jb = jb0; jb < jb1; jb += NB, ++it) {
+        const int nb = min(NB, jb1 - jb);
+        mbar_wait(b_empty, (it & 1) ^ 1);
+        const unsigned char* src = p.image + (size_t)jb * B_BLOCK;   // blocks are contiguous in the image too
+        const uint32_t bytes = (uint32_t)nb * B_BLOCK;
+        mbar_expect_tx(b_full, bytes);
+        for (uint32_t o = 0; o < bytes; o += 2048) tma_bulk_g2s(smem_u32(s_b + o), src + o, 2048, b_full);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // =========================== MMA issue ===========================
+    if (lane == 0) {
+      // block-scaled descriptor: A = B = E2M1 (MXF4Format 1) at bits 7 / 10, both K-major, N at 17, scale
+      // format UE8M0 (bit 23), M at 24, scale-factor ids 0, K = 64 (bit 31 = 0); accumulator FP32
+      const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(QB >> 3) << 17) | (1u << 23) | ((uint32_t)(TM >> 4) << 24);
+      const uint32_t tsfa = tmem_base + (uint32_t)SF_COL, tsfb = tmem_base + (uint32_t)(SF_COL + 8);
+      const uint64_t asyn_desc = umma_desc(smem_u32(s_asyn), TM * 16, 128);
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(s_a));
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(s_b));
+      const uint64_t bsyn_desc0 = umma_desc(smem_u32(s_b) + B_GROUP, QB * 16, 128);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      long long t[NB] = {0, 0};                                  // tiles issued per accumulator buffer
+      for (int jb = jb0; jb < jb1; jb += NB, ++it) {
+        const int nb = min(NB, jb1 - jb);
+        mbar_wait(b_full, it & 1);
+        tc_fence_after();
+        for (long long i = 0; i < my_tiles; ++i) {
+          mbar_wait(a_full + stage * 8, phase);
+          const uint64_t a_desc = a_desc0 + (uint64_t)(((uint32_t)stage * a_stage) >> 4);
+#pragma unroll
+          for (int blk = 0; blk < NB; ++blk) {
+            if (blk < nb) {
+              // one A tile, NB query blocks: accumulator buffer = block, so block 1's MMAs overlap block 0's epilogue
+              const uint32_t d_tmem = tmem_base + (uint32_t)(blk * ACC1_COL);
+              mbar_wait(acc_empty + blk * 8, (uint32_t)(t[blk] & 1) ^ 1);
+              tc_fence_after();
+              const uint64_t b_desc = b_desc0 + (uint64_t)((blk * B_BLOCK) >> 4);
+#pragma unroll
+              for (int ks = 0; ks < KSTEPS; ++ks)
+                umma_fp4(d_tmem, a_desc + (uint64_t)((ks * 32) >> 4), b_desc + (uint64_t)((ks * 32) >> 4), idesc,
+                         ks ? 1u : 0u, tsfa, tsfb);
+              umma_fp4(d_tmem, asyn_desc, bsyn_desc0 + (uint64_t)((blk * B_BLOCK) >> 4), idesc, 1u, tsfa, tsfb);
+              umma_commit(acc_full + blk * 8);
+              ++t[blk];
+            }
+          }
+          umma_commit(a_empty + stage * 8);
+          if (++stage == MAX_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(b_empty);                                   // B may be replaced once these MMAs retire
+      }
+    }
+  } else if (warp >= PROD_WARP0) {
+    // =========================== A: packed codes -> +-1 E2M1, swizzled ===========================
+    // thread -> (row r of the tile, half h of its words); a code word becomes one 16-byte chunk
+    constexpr int WH = (W >= 2) ? W / 2 : 1;                     // words per thread
+    const int pt = threadIdx.x - PROD_WARP0 * 32;
+    const int r = pt & (TM - 1), h = pt >> 7;
+    const bool worker = (W >= 2) || h == 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t cw[WH], cn[WH];
+    // granule of tile i for this thread: vg = vg_first + i * 4 * gridDim.x, physical pg = vg * P mod NG, kept incrementally
+    const long long vg_first = p.vg0 + (long long)blockIdx.x * 4 + (r >> 5);
+    const long long pg_first = (long long)(((unsigned long long)vg_first * (unsigned long long)p.P) % (unsigned long long)p.NG);
+    const long long pg_step = (long long)(((unsigned long long)(4 * gridDim.x) * (unsigned long long)p.P) % (unsigned long long)p.NG);
+    long long vg_ld = vg_first, pg_ld = pg_first;
+    auto load = [&](uint32_t (&w)[WH]) {                        // loads the NEXT tile in sequence
+      const bool in_chunk = vg_ld < p.vg1;
+      const long long row = pg_ld * GRAN + lane;
+      const bool valid = in_chunk && row < p.U;
+      vg_ld += 4 * gridDim.x;
+      pg_ld += pg_step;
+      if (pg_ld >= p.NG) pg_ld -= p.NG;
+#pragma unroll
+      for (int j = 0; j < WH; ++j) w[j] = 0u;
+      if (valid && worker) {
+        const uint32_t* src = p.db + row * W + h * WH;
+        if (WH == 4) {
+          const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(src));
+          w[0] = x0.x; w[1] = x0.y; w[2 % WH] = x0.z; w[3 % WH] = x0.w;
+        } else if (WH == 2) {
+          const uint2 x0 = __ldg(reinterpret_cast<const uint2*>(src));
+          w[0] = x0.x; w[1 % WH] = x0.y;
+        } else {
+          w[0] = __ldg(src);
+        }
+      }
+      return valid;
+    };
+    for (int jb = jb0; jb < jb1; jb += NB) {
+      vg_ld = vg_first;
+      pg_ld = pg_first;
+      bool vcur = (my_tiles > 0) ? load(cw) : false;
+      for (long long i = 0; i < my_tiles; ++i) {
+        bool vnext = false;
+        if (i + 1 < my_tiles) vnext = load(cn);
+        mbar_wait(a_empty + stage * 8, phase ^ 1);
+        unsigned char* dst = s_a + (size_t)stage * a_stage;
+        if (worker) {
+#pragma unroll
+          for (int j = 0; j < WH; ++j) {
+            const int wj = h * WH + j;                             // word of the row = 16-byte chunk of the 128-byte row
+            uint4 o = expand_word4(cw[j]);
+            if (!vcur) o = make_uint4(0u, 0u, 0u, 0u);             // rows past the table: all-zero operand
+            *reinterpret_cast<uint4*>(dst + sw128_off(r, wj)) = o;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + stage * 8);
+#pragma unroll
+        for (int j = 0; j < WH; ++j) cw[j] = cn[j];
+        vcur = vnext;
+        if (++stage == MAX_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp < EPI_WARPS) {
+    // =========================== epilogue: sign test, survivors queued ===========================
+    const int ew = warp;                                         // TMEM lane quadrant = granule of the tile
+    uint32_t par = 0u;                                           // bit blk: parity of accumulator buffer blk's next "full"
+    int* my_tq = s_tq + warp * (NB * QB);
+    const long long vg_first = p.vg0 + (long long)blockIdx.x * 4 + ew;
+    const long long pg_first = (long long)(((unsigned long long)vg_first * (unsigned long long)p.P) % (unsigned long long)p.NG);
+    const long long pg_step = (long long)(((unsigned long long)(4 * gridDim.x) * (unsigned long long)p.P) % (unsigned long long)p.NG);
+    constexpr int NGRP = (QB + 31) / 32;                         // 8 survivor groups per block, the last 16 columns wide
+    for (int jb = jb0; jb < jb1; jb += NB) {
+      const int nb = min(NB, jb1 - jb);
+      __syncwarp();
+      for (int c = lane; c < nb * QB; c += 32) my_tq[c] = __ldcg(p.tq + (long long)jb * QB + c);
+      __syncwarp();
+      long long vg = vg_first, pg = pg_first;
+      for (long long i = 0; i < my_tiles; ++i) {
+        const long long vt = blockIdx.x + i * gridDim.x;
+        const long long row = pg * GRAN + lane;
+        const bool rvalid = (vg < p.vg1) && (row < p.U);
+        vg += 4 * gridDim.x;
+        pg += pg_step;
+        if (pg >= p.NG) pg -= p.NG;
+        const unsigned long long row_key = (unsigned long long)(p.idx_base + row);
+#pragma unroll 1
+        for (int blk = 0; blk < nb; ++blk) {
+          const int q0 = (jb + blk) * QB;
+          const int* tq_blk = my_tq + blk * QB;
+          mbar_wait(acc_full + blk * 8, (par >> blk) & 1u);
+          par ^= 1u << blk;
+          tc_fence_after();
+          const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(blk * ACC1_COL);
+          unsigned hit[NGRP];                                        // lanes with a survivor in each 32-column group
+#pragma unroll
+          for (int c64 = 0; c64 < QB; c64 += 64) {
+            uint32_t va[32], vb[32];                               // 2 x 32 columns of FP32 accumulators
+            const bool full = (c64 + 64 <= QB);                     // the last pass covers 48 columns: 32 + 16
+            tmem_ld32_nowait(tbase + (uint32_t)c64, va);
+            if (full) {
+              tmem_ld32_nowait(tbase + (uint32_t)(c64 + 32), vb);
+            } else {
+              uint32_t vh[16];
+              tmem_ld16_nowait(tbase + (uint32_t)(c64 + 32), vh);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { vb[j] = vh[j]; vb[16 + j] = 0x80000000u; }   // absent columns: "no survivor"
+            }
+            tmem_ld_wait();
+            if (p.dense) {
+              // seed chunk: buf[query][virtual row] = key for every pair (virtual row < cap by construction)
+              const long long vrow = vt * TM + ew * 32 + lane;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) {
+                const int col = c64 + j;
+                if (col < QB) {
+                  const uint32_t reg = (j < 32) ? va[j & 31] : vb[j & 31];
+                  const int d = tq_blk[col] - (int)(__uint_as_float(reg) * 0.5f);
+                  p.cand_buf[(long long)(q0 + col) * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)d << 40) | row_key) : ~0ull;
+                }
+              }
+            } else {
+              // the common case (no survivor among 64 pairs) is an AND tree over the sign bits
+              uint32_t a0 = 0xffffffffu, b0 = 0xffffffffu;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { a0 &= va[j]; b0 &= vb[j]; }
+              hit[c64 / 32] = __ballot_sync(0xffffffffu, rvalid && (a0 & 0x80000000u) == 0u);
+              if (c64 / 32 + 1 < NGRP) hit[c64 / 32 + 1] = __ballot_sync(0xffffffffu, rvalid && (b0 & 0x80000000u) == 0u);
+            }
+          }
+          // the accumulator buffer is free: let the next tile's MMAs start, THEN pay for the appends
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + blk * 8);
+          if (!p.dense) {
+            int total = 0;
+#pragma unroll
+            for (int g32 = 0; g32 < NGRP; ++g32) total += __popc(hit[g32]);
+            if (total) {                                               // rare: one atomic per (warp, tile, block) with survivors
+              int base = 0;
+              if (lane == 0) base = atomicAdd(p.recheck_cnt, total);
+              base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+              for (int g32 = 0; g32 < NGRP; ++g32) {
+                const unsigned m = hit[g32];
+                if ((m >> lane) & 1u) {
+                  const int slot = base + __popc(m & ((1u << lane) - 1u));
+                  if (slot < p.recheck_cap)
+                    p.recheck[slot] = ((unsigned long long)row << 24) | (g32 == NGRP - 1 ? (1ull << 23) : 0ull) |
+                                      (unsigned long long)((q0 + 32 * g32) >> 4);
+                }
+                base += __popc(m);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// One warp per re-check entry (row, group of 32 or 16 queries): exact distances from the packed codes, survivors
+// appended to their query's candidate buffer.
+template <int W>
+__global__ void __launch_bounds__(256)
+ham4_recheck_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qcodes, int Q, long long idx_base,
+                    const unsigned long long* __restrict__ list, const int* __restrict__ list_cnt, int list_cap,
+                    const int* __restrict__ tq, unsigned long long* __restrict__ cand_buf, int* __restrict__ cand_cnt, int cap,
+                    int* __restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const int raw = *list_cnt;
+  if (raw > list_cap && blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+  const int n = min(raw, list_cap);
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
+    const unsigned long long ent = list[e];
+    const long long row = (long long)(ent >> 24);
+    const int qg0 = (int)(ent & 0x7fffffull) * 16;
+    const int width = (ent & (1ull << 23)) ? (QB & 31) : 32;
+    ham4_recheck_group<W>(db, qcodes, Q, row, (unsigned long long)(idx_base + row), qg0, width, tq, cand_buf, cand_cnt, cap, lane);
+  }
+}
+
+// Query codes -> per-block image: [240 rows x 128 B] in the SWIZZLE_128B K-major order (same bit -> nibble expansion
+// as the table rows), then the block's B_syn; columns past Q and K chunks past the code are zero (the image is
+// cleared first).  One thread per (column, word).
+__global__ void ham4_query_image_kernel(const uint32_t* __restrict__ q, int Q, int W, unsigned char* __restrict__ img) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Q * W) return;
+  const int col = (int)(i / W), j = (int)(i % W);
+  const int jb = col / QB, n = col % QB;
+  *reinterpret_cast<uint4*>(img + (size_t)jb * B_BLOCK + sw128_off(n, j)) = expand_word4(q[(long long)col * W + j]);
+}
+
+// B_syn of every block: up to 64 E2M1 slots per column that sum to s = 2 * tq - K + 1 (|s| <= 257: at most 42 slots of
+// 6 plus two for the remainder); padding columns get -258 (their data nibbles are zero: the accumulator is negative).
+__global__ void ham4_threshold_image_kernel(int Q, int cols, int K, const int* __restrict__ tq, unsigned char* __restrict__ img,
+                                            int* __restrict__ list_cnt) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col == 0) *list_cnt = 0;                                   // the re-check list restarts with every chunk
+  if (col >= cols) return;
+  const int jb = col / QB, n = col % QB;
+  const int s = (col < Q) ? (2 * min(tq[col], K) - K + 1) : -258;
+  const uint32_t sign = s < 0 ? 0x8u : 0u;
+  const int mag = s < 0 ? -s : s;
+  const int n6 = mag / 6, rem = mag - 6 * n6;
+  // E2M1 magnitude codes: 1.0 = 2, 2.0 = 4, 3.0 = 5, 4.0 = 6, 6.0 = 7; remainder 5 = 4 + 1 (two slots)
+  const uint32_t rem_code[6] = {0u, 2u, 4u, 5u, 6u, 6u};
+  uint32_t words[8];
+#pragma unroll
+  for (int wd = 0; wd < 8; ++wd) {
+    uint32_t v = 0u;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int slot = wd * 8 + b;
+      uint32_t nib = 0u;
+      if (slot < n6) nib = 7u | sign;
+      else if (slot == n6 && rem) nib = rem_code[rem] | sign;
+      else if (slot == n6 + 1 && rem == 5) nib = 2u | sign;
+      v |= nib << (4 * b);
+    }
+    words[wd] = v;
+  }
+  unsigned char* base = img + (size_t)jb * B_BLOCK + (size_t)B_GROUP;
+  *reinterpret_cast<uint4*>(base + n * 16) = make_uint4(words[0], words[1], words[2], words[3]);
+  *reinterpret_cast<uint4*>(base + QB * 16 + n * 16) = make_uint4(words[4], words[5], words[6], words[7]);
+}
+
+__global__ void ham4_init_kernel(int cols, int K, int* __restrict__ tq, int* __restrict__ cnt, int* __restrict__ overflow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *overflow = 0;
+  if (i >= cols) return;
+  tq[i] = K;
+  cnt[i] = 0;
+}
+
+__global__ void ham4_set_count_kernel(int* __restrict__ cnt, int Q, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Q) cnt[i] = v;
+}
+
+// One CTA per query: sort the survivors (canonical keys: distance, row), keep the best k, tighten
+// the threshold to the k-th distance (later rows may still tie with it at a smaller row index, so
+// the test stays "<="); `final` writes keys_out.
+__global__ void __launch_bounds__(CP_THREADS)
+ham4_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt, int cap, int k, int K, int* __restrict__ tq,
+                    int* __restrict__ overflow, int final, unsigned long long* __restrict__ keys_out) {
+  extern __shared__ unsigned long long s_key[];   // P = next pow2 >= min(count, cap)
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  const int raw = cnt[qi];
+  const int m = min(raw, cap);
+  if (raw > cap && tid == 0) *overflow = 1;
+  unsigned long long* mine = buf + (size_t)qi * cap;
+  int P = 1;
+  while (P < m) P <<= 1;
+  for (int i = tid; i < P; i += CP_THREADS) s_key[i] = (i < m) ? mine[i] : ~0ull;
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < P / 2; i += CP_THREADS) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long a = s_key[lo], b = s_key[hi];
+        if ((a > b) == up) { s_key[lo] = b; s_key[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  // rows past the table were stored as empty keys by the dense chunk: they sort last
+  int keep = min(m, k);
+  {
+    int lo = 0, hi = keep;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_key[mid] != ~0ull) lo = mid + 1; else hi = mid;
+    }
+    keep = lo;
+  }
+  for (int i = tid; i < keep; i += CP_THREADS) mine[i] = s_key[i];
+  if (tid == 0) {
+    cnt[qi] = keep;
+    tq[qi] = (keep >= k) ? (int)(s_key[k - 1] >> 40) : K;
+  }
+  if (final)
+    for (int i = tid; i < k; i += CP_THREADS) keys_out[(size_t)qi * k + i] = (i < keep) ? s_key[i] : ~0ull;
+}
+
+struct HamTc4Plan {
+  int K, col_blocks, cols, cap, first_rows;
+  size_t smem_bytes;
+  size_t off_img, off_tq, off_cnt, off_flag, off_list, off_buf, total;
+  int list_cap;
+};
+
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
+  HamTc4Plan p;
+  p.K = 32 * W;
+  p.col_blocks = (Q + QB - 1) / QB;
+  p.cols = p.col_blocks * QB;
+  p.cap = 4096;
+  while (p.cap < 4 * (GROWTH + 1) * k) p.cap <<= 1;
+  p.first_rows = 256;                                          // dense seed chunk: at least 8 k rows (its sort costs Q * rows)
+  while (p.first_rows < 8 * k) p.first_rows <<= 1;
+  if (p.first_rows > p.cap) p.first_rows = p.cap;
+  p.smem_bytes = 1024 + (size_t)NB * B_BLOCK + A_SYN + (size_t)MAX_STAGES * A_GROUP + (2 * MAX_STAGES + 8) * 8 +
+                 EPI_WARPS * NB * QB * sizeof(int);
+  size_t o = 0;
+  p.off_img = o;  o += align256((size_t)(p.col_blocks + 1) * B_BLOCK);   // + 1: the B loader always fetches whole pairs
+  p.off_tq = o;   o += align256((size_t)p.cols * sizeof(int));
+  p.off_cnt = o;  o += align256((size_t)p.cols * sizeof(int));
+  p.off_flag = o; o += 256;                                   // [0] overflow flag, [1] re-check list length
+  p.list_cap = 1 << 22;
+  p.off_list = o; o += align256((size_t)p.list_cap * sizeof(unsigned long long));
+  p.off_buf = o;  o += align256((size_t)p.cols * p.cap * sizeof(unsigned long long));
+  p.total = o;
+  return p;
+}
+
+long long gcd_ll(long long a, long long b) {
+  while (b) { const long long t = a % b; a = b; b = t; }
+  return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_hamming_scan_tc4_supported(int64_t U, int32_t W, int32_t Q, int32_t k) {
+  return U >= 1 && (W == 1 || W == 2 || W == 4 || W == 8) && Q >= 1 && k >= 1 && k <= 256 && U < (1ll << 38) && Q < (1 << 26);
+}
+
+size_t sb_hamming_scan_tc4_workspace_bytes(int64_t U, int32_t W, int32_t Q, int32_t k) {
+  if (!sb_hamming_scan_tc4_supported(U, W, Q, k)) return 0;
+  return make_plan(W, Q, k).total;
+}
+
+// Same contract as sb_hamming_scan_tc (hamming_tc.cu), packed FP4 operands.
+int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q, int32_t Q, int32_t k, int64_t idx_base,
+                        uint64_t* keys_out, int32_t* overflow_out, void* workspace, size_t workspace_bytes, void* stream) {
+  SB_REQUIRE(db && q && keys_out && overflow_out, "sb_hamming_scan_tc4: NULL pointer");
+  if (!sb_hamming_scan_tc4_supported(U, W, Q, k) || idx_base < 0 || idx_base + U >= (1ll << 40) ||
+      (reinterpret_cast<uintptr_t>(db) & 15u)) {
+    sb::set_error("sb_hamming_scan_tc4: needs W in {1, 2, 4, 8}, 1 <= k <= 256, U < 2^38, 16-byte aligned table");
+    return SB_ERR_UNSUPPORTED;
+  }
+  const HamTc4Plan p = make_plan(W, Q, k);
+  if (workspace == nullptr || workspace_bytes < p.total) {
+    sb::set_error("sb_hamming_scan_tc4: workspace too small (%zu < %zu bytes)", workspace_bytes, p.total);
+    return SB_ERR_WORKSPACE;
+  }
+  SB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sb_hamming_scan_tc4: workspace must be 256-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  unsigned char* img = ws + p.off_img;
+  int* tq = reinterpret_cast<int*>(ws + p.off_tq);
+  int* cnt = reinterpret_cast<int*>(ws + p.off_cnt);
+  int* flag = reinterpret_cast<int*>(ws + p.off_flag);
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(ws + p.off_buf);
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(ws + p.off_list);
+
+  SB_CUDA_TRY(cudaMemsetAsync(img, 0, (size_t)(p.col_blocks + 1) * B_BLOCK, st));
+  {
+    sb::ProfScope prof("ham_query_image_kernel", st);
+    const long long items = (long long)Q * W;
+    ham4_query_image_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(q, Q, W, img);
+    sb::count_launch();
+    if (int rc = sb::check_launch("ham4_query_image_kernel")) return rc;
+  }
+  ham4_init_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(p.cols, p.K, tq, cnt, flag);
+  sb::count_launch();
+  if (int rc = sb::check_launch("ham4_init_kernel")) return rc;
+
+  // visiting order: 32-row granules in a golden-ratio stride permutation (any prefix is spread evenly over the table)
+  const long long NG = (U + GRAN - 1) / GRAN;
+  long long P = 1;
+  if (NG > 2) {
+    P = (long long)(0.6180339887498949 * (double)NG);
+    if (P < 1) P = 1;
+    while (gcd_ll(P, NG) != 1) ++P;
+    if (P >= NG) P = 1;
+  }
+
+  void (*kernel)(const HamTc4Params) = W == 8   ? ham_filter_fp4_kernel<8>
+                                       : W == 4 ? ham_filter_fp4_kernel<4>
+                                       : W == 2 ? ham_filter_fp4_kernel<2>
+                                                : ham_filter_fp4_kernel<1>;
+  SB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+  SB_CUDA_TRY(cudaFuncSetAttribute(ham4_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(p.cap * sizeof(unsigned long long))));
+  const int sms = sb::sm_count();
+  long long done = 0;                                         // granules
+  while (done < NG) {
+    long long len = (done == 0) ? p.first_rows / GRAN : done * (GROWTH - 1);
+    if (len > NG - done) len = NG - done;
+    const int dense = (done == 0) ? 1 : 0;
+    ham4_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.K, tq, img, flag + 1);
+    sb::count_launch();
+    if (int rc = sb::check_launch("ham4_threshold_image_kernel")) return rc;
+    HamTc4Params hp;
+    hp.db = db; hp.U = U; hp.W = W; hp.G = 1; hp.ksteps = 0; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
+    hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.recheck = list; hp.recheck_cnt = flag + 1; hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
+    hp.idx_base = idx_base; hp.dense = dense; hp.stages = MAX_STAGES;
+    const long long n_tiles = (len + 3) / 4;
+    const int gx = (int)(n_tiles < sms ? n_tiles : sms);
+    int gy = sms / gx;
+    if (gy < 1) gy = 1;
+    if (gy > p.col_blocks) gy = p.col_blocks;
+    hp.cb_per = (p.col_blocks + gy - 1) / gy;
+    hp.cb_per = (hp.cb_per + NB - 1) / NB * NB;                 // whole groups of resident query blocks
+    gy = (p.col_blocks + hp.cb_per - 1) / hp.cb_per;
+    {
+      sb::ProfScope prof("ham_filter_tc_kernel", st);
+      kernel<<<dim3(gx, gy), THREADS, p.smem_bytes, st>>>(hp);
+      sb::count_launch();
+      if (int rc = sb::check_launch("ham_filter_fp4_kernel")) return rc;
+    }
+    if (!dense) {
+      sb::ProfScope prof("ham_recheck_kernel", st);
+      const int blocks = 8 * sms;                               // 64 warps per SM: the re-check is load-latency bound
+      if (W == 8) ham4_recheck_kernel<8><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
+      else if (W == 4) ham4_recheck_kernel<4><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
+      else if (W == 2) ham4_recheck_kernel<2><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
+      else ham4_recheck_kernel<1><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
+      sb::count_launch();
+      if (int rc = sb::check_launch("ham4_recheck_kernel")) return rc;
+    }
+    if (dense) {
+      ham4_set_count_kernel<<<(Q + 255) / 256, 256, 0, st>>>(cnt, Q, (int)(len * GRAN));
+      sb::count_launch();
+      if (int rc = sb::check_launch("ham4_set_count_kernel")) return rc;
+    }
+    done += len;
+    const int final = (done >= NG) ? 1 : 0;
+    sb::ProfScope prof("ham_compact_kernel", st);
+    ham4_compact_kernel<<<Q, CP_THREADS, p.cap * sizeof(unsigned long long), st>>>(buf, cnt, p.cap, k, p.K, tq, flag, final,
+                                                                                   reinterpret_cast<unsigned long long*>(keys_out));
+    sb::count_launch();
+    if (int rc = sb::check_launch("ham4_compact_kernel")) return rc;
+  }
+  SB_CUDA_TRY(cudaMemcpyAsync(overflow_out, flag, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return SB_OK;
+}
+
+}  // extern "C"

@@ -9,6 +9,7 @@ using, so raw bits are carried in signed tensors of the same width):
   codes  uint32[rows, W]  -> torch.int32
   keys   uint64[...]      -> torch.int64
 """
+import os
 import threading
 from typing import Optional, Tuple
 
@@ -215,18 +216,26 @@ def hamming_scan_tc_supported(U: int, W: int, Q: int, k: int) -> bool:
     return bool(_lib.load().sb_hamming_scan_tc_supported(U, W, Q, k))
 
 
-def hamming_scan_keys_tc(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0):
-    """Tensor-core scan (``sb_hamming_scan_tc``) -> (keys int64[Q, k], overflow int32[1])."""
+#: operand format of the tensor-core scan: "fp4" (packed E2M1, kind::mxf4 -- half the tensor-pipe time) or
+#: "fp8" (E4M3, kind::f8f6f4: the round-1 kernel, kept for comparison); same keys either way
+TC_SCAN_FORMAT = os.environ.get("SB_TC_SCAN_FORMAT", "fp4")
+
+
+def hamming_scan_keys_tc(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0, fmt: Optional[str] = None):
+    """Tensor-core scan (``sb_hamming_scan_tc4`` / ``sb_hamming_scan_tc``) -> (keys int64[Q, k], overflow int32[1])."""
     U, W = db.shape
     Q = q.shape[0]
     lib = _lib.load()
-    ws_bytes = lib.sb_hamming_scan_tc_workspace_bytes(U, W, Q, k)
+    fmt = fmt or TC_SCAN_FORMAT
+    fp4 = fmt == "fp4" and bool(lib.sb_hamming_scan_tc4_supported(U, W, Q, k))
+    ws_fn, scan_fn = ((lib.sb_hamming_scan_tc4_workspace_bytes, lib.sb_hamming_scan_tc4) if fp4 else
+                      (lib.sb_hamming_scan_tc_workspace_bytes, lib.sb_hamming_scan_tc))
+    ws_bytes = ws_fn(U, W, Q, k)
     ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=db.device)
     keys = torch.empty((Q, k), dtype=torch.int64, device=db.device)
     flag = torch.empty((1,), dtype=torch.int32, device=db.device)
     with torch.cuda.device(db.device):
-        _lib.check(lib.sb_hamming_scan_tc(_ptr(db), U, W, _ptr(q), Q, k, idx_base, _ptr(keys), _ptr(flag),
-                                          _ptr(ws), ws_bytes, _stream()))
+        _lib.check(scan_fn(_ptr(db), U, W, _ptr(q), Q, k, idx_base, _ptr(keys), _ptr(flag), _ptr(ws), ws_bytes, _stream()))
     return keys, flag
 
 

@@ -137,11 +137,20 @@ def _tc_keys(dev, table, q, k, idx_base=0):
     return d.cpu().numpy(), i.cpu().numpy(), int(flag.item())
 
 
+@pytest.fixture(params=["fp4", "fp8"])
+def tc_fmt(request, dev):
+    """Both operand formats of the tensor-core scan: packed FP4 (kind::mxf4, the default) and FP8 (kind::f8f6f4)."""
+    old = dev.TC_SCAN_FORMAT
+    dev.TC_SCAN_FORMAT = request.param
+    yield request.param
+    dev.TC_SCAN_FORMAT = old
+
+
 @pytest.mark.parametrize("b,W", [(1, 1), (5, 1), (32, 1), (33, 2), (64, 2), (100, 4), (128, 4), (200, 8), (256, 8)])
-def test_hamming_tensor_core_scan_bit_exact(dev, b, W):
-    """sb_hamming_scan_tc (FP8 +-1 dot products on tcgen05) returns the oracle's keys exactly:
-    ragged table sizes (partial granules / tiles / chunks), Q across query-block boundaries, k up to
-    256, idx_base, a query equal to a table row."""
+def test_hamming_tensor_core_scan_bit_exact(dev, tc_fmt, b, W):
+    """sb_hamming_scan_tc4 / sb_hamming_scan_tc (+-1 E2M1 / E4M3 dot products on tcgen05) return the oracle's
+    keys exactly: ragged table sizes (partial granules / tiles / chunks), Q across query-block boundaries
+    (240- and 256-column blocks), k up to 256, idx_base, a query equal to a table row."""
     rng = np.random.RandomState(100 + b)
     for U, Q, k in [(1, 1, 1), (7, 3, 10), (1000, 5, 10), (4097, 257, 10), (20000, 130, 7), (3000, 2, 100),
                     (70001, 300, 33), (9000, 20, 256), (5000, 600, 5), (3000, 1500, 3)]:
@@ -163,7 +172,7 @@ def test_hamming_tensor_core_scan_bit_exact(dev, b, W):
         assert (d[:, kk:] == -1).all() and (i[:, kk:] == -1).all()
 
 
-def test_hamming_tensor_core_scan_ties_and_clusters(dev):
+def test_hamming_tensor_core_scan_ties_and_clusters(dev, tc_fmt):
     """Tie-heavy tables, and a sorted table with large near-duplicate clusters (the order real ITQ
     codes arrive in): the golden-ratio visiting order keeps every chunk a uniform sample."""
     rng = np.random.RandomState(23)

@@ -121,7 +121,14 @@ def test_sharded_lsh_index_on_nccl_equals_oracle_in_every_mode():
     (m_sh, r_sh), (m_one, r_one) = res.pop("fit"), res.pop("fit_single")
     np.testing.assert_allclose(m_sh, m_one, rtol=0, atol=1e-6)
     np.testing.assert_allclose(r_sh.T @ r_sh, np.eye(32), atol=1e-9)
-    np.testing.assert_allclose(r_sh, r_one, rtol=0, atol=1e-6)           # summation order differs, nothing else
+    # The partial sums differ from the single-process ones at rounding level only, but LAPACK's eig may then
+    # hand back an eigenvector with the opposite sign, which sends the ITQ iteration to a different -- equally
+    # good -- local optimum (SURVEY 7 hard part 4): compare what the model is FOR, its quantisation loss.
+    xc = _data()[0][:20_000].astype(np.float64) - m_one.astype(np.float64)
+    loss = [np.square(np.sign(xc @ r) - xc @ r).sum() for r in (r_one, r_sh)]
+    assert abs(loss[1] - loss[0]) < 0.02 * loss[0], loss
+    # same principal subspace (the all-reduced covariance is the covariance): projectors agree
+    np.testing.assert_allclose(r_sh @ r_sh.T, r_one @ r_one.T, atol=1e-6)
     for key, (rows, d) in res.items():
         ref = res[("peer", "queries", key[2], key[3])]
         assert np.array_equal(rows, ref[0]), key                # every mode: identical rows and distance bits

@@ -11,7 +11,12 @@ W = int(sys.argv[4]) if len(sys.argv) > 4 else 8
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 db = torch.randint(-2**31, 2**31 - 1, (U, W), dtype=torch.int32, device="cuda", generator=g)
 q = torch.randint(-2**31, 2**31 - 1, (Q, W), dtype=torch.int32, device="cuda", generator=g)
-for name, fn in (("tc", lambda: dev.hamming_scan_keys_tc(db, q, k)[0]), ("popc", lambda: dev.hamming_scan_keys(db, q, k, variant=1))):
+WITH_POPC = os.environ.get("WITH_POPC", "1") != "0"
+cases = [("fp4", lambda: dev.hamming_scan_keys_tc(db, q, k, fmt="fp4")[0]), ("fp8", lambda: dev.hamming_scan_keys_tc(db, q, k, fmt="fp8")[0])]
+if WITH_POPC:
+    cases.append(("popc", lambda: dev.hamming_scan_keys(db, q, k, variant=1)))
+ref = None
+for name, fn in cases:
     out = fn(); torch.cuda.synchronize()
     _lib.profile_fetch(); _lib.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -27,7 +32,7 @@ for name, fn in (("tc", lambda: dev.hamming_scan_keys_tc(db, q, k)[0]), ("popc",
     ms = e0.elapsed_time(e1) / reps
     print("%-5s U=%d Q=%d k=%d W=%d: %.3f ms/batch  %.1f q/s | %s" % (name, U, Q, k, W, ms, Q / ms * 1e3,
           {a: round(b, 3) for a, b in sorted(agg.items(), key=lambda kv: -kv[1])}))
-    if name == "tc":
+    if ref is None:
         ref = out
     else:
         print("   identical keys:", bool(torch.equal(ref, out)))
