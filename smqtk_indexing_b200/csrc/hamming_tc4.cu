@@ -21,8 +21,8 @@
 //     3, 2, 1) that sum to 2 * tq - K + 1; "d <= tq" stays a sign test on the accumulator.
 //   * Survivor groups are 32 columns of a 240-column block: the re-check list stores the group's first query in
 //     units of 16 (240 = 15 * 16) and a flag for the last, half-width group of a block.
-// Warp roles: 0-3 epilogue (TMEM lane quadrants), 4 MMA issue + TMEM alloc, 5 B loader,
-// 6-13 producers (half a table row per thread and tile).
+// Warp roles: 0-15 epilogue (lane quadrant x query block x column half), 16 MMA issue + TMEM alloc, 17 B loader,
+// 18-25 producers (half a table row per thread and tile).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -33,19 +33,22 @@ using namespace tcptx;
 namespace {
 
 constexpr int TM = 128;                     // rows per tile (UMMA M)
-constexpr int QB = 240;                     // query columns per block (UMMA N): 2 x 240 FP32 accumulators + SF columns <= 512
+constexpr int QB = 240;                     // most query columns per block (UMMA N): 2 x 240 FP32 accumulators + SF columns <= 512
 constexpr int A_GROUP = TM * 128;           // 16 KB: 128 rows x 256 E2M1 (8 code words)
-constexpr int B_GROUP = QB * 128;           // 30 KB
-constexpr int B_SYN = 2 * QB * 16;          // 7.5 KB  (no-swizzle, 2 K chunks of 16 bytes = 64 E2M1)
-constexpr int B_BLOCK = 38 * 1024;          // B_GROUP + B_SYN rounded up to the 1024-byte swizzle atom
+// one query block in shared memory: qb rows x 128 B (SWIZZLE_128B) + B_syn 2 x qb x 16 B (no swizzle), rounded up
+// to the 1024-byte swizzle atom -- 38 KB at qb = 240; two of them (the next block streams in during the current pass)
 constexpr int A_SYN = 2 * TM * 16;          // 4 KB
 constexpr int SF_COL = QB;                  // TMEM columns [240, 256): scale factors (all 2^0)
 constexpr int ACC1_COL = 256;               // second accumulator
 constexpr int MAX_STAGES = 4;
-constexpr int NB = 2;                       // query blocks resident per pass: every expanded A tile feeds 2 x 256 queries
+constexpr int NB = 2;                       // (kept from hamming_tc.cu; unused: one block is resident, its successor streams in)
 constexpr int GRAN = 32;                    // rows per granule of the visiting order
-constexpr int EPI_WARPS = 4, MMA_WARP = 4, B_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 8;
-constexpr int THREADS = (PROD_WARP0 + PROD_WARPS) * 32;   // 448
+// 16 epilogue warps: (TMEM lane quadrant) x (accumulator buffer = tile parity) x (column half).  tcgen05.wait::ld
+// waits for ALL of a thread's loads, so tensor-memory latency can only be hidden by other warps -- with FP32
+// accumulators (twice the registers per column of the FP8 kernel's packed halves) and half the MMA time per
+// tile, four epilogue warps were the bottleneck (measured: 6.8 ms vs the FP8 kernel's 6.3 ms).
+constexpr int EPI_WARPS = 16, EPI_PER_BUF = 8, MMA_WARP = 16, B_WARP = 17, PROD_WARP0 = 18, PROD_WARPS = 8;
+constexpr int THREADS = (PROD_WARP0 + PROD_WARPS) * 32;   // 832
 constexpr int GROWTH = 4;                   // rows of a chunk = 3 x the rows before it: ~3 (k + ties) survivors per query
 constexpr int CP_THREADS = 256;            // 7-8 compaction CTAs per SM: most queries hold a few hundred keys
 
@@ -58,7 +61,8 @@ struct HamTc4Params {
   int col_blocks, cb_per;      // query blocks in total / per blockIdx.y
   const unsigned char* image;  // per block: G x B_GROUP (SW128) then B_SYN
   const int* tq;               // thresholds (Hamming distance) per query column
-  unsigned long long* recheck; // (row << 24 | half-width flag << 23 | first query of the 32-column group / 16) entries
+  unsigned long long* recheck; // (row << 24 | (group width - 1) << 19 | first query of the group / 16) entries
+  int qb, b_block;             // query columns per block (multiple of 16, <= 240), bytes of one block image
   int* recheck_cnt;
   int recheck_cap;
   unsigned long long* cand_buf;
@@ -119,7 +123,12 @@ __device__ __forceinline__ void ham4_recheck_group(const uint32_t* __restrict__ 
   }
 }
 
-// W = code words per row (1, 2, 4, 8); KSTEPS = MMAs of K = 64 elements per tile and block
+// W = code words per row (1, 2, 4, 8); W / 2 MMAs of K = 64 elements per tile (+ the threshold step).
+// ONE query block (qb <= 240 columns) is resident at a time and the accumulator is DOUBLE-BUFFERED over tiles:
+// the MMAs of tile i + 1 run while the 8 epilogue warps of the other buffer still read tile i.  (With one
+// accumulator per block the critical path per tile was MMA + epilogue latency, ~2000 cycles for 650 cycles of
+// MMA work; the expansion of a table tile is two instructions per 8 elements here, so re-expanding it for every
+// query block is cheap and the table stays L2 / HBM resident: 18 passes x 320 MB per 4096-query batch.)
 template <int W>
 __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -127,28 +136,33 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int KSTEPS = (W >= 2) ? W / 2 : 1;                    // 64 elements = 2 code words per MMA
   constexpr uint32_t a_stage = (uint32_t)A_GROUP;
-  // layout (offsets are multiples of 1024): [B block 0][B block 1][A_syn][A ring][barriers, thresholds]
+  const int qb = p.qb;                                           // query columns per block (multiple of 16, <= 240)
+  const uint32_t b_block = (uint32_t)p.b_block;                  // bytes of one block image (data rows + B_syn), 1024-aligned
+  // layout (offsets are multiples of 1024): [B buffer 0][B buffer 1][A_syn][A ring][barriers, thresholds]
   unsigned char* s_b = smem;
-  unsigned char* s_asyn = s_b + NB * B_BLOCK;
+  unsigned char* s_asyn = s_b + 2 * b_block;
   unsigned char* s_a = s_asyn + A_SYN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + (size_t)MAX_STAGES * a_stage);
   const uint32_t a_full = smem_u32(bars), a_empty = a_full + MAX_STAGES * 8;
   const uint32_t acc_full = a_empty + MAX_STAGES * 8, acc_empty = acc_full + 16;
-  const uint32_t b_full = acc_empty + 16, b_empty = b_full + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
-  int* s_tq = reinterpret_cast<int*>(bars + 2 * MAX_STAGES + 8);  // [4 warps][2 blocks x 240]: thresholds
+  const uint32_t b_full = acc_empty + 16, b_empty = b_full + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 8);
+  int* s_tq = reinterpret_cast<int*>(bars + 2 * MAX_STAGES + 10);  // [16 warps][128]: thresholds of the warp's columns
 
   const long long n_gran = p.vg1 - p.vg0;
   const long long n_tiles = (n_gran + 3) / 4;
   const long long my_tiles = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int jb0 = blockIdx.y * p.cb_per;                         // cb_per is a multiple of NB
+  const int jb0 = blockIdx.y * p.cb_per;
   const int jb1 = min(p.col_blocks, jb0 + p.cb_per);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(a_full + s * 8, PROD_WARPS); mbar_init(a_empty + s * 8, 1); }
-    for (int b = 0; b < NB; ++b) { mbar_init(acc_full + b * 8, 1); mbar_init(acc_empty + b * 8, EPI_WARPS); }
-    mbar_init(b_full, 1);
-    mbar_init(b_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full + b * 8, 1);
+      mbar_init(acc_empty + b * 8, EPI_PER_BUF);
+      mbar_init(b_full + b * 8, 1);
+      mbar_init(b_empty + b * 8, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -181,16 +195,15 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
   tc_fence_after();
 
   if (warp == B_WARP) {
-    // =========================== B: NB resident query blocks ===========================
+    // =========================== B: the next query block streams in while the current one is used ===========
     if (lane == 0) {
       int it = 0;
-      for (int jb = jb0; jb < jb1; jb += NB, ++it) {
-        const int nb = min(NB, jb1 - jb);
-        mbar_wait(b_empty, (it & 1) ^ 1);
-        const unsigned char* src = p.image + (size_t)jb * B_BLOCK;   // blocks are contiguous in the image too
-        const uint32_t bytes = (uint32_t)nb * B_BLOCK;
-        mbar_expect_tx(b_full, bytes);
-        for (uint32_t o = 0; o < bytes; o += 2048) tma_bulk_g2s(smem_u32(s_b + o), src + o, 2048, b_full);
+      for (int jb = jb0; jb < jb1; ++jb, ++it) {
+        const int sb = it & 1;
+        mbar_wait(b_empty + sb * 8, ((it >> 1) & 1) ^ 1);
+        const unsigned char* src = p.image + (size_t)jb * b_block;
+        mbar_expect_tx(b_full + sb * 8, b_block);
+        for (uint32_t o = 0; o < b_block; o += 1024) tma_bulk_g2s(smem_u32(s_b + sb * b_block + o), src + o, 1024, b_full + sb * 8);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -198,43 +211,36 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
     if (lane == 0) {
       // block-scaled descriptor: A = B = E2M1 (MXF4Format 1) at bits 7 / 10, both K-major, N at 17, scale
       // format UE8M0 (bit 23), M at 24, scale-factor ids 0, K = 64 (bit 31 = 0); accumulator FP32
-      const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(QB >> 3) << 17) | (1u << 23) | ((uint32_t)(TM >> 4) << 24);
+      const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(qb >> 3) << 17) | (1u << 23) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t tsfa = tmem_base + (uint32_t)SF_COL, tsfb = tmem_base + (uint32_t)(SF_COL + 8);
       const uint64_t asyn_desc = umma_desc(smem_u32(s_asyn), TM * 16, 128);
       const uint64_t a_desc0 = umma_desc_sw128(smem_u32(s_a));
-      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(s_b));
-      const uint64_t bsyn_desc0 = umma_desc(smem_u32(s_b) + B_GROUP, QB * 16, 128);
       int stage = 0, it = 0;
       uint32_t phase = 0;
-      long long t[NB] = {0, 0};                                  // tiles issued per accumulator buffer
-      for (int jb = jb0; jb < jb1; jb += NB, ++it) {
-        const int nb = min(NB, jb1 - jb);
-        mbar_wait(b_full, it & 1);
+      long long t = 0;                                           // tiles issued (accumulator buffer = t & 1)
+      for (int jb = jb0; jb < jb1; ++jb, ++it) {
+        const int sb = it & 1;
+        mbar_wait(b_full + sb * 8, (it >> 1) & 1);
         tc_fence_after();
-        for (long long i = 0; i < my_tiles; ++i) {
+        const uint64_t b_desc = umma_desc_sw128(smem_u32(s_b) + sb * b_block);
+        const uint64_t bsyn_desc = umma_desc(smem_u32(s_b) + sb * b_block + (uint32_t)qb * 128u, (uint32_t)qb * 16u, 128);
+        for (long long i = 0; i < my_tiles; ++i, ++t) {
+          const int buf = (int)(t & 1);
           mbar_wait(a_full + stage * 8, phase);
+          mbar_wait(acc_empty + buf * 8, (uint32_t)((t >> 1) & 1) ^ 1);
+          tc_fence_after();
           const uint64_t a_desc = a_desc0 + (uint64_t)(((uint32_t)stage * a_stage) >> 4);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC1_COL);
 #pragma unroll
-          for (int blk = 0; blk < NB; ++blk) {
-            if (blk < nb) {
-              // one A tile, NB query blocks: accumulator buffer = block, so block 1's MMAs overlap block 0's epilogue
-              const uint32_t d_tmem = tmem_base + (uint32_t)(blk * ACC1_COL);
-              mbar_wait(acc_empty + blk * 8, (uint32_t)(t[blk] & 1) ^ 1);
-              tc_fence_after();
-              const uint64_t b_desc = b_desc0 + (uint64_t)((blk * B_BLOCK) >> 4);
-#pragma unroll
-              for (int ks = 0; ks < KSTEPS; ++ks)
-                umma_fp4(d_tmem, a_desc + (uint64_t)((ks * 32) >> 4), b_desc + (uint64_t)((ks * 32) >> 4), idesc,
-                         ks ? 1u : 0u, tsfa, tsfb);
-              umma_fp4(d_tmem, asyn_desc, bsyn_desc0 + (uint64_t)((blk * B_BLOCK) >> 4), idesc, 1u, tsfa, tsfb);
-              umma_commit(acc_full + blk * 8);
-              ++t[blk];
-            }
-          }
+          for (int ks = 0; ks < KSTEPS; ++ks)
+            umma_fp4(d_tmem, a_desc + (uint64_t)((ks * 32) >> 4), b_desc + (uint64_t)((ks * 32) >> 4), idesc, ks ? 1u : 0u, tsfa,
+                     tsfb);
+          umma_fp4(d_tmem, asyn_desc, bsyn_desc, idesc, 1u, tsfa, tsfb);
+          umma_commit(acc_full + buf * 8);
           umma_commit(a_empty + stage * 8);
           if (++stage == MAX_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(b_empty);                                   // B may be replaced once these MMAs retire
+        umma_commit(b_empty + sb * 8);                          // this B buffer may be replaced once these MMAs retire
       }
     }
   } else if (warp >= PROD_WARP0) {
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
       }
       return valid;
     };
-    for (int jb = jb0; jb < jb1; jb += NB) {
+    for (int jb = jb0; jb < jb1; ++jb) {
       vg_ld = vg_first;
       pg_ld = pg_first;
       bool vcur = (my_tiles > 0) ? load(cw) : false;
@@ -304,99 +310,92 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
     }
   } else if (warp < EPI_WARPS) {
     // =========================== epilogue: sign test, survivors queued ===========================
-    const int ew = warp;                                         // TMEM lane quadrant = granule of the tile
-    uint32_t par = 0u;                                           // bit blk: parity of accumulator buffer blk's next "full"
-    int* my_tq = s_tq + warp * (NB * QB);
-    const long long vg_first = p.vg0 + (long long)blockIdx.x * 4 + ew;
-    const long long pg_first = (long long)(((unsigned long long)vg_first * (unsigned long long)p.P) % (unsigned long long)p.NG);
-    const long long pg_step = (long long)(((unsigned long long)(4 * gridDim.x) * (unsigned long long)p.P) % (unsigned long long)p.NG);
-    constexpr int NGRP = (QB + 31) / 32;                         // 8 survivor groups per block, the last 16 columns wide
-    for (int jb = jb0; jb < jb1; jb += NB) {
-      const int nb = min(NB, jb1 - jb);
+    const int ew = warp & 3;                                     // TMEM lane quadrant = granule of the tile
+    const int buf = (warp >> 2) & 1;                             // accumulator buffer: this warp takes the tiles t = buf (mod 2)
+    const int col0 = (warp >> 3) * 128;                          // this warp's columns: [0, 128) or [128, qb)
+    constexpr int GRP = 4;                                       // 32-column survivor groups per warp
+    int* my_tq = s_tq + warp * 128;
+    const long long vg_base = p.vg0 + (long long)blockIdx.x * 4 + ew;
+    const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * ACC1_COL + col0);
+    long long t0 = 0;                                            // global tile counter at the start of this block's pass
+    for (int jb = jb0; jb < jb1; ++jb, t0 += my_tiles) {
+      const int q0 = jb * qb + col0;                             // first query of this warp's columns
       __syncwarp();
-      for (int c = lane; c < nb * QB; c += 32) my_tq[c] = __ldcg(p.tq + (long long)jb * QB + c);
+      for (int c = lane; c < 128; c += 32) my_tq[c] = (col0 + c < qb) ? __ldcg(p.tq + q0 + c) : 0;
       __syncwarp();
-      long long vg = vg_first, pg = pg_first;
-      for (long long i = 0; i < my_tiles; ++i) {
+      // first tile of this pass that lands in this warp's buffer
+      for (long long i = ((t0 & 1) == buf) ? 0 : 1; i < my_tiles; i += 2) {
+        const long long t = t0 + i;
         const long long vt = blockIdx.x + i * gridDim.x;
+        const long long vg = vg_base + i * 4 * (long long)gridDim.x;
+        const long long pg = (long long)(((unsigned long long)vg * (unsigned long long)p.P) % (unsigned long long)p.NG);
         const long long row = pg * GRAN + lane;
         const bool rvalid = (vg < p.vg1) && (row < p.U);
-        vg += 4 * gridDim.x;
-        pg += pg_step;
-        if (pg >= p.NG) pg -= p.NG;
         const unsigned long long row_key = (unsigned long long)(p.idx_base + row);
-#pragma unroll 1
-        for (int blk = 0; blk < nb; ++blk) {
-          const int q0 = (jb + blk) * QB;
-          const int* tq_blk = my_tq + blk * QB;
-          mbar_wait(acc_full + blk * 8, (par >> blk) & 1u);
-          par ^= 1u << blk;
-          tc_fence_after();
-          const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(blk * ACC1_COL);
-          unsigned hit[NGRP];                                        // lanes with a survivor in each 32-column group
+        mbar_wait(acc_full + buf * 8, (uint32_t)((t >> 1) & 1));
+        tc_fence_after();
+        unsigned hit[GRP];                                         // lanes with a survivor in each 32-column group
 #pragma unroll
-          for (int c64 = 0; c64 < QB; c64 += 64) {
-            uint32_t va[32], vb[32];                               // 2 x 32 columns of FP32 accumulators
-            const bool full = (c64 + 64 <= QB);                     // the last pass covers 48 columns: 32 + 16
-            tmem_ld32_nowait(tbase + (uint32_t)c64, va);
-            if (full) {
-              tmem_ld32_nowait(tbase + (uint32_t)(c64 + 32), vb);
-            } else {
-              uint32_t vh[16];
-              tmem_ld16_nowait(tbase + (uint32_t)(c64 + 32), vh);
-              tmem_ld_wait();
+        for (int g = 0; g < GRP; ++g) {
+          const int width = qb - (col0 + 32 * g);                  // columns of this group that exist (<= 0: none)
+          hit[g] = 0u;
+          if (width <= 0) continue;
+          uint32_t va[32];
+          tmem_ld32_nowait(tbase + (uint32_t)(32 * g), va);        // (may run into unused / SF columns: masked below)
+          tmem_ld_wait();
+          if (p.dense) {
+            // seed chunk: buf[query][virtual row] = key for every pair (virtual row < cap by construction)
+            const long long vrow = vt * TM + ew * 32 + lane;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) { vb[j] = vh[j]; vb[16 + j] = 0x80000000u; }   // absent columns: "no survivor"
-            }
-            tmem_ld_wait();
-            if (p.dense) {
-              // seed chunk: buf[query][virtual row] = key for every pair (virtual row < cap by construction)
-              const long long vrow = vt * TM + ew * 32 + lane;
-#pragma unroll
-              for (int j = 0; j < 64; ++j) {
-                const int col = c64 + j;
-                if (col < QB) {
-                  const uint32_t reg = (j < 32) ? va[j & 31] : vb[j & 31];
-                  const int d = tq_blk[col] - (int)(__uint_as_float(reg) * 0.5f);
-                  p.cand_buf[(long long)(q0 + col) * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)d << 40) | row_key) : ~0ull;
-                }
-              }
-            } else {
-              // the common case (no survivor among 64 pairs) is an AND tree over the sign bits
-              uint32_t a0 = 0xffffffffu, b0 = 0xffffffffu;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { a0 &= va[j]; b0 &= vb[j]; }
-              hit[c64 / 32] = __ballot_sync(0xffffffffu, rvalid && (a0 & 0x80000000u) == 0u);
-              if (c64 / 32 + 1 < NGRP) hit[c64 / 32 + 1] = __ballot_sync(0xffffffffu, rvalid && (b0 & 0x80000000u) == 0u);
-            }
-          }
-          // the accumulator buffer is free: let the next tile's MMAs start, THEN pay for the appends
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty + blk * 8);
-          if (!p.dense) {
-            int total = 0;
-#pragma unroll
-            for (int g32 = 0; g32 < NGRP; ++g32) total += __popc(hit[g32]);
-            if (total) {                                               // rare: one atomic per (warp, tile, block) with survivors
-              int base = 0;
-              if (lane == 0) base = atomicAdd(p.recheck_cnt, total);
-              base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-              for (int g32 = 0; g32 < NGRP; ++g32) {
-                const unsigned m = hit[g32];
-                if ((m >> lane) & 1u) {
-                  const int slot = base + __popc(m & ((1u << lane) - 1u));
-                  if (slot < p.recheck_cap)
-                    p.recheck[slot] = ((unsigned long long)row << 24) | (g32 == NGRP - 1 ? (1ull << 23) : 0ull) |
-                                      (unsigned long long)((q0 + 32 * g32) >> 4);
-                }
-                base += __popc(m);
+            for (int j = 0; j < 32; ++j) {
+              if (j < width) {
+                const int c = 32 * g + j;
+                const int d = my_tq[c] - (int)(__uint_as_float(va[j]) * 0.5f);
+                p.cand_buf[(long long)(q0 + c) * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)d << 40) | row_key) : ~0ull;
               }
             }
+          } else {
+            if (width < 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j >= width) va[j] = 0x80000000u;                 // absent columns: "no survivor"
+            }
+            // the common case (no survivor among 32 pairs) is an AND tree over the sign bits: 8 independent
+            // 4-input terms, then a 3-level combine (a dependent chain of 32 ANDs costs ~150 cycles of latency)
+            uint32_t r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = va[4 * j] & va[4 * j + 1] & va[4 * j + 2] & va[4 * j + 3];
+            const uint32_t a = (r[0] & r[1] & r[2]) & (r[3] & r[4] & r[5]) & (r[6] & r[7]);
+            hit[g] = __ballot_sync(0xffffffffu, rvalid && (a & 0x80000000u) == 0u);
           }
-          __syncwarp();
         }
+        // the accumulator buffer is free: let the MMAs of tile t + 2 start, THEN pay for the appends
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + buf * 8);
+        if (!p.dense) {
+          int total = 0;
+#pragma unroll
+          for (int g = 0; g < GRP; ++g) total += __popc(hit[g]);
+          if (total) {                                               // rare: one atomic per (warp, tile) with survivors
+            int base = 0;
+            if (lane == 0) base = atomicAdd(p.recheck_cnt, total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+            for (int g = 0; g < GRP; ++g) {
+              const unsigned m = hit[g];
+              if ((m >> lane) & 1u) {
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                const int width = min(32, qb - (col0 + 32 * g));
+                if (slot < p.recheck_cap)
+                  p.recheck[slot] = ((unsigned long long)row << 24) | ((unsigned long long)(width - 1) << 19) |
+                                    (unsigned long long)((q0 + 32 * g) >> 4);
+              }
+              base += __popc(m);
+            }
+          }
+        }
+        __syncwarp();
       }
     }
   }
@@ -425,31 +424,32 @@ ham4_recheck_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict_
   for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
     const unsigned long long ent = list[e];
     const long long row = (long long)(ent >> 24);
-    const int qg0 = (int)(ent & 0x7fffffull) * 16;
-    const int width = (ent & (1ull << 23)) ? (QB & 31) : 32;
+    const int qg0 = (int)(ent & 0x7ffffull) * 16;
+    const int width = (int)((ent >> 19) & 31ull) + 1;
     ham4_recheck_group<W>(db, qcodes, Q, row, (unsigned long long)(idx_base + row), qg0, width, tq, cand_buf, cand_cnt, cap, lane);
   }
 }
 
-// Query codes -> per-block image: [240 rows x 128 B] in the SWIZZLE_128B K-major order (same bit -> nibble expansion
+// Query codes -> per-block image: [qb rows x 128 B] in the SWIZZLE_128B K-major order (same bit -> nibble expansion
 // as the table rows), then the block's B_syn; columns past Q and K chunks past the code are zero (the image is
 // cleared first).  One thread per (column, word).
-__global__ void ham4_query_image_kernel(const uint32_t* __restrict__ q, int Q, int W, unsigned char* __restrict__ img) {
+__global__ void ham4_query_image_kernel(const uint32_t* __restrict__ q, int Q, int W, int qb, int b_block,
+                                        unsigned char* __restrict__ img) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Q * W) return;
   const int col = (int)(i / W), j = (int)(i % W);
-  const int jb = col / QB, n = col % QB;
-  *reinterpret_cast<uint4*>(img + (size_t)jb * B_BLOCK + sw128_off(n, j)) = expand_word4(q[(long long)col * W + j]);
+  const int jb = col / qb, n = col % qb;
+  *reinterpret_cast<uint4*>(img + (size_t)jb * b_block + sw128_off(n, j)) = expand_word4(q[(long long)col * W + j]);
 }
 
 // B_syn of every block: up to 64 E2M1 slots per column that sum to s = 2 * tq - K + 1 (|s| <= 257: at most 42 slots of
 // 6 plus two for the remainder); padding columns get -258 (their data nibbles are zero: the accumulator is negative).
-__global__ void ham4_threshold_image_kernel(int Q, int cols, int K, const int* __restrict__ tq, unsigned char* __restrict__ img,
-                                            int* __restrict__ list_cnt) {
+__global__ void ham4_threshold_image_kernel(int Q, int cols, int K, int qb, int b_block, const int* __restrict__ tq,
+                                            unsigned char* __restrict__ img, int* __restrict__ list_cnt) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col == 0) *list_cnt = 0;                                   // the re-check list restarts with every chunk
   if (col >= cols) return;
-  const int jb = col / QB, n = col % QB;
+  const int jb = col / qb, n = col % qb;
   const int s = (col < Q) ? (2 * min(tq[col], K) - K + 1) : -258;
   const uint32_t sign = s < 0 ? 0x8u : 0u;
   const int mag = s < 0 ? -s : s;
@@ -471,9 +471,9 @@ __global__ void ham4_threshold_image_kernel(int Q, int cols, int K, const int* _
     }
     words[wd] = v;
   }
-  unsigned char* base = img + (size_t)jb * B_BLOCK + (size_t)B_GROUP;
+  unsigned char* base = img + (size_t)jb * b_block + (size_t)qb * 128;
   *reinterpret_cast<uint4*>(base + n * 16) = make_uint4(words[0], words[1], words[2], words[3]);
-  *reinterpret_cast<uint4*>(base + QB * 16 + n * 16) = make_uint4(words[4], words[5], words[6], words[7]);
+  *reinterpret_cast<uint4*>(base + qb * 16 + n * 16) = make_uint4(words[4], words[5], words[6], words[7]);
 }
 
 __global__ void ham4_init_kernel(int cols, int K, int* __restrict__ tq, int* __restrict__ cnt, int* __restrict__ overflow) {
@@ -537,7 +537,7 @@ ham4_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt,
 }
 
 struct HamTc4Plan {
-  int K, col_blocks, cols, cap, first_rows;
+  int K, qb, b_block, col_blocks, cols, cap, first_rows;
   size_t smem_bytes;
   size_t off_img, off_tq, off_cnt, off_flag, off_list, off_buf, total;
   int list_cap;
@@ -548,17 +548,21 @@ size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
   HamTc4Plan p;
   p.K = 32 * W;
-  p.col_blocks = (Q + QB - 1) / QB;
-  p.cols = p.col_blocks * QB;
+  // equal blocks of at most 240 columns (a multiple of 16): 4096 queries -> 18 x 240, 512 -> 3 x 176
+  const int nblk = (Q + QB - 1) / QB;
+  p.qb = ((Q + nblk - 1) / nblk + 15) / 16 * 16;
+  p.col_blocks = (Q + p.qb - 1) / p.qb;
+  p.cols = p.col_blocks * p.qb;
+  p.b_block = (p.qb * 160 + 1023) / 1024 * 1024;               // qb rows x 128 B + B_syn (2 x qb x 16 B)
   p.cap = 4096;
   while (p.cap < 4 * (GROWTH + 1) * k) p.cap <<= 1;
   p.first_rows = 256;                                          // dense seed chunk: at least 8 k rows (its sort costs Q * rows)
   while (p.first_rows < 8 * k) p.first_rows <<= 1;
   if (p.first_rows > p.cap) p.first_rows = p.cap;
-  p.smem_bytes = 1024 + (size_t)NB * B_BLOCK + A_SYN + (size_t)MAX_STAGES * A_GROUP + (2 * MAX_STAGES + 8) * 8 +
-                 EPI_WARPS * NB * QB * sizeof(int);
+  p.smem_bytes = 1024 + (size_t)2 * p.b_block + A_SYN + (size_t)MAX_STAGES * A_GROUP + (2 * MAX_STAGES + 10) * 8 +
+                 EPI_WARPS * 128 * sizeof(int);
   size_t o = 0;
-  p.off_img = o;  o += align256((size_t)(p.col_blocks + 1) * B_BLOCK);   // + 1: the B loader always fetches whole pairs
+  p.off_img = o;  o += align256((size_t)p.col_blocks * p.b_block);
   p.off_tq = o;   o += align256((size_t)p.cols * sizeof(int));
   p.off_cnt = o;  o += align256((size_t)p.cols * sizeof(int));
   p.off_flag = o; o += 256;                                   // [0] overflow flag, [1] re-check list length
@@ -579,7 +583,7 @@ long long gcd_ll(long long a, long long b) {
 extern "C" {
 
 int sb_hamming_scan_tc4_supported(int64_t U, int32_t W, int32_t Q, int32_t k) {
-  return U >= 1 && (W == 1 || W == 2 || W == 4 || W == 8) && Q >= 1 && k >= 1 && k <= 256 && U < (1ll << 38) && Q < (1 << 26);
+  return U >= 1 && (W == 1 || W == 2 || W == 4 || W == 8) && Q >= 1 && k >= 1 && k <= 256 && U < (1ll << 38) && Q < (1 << 22);
 }
 
 size_t sb_hamming_scan_tc4_workspace_bytes(int64_t U, int32_t W, int32_t Q, int32_t k) {
@@ -611,11 +615,11 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(ws + p.off_buf);
   unsigned long long* list = reinterpret_cast<unsigned long long*>(ws + p.off_list);
 
-  SB_CUDA_TRY(cudaMemsetAsync(img, 0, (size_t)(p.col_blocks + 1) * B_BLOCK, st));
+  SB_CUDA_TRY(cudaMemsetAsync(img, 0, (size_t)p.col_blocks * p.b_block, st));
   {
     sb::ProfScope prof("ham_query_image_kernel", st);
     const long long items = (long long)Q * W;
-    ham4_query_image_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(q, Q, W, img);
+    ham4_query_image_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(q, Q, W, p.qb, p.b_block, img);
     sb::count_launch();
     if (int rc = sb::check_launch("ham4_query_image_kernel")) return rc;
   }
@@ -646,20 +650,19 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
     long long len = (done == 0) ? p.first_rows / GRAN : done * (GROWTH - 1);
     if (len > NG - done) len = NG - done;
     const int dense = (done == 0) ? 1 : 0;
-    ham4_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.K, tq, img, flag + 1);
+    ham4_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.K, p.qb, p.b_block, tq, img, flag + 1);
     sb::count_launch();
     if (int rc = sb::check_launch("ham4_threshold_image_kernel")) return rc;
     HamTc4Params hp;
     hp.db = db; hp.U = U; hp.W = W; hp.G = 1; hp.ksteps = 0; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
     hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.recheck = list; hp.recheck_cnt = flag + 1; hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
-    hp.idx_base = idx_base; hp.dense = dense; hp.stages = MAX_STAGES;
+    hp.idx_base = idx_base; hp.dense = dense; hp.stages = MAX_STAGES; hp.qb = p.qb; hp.b_block = p.b_block;
     const long long n_tiles = (len + 3) / 4;
     const int gx = (int)(n_tiles < sms ? n_tiles : sms);
     int gy = sms / gx;
     if (gy < 1) gy = 1;
     if (gy > p.col_blocks) gy = p.col_blocks;
     hp.cb_per = (p.col_blocks + gy - 1) / gy;
-    hp.cb_per = (hp.cb_per + NB - 1) / NB * NB;                 // whole groups of resident query blocks
     gy = (p.col_blocks + hp.cb_per - 1) / hp.cb_per;
     {
       sb::ProfScope prof("ham_filter_tc_kernel", st);
