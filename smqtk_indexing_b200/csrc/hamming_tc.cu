@@ -37,6 +37,8 @@
 // 6-13 producers (half a table row per thread and tile).
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -56,6 +58,8 @@ constexpr int GRAN = 32;                    // rows per granule of the visiting 
 constexpr int EPI_WARPS = 4, MMA_WARP = 4, B_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 8;
 constexpr int THREADS = (PROD_WARP0 + PROD_WARPS) * 32;   // 448
 constexpr int GROWTH = 4;                   // rows of a chunk = 3 x the rows before it: ~3 (k + ties) survivors per query
+constexpr int GROWTH_SMALL_Q = 8;           // few queries: every chunk's launch / fill / drain weighs more than the
+constexpr int SMALL_Q = 1024;               // extra survivors -- 6 chunks of 7 (k + ties) instead of 9 of 3 (k + ties)
 constexpr int CP_THREADS = 256;            // 7-8 compaction CTAs per SM: most queries hold a few hundred keys
 
 struct HamTcParams {
@@ -538,13 +542,21 @@ ham_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt, 
 }
 
 struct HamTcPlan {
-  int G, ksteps, K, col_blocks, cols, cap, first_rows, stages;
+  int G, ksteps, K, col_blocks, cols, cap, first_rows, stages, growth;
   size_t block_bytes, smem_bytes;
   size_t off_img, off_tq, off_cnt, off_flag, off_list, off_buf, total;
   int list_cap;
 };
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+int growth_for(int Q) {
+  if (const char* e = getenv("SB_TC_GROWTH")) {               // tuning knob
+    const int g = atoi(e);
+    if (g >= 2 && g <= 64) return g;
+  }
+  return Q <= SMALL_Q ? GROWTH_SMALL_Q : GROWTH;
+}
 
 HamTcPlan make_plan(int32_t W, int32_t Q, int32_t k) {
   HamTcPlan p;
@@ -554,8 +566,9 @@ HamTcPlan make_plan(int32_t W, int32_t Q, int32_t k) {
   p.col_blocks = (Q + QB - 1) / QB;
   p.cols = p.col_blocks * QB;
   p.cap = 4096;
-  while (p.cap < 4 * (GROWTH + 1) * k) p.cap <<= 1;
-  p.first_rows = 256;                                          // dense seed chunk: at least 8 k rows (its sort costs Q * rows)
+  p.growth = growth_for(Q);
+  while (p.cap < 4 * (p.growth + 1) * k) p.cap <<= 1;
+  p.first_rows = Q <= SMALL_Q ? 1024 : 256;                    // dense seed chunk: at least 8 k rows (its sort costs Q * rows)
   while (p.first_rows < 8 * k) p.first_rows <<= 1;
   if (p.first_rows > p.cap) p.first_rows = p.cap;
   p.stages = p.G == 2 ? 2 : MAX_STAGES;
@@ -649,7 +662,7 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
   const int sms = sb::sm_count();
   long long done = 0;                                         // granules
   while (done < NG) {
-    long long len = (done == 0) ? p.first_rows / GRAN : done * (GROWTH - 1);
+    long long len = (done == 0) ? p.first_rows / GRAN : done * (p.growth - 1);
     if (len > NG - done) len = NG - done;
     const int dense = (done == 0) ? 1 : 0;
     ham_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.G, p.K, tq, img, flag + 1);

@@ -25,6 +25,8 @@
 // 18-25 producers (half a table row per thread and tile).
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -33,12 +35,12 @@ using namespace tcptx;
 namespace {
 
 constexpr int TM = 128;                     // rows per tile (UMMA M)
-constexpr int QB = 240;                     // most query columns per block (UMMA N): 2 x 240 FP32 accumulators + SF columns <= 512
+constexpr int QB = 224;                     // most query columns per block (UMMA N): 2 FP32 accumulators + SF columns <= 512
 constexpr int A_GROUP = TM * 128;           // 16 KB: 128 rows x 256 E2M1 (8 code words)
 // one query block in shared memory: qb rows x 128 B (SWIZZLE_128B) + B_syn 2 x qb x 16 B (no swizzle), rounded up
 // to the 1024-byte swizzle atom -- 38 KB at qb = 240; two of them (the next block streams in during the current pass)
 constexpr int A_SYN = 2 * TM * 16;          // 4 KB
-constexpr int SF_COL = QB;                  // TMEM columns [240, 256): scale factors (all 2^0)
+constexpr int SF_COL = 240;                 // TMEM columns [240, 256): scale factors (all 2^0)
 constexpr int ACC1_COL = 256;               // second accumulator
 constexpr int MAX_STAGES = 4;
 constexpr int NB = 2;                       // (kept from hamming_tc.cu; unused: one block is resident, its successor streams in)
@@ -50,6 +52,8 @@ constexpr int GRAN = 32;                    // rows per granule of the visiting 
 constexpr int EPI_WARPS = 16, EPI_PER_BUF = 8, MMA_WARP = 16, B_WARP = 17, PROD_WARP0 = 18, PROD_WARPS = 8;
 constexpr int THREADS = (PROD_WARP0 + PROD_WARPS) * 32;   // 832
 constexpr int GROWTH = 4;                   // rows of a chunk = 3 x the rows before it: ~3 (k + ties) survivors per query
+constexpr int GROWTH_SMALL_Q = 8;           // few queries: every chunk's launch / fill / drain weighs more than the
+constexpr int SMALL_Q = 1024;               // extra survivors -- 6 chunks of 7 (k + ties) instead of 9 of 3 (k + ties)
 constexpr int CP_THREADS = 256;            // 7-8 compaction CTAs per SM: most queries hold a few hundred keys
 
 struct HamTc4Params {
@@ -252,7 +256,11 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
     const bool worker = (W >= 2) || h == 0;
     int stage = 0;
     uint32_t phase = 0;
-    uint32_t cw[WH], cn[WH];
+    // PF tiles of packed words are in flight per thread: a tile is consumed every ~650 cycles (its MMAs), one
+    // HBM / L2 round trip is 1000+, and the 320 MB table does not stay in L2 between the passes
+    constexpr int PF = 4;
+    uint32_t cw[PF][WH];
+    bool cv[PF];
     // granule of tile i for this thread: vg = vg_first + i * 4 * gridDim.x, physical pg = vg * P mod NG, kept incrementally
     const long long vg_first = p.vg0 + (long long)blockIdx.x * 4 + (r >> 5);
     const long long pg_first = (long long)(((unsigned long long)vg_first * (unsigned long long)p.P) % (unsigned long long)p.NG);
@@ -284,28 +292,30 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
     for (int jb = jb0; jb < jb1; ++jb) {
       vg_ld = vg_first;
       pg_ld = pg_first;
-      bool vcur = (my_tiles > 0) ? load(cw) : false;
-      for (long long i = 0; i < my_tiles; ++i) {
-        bool vnext = false;
-        if (i + 1 < my_tiles) vnext = load(cn);
-        mbar_wait(a_empty + stage * 8, phase ^ 1);
-        unsigned char* dst = s_a + (size_t)stage * a_stage;
-        if (worker) {
 #pragma unroll
-          for (int j = 0; j < WH; ++j) {
-            const int wj = h * WH + j;                             // word of the row = 16-byte chunk of the 128-byte row
-            uint4 o = expand_word4(cw[j]);
-            if (!vcur) o = make_uint4(0u, 0u, 0u, 0u);             // rows past the table: all-zero operand
-            *reinterpret_cast<uint4*>(dst + sw128_off(r, wj)) = o;
+      for (int d = 0; d < PF; ++d) cv[d] = (d < my_tiles) ? load(cw[d]) : false;
+      for (long long i0 = 0; i0 < my_tiles; i0 += PF) {
+#pragma unroll
+        for (int d = 0; d < PF; ++d) {
+          if (i0 + d < my_tiles) {
+            mbar_wait(a_empty + stage * 8, phase ^ 1);
+            unsigned char* dst = s_a + (size_t)stage * a_stage;
+            if (worker) {
+#pragma unroll
+              for (int j = 0; j < WH; ++j) {
+                const int wj = h * WH + j;                         // word of the row = 16-byte chunk of the 128-byte row
+                uint4 o = expand_word4(cw[d][j]);
+                if (!cv[d]) o = make_uint4(0u, 0u, 0u, 0u);        // rows past the table: all-zero operand
+                *reinterpret_cast<uint4*>(dst + sw128_off(r, wj)) = o;
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full + stage * 8);
+            cv[d] = (i0 + d + PF < my_tiles) ? load(cw[d]) : false;   // refill this slot with the tile PF ahead
+            if (++stage == MAX_STAGES) { stage = 0; phase ^= 1; }
           }
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full + stage * 8);
-#pragma unroll
-        for (int j = 0; j < WH; ++j) cw[j] = cn[j];
-        vcur = vnext;
-        if (++stage == MAX_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp < EPI_WARPS) {
@@ -314,8 +324,12 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
     const int buf = (warp >> 2) & 1;                             // accumulator buffer: this warp takes the tiles t = buf (mod 2)
     const int col0 = (warp >> 3) * 128;                          // this warp's columns: [0, 128) or [128, qb)
     constexpr int GRP = 4;                                       // 32-column survivor groups per warp
+    const int ngrp = max(0, min(GRP, (qb - col0) >> 5));         // qb is a multiple of 32: whole groups only
     int* my_tq = s_tq + warp * 128;
     const long long vg_base = p.vg0 + (long long)blockIdx.x * 4 + ew;
+    const long long vg_step2 = 8ll * gridDim.x;                  // this warp sees every second tile
+    const unsigned long long NGu = (unsigned long long)p.NG;
+    const long long pg_step2 = (long long)(((unsigned long long)vg_step2 * (unsigned long long)p.P) % NGu);
     const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * ACC1_COL + col0);
     long long t0 = 0;                                            // global tile counter at the start of this block's pass
     for (int jb = jb0; jb < jb1; ++jb, t0 += my_tiles) {
@@ -323,50 +337,50 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
       __syncwarp();
       for (int c = lane; c < 128; c += 32) my_tq[c] = (col0 + c < qb) ? __ldcg(p.tq + q0 + c) : 0;
       __syncwarp();
-      // first tile of this pass that lands in this warp's buffer
-      for (long long i = ((t0 & 1) == buf) ? 0 : 1; i < my_tiles; i += 2) {
-        const long long t = t0 + i;
-        const long long vt = blockIdx.x + i * gridDim.x;
-        const long long vg = vg_base + i * 4 * (long long)gridDim.x;
-        const long long pg = (long long)(((unsigned long long)vg * (unsigned long long)p.P) % (unsigned long long)p.NG);
+      const long long i_first = ((t0 & 1) == buf) ? 0 : 1;       // first tile of this pass that lands in this warp's buffer
+      long long vg = vg_base + i_first * 4 * (long long)gridDim.x;
+      long long pg = (long long)(((unsigned long long)vg * (unsigned long long)p.P) % NGu);
+      uint32_t par = (uint32_t)(((t0 + i_first) >> 1) & 1);
+      for (long long i = i_first; i < my_tiles; i += 2) {
         const long long row = pg * GRAN + lane;
         const bool rvalid = (vg < p.vg1) && (row < p.U);
-        const unsigned long long row_key = (unsigned long long)(p.idx_base + row);
-        mbar_wait(acc_full + buf * 8, (uint32_t)((t >> 1) & 1));
+        mbar_wait(acc_full + buf * 8, par);
+        par ^= 1u;
         tc_fence_after();
         unsigned hit[GRP];                                         // lanes with a survivor in each 32-column group
+        if (!p.dense) {
 #pragma unroll
-        for (int g = 0; g < GRP; ++g) {
-          const int width = qb - (col0 + 32 * g);                  // columns of this group that exist (<= 0: none)
-          hit[g] = 0u;
-          if (width <= 0) continue;
-          uint32_t va[32];
-          tmem_ld32_nowait(tbase + (uint32_t)(32 * g), va);        // (may run into unused / SF columns: masked below)
-          tmem_ld_wait();
-          if (p.dense) {
-            // seed chunk: buf[query][virtual row] = key for every pair (virtual row < cap by construction)
-            const long long vrow = vt * TM + ew * 32 + lane;
+          for (int g = 0; g < GRP; ++g) {
+            hit[g] = 0u;
+            if (g < ngrp) {                                        // warp-uniform
+              uint32_t va[32];
+              tmem_ld32_nowait(tbase + (uint32_t)(32 * g), va);
+              tmem_ld_wait();
+              // the common case (no survivor among 32 pairs) is an AND tree over the sign bits: 8 independent
+              // 4-input terms, then a 3-level combine (a dependent chain of 32 ANDs costs ~150 cycles of latency)
+              uint32_t r[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r[j] = va[4 * j] & va[4 * j + 1] & va[4 * j + 2] & va[4 * j + 3];
+              const uint32_t a = (r[0] & r[1] & r[2]) & (r[3] & r[4] & r[5]) & (r[6] & r[7]);
+              hit[g] = __ballot_sync(0xffffffffu, rvalid && (a & 0x80000000u) == 0u);
+            }
+          }
+        } else {
+          // seed chunk: buf[query][virtual row] = key for every pair (virtual row < cap by construction)
+          const long long vt = blockIdx.x + i * gridDim.x;
+          const long long vrow = vt * TM + ew * 32 + lane;
+          const unsigned long long row_key = (unsigned long long)(p.idx_base + row);
+#pragma unroll 1
+          for (int g = 0; g < ngrp; ++g) {
+            uint32_t va[32];
+            tmem_ld32_nowait(tbase + (uint32_t)(32 * g), va);
+            tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              if (j < width) {
-                const int c = 32 * g + j;
-                const int d = my_tq[c] - (int)(__uint_as_float(va[j]) * 0.5f);
-                p.cand_buf[(long long)(q0 + c) * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)d << 40) | row_key) : ~0ull;
-              }
+              const int c = 32 * g + j;
+              const int d = my_tq[c] - (int)(__uint_as_float(va[j]) * 0.5f);
+              p.cand_buf[(long long)(q0 + c) * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)d << 40) | row_key) : ~0ull;
             }
-          } else {
-            if (width < 32) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j >= width) va[j] = 0x80000000u;                 // absent columns: "no survivor"
-            }
-            // the common case (no survivor among 32 pairs) is an AND tree over the sign bits: 8 independent
-            // 4-input terms, then a 3-level combine (a dependent chain of 32 ANDs costs ~150 cycles of latency)
-            uint32_t r[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = va[4 * j] & va[4 * j + 1] & va[4 * j + 2] & va[4 * j + 3];
-            const uint32_t a = (r[0] & r[1] & r[2]) & (r[3] & r[4] & r[5]) & (r[6] & r[7]);
-            hit[g] = __ballot_sync(0xffffffffu, rvalid && (a & 0x80000000u) == 0u);
           }
         }
         // the accumulator buffer is free: let the MMAs of tile t + 2 start, THEN pay for the appends
@@ -374,9 +388,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + buf * 8);
         if (!p.dense) {
-          int total = 0;
-#pragma unroll
-          for (int g = 0; g < GRP; ++g) total += __popc(hit[g]);
+          const int total = __popc(hit[0]) + __popc(hit[1]) + __popc(hit[2]) + __popc(hit[3]);
           if (total) {                                               // rare: one atomic per (warp, tile) with survivors
             int base = 0;
             if (lane == 0) base = atomicAdd(p.recheck_cnt, total);
@@ -386,16 +398,16 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
               const unsigned m = hit[g];
               if ((m >> lane) & 1u) {
                 const int slot = base + __popc(m & ((1u << lane) - 1u));
-                const int width = min(32, qb - (col0 + 32 * g));
                 if (slot < p.recheck_cap)
-                  p.recheck[slot] = ((unsigned long long)row << 24) | ((unsigned long long)(width - 1) << 19) |
-                                    (unsigned long long)((q0 + 32 * g) >> 4);
+                  p.recheck[slot] = ((unsigned long long)row << 24) | (31ull << 19) | (unsigned long long)((q0 + 32 * g) >> 4);
               }
               base += __popc(m);
             }
           }
         }
-        __syncwarp();
+        vg += vg_step2;
+        pg += pg_step2;
+        if (pg >= p.NG) pg -= p.NG;
       }
     }
   }
@@ -537,7 +549,7 @@ ham4_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt,
 }
 
 struct HamTc4Plan {
-  int K, qb, b_block, col_blocks, cols, cap, first_rows;
+  int K, qb, b_block, col_blocks, cols, cap, first_rows, growth;
   size_t smem_bytes;
   size_t off_img, off_tq, off_cnt, off_flag, off_list, off_buf, total;
   int list_cap;
@@ -545,18 +557,28 @@ struct HamTc4Plan {
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
+int growth_for(int Q) {
+  if (const char* e = getenv("SB_TC_GROWTH")) {               // tuning knob
+    const int g = atoi(e);
+    if (g >= 2 && g <= 64) return g;
+  }
+  return Q <= SMALL_Q ? GROWTH_SMALL_Q : GROWTH;
+}
+
 HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
   HamTc4Plan p;
   p.K = 32 * W;
-  // equal blocks of at most 240 columns (a multiple of 16): 4096 queries -> 18 x 240, 512 -> 3 x 176
+  // equal blocks of at most 224 columns, a multiple of 32 (whole 32-column survivor groups; the scale factors
+  // sit in TMEM columns [240, 256) between the two accumulators): 4096 queries -> 19 x 224, 512 -> 3 x 192
   const int nblk = (Q + QB - 1) / QB;
-  p.qb = ((Q + nblk - 1) / nblk + 15) / 16 * 16;
+  p.qb = ((Q + nblk - 1) / nblk + 31) / 32 * 32;
   p.col_blocks = (Q + p.qb - 1) / p.qb;
   p.cols = p.col_blocks * p.qb;
   p.b_block = (p.qb * 160 + 1023) / 1024 * 1024;               // qb rows x 128 B + B_syn (2 x qb x 16 B)
   p.cap = 4096;
-  while (p.cap < 4 * (GROWTH + 1) * k) p.cap <<= 1;
-  p.first_rows = 256;                                          // dense seed chunk: at least 8 k rows (its sort costs Q * rows)
+  p.growth = growth_for(Q);
+  while (p.cap < 4 * (p.growth + 1) * k) p.cap <<= 1;
+  p.first_rows = Q <= SMALL_Q ? 1024 : 256;                    // dense seed chunk: at least 8 k rows (its sort costs Q * rows)
   while (p.first_rows < 8 * k) p.first_rows <<= 1;
   if (p.first_rows > p.cap) p.first_rows = p.cap;
   p.smem_bytes = 1024 + (size_t)2 * p.b_block + A_SYN + (size_t)MAX_STAGES * A_GROUP + (2 * MAX_STAGES + 10) * 8 +
@@ -647,7 +669,7 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
   const int sms = sb::sm_count();
   long long done = 0;                                         // granules
   while (done < NG) {
-    long long len = (done == 0) ? p.first_rows / GRAN : done * (GROWTH - 1);
+    long long len = (done == 0) ? p.first_rows / GRAN : done * (p.growth - 1);
     if (len > NG - done) len = NG - done;
     const int dense = (done == 0) ? 1 : 0;
     ham4_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.K, p.qb, p.b_block, tq, img, flag + 1);

@@ -137,7 +137,7 @@ def _tc_keys(dev, table, q, k, idx_base=0):
     return d.cpu().numpy(), i.cpu().numpy(), int(flag.item())
 
 
-@pytest.fixture(params=["fp4", "fp8"])
+@pytest.fixture(params=["fp8", "fp4"])
 def tc_fmt(request, dev):
     """Both operand formats of the tensor-core scan: packed FP4 (kind::mxf4, the default) and FP8 (kind::f8f6f4)."""
     old = dev.TC_SCAN_FORMAT

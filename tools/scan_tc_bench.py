@@ -15,6 +15,9 @@ WITH_POPC = os.environ.get("WITH_POPC", "1") != "0"
 cases = [("fp4", lambda: dev.hamming_scan_keys_tc(db, q, k, fmt="fp4")[0]), ("fp8", lambda: dev.hamming_scan_keys_tc(db, q, k, fmt="fp8")[0])]
 if WITH_POPC:
     cases.append(("popc", lambda: dev.hamming_scan_keys(db, q, k, variant=1)))
+ONLY = os.environ.get("ONLY")
+if ONLY:
+    cases = [c for c in cases if c[0] == ONLY]
 ref = None
 for name, fn in cases:
     out = fn(); torch.cuda.synchronize()
