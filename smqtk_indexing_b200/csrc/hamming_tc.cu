@@ -253,7 +253,12 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
     const bool worker = (W >= 2) || h == 0;
     int stage = 0;
     uint32_t phase = 0;
-    uint32_t cw[WH], cn[WH];
+    // PF tiles of packed words are in flight per thread: with few queries (one pass per chunk) every tile comes
+    // straight from HBM, one round trip (~1.5 us under load) is longer than a tile's MMAs (1.2 us), and a single
+    // tile of look-ahead made the LOAD LATENCY the pace: 3170 cycles per tile at Q = 512 vs 2300 at Q = 4096
+    constexpr int PF = 4;
+    uint32_t cw[PF][WH];
+    bool cv[PF];
     // granule of tile i for this thread: vg = vg_first + i * 4 * gridDim.x, physical pg = vg * P mod NG, kept incrementally
     const long long vg_first = p.vg0 + (long long)blockIdx.x * 4 + (r >> 5);
     const long long pg_first = (long long)(((unsigned long long)vg_first * (unsigned long long)p.P) % (unsigned long long)p.NG);
@@ -285,31 +290,33 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
     for (int jb = jb0; jb < jb1; jb += NB) {
       vg_ld = vg_first;
       pg_ld = pg_first;
-      bool vcur = (my_tiles > 0) ? load(cw) : false;
-      for (long long i = 0; i < my_tiles; ++i) {
-        bool vnext = false;
-        if (i + 1 < my_tiles) vnext = load(cn);
-        mbar_wait(a_empty + stage * 8, phase ^ 1);
-        unsigned char* dst = s_a + (size_t)stage * a_stage;
-        if (worker) {
 #pragma unroll
-          for (int j = 0; j < WH; ++j) {
-            const int wj = h * WH + j;                             // word of the row
-            uint4 lo, hi;
-            expand_word(cw[j], lo, hi);
-            if (!vcur) { lo = make_uint4(0u, 0u, 0u, 0u); hi = lo; }   // rows past the table: all-zero operand
-            unsigned char* grp = dst + (wj >> 2) * A_GROUP;
-            *reinterpret_cast<uint4*>(grp + sw128_off(r, 2 * (wj & 3))) = lo;
-            *reinterpret_cast<uint4*>(grp + sw128_off(r, 2 * (wj & 3) + 1)) = hi;
+      for (int d = 0; d < PF; ++d) cv[d] = (d < my_tiles) ? load(cw[d]) : false;
+      for (long long i0 = 0; i0 < my_tiles; i0 += PF) {
+#pragma unroll
+        for (int d = 0; d < PF; ++d) {
+          if (i0 + d < my_tiles) {
+            mbar_wait(a_empty + stage * 8, phase ^ 1);
+            unsigned char* dst = s_a + (size_t)stage * a_stage;
+            if (worker) {
+#pragma unroll
+              for (int j = 0; j < WH; ++j) {
+                const int wj = h * WH + j;                         // word of the row
+                uint4 lo, hi;
+                expand_word(cw[d][j], lo, hi);
+                if (!cv[d]) { lo = make_uint4(0u, 0u, 0u, 0u); hi = lo; }   // rows past the table: all-zero operand
+                unsigned char* grp = dst + (wj >> 2) * A_GROUP;
+                *reinterpret_cast<uint4*>(grp + sw128_off(r, 2 * (wj & 3))) = lo;
+                *reinterpret_cast<uint4*>(grp + sw128_off(r, 2 * (wj & 3) + 1)) = hi;
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full + stage * 8);
+            cv[d] = (i0 + d + PF < my_tiles) ? load(cw[d]) : false;   // refill this slot with the tile PF ahead
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full + stage * 8);
-#pragma unroll
-        for (int j = 0; j < WH; ++j) cw[j] = cn[j];
-        vcur = vnext;
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp < EPI_WARPS) {
