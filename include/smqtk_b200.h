@@ -23,7 +23,9 @@
  *     scratch space is passed in, its size comes from the *_workspace_bytes query;
  *   - return value 0 = success, otherwise an SB_ERR_* code; sb_last_error()
  *     gives a thread-local message;
- *   - no global mutable state: calls on different streams may run concurrently.
+ *   - no global mutable state on the compute path: calls on different streams may run concurrently
+ *     (process-wide bookkeeping only: the launch counter of sb_launch_count and the optional
+ *     per-launch event records of sb_profile_enable / sb_profile_fetch).
  *
  * Hash-code layout (device): uint32[rows][W], each row is the INTEGER VALUE of
  * the reference's big-endian bit vector (bits.py:17-20) written in W 32-bit

@@ -669,6 +669,20 @@ merge_kernel(const uint64_t* __restrict__ lists, int P, int Q, int k, int q_majo
   }
 }
 
+// One list per query (a single part): nothing to merge, the keys are already the answer -- decode them.
+__global__ void __launch_bounds__(256)
+decode_keys_kernel(const uint64_t* __restrict__ keys, long long n, uint64_t* __restrict__ out_keys, int32_t* __restrict__ out_dist,
+                   long long* __restrict__ out_idx, const int* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = keys[i];
+  const uint64_t row_mask = (1ull << SB_KEY_ROW_BITS) - 1;
+  if (out_keys) out_keys[i] = key;
+  if (out_dist) out_dist[i] = (key == SB_KEY_EMPTY) ? -1 : (int32_t)(key >> SB_KEY_ROW_BITS);
+  if (out_idx) out_idx[i] = (key == SB_KEY_EMPTY) ? -1ll : (long long)(key & row_mask);
+}
+
 size_t merge_smem_bytes(int k) { return (size_t)MERGE_CAP * 8 + (size_t)k * 8 + (size_t)MERGE_BINS * 4; }
 
 struct ScanPlan {
@@ -789,7 +803,15 @@ int launch_scan(const ScanPlan& p, int mode, const uint32_t* db, long long U, co
 }
 
 int launch_merge(const uint64_t* lists, int P, int Q, int k, int q_major, uint64_t* out_keys, int32_t* out_dist,
-                 int64_t* out_idx, cudaStream_t st, const int* enable = nullptr) {
+                 int64_t* out_idx, cudaStream_t st, const int* enable = nullptr, bool sorted_lists = false) {
+  if (P == 1 && sorted_lists) {                               // (the scan's own per-chunk lists are unordered)
+    sb::ProfScope prof("decode_keys_kernel", st);
+    const long long n = (long long)Q * k;
+    decode_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lists, n, out_keys, out_dist,
+                                                                    reinterpret_cast<long long*>(out_idx), enable);
+    sb::count_launch();
+    return sb::check_launch("decode_keys_kernel");
+  }
   const size_t dyn = merge_smem_bytes(k);
   SB_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   sb::ProfScope prof("merge_kernel", st);
@@ -882,7 +904,7 @@ int sb_topk_merge(const uint64_t* keys_in, int32_t parts, int32_t Q, int32_t k, 
                   int32_t* out_dist, int64_t* out_idx, void* stream) {
   SB_REQUIRE(keys_in != nullptr && parts >= 1 && Q >= 1 && k >= 1, "sb_topk_merge: bad arguments");
   return launch_merge(keys_in, parts, Q, k, /*q_major=*/0, out_keys, out_dist, out_idx,
-                      reinterpret_cast<cudaStream_t>(stream));
+                      reinterpret_cast<cudaStream_t>(stream), nullptr, /*sorted_lists=*/true);
 }
 
 }  // extern "C"

@@ -455,15 +455,10 @@ __global__ void ham_query_image_kernel(const uint32_t* __restrict__ q, int Q, in
   *reinterpret_cast<uint4*>(grp + sw128_off(n, 2 * (j & 3) + 1)) = hi;
 }
 
-// B_syn of every block: 32 E4M3 slots per column that sum to s = 2 * tq - K + 1 (|s| <= 16 * 32);
-// padding columns get -512 (their data bytes are zero: the accumulator is negative).
-__global__ void ham_threshold_image_kernel(int Q, int cols, int G, int K, const int* __restrict__ tq,
-                                           unsigned char* __restrict__ img, int* __restrict__ list_cnt) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col == 0) *list_cnt = 0;                                   // the re-check list restarts with every chunk
-  if (col >= cols) return;
+// B_syn of one column: 32 E4M3 slots that sum to s = 2 * tq - K + 1 (|s| <= 16 * 32); padding columns get -512
+// (their data bytes are zero: the accumulator is negative).
+__device__ __forceinline__ void write_threshold_slots(unsigned char* __restrict__ img, int col, int G, int s) {
   const int jb = col / QB, n = col % QB;
-  const int s = (col < Q) ? (2 * min(tq[col], K) - K + 1) : -512;
   const uint32_t sign = s < 0 ? 0x80u : 0u;
   const int mag = s < 0 ? -s : s;
   const int n16 = mag >> 4, rem = mag & 15;
@@ -488,17 +483,16 @@ __global__ void ham_threshold_image_kernel(int Q, int cols, int G, int K, const 
   *reinterpret_cast<uint4*>(base + QB * 16 + n * 16) = make_uint4(words[4], words[5], words[6], words[7]);
 }
 
-__global__ void ham_init_kernel(int cols, int K, int* __restrict__ tq, int* __restrict__ cnt, int* __restrict__ overflow) {
+// Start of a batch: no threshold yet (tq = K: every pair passes), empty candidate lists, the threshold K step of
+// every column (padding columns: always negative), empty re-check list.
+__global__ void ham_init_kernel(int Q, int cols, int G, int K, int* __restrict__ tq, int* __restrict__ cnt,
+                                int* __restrict__ overflow, unsigned char* __restrict__ img, int* __restrict__ list_cnt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *overflow = 0;
+  if (i == 0) { *overflow = 0; *list_cnt = 0; }
   if (i >= cols) return;
   tq[i] = K;
   cnt[i] = 0;
-}
-
-__global__ void ham_set_count_kernel(int* __restrict__ cnt, int Q, int v) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < Q) cnt[i] = v;
+  write_threshold_slots(img, i, G, i < Q ? K + 1 : -512);
 }
 
 // One CTA per query: sort the survivors (canonical keys: distance, row), keep the best k, tighten
@@ -506,10 +500,11 @@ __global__ void ham_set_count_kernel(int* __restrict__ cnt, int Q, int v) {
 // the test stays "<="); `final` writes keys_out.
 __global__ void __launch_bounds__(CP_THREADS)
 ham_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt, int cap, int k, int K, int* __restrict__ tq,
-                   int* __restrict__ overflow, int final, unsigned long long* __restrict__ keys_out) {
+                   int* __restrict__ overflow, int final, unsigned long long* __restrict__ keys_out, int dense_count,
+                   unsigned char* __restrict__ img, int G, int* __restrict__ list_cnt) {
   extern __shared__ unsigned long long s_key[];   // P = next pow2 >= min(count, cap)
   const int qi = blockIdx.x, tid = threadIdx.x;
-  const int raw = cnt[qi];
+  const int raw = dense_count >= 0 ? dense_count : cnt[qi];      // the dense seed chunk filled buf[query][0 .. rows)
   const int m = min(raw, cap);
   if (raw > cap && tid == 0) *overflow = 1;
   unsigned long long* mine = buf + (size_t)qi * cap;
@@ -542,7 +537,12 @@ ham_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt, 
   for (int i = tid; i < keep; i += CP_THREADS) mine[i] = s_key[i];
   if (tid == 0) {
     cnt[qi] = keep;
-    tq[qi] = (keep >= k) ? (int)(s_key[k - 1] >> 40) : K;
+    const int t = (keep >= k) ? (int)(s_key[k - 1] >> 40) : K;
+    tq[qi] = t;
+    // the next chunk's threshold K step for this query, and an empty re-check list (this kernel runs after the
+    // re-check of the chunk: one launch per chunk less than a separate threshold-image kernel)
+    if (!final) write_threshold_slots(img, qi, G, 2 * min(t, K) - K + 1);
+    if (qi == 0) *list_cnt = 0;
   }
   if (final)
     for (int i = tid; i < k; i += CP_THREADS) keys_out[(size_t)qi * k + i] = (i < keep) ? s_key[i] : ~0ull;
@@ -645,7 +645,7 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
     sb::count_launch();
     if (int rc = sb::check_launch("ham_query_image_kernel")) return rc;
   }
-  ham_init_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(p.cols, p.K, tq, cnt, flag);
+  ham_init_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.G, p.K, tq, cnt, flag, img, flag + 1);
   sb::count_launch();
   if (int rc = sb::check_launch("ham_init_kernel")) return rc;
 
@@ -672,9 +672,6 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
     long long len = (done == 0) ? p.first_rows / GRAN : done * (p.growth - 1);
     if (len > NG - done) len = NG - done;
     const int dense = (done == 0) ? 1 : 0;
-    ham_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.G, p.K, tq, img, flag + 1);
-    sb::count_launch();
-    if (int rc = sb::check_launch("ham_threshold_image_kernel")) return rc;
     HamTcParams hp;
     hp.db = db; hp.U = U; hp.W = W; hp.G = p.G; hp.ksteps = p.ksteps; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
     hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.recheck = list; hp.recheck_cnt = flag + 1; hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
@@ -703,16 +700,12 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
       sb::count_launch();
       if (int rc = sb::check_launch("ham_recheck_kernel")) return rc;
     }
-    if (dense) {
-      ham_set_count_kernel<<<(Q + 255) / 256, 256, 0, st>>>(cnt, Q, (int)(len * GRAN));
-      sb::count_launch();
-      if (int rc = sb::check_launch("ham_set_count_kernel")) return rc;
-    }
     done += len;
     const int final = (done >= NG) ? 1 : 0;
     sb::ProfScope prof("ham_compact_kernel", st);
-    ham_compact_kernel<<<Q, CP_THREADS, p.cap * sizeof(unsigned long long), st>>>(buf, cnt, p.cap, k, p.K, tq, flag, final,
-                                                                                  reinterpret_cast<unsigned long long*>(keys_out));
+    ham_compact_kernel<<<Q, CP_THREADS, p.cap * sizeof(unsigned long long), st>>>(
+        buf, cnt, p.cap, k, p.K, tq, flag, final, reinterpret_cast<unsigned long long*>(keys_out),
+        dense ? (int)(len * GRAN) : -1, img, p.G, flag + 1);
     sb::count_launch();
     if (int rc = sb::check_launch("ham_compact_kernel")) return rc;
   }
