@@ -506,8 +506,7 @@ def run_b200(args):
 
         def query_host(qh):
             index.graph = use_graph[0]
-            rows, d = index.query(qh.to(dev, non_blocking=True), k)
-            return rows.cpu().numpy(), d.cpu().numpy()
+            return index.query_host(qh, k)
         parallelism = ("x%d: descriptors row-sharded; %s; re-rank %s" % (
             world,
             "scan split over the QUERIES (code table replicated, each rank scans all %d codes for %d of the %d queries)"
@@ -693,8 +692,12 @@ def run_b200(args):
             "config": workload_config(args, world, parallelism),
             "clocks": clocks,
             "e2e": {"value": Q * args.steps / (ms_e2e * 1e-3), "unit": "queries/s",
-                    "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 16,
+                    "h2d_bytes_per_step": (q_per_rank if (world > 1 and peers is not None) else Q) * D * 4,
+                    "d2h_bytes_per_step": Q * k * 16,
                     "ms_per_step": ms_e2e / args.steps},
+            "e2e_note": ("per rank: with the scan split over the queries a rank copies only its slice of the batch "
+                         "to the device (h2d_bytes_per_step) and reads the whole all-gathered result back"
+                         if world > 1 and peers is not None else "whole batch in, whole result out"),
             "gpu_launches": int(launches),
             "gpu_launches_note": "kernels of this repo per %d steps, counted in the kernel-by-kernel pass (region B); the "
                                  "graph-replayed pass (region A) runs the same kernels from one cudaGraphLaunch per step%s"

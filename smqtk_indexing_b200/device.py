@@ -79,7 +79,9 @@ def norm_spec(normalize) -> Tuple[int, float]:
     raise ValueError("normalize=%r: only ord in {None, 0, p > 0, inf} is supported on the device" % (normalize,))
 
 
-TC_MIN_ROWS = 512     # below this the FFMA kernel's launch is as fast as the tensor-core one
+#: below this the FFMA kernel is faster: the persistent tensor-core kernel streams the whole pre-split rotation
+#: (2 MB at 512 x 256) into every CTA it starts, a fixed ~50 us that 512 or 1024 query rows cannot amortise
+TC_MIN_ROWS = 2048
 
 
 def itq_rotation_image(R: torch.Tensor) -> Optional[torch.Tensor]:

@@ -224,19 +224,63 @@ class ShardedLshIndex:
     def query(self, q: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Collective: all ranks pass the SAME queries; all get the full result
         (global rows int64[Q, n], dists f64[Q, n])."""
+        Q = q.shape[0]
+        if self.peers is not None and self._by_queries(Q):
+            # every rank needs only ITS slice of the batch on the device (hash, scan, re-rank are per slice)
+            per, lo, hi = self._slice(Q)
+            return self._unpack(self._run_slice(self._padded(q, lo, hi, per), Q, n), Q, n)
         from . import engine
         if not (self.graph and q.is_cuda and self.peers is not None) or engine.STAGE_EVENTS is not None:
             return self._query(q, n)
-        key = (int(q.shape[0]), int(q.shape[1]), int(n), q.dtype, self.scan_partition)
+        key = ("full", int(Q), int(q.shape[1]), int(n), q.dtype, self.scan_partition)
         ent = self._graphs.get(key)
         if isinstance(ent, engine.GraphedCall):
             return ent(q)
         seen = (ent or 0) + 1
-        if seen >= self.GRAPH_AFTER and self._fixed_pitch(q.shape[0], n):
+        if seen >= self.GRAPH_AFTER and self._fixed_pitch(Q, n):
             self._graphs[key] = g = engine.GraphedCall(lambda qq: self._query(qq, n), q.contiguous())
             return g(q)
         self._graphs[key] = seen
         return self._query(q, n)
+
+    def query_host(self, q_host: torch.Tensor, n: int):
+        """``query`` for a HOST batch (pinned memory makes the copy asynchronous): with the scan split over the
+        queries only this rank's slice crosses PCIe (Q / N rows instead of Q), and the result comes back in ONE
+        device-to-host copy.  Returns numpy ``(rows int64[Q, n], dists float64[Q, n])``."""
+        Q = q_host.shape[0]
+        dev = self.x_local.device
+        if self.peers is not None and self._by_queries(Q):
+            per, lo, hi = self._slice(Q)
+            mine = torch.zeros((per, q_host.shape[1]), dtype=torch.float32, device=dev)
+            if hi > lo:
+                mine[:hi - lo].copy_(q_host[lo:hi], non_blocking=True)
+            packed = self._run_slice(mine, Q, n)
+            host = packed.cpu()                                   # one copy, one synchronisation
+            return host[:, :n].numpy(), host[:, n:].contiguous().view(torch.float64).numpy()
+        rows, d = self.query(q_host.to(dev, non_blocking=True), n)
+        return rows.cpu().numpy(), d.cpu().numpy()
+
+    @staticmethod
+    def _unpack(packed: torch.Tensor, Q: int, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        return packed[:, :n].contiguous(), packed[:, n:].contiguous().view(torch.float64)
+
+    def _run_slice(self, q_mine: torch.Tensor, Q: int, n: int) -> torch.Tensor:
+        """This rank's query slice through the pipeline (graph replay once the shape repeats) ->
+        the all-gathered packed result int64[Q, 2n] = (rows | distance bits)."""
+        from . import engine
+        per = q_mine.shape[0]
+        if not self.graph or engine.STAGE_EVENTS is not None or not self._fixed_pitch(per, n):
+            return self._slice_pipeline(q_mine, n)[:Q]
+        key = ("slice", int(per), int(q_mine.shape[1]), int(n), q_mine.dtype)
+        ent = self._graphs.get(key)
+        if isinstance(ent, engine.GraphedCall):
+            return ent(q_mine)[0][:Q]
+        seen = (ent or 0) + 1
+        if seen >= self.GRAPH_AFTER:
+            self._graphs[key] = g = engine.GraphedCall(lambda qq: (self._slice_pipeline(qq, n),), q_mine.contiguous())
+            return g(q_mine)[0][:Q]
+        self._graphs[key] = seen
+        return self._slice_pipeline(q_mine, n)[:Q]
 
     def _fixed_pitch(self, Q: int, n: int) -> bool:
         from .engine import FIXED_PITCH_LIMIT
@@ -249,22 +293,18 @@ class ShardedLshIndex:
             q_codes = self.ops.hash(q)
         return self._query_allreduce(q, q_codes, n)
 
-    def _query_peer(self, q: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Every rank answers ITS slice of the batch; one all-gather assembles the batch."""
-        Q = q.shape[0]
-        per, lo, hi = self._slice(Q)
-        q_mine = self._padded(q, lo, hi, per)
-        if self._by_queries(Q):
-            with _stage("itq_hash"):
-                codes_mine = self.ops.hash(q_mine)
-            with _stage("hamming_scan"):
-                keys = self.ops.scan_keys(self.table, codes_mine, n, 0).contiguous()
-                _, code_rows = self.ops.merge_keys(keys.unsqueeze(0))                 # one part: decode only
-        else:
-            with _stage("itq_hash"):
-                q_codes = self.ops.hash(q)
-            _, code_rows_all = self.near_codes(q_codes, n)
-            code_rows = self._padded(code_rows_all, lo, hi, per, fill=-1)
+    def _slice_pipeline(self, q_mine: torch.Tensor, n: int) -> torch.Tensor:
+        """Scan split over the queries: hash, scan of the whole table, expansion, peer re-rank and selection for
+        this rank's slice, then ONE all-gather of the packed (row | distance bits) results of all slices."""
+        with _stage("itq_hash"):
+            codes_mine = self.ops.hash(q_mine)
+        with _stage("hamming_scan"):
+            keys = self.ops.scan_keys(self.table, codes_mine, n, 0).contiguous()
+            _, code_rows = self.ops.merge_keys(keys.unsqueeze(0))                 # one part: decode only
+        return self._finish_slice(q_mine, code_rows, n)
+
+    def _finish_slice(self, q_mine: torch.Tensor, code_rows: torch.Tensor, n: int) -> torch.Tensor:
+        per = q_mine.shape[0]
         pitch = n * max(self.max_rows_per_code, 1)
         with _stage("expand"):
             if self._fixed_pitch(per, n):                      # device-only, fixed-pitch segments padded with -1
@@ -280,9 +320,20 @@ class ShardedLshIndex:
                 pos, od = self.ops.rerank_select(d, cand_off, n)
                 rows = torch.where(pos >= 0, cand_idx[pos.clamp(min=0)], pos) if cand_idx.numel() else pos
         with _stage("allgather_results"):
-            packed = torch.cat([rows, od.view(torch.int64)], dim=1)                   # (row | distance bits)[per, 2n]
-            full = self._gather(packed)[:Q]
-            return full[:, :n].contiguous(), full[:, n:].contiguous().view(torch.float64)
+            return self._gather(torch.cat([rows, od.view(torch.int64)], dim=1))     # (row | distance bits)[N * per, 2n]
+
+    def _query_peer(self, q: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Every rank answers ITS slice of the batch; one all-gather assembles the batch."""
+        Q = q.shape[0]
+        per, lo, hi = self._slice(Q)
+        q_mine = self._padded(q, lo, hi, per)
+        if self._by_queries(Q):
+            return self._unpack(self._slice_pipeline(q_mine, n)[:Q], Q, n)
+        with _stage("itq_hash"):
+            q_codes = self.ops.hash(q)
+        _, code_rows_all = self.near_codes(q_codes, n)
+        code_rows = self._padded(code_rows_all, lo, hi, per, fill=-1)
+        return self._unpack(self._finish_slice(q_mine, code_rows, n)[:Q], Q, n)
 
     def _query_allreduce(self, q: torch.Tensor, q_codes: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
         _, code_rows = self.near_codes(q_codes, n)
