@@ -193,88 +193,6 @@ extern "C" int sb_itq_row_div(const float* X, int64_t n, int32_t D, int64_t ldx,
   return sb::check_launch("row_div_f32_kernel");
 }
 
-namespace {
-
-// Few rows (a query slice: the 512 queries of one rank, a single get_hash call): the tiled kernels above and in
-// itq_hash_tc.cu pay ~50 us of fixed cost whatever n (4 x 4 CTAs looping over K / every CTA streaming the whole
-// pre-split rotation).  Here a CTA takes FEW_ROWS rows, keeps them centred in shared memory and gives every
-// thread one output bit: R is read coalesced from L2 once per CTA (n / FEW_ROWS x D x b x 4 bytes in total).
-constexpr int FEW_ROWS = 4;
-constexpr int FEW_THREADS = 256;
-
-__global__ void __launch_bounds__(FEW_THREADS)
-itq_hash_few_kernel(const float* __restrict__ X, long long n, int D, long long ldx, const float* __restrict__ mean,
-                    const float* __restrict__ R, int b, int norm_kind, float norm_p, uint32_t* __restrict__ codes, int W,
-                    float* __restrict__ z_out) {
-  extern __shared__ float s_a[];                       // [FEW_ROWS][D] centred rows
-  __shared__ float s_red[FEW_ROWS][FEW_THREADS / 32];
-  __shared__ float s_div[FEW_ROWS];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long row0 = (long long)blockIdx.x * FEW_ROWS;
-#pragma unroll
-  for (int j = 0; j < FEW_ROWS; ++j) {
-    const long long r = row0 + j;
-    float acc = 0.0f;
-    if (norm_kind != SB_NORM_NONE && r < n) {
-      for (int k = tid; k < D; k += FEW_THREADS) {
-        const float t = norm_term(X[r * ldx + k], norm_kind, norm_p);
-        acc = (norm_kind == SB_NORM_INF) ? fmaxf(acc, t) : acc + t;
-      }
-      for (int o = 16; o; o >>= 1) {
-        const float t = __shfl_xor_sync(sb::FULL_MASK, acc, o);
-        acc = (norm_kind == SB_NORM_INF) ? fmaxf(acc, t) : acc + t;
-      }
-    }
-    if (lane == 0) s_red[j][warp] = acc;
-  }
-  __syncthreads();
-  if (tid < FEW_ROWS) {
-    float acc = 0.0f;
-    for (int w = 0; w < FEW_THREADS / 32; ++w)
-      acc = (norm_kind == SB_NORM_INF) ? fmaxf(acc, s_red[tid][w]) : acc + s_red[tid][w];
-    s_div[tid] = (norm_kind == SB_NORM_NONE) ? 1.0f : finish_norm(acc, norm_kind, norm_p);
-  }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < FEW_ROWS; ++j) {
-    const long long r = row0 + j;
-    const float div = s_div[j];
-    for (int k = tid; k < D; k += FEW_THREADS) {
-      float v = 0.0f;
-      if (r < n) {
-        v = X[r * ldx + k];
-        if (norm_kind != SB_NORM_NONE) v = v / div;
-        if (mean != nullptr) v -= mean[k];
-      }
-      s_a[j * D + k] = v;
-    }
-  }
-  __syncthreads();
-  for (int bit = tid; bit < b; bit += FEW_THREADS) {
-    float acc[FEW_ROWS];
-#pragma unroll
-    for (int j = 0; j < FEW_ROWS; ++j) acc[j] = 0.0f;
-#pragma unroll 8
-    for (int k = 0; k < D; ++k) {
-      const float rv = __ldg(R + (long long)k * b + bit);
-#pragma unroll
-      for (int j = 0; j < FEW_ROWS; ++j) acc[j] = fmaf(s_a[j * D + k], rv, acc[j]);
-    }
-    const int p = b - 1 - bit;                         // integer bit of this column (bits.py:17-20: index 0 = MSB)
-    const int word = W - 1 - (p >> 5);
-#pragma unroll
-    for (int j = 0; j < FEW_ROWS; ++j) {
-      const long long r = row0 + j;
-      if (r < n) {
-        if (z_out != nullptr) z_out[r * b + bit] = acc[j];
-        if (acc[j] >= 0.0f) atomicOr(codes + r * W + word, 1u << (p & 31));
-      }
-    }
-  }
-}
-
-}  // namespace
-
 extern "C" int sb_itq_hash(const float* X, int64_t n, int32_t D, int64_t ldx, const float* mean, const float* R,
                            int32_t b, int32_t norm_kind, float norm_p, uint32_t* codes_out, int32_t W, float* z_out,
                            int32_t variant, void* stream) {
@@ -290,16 +208,6 @@ extern "C" int sb_itq_hash(const float* X, int64_t n, int32_t D, int64_t ldx, co
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   SB_CUDA_TRY(cudaMemsetAsync(codes_out, 0, (size_t)n * W * sizeof(uint32_t), st));
-  if (variant == 0 && n <= 1024 && D <= 8192) {
-    const size_t smem = (size_t)FEW_ROWS * D * sizeof(float);
-    if (smem > 48 * 1024)
-      SB_CUDA_TRY(cudaFuncSetAttribute(itq_hash_few_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sb::ProfScope prof("itq_hash_few_kernel", st);
-    itq_hash_few_kernel<<<(unsigned)((n + FEW_ROWS - 1) / FEW_ROWS), FEW_THREADS, smem, st>>>(X, n, D, ldx, mean, R, b, norm_kind,
-                                                                                        norm_p, codes_out, W, z_out);
-    sb::count_launch();
-    return sb::check_launch("itq_hash_few_kernel");
-  }
   dim3 grid((unsigned)((n + BM - 1) / BM), (unsigned)((b + BN - 1) / BN));
   sb::ProfScope prof("itq_hash_simt_kernel", st);
   itq_hash_simt_kernel<<<grid, THREADS, 0, st>>>(X, n, D, ldx, mean, R, b, norm_kind, norm_p, codes_out, W, z_out);

@@ -79,9 +79,10 @@ def norm_spec(normalize) -> Tuple[int, float]:
     raise ValueError("normalize=%r: only ord in {None, 0, p > 0, inf} is supported on the device" % (normalize,))
 
 
-#: up to 1024 rows ``sb_itq_hash`` takes its few-rows kernel (the persistent tensor-core kernel streams the whole
-#: pre-split rotation, 2 MB at 512 x 256, into every CTA it starts: a fixed ~50 us whatever n)
-TC_MIN_ROWS = 1025
+#: below this the FFMA kernel's launch is as fast as the tensor-core one.  (Both cost ~50 us for a few hundred
+#: rows -- the persistent tensor-core kernel streams the whole pre-split rotation, 2 MB at 512 x 256, into every
+#: CTA it starts; a dedicated few-rows kernel was tried in round 2 and was slower, 139 us at 512 rows.)
+TC_MIN_ROWS = 512
 
 
 def itq_rotation_image(R: torch.Tensor) -> Optional[torch.Tensor]:
@@ -151,9 +152,8 @@ def itq_hash(X: torch.Tensor, mean: Optional[torch.Tensor], R: torch.Tensor, nor
             _lib.check(lib.sb_itq_hash_tc(_ptr(X), n, D, ldx, _ptr(mean), _ptr(r_image), b, _ptr(div),
                                           _ptr(codes), W, _ptr(z), _stream()))
         else:
-            # C variant 0 = automatic (few-rows kernel up to 1024 rows, else the tiled FFMA kernel), 1 = tiled kernel
             _lib.check(lib.sb_itq_hash(_ptr(X), n, D, ldx, _ptr(mean), _ptr(R), b, kind, p,
-                                       _ptr(codes), W, _ptr(z), 1 if variant == 1 else 0, _stream()))
+                                       _ptr(codes), W, _ptr(z), 0, _stream()))
     return (codes, z) if want_z else codes
 
 

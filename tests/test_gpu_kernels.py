@@ -353,8 +353,7 @@ def test_itq_hash_shapes(dev, n, D, b):
     mean = x.mean(0).astype(np.float64)
     rot = np.linalg.qr(rng.randn(max(D, b), max(D, b)))[0][:D, :b]
     for normalize in (None, 2, 1, np.inf):
-        _check_hash(dev, x, mean, rot, normalize, variant=1)      # tiled FFMA kernel
-        _check_hash(dev, x, mean, rot, normalize, variant=0)      # automatic: the few-rows kernel at these sizes
+        _check_hash(dev, x, mean, rot, normalize)
 
 
 @pytest.mark.parametrize("n,D,b", [(256, 16, 32), (1000, 512, 256), (777, 64, 64), (4096, 512, 256),
