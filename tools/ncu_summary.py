@@ -110,8 +110,44 @@ def full(src, dst, traffic_json=None):
         print("wrote", traffic_json)
 
 
+def traffic(src, dst, traffic_json, title, kernel_prefix):
+    """ncu --csv launch list with several metrics per launch (time + DRAM bytes) -> table + per-step traffic json."""
+    rows = list(csv.reader(open(src)))
+    hdr = next(r for r in rows if "Metric Name" in r)
+    ci = {h: i for i, h in enumerate(hdr)}
+    per = OrderedDict()
+    for r in rows:
+        if len(r) != len(hdr) or not r[0].isdigit():
+            continue
+        d = per.setdefault(int(r[ci["ID"]]), {"kernel": short(r[ci["Kernel Name"]])})
+        v = float(r[ci["Metric Value"]].replace(",", ""))
+        unit = r[ci["Metric Unit"]].lower()
+        scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6,
+                 "nsecond": 1e-3, "usecond": 1, "msecond": 1e3, "second": 1e6}.get(unit, 1)
+        d[r[ci["Metric Name"]]] = v * scale
+    out = ["# %s" % title, "", "`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none` "
+           "(cold-cache, serialised: shares matter, not absolutes)", "", "| # | kernel | time (us) | DRAM read (MB) | DRAM write (MB) |",
+           "|---|---|---:|---:|---:|"]
+    tot = 0.0
+    n_k = 0
+    for i, (_, d) in enumerate(per.items()):
+        rd, wr = d.get("dram__bytes_read.sum", 0.0), d.get("dram__bytes_write.sum", 0.0)
+        out.append("| %d | `%s` | %.1f | %.2f | %.2f |" % (i, d["kernel"], d.get("gpu__time_duration.sum", 0.0), rd / 1e6, wr / 1e6))
+        if d["kernel"].startswith(kernel_prefix):
+            tot += rd + wr
+            n_k += 1
+    out += ["", "`%s`: %d launches, %.1f MB of DRAM traffic in total." % (kernel_prefix, n_k, tot / 1e6)]
+    open(dst, "w").write("\n".join(out) + "\n")
+    json.dump({"kernel": kernel_prefix, "source": "%s (ncu dram__bytes_read.sum + dram__bytes_write.sum, summed over the "
+               "launches of one batch)" % dst, "dram_bytes_per_step": tot, "launches_per_step": n_k, "workload": title},
+              open(traffic_json, "w"), indent=1)
+    print("wrote", dst, traffic_json)
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:7])
     else:
         full(*sys.argv[2:])
