@@ -69,9 +69,16 @@ class GraphedCall:
 
     def __call__(self, *inputs: torch.Tensor):
         for dst, src in zip(self.static_in, inputs):
-            dst.copy_(src, non_blocking=True)
+            dst.copy_(src, non_blocking=True)                      # (host sources: pinned memory makes this asynchronous)
         self.graph.replay()
         return tuple(o.clone() for o in self.static_out)
+
+    def run_to_host(self, *inputs: torch.Tensor):
+        """Same, returning HOST copies straight from the static outputs (no device-side clone)."""
+        for dst, src in zip(self.static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return tuple(o.cpu() for o in self.static_out)
 
 
 def expand_candidates(code_rows: torch.Tensor, csr_off: torch.Tensor, csr_rows: torch.Tensor):
@@ -278,7 +285,7 @@ class DeviceLshIndex:
     #: capture the pipeline of a (Q, n) shape into a CUDA graph once it has been asked for this often
     GRAPH_AFTER = 2
 
-    def query_graphed(self, functor, q: torch.Tensor, n: int, distance_method: str):
+    def query_graphed(self, functor, q: torch.Tensor, n: int, distance_method: str, to_host: bool = False):
         """``query`` through a per-shape CUDA graph (captured on the ``GRAPH_AFTER``-th batch of the
         shape; any re-index drops the graphs).  Shapes whose candidate expansion needs the host
         (heavy code collisions) and batches recorded with stage events stay eager."""
@@ -287,16 +294,23 @@ class DeviceLshIndex:
         eager = (STAGE_EVENTS is not None or n > 2048 or q.shape[0] * pitch > FIXED_PITCH_LIMIT
                  or torch.cuda.is_current_stream_capturing())
         if eager:
-            return self.query(functor, q, n, distance_method)
+            if q.device != self.x.device:
+                q = q.to(self.x.device, non_blocking=True)
+            out = self.query(functor, q, n, distance_method)
+            return tuple(o.cpu() for o in out) if to_host else out
         ent = self._graphs.get(key)
         if isinstance(ent, GraphedCall):
-            return ent(q)
+            return ent.run_to_host(q) if to_host else ent(q)      # q may live on the host: copied into the static input
+        if q.device != self.x.device:
+            q = q.to(self.x.device, non_blocking=True)
         seen = (ent or 0) + 1
         if seen >= self.GRAPH_AFTER:
             self._graphs[key] = g = GraphedCall(lambda qq: self.query(functor, qq, n, distance_method), q)
-            return g(q)
-        self._graphs[key] = seen
-        return self.query(functor, q, n, distance_method)
+            out = g(q)
+        else:
+            self._graphs[key] = seen
+            out = self.query(functor, q, n, distance_method)
+        return tuple(o.cpu() for o in out) if to_host else out
 
     def query(self, functor, q: torch.Tensor, n: int, distance_method: str):
         """hash -> Hamming top-n unique codes -> candidates -> re-rank -> top-n."""

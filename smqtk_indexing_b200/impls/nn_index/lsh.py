@@ -634,16 +634,25 @@ class LSHNearestNeighborIndex(NearestNeighborsIndex):
             if m.table is None:
                 raise ValueError("No index currently set to query from!")
             dev = m.x.device
+            use_graph = graph and hasattr(self.lsh_functor, "get_hash_packed")
             if isinstance(queries, torch.Tensor):
-                q = queries.to(dev, torch.float32)
+                q = queries if (use_graph and not queries.is_cuda and queries.dtype == torch.float32) else \
+                    queries.to(dev, torch.float32)
             else:
-                q = torch.from_numpy(numpy.ascontiguousarray(queries, dtype=numpy.float32)).to(dev, non_blocking=True)
+                q = torch.from_numpy(numpy.ascontiguousarray(queries, dtype=numpy.float32))
+                if not use_graph:
+                    q = q.to(dev, non_blocking=True)
             if q.dim() == 1:
                 q = q.unsqueeze(0)
-            if graph and q.dtype == torch.float32 and hasattr(self.lsh_functor, "get_hash_packed"):
-                rows, dists = m.query_graphed(self.lsh_functor, q.contiguous(), n, self.distance_method)
-            else:
-                rows, dists = m.query(self.lsh_functor, q, n, self.distance_method)
+            if use_graph:
+                # host batches go straight into the captured pipeline's static input, results straight out of
+                # its static output: one H2D and one D2H copy per call, nothing else on the host
+                out = m.query_graphed(self.lsh_functor, q.contiguous(), n, self.distance_method,
+                                      to_host=not return_device)
+                if not return_device:
+                    return out[0].numpy(), out[1].numpy()
+                return out
+            rows, dists = m.query(self.lsh_functor, q, n, self.distance_method)
         if return_device:
             return rows, dists
         return rows.cpu().numpy(), dists.cpu().numpy()
