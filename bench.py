@@ -69,6 +69,11 @@ def parse_args():
     ap.add_argument("--rerank", default="auto", choices=["auto", "peer", "allreduce"],
                     help="N > 1: candidate rows read from the owners' HBM (peer) or owner-computes + all-reduce")
     ap.add_argument("--no-graph", action="store_true", help="never replay the pipeline as a CUDA graph")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configs: c2 = configs[1] (the headline; default), c3 = configs[2] exact flat L2 "
+                         "kNN k=100 over 12.5M x 128-d rows PER GPU (100M on 8), c4 = configs[3] LSH + histogram "
+                         "intersection re-rank on 1M x 4096-d, k=50, c5 = configs[4] ItqFunctor.fit + build on 50M x 256-d")
+    ap.add_argument("--c5-rows", type=int, default=50_000_000)
     ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU-baseline sample size (seconds of CPU work)")
     ap.add_argument("--ref-budget-s", type=float, default=100.0, help="--impl reference: seconds of CPU work in total")
     return ap.parse_args()
@@ -355,8 +360,10 @@ def run_reference(args):
 
 def workload_config(args, n_gpus, parallelism=None):
     return {
-        "workload": "configs[1]: ITQ-%d hashing + LinearHashIndex Hamming top-k over %dx%d-d fp32 descriptors, "
-                    "batch %d queries, k=%d, euclidean re-rank" % (args.bits, args.rows, args.dim, args.queries, args.k),
+        "workload": "%s: ITQ-%d hashing + LinearHashIndex Hamming top-k over %dx%d-d fp32 descriptors, "
+                    "batch %d queries, k=%d, %s re-rank" % (
+                        "configs[3]" if args.config == "c4" else "configs[1]", args.bits, args.rows, args.dim, args.queries, args.k,
+                        "histogram-intersection" if args.config == "c4" else "euclidean"),
         "rows": args.rows, "dim": args.dim, "bits": args.bits, "queries_per_step": args.queries, "k": args.k,
         "parallelism": parallelism or ("x%d" % n_gpus if n_gpus > 1 else "single GPU"),
         "l2": "L2 flushed between timed steps (512 MiB write + read-back); code table %d MB" % (args.rows * args.bits // 8 // 10 ** 6),
@@ -364,7 +371,7 @@ def workload_config(args, n_gpus, parallelism=None):
 
 
 # --------------------------------------------------------------------------- parity (plain torch, outside the timed region)
-def parity_check(torch, dist, functor, state, x_local, row_lo, q_dev, k, result, n_check=8):
+def parity_check(torch, dist, functor, state, x_local, row_lo, q_dev, k, result, n_check=8, method="euclidean"):
     """Re-derive the answers of `n_check` queries of the timed batch WITHOUT any kernel of this repo:
     float64 hash (itq.py:404-408), byte-LUT popcount over the whole unique-code table + torch.topk on
     (distance, row) keys (linear.py:232-240 with the canonical tie order), CSR expansion (lsh.py:490-496),
@@ -407,14 +414,17 @@ def parity_check(torch, dist, functor, state, x_local, row_lo, q_dev, k, result,
         dd = torch.zeros(cand.numel(), dtype=torch.float64, device=dev)
         if bool(mine.any()):
             xr = x_local[(cand[mine] - row_lo)].double()
-            dd[mine] = ((xr - q_dev[qi].double()[None, :]) ** 2).sum(dim=1).sqrt()
+            if method == "hik":                                 # metrics.py:70: 1 - sum(min(a, b))
+                dd[mine] = 1.0 - torch.minimum(xr, q_dev[qi].double()[None, :]).sum(dim=1)
+            else:
+                dd[mine] = ((xr - q_dev[qi].double()[None, :]) ** 2).sum(dim=1).sqrt()
         if dist is not None:
             dist.all_reduce(dd, op=dist.ReduceOp.SUM)
         order = torch.sort(dd, stable=True).indices[:k]
         want_rows, want_d = cand[order], dd[order]
         m = want_rows.numel()
         got_rows, got_d = rows_out[qi][:m], d_out[qi][:m]
-        rel = float(((got_d - want_d).abs() / want_d.clamp(min=1e-30)).max()) if m else 0.0
+        rel = float(((got_d - want_d).abs() / want_d.abs().clamp(min=1e-9)).max()) if m else 0.0
         worst = max(worst, rel)
         gaps_ok = m < 2 or float((want_d[1:] - want_d[:-1]).min()) > 1e-6 * float(want_d.max())
         if rel > 1e-5 or (gaps_ok and not torch.equal(got_rows, want_rows)) or bool((rows_out[qi][m:] != -1).any()):
@@ -426,6 +436,198 @@ def parity_check(torch, dist, functor, state, x_local, row_lo, q_dev, k, result,
             "how": "plain torch: float64 hash, byte-LUT popcount + topk over all %d codes, CSR expansion, float64 "
                    "euclidean on the owning rank%s, stable sort; rows exact, distances rtol 1e-5" % (
                        U, " + one SUM all-reduce" if dist is not None else "")}
+
+
+# --------------------------------------------------------------------------- secondary BASELINE configs
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the LSH hot path has no CPU implementation")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    return torch, dist, world, rank, dev
+
+
+def _timed_steps(torch, dist, world, fn, steps, flush):
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    evs = []
+    barrier()
+    for _ in range(steps):
+        flush.zero_()
+        flush.view(torch.int64).sum()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    ms = torch.tensor([sum(a.elapsed_time(b_) for a, b_ in evs)], dtype=torch.float64, device=flush.device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms[0])
+
+
+def _finish(torch, dist, world, index=None):
+    if world > 1:
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if index is not None and hasattr(index, "close"):
+            index.close()
+        os._exit(0)
+
+
+def run_c3(args):
+    """BASELINE configs[2]: exact brute-force L2 kNN, k = 100, 12.5M x 128-d fp32 rows PER GPU (100M rows on 8)."""
+    torch, dist, world, rank, dev = _dist_setup()
+    from smqtk_indexing_b200 import _lib
+    rows, D, k, Q = 12_500_000, 128, 100, args.queries
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    x = torch.rand((rows, D), device=dev, generator=g)
+    if world > 1:
+        from smqtk_indexing_b200.distributed import ShardedFlatL2Index
+        index = ShardedFlatL2Index()
+        index.build(x)
+        query = lambda qq: index.query(qq, k)
+    else:
+        from smqtk_descriptors.impls.descriptor_set.memory import MemoryDescriptorSet
+        from smqtk_indexing_b200.impls.nn_index.flat import FlatL2NearestNeighborsIndex
+        index = FlatL2NearestNeighborsIndex(MemoryDescriptorSet())
+        index.build_index_matrix(x)
+        query = lambda qq: index.nn_batch(qq, k, return_device=True)
+    gq = torch.Generator(device=dev).manual_seed(7)
+    q = torch.rand((Q, D), device=dev, generator=gq)
+    q_host = q.cpu().pin_memory()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        r, d = query(q)
+    # parity: float64 brute force over ALL shards for 3 queries (each rank its rows, minima all-gathered)
+    worst = 0.0
+    for qi in (0, Q // 2, Q - 1):
+        acc = []
+        for s0 in range(0, rows, 2_000_000):
+            xs = x[s0:s0 + 2_000_000].double()
+            acc.append(((xs - q[qi].double()[None, :]) ** 2).sum(1).sqrt().topk(k, largest=False).values)
+            del xs
+        loc = torch.cat(acc).topk(k, largest=False).values
+        if world > 1:
+            allv = [torch.empty_like(loc) for _ in range(world)]
+            dist.all_gather(allv, loc)
+            loc = torch.cat(allv).topk(k, largest=False).values
+        err = float(((d[qi] - loc).abs() / loc.clamp(min=1e-30)).max())
+        worst = max(worst, err)
+        if err > 1e-9:
+            raise SystemExit("bench.py --config c3: PARITY FAILURE on query %d (max rel err %.3g)" % (qi, err))
+    _lib.profile_fetch()
+    _lib.profile_enable(True)
+    launches0 = _lib.launch_count()
+    ms = _timed_steps(torch, dist, world, lambda: query(q), args.steps, flush)
+    _lib.profile_enable(False)
+    launches = _lib.launch_count() - launches0
+    per = {}
+    for name, t in _lib.profile_fetch():
+        per[name] = per.get(name, 0.0) + t / args.steps
+
+    def host_step():
+        rr, dd = query(q_host.to(dev, non_blocking=True))
+        return rr.cpu(), dd.cpu()
+    host_step()
+    ms_e2e = _timed_steps(torch, dist, world, host_step, args.steps, flush)
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        filt = per.get("l2_filter_tma_kernel", 0.0)
+        flops = 2.0 * Q * rows * D
+        line = {
+            "metric": "exact flat L2 kNN queries/s @k=100, 12.5M x 128-d fp32 rows per GPU (BASELINE configs[2]: 100M rows on 8 B200)",
+            "value": Q * args.steps / (ms * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32 filter (rigorous margin) + fp32 error-free re-rank", "data": "synthetic",
+            "config": {"workload": "configs[2]: exact brute-force L2 kNN over %d x 128-d fp32 rows (%d per GPU x %d GPUs), "
+                                   "batch %d queries, k=100" % (rows * world, rows, world, Q),
+                       "rows_total": rows * world, "rows_per_gpu": rows, "dim": D, "k": k, "queries_per_step": Q,
+                       "parallelism": "rows sharded x%d, local exact top-k, one all-gather of (distance, row), merge" % world
+                                      if world > 1 else "single GPU",
+                       "l2": "L2 flushed between timed steps; table %.1f GB per GPU" % (rows * D * 4 / 1e9)},
+            "e2e": {"value": Q * args.steps / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4,
+                    "d2h_bytes_per_step": Q * k * 16, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "parity_checked": True, "parity": {"queries": [0, Q // 2, Q - 1], "max_rel_dist_err": worst,
+                                               "how": "float64 torch brute force over all shards, k-th distance profile, rtol 1e-9"},
+            "roofline": {"kernel": "l2_filter_tma_kernel", "bound": "tensor", "achieved": flops / (filt * 1e-3) / 1e12 if filt else None,
+                         "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None, "kernel_ms": filt,
+                         "algorithmic_flops_per_step": flops,
+                         "note": "single-pass TF32 filter: 2*Q*N*D flop per rank and step; no TF32 GEMM peak is measured on "
+                                 "this pool (MEASURED_PEAKS.json has bf16 only; TF32 is nominally half of it) -- see "
+                                 "profiles/ for the ncu tensor-pipe and DRAM figures of this kernel"},
+            "kernel_ms_per_step": per,
+        }
+        print(json.dumps(line))
+    _finish(torch, dist, world)
+
+
+def run_c5(args):
+    """BASELINE configs[4]: ItqFunctor.fit + index build throughput on 50M x 256-d descriptors (row-sharded over N GPUs)."""
+    torch, dist, world, rank, dev = _dist_setup()
+    from smqtk_indexing_b200 import engine
+    from smqtk_indexing_b200.impls.lsh_functor.itq import ItqFunctor
+    n_total, D, b = args.c5_rows, 256, args.bits
+    n = n_total // world
+    X = torch.empty((n, D), device=dev)
+    g = torch.Generator(device=dev).manual_seed(50 + rank)
+    for s0 in range(0, n, 4_000_000):
+        X[s0:s0 + 4_000_000].uniform_(generator=g)
+    torch.cuda.synchronize()
+
+    def step():
+        f = ItqFunctor(bit_length=b, itq_iterations=args.fit_iters, random_seed=0)
+        t0 = time.perf_counter()
+        f.fit_matrix(X, want_codes=False, group=dist.group.WORLD if world > 1 else None)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        m = engine.DeviceLshIndex()
+        m.set_rows(X, f.get_hash_packed(X))            # hash + sb_unique_codes of the local rows
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        return f, m, t1 - t0, t2 - t1
+    step()                                              # warm-up
+    fits, builds = [], []
+    for _ in range(max(1, min(args.steps, 3))):
+        f, m, tf, tb = step()
+        fits.append(tf)
+        builds.append(tb)
+    import numpy as np
+    r = np.asarray(f.rotation)
+    ortho = float(np.abs(r.T @ r - np.eye(b)).max())
+    t = torch.tensor([min(fits), min(builds)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        fit_s, build_s = float(t[0]), float(t[1])
+        line = {"metric": "ItqFunctor.fit + build_index descriptors/s on %dM x 256-d (BASELINE configs[4])" % (n_total // 10 ** 6),
+                "value": n_total / (fit_s + build_s), "unit": "descriptors/s", "n_gpus": world, "steps": len(fits), "warmup": 1,
+                "ms_per_step": 1e3 * (fit_s + build_s), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "fp64 covariance + tensor-core streaming ITQ iterations (3xTF32 sign step, fixed-point TF32 Gram)",
+                "data": "synthetic",
+                "config": {"workload": "configs[4]: ItqFunctor.fit (%d iterations, %d bits) + hash + unique table + CSR over %d x 256-d "
+                                       "fp32 descriptors" % (args.fit_iters, b, n_total), "rows": n_total, "rows_per_gpu": n,
+                           "parallelism": "rows sharded x%d: all-reduce of [D], [D,D], [b,D] partial sums in fit; every rank "
+                                          "indexes its own rows" % world if world > 1 else "single GPU"},
+                "fit_s": fit_s, "build_s": build_s, "fit_descriptors_per_s": n_total / fit_s, "build_descriptors_per_s": n_total / build_s,
+                "model_orthonormality_err": ortho, "parity_checked": ortho < 1e-8,
+                "e2e": {"value": n_total / (fit_s + build_s), "unit": "descriptors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "note": "training data is generated on the device (51 GB would not stream through PCIe per step); no host leg"}}
+        print(json.dumps(line))
+    _finish(torch, dist, world)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -448,6 +650,12 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
+    if args.config == "c4":      # BASELINE configs[3]: 1M x 4096-d L1-normalised histograms, hik re-rank, k = 50
+        args.rows, args.dim, args.bits, args.k = 1_000_000, 4096, 256, 50
+        args.queries = min(args.queries, 1024)
+        args.fit_rows = min(args.fit_rows, 20_000)
+        args.no_cpu_baseline = True      # the literal port's CPU leg is sized for configs[1]
+    METHOD = "hik" if args.config == "c4" else "euclidean"
     U, D, b, Q, k = args.rows, args.dim, args.bits, args.queries, args.k
     bounds = [U * r // world for r in range(world + 1)]
     n_local = bounds[rank + 1] - bounds[rank]
@@ -455,6 +663,9 @@ def run_b200(args):
     # ---- synthetic descriptors (shard generated on its GPU), model, index ----
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     x_local = torch.rand((n_local, D), generator=g, device=dev, dtype=torch.float32)
+    if METHOD == "hik":
+        for s0 in range(0, n_local, 100_000):
+            x_local[s0:s0 + 100_000] /= x_local[s0:s0 + 100_000].sum(dim=1, keepdim=True)
     functor = ItqFunctor(bit_length=b, itq_iterations=args.fit_iters, random_seed=0)
     t_fit0 = time.perf_counter()
     if world == 1:
@@ -474,7 +685,7 @@ def run_b200(args):
         from smqtk_indexing_b200.impls.hash_index.linear import LinearHashIndex
         from smqtk_indexing_b200.impls.nn_index.lsh import LSHNearestNeighborIndex
         index = LSHNearestNeighborIndex(functor, MemoryDescriptorSet(), MemoryKeyValueStore(), LinearHashIndex(),
-                                        distance_method="euclidean")
+                                        distance_method=METHOD)
         index.build_index_matrix(x_local)
         n_codes = index._mirror.num_codes
         scan_rows = n_codes
@@ -491,7 +702,7 @@ def run_b200(args):
         peers = None
     else:
         from smqtk_indexing_b200.distributed import ShardedLshIndex
-        index = ShardedLshIndex(functor, "euclidean", scan_partition=args.scan_partition, rerank=args.rerank,
+        index = ShardedLshIndex(functor, METHOD, scan_partition=args.scan_partition, rerank=args.rerank,
                                 graph=not args.no_graph)
         index.build(x_local)
         n_codes = index.num_codes
@@ -523,7 +734,10 @@ def run_b200(args):
 
     # ---- queries: identical on every rank, pinned on the host ----
     gq = torch.Generator().manual_seed(1)
-    q_host = torch.rand((Q, D), generator=gq, dtype=torch.float32).pin_memory()
+    q_host = torch.rand((Q, D), generator=gq, dtype=torch.float32)
+    if METHOD == "hik":
+        q_host /= q_host.sum(dim=1, keepdim=True)
+    q_host = q_host.pin_memory()
     q_dev = q_host.to(dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
@@ -563,7 +777,7 @@ def run_b200(args):
 
     # ---- parity, outside the timed region, at every N: 8 queries of the batch re-derived with plain torch ----
     parity = parity_check(torch, dist if world > 1 else None, functor, state, x_local, bounds[rank], q_dev, k,
-                          query_dev(q_dev))
+                          query_dev(q_dev), method=METHOD)
     barrier()
 
     gpu_id = "GPU-%s" % torch.cuda.get_device_properties(dev).uuid if hasattr(
@@ -676,16 +890,18 @@ def run_b200(args):
         rerank_line = None
         if rr_ms:
             rr_bytes = float(q_per_rank) * k * max(state.max_rows_per_code, 1) * D * 4
-            rerank_line = {"kernel": "rerank_kernel<euclidean>", "bound": "hbm", "kernel_ms": rr_ms,
+            rerank_line = {"kernel": "rerank_kernel<%s>" % METHOD, "bound": "hbm", "kernel_ms": rr_ms,
                            "candidate_slots_per_step": int(q_per_rank * k * max(state.max_rows_per_code, 1)),
                            "algorithmic_bytes_per_step": rr_bytes, "achieved_gbs": rr_bytes / (rr_ms * 1e-3) / 1e9,
                            "frac_of_peak": rr_bytes / (rr_ms * 1e-3) / 1e9 / peak, "peak": peak, "peak_source": peak_src,
-                           "note": "one warp per candidate row (random 2 KB gathers%s); %d slots x %d B in %.1f us -- "
-                                   "latency-bound at this size, see profiles/ for the C4 shape (1M x 4096-d, k=50)" % (
+                           "note": "one warp per candidate row (random row gathers%s); %d slots x %d B in %.1f us -- "
+                                   "latency-bound at the C2 size, see profiles/r2_rerank_c4_full.md for the C4 shape" % (
                                        ", peer rows over NVLink" if peers is not None else "",
                                        int(q_per_rank * k * max(state.max_rows_per_code, 1)), D * 4, rr_ms * 1e3)}
         line = {
-            "metric": METRIC, "value": Q * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
+            "metric": METRIC if args.config == "c2" else
+            "LSH kNN queries/s @k=50, 1M x 4096-d L1-normalised histograms, ITQ-256, histogram-intersection re-rank (BASELINE configs[3])",
+            "value": Q * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "fp8 (+-1, exact integer distances)" if tc else "u32", "data": "synthetic",
@@ -745,6 +961,9 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.config in ("c3", "c5") and not (args.gpus > 1 and "RANK" not in os.environ):
+        (run_c3 if args.config == "c3" else run_c5)(args)
         return
     if args.gpus > 1 and "RANK" not in os.environ:
         # convenience: re-launch under torchrun (the driver launches torchrun itself)
