@@ -16,12 +16,18 @@
 //     x.q - |x|^2/2 - h and "d2 <= tq" is a sign test.
 //   * Tile = 128 rows x 256 queries, accumulators double-buffered in TMEM (2 x 256 columns):
 //     the epilogue of tile t overlaps the MMAs of tile t+1.
+//   * Loop order (round 2): for super-chunk of rows { for query block { for tile } }.  With the query blocks
+//     outermost (round 1) every block's pass streamed the whole chunk from HBM again -- ncu: 60.6 GB of DRAM
+//     reads for a 3.75 GB chunk at 16 blocks, the kernel DRAM-bound at 55 % of peak.  A super-chunk of
+//     148 x 8 tiles (78 MB) stays in the 126 MB L2 while the 16 query blocks take their turn on it; the price
+//     is re-loading the 136 KB query block image (from L2) once per super-chunk and block.
 // Warp roles (12 warps): 0 TMA producer (A ring), 1 MMA issue + TMEM alloc, 2 B loader,
 // 3 synthetic-A writer, 4-11 epilogue (TMEM lane quadrant = (warp - 4) % 4, column half =
 // (warp - 4) / 4).  The epilogue is a chain of dependent integer ops per warp, so it wants warps:
 // it reads 32 accumulators per tcgen05.ld and ANDs their sign bits -- no survivor among the 32
 // (the common case), no per-element work.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -55,6 +61,8 @@ struct TmaL2Params {
   int cap;
   unsigned int row_base;
   int dense;                   // first chunk: every (row, query) pair is kept -> key stored at buf[query][row], no atomics
+  int sc;                      // tiles per CTA and super-chunk: ALL query blocks visit a super-chunk of the rows
+                               // (gridDim.x * sc tiles, sized to stay in L2) before the next one is touched
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -108,16 +116,17 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int jb = 0; jb < p.col_blocks; ++jb)
-        for (long long i = 0; i < my_tiles; ++i) {
-          const long long rt = blockIdx.x + i * gridDim.x;
-          for (int g = 0; g < G; ++g) {
-            mbar_wait(a_empty + stage * 8, phase ^ 1);
-            mbar_expect_tx(a_full + stage * 8, A_STAGE);
-            tma_tensor_2d_g2s(smem_u32(s_a + (size_t)stage * A_STAGE), &tmap, g * GK, (int)(rt * TM), a_full + stage * 8);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (long long i0 = 0; i0 < my_tiles; i0 += p.sc)
+        for (int jb = 0; jb < p.col_blocks; ++jb)
+          for (long long i = i0; i < min(i0 + (long long)p.sc, my_tiles); ++i) {
+            const long long rt = blockIdx.x + i * gridDim.x;
+            for (int g = 0; g < G; ++g) {
+              mbar_wait(a_empty + stage * 8, phase ^ 1);
+              mbar_expect_tx(a_full + stage * 8, A_STAGE);
+              tma_tensor_2d_g2s(smem_u32(s_a + (size_t)stage * A_STAGE), &tmap, g * GK, (int)(rt * TM), a_full + stage * 8);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
           }
-        }
     }
   } else if (warp == 1) {
     // =========================== MMA issue ===========================
@@ -132,10 +141,12 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
       int stage = 0;
       uint32_t phase = 0;
       long long t = 0;
-      for (int jb = 0; jb < p.col_blocks; ++jb) {
-        mbar_wait(b_full, jb & 1);
+      uint32_t seg = 0;                                          // (super-chunk, query block) segments = B loads so far
+      for (long long i0 = 0; i0 < my_tiles; i0 += p.sc)
+      for (int jb = 0; jb < p.col_blocks; ++jb, ++seg) {
+        mbar_wait(b_full, seg & 1u);
         tc_fence_after();
-        for (long long i = 0; i < my_tiles; ++i, ++t) {
+        for (long long i = i0; i < min(i0 + (long long)p.sc, my_tiles); ++i, ++t) {
           const int buf = (int)(t & 1);
           const uint32_t use = (uint32_t)((t >> 1) & 1);
           const uint32_t d_tmem = tmem_base + (uint32_t)(buf * QB);
@@ -165,8 +176,10 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
     // =========================== B: resident query block ===========================
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)G * B_GROUP;
-      for (int jb = 0; jb < p.col_blocks; ++jb) {
-        mbar_wait(b_empty, (jb & 1) ^ 1);
+      uint32_t seg = 0;
+      for (long long i0 = 0; i0 < my_tiles; i0 += p.sc)
+      for (int jb = 0; jb < p.col_blocks; ++jb, ++seg) {
+        mbar_wait(b_empty, (seg & 1u) ^ 1u);
         const unsigned char* src = p.image + (size_t)jb * (bytes + B_SYN);
         mbar_expect_tx(b_full, bytes + B_SYN);
         for (int g = 0; g < G; ++g) tma_bulk_g2s(smem_u32(s_b + (size_t)g * B_GROUP), src + (size_t)g * B_GROUP, B_GROUP, b_full);
@@ -177,8 +190,9 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
     // =========================== synthetic A: (-|x|^2/2 hi, lo, 1, 1) per row ===========================
     long long t = 0;
     const uint32_t one = __float_as_uint(1.0f);
+    for (long long i0 = 0; i0 < my_tiles; i0 += p.sc)
     for (int jb = 0; jb < p.col_blocks; ++jb)
-      for (long long i = 0; i < my_tiles; ++i, ++t) {
+      for (long long i = i0; i < min(i0 + (long long)p.sc, my_tiles); ++i, ++t) {
         const long long rt = blockIdx.x + i * gridDim.x;
         const int buf = (int)(t & 1);
         const uint32_t use = (uint32_t)((t >> 1) & 1);
@@ -213,13 +227,14 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
     unsigned long long* myq_key = sq_key + ewi * SQ_CAP;
     int* myq_q = sq_q + ewi * SQ_CAP;
     int* myq_cnt = sq_cnt + ewi;
+    for (long long i0 = 0; i0 < my_tiles; i0 += p.sc)
     for (int jb = 0; jb < p.col_blocks; ++jb) {
       // thresholds of this warp's columns, private copy (a survivor's d2 = tq - 2 * accumulator)
       __syncwarp();
       for (int c = lane; c < EPI_COLS; c += 32) my_tq[c] = __ldcg(p.tq + (long long)jb * QB + half * EPI_COLS + c);
       __syncwarp();
       const int q0 = jb * QB + half * EPI_COLS;
-      for (long long i = 0; i < my_tiles; ++i, ++t) {
+      for (long long i = i0; i < min(i0 + (long long)p.sc, my_tiles); ++i, ++t) {
         const long long rt = blockIdx.x + i * gridDim.x;
         const int buf = (int)(t & 1);
         const uint32_t use = (uint32_t)((t >> 1) & 1);
@@ -427,6 +442,14 @@ int tc_l2_filter_tma(const float* X, int64_t n, int32_t D, int64_t ldx, const vo
   const size_t smem_bytes = tma_smem_bytes(p.G);
   const long long row_tiles = (n + TM - 1) / TM;
   const int grid = (int)(row_tiles < sm_count() ? row_tiles : sm_count());
+  // super-chunk: grid * sc tiles of 128 rows x D floats must stay in L2 while every query block visits them
+  // (~80 MB of the 126 MB); one query block: order does not matter, no re-loads of its image
+  {
+    long long sc = (80ll << 20) / ((long long)grid * TM * D * (long long)sizeof(float));
+    if (const char* e = getenv("SB_L2_SUPERCHUNK_TILES")) sc = atoll(e);   // tuning knob (0 = query blocks outermost)
+    if (sc < 1 || col_blocks == 1) sc = 1ll << 40;
+    p.sc = (int)(sc > (1 << 30) ? (1 << 30) : sc);
+  }
   SB_CUDA_TRY(cudaFuncSetAttribute(l2_filter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   ProfScope prof("l2_filter_tc_kernel", st);
   l2_filter_tma_kernel<<<grid, THREADS, smem_bytes, st>>>(tmap, p);
