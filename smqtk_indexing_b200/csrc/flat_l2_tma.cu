@@ -22,7 +22,7 @@
 //     148 x 8 tiles (78 MB) stays in the 126 MB L2 while the 16 query blocks take their turn on it; the price
 //     is re-loading the 136 KB query block image (from L2) once per super-chunk and block.
 // Warp roles (12 warps): 0 TMA producer (A ring), 1 MMA issue + TMEM alloc, 2 B loader,
-// 3 synthetic-A writer, 4-11 epilogue (TMEM lane quadrant = (warp - 4) % 4, column half =
+// 3 synthetic-A writer, 4-19 epilogue (TMEM lane quadrant = (warp - 4) % 4, column quarter =
 // (warp - 4) / 4).  The epilogue is a chain of dependent integer ops per warp, so it wants warps:
 // it reads 32 accumulators per tcgen05.ld and ANDs their sign bits -- no survivor among the 32
 // (the common case), no per-element work.
@@ -45,8 +45,8 @@ constexpr int B_SYN = 2 * QB * 16;          // 8 KB  (no-swizzle, 2 K chunks)
 constexpr int A_SYN = 2 * TM * 16;          // 4 KB  (no-swizzle, 2 K chunks)
 constexpr int STAGES = 4;
 constexpr int SQ_CAP = 64;                  // survivor queue entries per epilogue warp and tile
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_COLS = QB / 2;            // columns per epilogue warp
+constexpr int EPI_WARPS = 16;               // 4 TMEM lane quadrants x 4 column quarters: tcgen05.wait::ld waits for all of a
+constexpr int EPI_COLS = QB / 4;            // thread's loads, so only more warps hide the tensor-memory latency (columns per warp)
 constexpr int THREADS = (4 + EPI_WARPS) * 32;   // 384
 
 struct TmaL2Params {
@@ -221,7 +221,7 @@ l2_filter_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaL2Params
     // =========================== epilogue: sign test, survivors appended ===========================
     const int ewi = warp - 4;                                    // epilogue warp index
     const int ew = ewi & 3;                                      // TMEM lane quadrant
-    const int half = ewi >> 2;                                   // which 128 of the 256 query columns
+    const int half = ewi >> 2;                                   // which EPI_COLS-wide part of the 256 query columns
     long long t = 0;
     float* my_tq = s_tq + ewi * EPI_COLS;
     unsigned long long* myq_key = sq_key + ewi * SQ_CAP;
