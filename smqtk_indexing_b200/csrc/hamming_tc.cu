@@ -71,9 +71,9 @@ struct HamTcParams {
   int col_blocks, cb_per;      // query blocks in total / per blockIdx.y
   const unsigned char* image;  // per block: G x B_GROUP (SW128) then B_SYN
   const int* tq;               // thresholds (Hamming distance) per query column
-  unsigned long long* recheck; // (row << 24 | 32-column group) entries
-  int* recheck_cnt;
-  int recheck_cap;
+  unsigned long long* recheck; // per 32-query group: rows with a survivor in the group, [group][recheck_cap]
+  int* recheck_cnt;            // entries per group
+  int recheck_cap;             // capacity of one group's list
   unsigned long long* cand_buf;
   int* cand_cnt;
   int cap;
@@ -117,25 +117,6 @@ __device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_
 // then recomputes each listed row against the group's 32 queries with XOR/POPC from the packed
 // codes -- one warp per entry, one query per lane, the whole GPU hiding the load latency that a
 // re-check inside the epilogue would expose.
-template <int W>
-__device__ __forceinline__ void ham_recheck_group(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qcodes, int Q,
-                                                  long long row, unsigned long long row_key, int qg0, const int* tq_grp,
-                                                  unsigned long long* cand_buf, int* cand_cnt, int cap, int lane) {
-  uint32_t x[W];
-#pragma unroll
-  for (int w = 0; w < W; ++w) x[w] = __ldg(db + row * W + w);
-  const int qg = qg0 + lane;
-  if (qg < Q) {
-    int d = 0;
-#pragma unroll
-    for (int w = 0; w < W; ++w) d += __popc(x[w] ^ __ldg(qcodes + (long long)qg * W + w));
-    if (d <= tq_grp[lane]) {
-      const int slot = atomicAdd(cand_cnt + qg, 1);
-      if (slot < cap) cand_buf[(long long)qg * cap + slot] = ((unsigned long long)(unsigned)d << 40) | row_key;
-    }
-  }
-}
-
 template <int G, int KSTEPS>
 __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -337,7 +318,6 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
         const long long vt = blockIdx.x + i * gridDim.x;
         const long long row = pg * GRAN + lane;
         const bool rvalid = (vg < p.vg1) && (row < p.U);
-        const long long row0 = pg * GRAN;                            // lane 0's row: the granule is contiguous
         vg += 4 * gridDim.x;
         pg += pg_step;
         if (pg >= p.NG) pg -= p.NG;
@@ -386,22 +366,23 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty + blk * 8);
           if (!p.dense) {
-            int total = 0;
+            unsigned any = 0u;
 #pragma unroll
-            for (int g32 = 0; g32 < QB / 32; ++g32) total += __popc(hit[g32]);
-            if (total) {                                               // rare: one atomic per (warp, tile, block) with survivors
-              int base = 0;
-              if (lane == 0) base = atomicAdd(p.recheck_cnt, total);
-              base = __shfl_sync(0xffffffffu, base, 0);
+            for (int g32 = 0; g32 < QB / 32; ++g32) any |= hit[g32];
+            if (any) {                                                 // rare: one atomic per (warp, tile, group) with survivors
 #pragma unroll
               for (int g32 = 0; g32 < QB / 32; ++g32) {
                 const unsigned m = hit[g32];
-                if ((m >> lane) & 1u) {
-                  const int slot = base + __popc(m & ((1u << lane) - 1u));
-                  if (slot < p.recheck_cap)
-                    p.recheck[slot] = ((unsigned long long)row << 24) | (unsigned long long)((q0 >> 5) + g32);
+                if (m) {                                               // warp-uniform (ballot result)
+                  const int grp = (q0 >> 5) + g32;
+                  int base = 0;
+                  if (lane == 0) base = atomicAdd(p.recheck_cnt + grp, __popc(m));
+                  base = __shfl_sync(0xffffffffu, base, 0);
+                  if ((m >> lane) & 1u) {
+                    const int slot = base + __popc(m & ((1u << lane) - 1u));
+                    if (slot < p.recheck_cap) p.recheck[(size_t)grp * p.recheck_cap + slot] = (unsigned long long)row;
+                  }
                 }
-                base += __popc(m);
               }
             }
           }
@@ -419,8 +400,11 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
   }
 }
 
-// One warp per re-check entry (row, 32-query group): exact distances from the packed codes, survivors
-// appended to their query's candidate buffer.
+// Re-check, one CTA column per 32-query group (blockIdx.x = group, blockIdx.y splits the group's list): every lane
+// keeps ITS query of the group in registers for the whole kernel, so an entry costs one 32-byte row read instead
+// of the row plus the group's 32 query codes (1 KB from L2 per entry with the unordered global list of round 1).
+// A warp takes 32 entries at a time: lane l loads entry l's row, then the 32 rows are broadcast one after the
+// other with shuffles and every lane tests its own query -- 32 independent loads in flight per warp.
 template <int W>
 __global__ void __launch_bounds__(256)
 ham_recheck_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qcodes, int Q, long long idx_base,
@@ -428,15 +412,49 @@ ham_recheck_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__
                    const int* __restrict__ tq, unsigned long long* __restrict__ cand_buf, int* __restrict__ cand_cnt, int cap,
                    int* __restrict__ overflow) {
   const int lane = threadIdx.x & 31;
-  const int raw = *list_cnt;
-  if (raw > list_cap && blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+  const int grp = blockIdx.x;
+  const int raw = list_cnt[grp];
+  if (raw > list_cap && blockIdx.y == 0 && threadIdx.x == 0) *overflow = 1;
   const int n = min(raw, list_cap);
-  const int warps = gridDim.x * (blockDim.x >> 5);
-  for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
-    const unsigned long long ent = list[e];
-    const long long row = (long long)(ent >> 24);
-    const int qg0 = (int)(ent & 0xffffffull) * 32;
-    ham_recheck_group<W>(db, qcodes, Q, row, (unsigned long long)(idx_base + row), qg0, tq + qg0, cand_buf, cand_cnt, cap, lane);
+  if (n == 0) return;
+  const int qg = grp * 32 + lane;
+  const bool qvalid = qg < Q;
+  uint32_t qw[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) qw[w] = qvalid ? __ldg(qcodes + (long long)qg * W + w) : 0u;
+  const int my_tq = qvalid ? tq[qg] : -1;
+  const unsigned long long* mine = list + (size_t)grp * list_cap;
+  const int warps = gridDim.y * (blockDim.x >> 5);
+  for (int e0 = (blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; e0 < n; e0 += warps * 32) {
+    const int cnt = min(32, n - e0);
+    long long row = 0;
+    uint32_t x[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) x[w] = 0u;
+    if (lane < cnt) {
+      row = (long long)mine[e0 + lane];
+      const uint32_t* src = db + row * W;
+      if (W >= 4) {
+#pragma unroll
+        for (int w = 0; w < W; w += 4) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + w));
+          x[w] = v.x; x[(w + 1) % W] = v.y; x[(w + 2) % W] = v.z; x[(w + 3) % W] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < W; ++w) x[w] = __ldg(src + w);
+      }
+    }
+    for (int i = 0; i < cnt; ++i) {
+      int d = 0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) d += __popc(__shfl_sync(0xffffffffu, x[w], i) ^ qw[w]);
+      const long long ri = __shfl_sync(0xffffffffu, row, i);
+      if (d <= my_tq) {
+        const int slot = atomicAdd(cand_cnt + qg, 1);
+        if (slot < cap) cand_buf[(long long)qg * cap + slot] = ((unsigned long long)(unsigned)d << 40) | (unsigned long long)(idx_base + ri);
+      }
+    }
   }
 }
 
@@ -488,8 +506,9 @@ __device__ __forceinline__ void write_threshold_slots(unsigned char* __restrict_
 __global__ void ham_init_kernel(int Q, int cols, int G, int K, int* __restrict__ tq, int* __restrict__ cnt,
                                 int* __restrict__ overflow, unsigned char* __restrict__ img, int* __restrict__ list_cnt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { *overflow = 0; *list_cnt = 0; }
+  if (i == 0) *overflow = 0;
   if (i >= cols) return;
+  if ((i & 31) == 0) list_cnt[i >> 5] = 0;                       // one re-check list per 32-query group
   tq[i] = K;
   cnt[i] = 0;
   write_threshold_slots(img, i, G, i < Q ? K + 1 : -512);
@@ -539,10 +558,10 @@ ham_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt, 
     cnt[qi] = keep;
     const int t = (keep >= k) ? (int)(s_key[k - 1] >> 40) : K;
     tq[qi] = t;
-    // the next chunk's threshold K step for this query, and an empty re-check list (this kernel runs after the
-    // re-check of the chunk: one launch per chunk less than a separate threshold-image kernel)
+    // the next chunk's threshold K step for this query, and an empty re-check list for its group (this kernel runs
+    // after the re-check of the chunk: one launch per chunk less than a separate threshold-image kernel)
     if (!final) write_threshold_slots(img, qi, G, 2 * min(t, K) - K + 1);
-    if (qi == 0) *list_cnt = 0;
+    if ((qi & 31) == 0) list_cnt[qi >> 5] = 0;
   }
   if (final)
     for (int i = tid; i < k; i += CP_THREADS) keys_out[(size_t)qi * k + i] = (i < keep) ? s_key[i] : ~0ull;
@@ -551,7 +570,7 @@ ham_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt, 
 struct HamTcPlan {
   int G, ksteps, K, col_blocks, cols, cap, first_rows, stages, growth;
   size_t block_bytes, smem_bytes;
-  size_t off_img, off_tq, off_cnt, off_flag, off_list, off_buf, total;
+  size_t off_img, off_tq, off_cnt, off_flag, off_gcnt, off_list, off_buf, total;
   int list_cap;
 };
 
@@ -586,9 +605,15 @@ HamTcPlan make_plan(int32_t W, int32_t Q, int32_t k) {
   p.off_img = o;  o += align256((size_t)p.col_blocks * p.block_bytes);
   p.off_tq = o;   o += align256((size_t)p.cols * sizeof(int));
   p.off_cnt = o;  o += align256((size_t)p.cols * sizeof(int));
-  p.off_flag = o; o += 256;                                   // [0] overflow flag, [1] re-check list length
-  p.list_cap = 1 << 22;
-  p.off_list = o; o += align256((size_t)p.list_cap * sizeof(unsigned long long));
+  p.off_flag = o; o += 256;                                   // [0] overflow flag
+  p.off_gcnt = o; o += align256((size_t)(p.cols / 32) * sizeof(int));   // re-check entries per 32-query group
+  // entries per group list: a chunk yields ~(growth - 1) * (k + ties) survivors per query, 32 queries per group
+  {
+    const long long need = 32ll * p.growth * (k + 32) * 4 / 3;
+    p.list_cap = 8192;
+    while (p.list_cap < need && p.list_cap < (1 << 16)) p.list_cap <<= 1;
+  }
+  p.off_list = o; o += align256((size_t)(p.cols / 32) * p.list_cap * sizeof(unsigned long long));
   p.off_buf = o;  o += align256((size_t)p.cols * p.cap * sizeof(unsigned long long));
   p.total = o;
   return p;
@@ -634,6 +659,7 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
   int* tq = reinterpret_cast<int*>(ws + p.off_tq);
   int* cnt = reinterpret_cast<int*>(ws + p.off_cnt);
   int* flag = reinterpret_cast<int*>(ws + p.off_flag);
+  int* gcnt = reinterpret_cast<int*>(ws + p.off_gcnt);
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(ws + p.off_buf);
   unsigned long long* list = reinterpret_cast<unsigned long long*>(ws + p.off_list);
 
@@ -645,7 +671,7 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
     sb::count_launch();
     if (int rc = sb::check_launch("ham_query_image_kernel")) return rc;
   }
-  ham_init_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.G, p.K, tq, cnt, flag, img, flag + 1);
+  ham_init_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.G, p.K, tq, cnt, flag, img, gcnt);
   sb::count_launch();
   if (int rc = sb::check_launch("ham_init_kernel")) return rc;
 
@@ -674,7 +700,7 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
     const int dense = (done == 0) ? 1 : 0;
     HamTcParams hp;
     hp.db = db; hp.U = U; hp.W = W; hp.G = p.G; hp.ksteps = p.ksteps; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
-    hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.recheck = list; hp.recheck_cnt = flag + 1; hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
+    hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.recheck = list; hp.recheck_cnt = gcnt; hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
     hp.idx_base = idx_base; hp.dense = dense; hp.stages = p.stages;
     const long long n_tiles = (len + 3) / 4;
     const int gx = (int)(n_tiles < sms ? n_tiles : sms);
@@ -692,11 +718,16 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
     }
     if (!dense) {
       sb::ProfScope prof("ham_recheck_kernel", st);
-      const int blocks = 8 * sms;                               // 64 warps per SM: the re-check is load-latency bound
-      if (W == 8) ham_recheck_kernel<8><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
-      else if (W == 4) ham_recheck_kernel<4><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
-      else if (W == 2) ham_recheck_kernel<2><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
-      else ham_recheck_kernel<1><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
+      // one CTA column per 32-query group, split so that the grid fills the GPU about four times over
+      const int groups = (Q + 31) / 32;
+      int split = (4 * sms + groups - 1) / groups;
+      if (split < 1) split = 1;
+      if (split > 32) split = 32;
+      const dim3 blocks((unsigned)groups, (unsigned)split);
+      if (W == 8) ham_recheck_kernel<8><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
+      else if (W == 4) ham_recheck_kernel<4><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
+      else if (W == 2) ham_recheck_kernel<2><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
+      else ham_recheck_kernel<1><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
       sb::count_launch();
       if (int rc = sb::check_launch("ham_recheck_kernel")) return rc;
     }
@@ -705,7 +736,7 @@ int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W, const uint32_t*
     sb::ProfScope prof("ham_compact_kernel", st);
     ham_compact_kernel<<<Q, CP_THREADS, p.cap * sizeof(unsigned long long), st>>>(
         buf, cnt, p.cap, k, p.K, tq, flag, final, reinterpret_cast<unsigned long long*>(keys_out),
-        dense ? (int)(len * GRAN) : -1, img, p.G, flag + 1);
+        dense ? (int)(len * GRAN) : -1, img, p.G, gcnt);
     sb::count_launch();
     if (int rc = sb::check_launch("ham_compact_kernel")) return rc;
   }

@@ -238,6 +238,7 @@ class ShardedLshIndex:
             return ent(q)
         seen = (ent or 0) + 1
         if seen >= self.GRAPH_AFTER and self._fixed_pitch(Q, n):
+            engine.evict_graphs(self._graphs, engine.DeviceLshIndex.MAX_GRAPHS - 1)
             self._graphs[key] = g = engine.GraphedCall(lambda qq: self._query(qq, n), q.contiguous())
             return g(q)
         self._graphs[key] = seen
@@ -285,6 +286,7 @@ class ShardedLshIndex:
             return ent(q_mine)[0][:Q]
         seen = (ent or 0) + 1
         if seen >= self.GRAPH_AFTER:
+            engine.evict_graphs(self._graphs, engine.DeviceLshIndex.MAX_GRAPHS - 1)
             self._graphs[key] = g = engine.GraphedCall(lambda qq: (self._slice_pipeline(qq, n),), q_mine.contiguous())
             return g(q_mine)[0][:Q]
         self._graphs[key] = seen

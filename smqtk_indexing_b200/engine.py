@@ -81,6 +81,16 @@ class GraphedCall:
         return tuple(o.cpu() for o in self.static_out)
 
 
+def evict_graphs(graphs: dict, keep: int) -> None:
+    """Drop the oldest captured graphs (and stale shape counters) so that at most ``keep`` graphs remain."""
+    captured = [k for k, v in graphs.items() if isinstance(v, GraphedCall)]
+    for k in captured[:max(0, len(captured) - keep)]:
+        del graphs[k]
+    if len(graphs) > 64:                                   # shape counters of one-off batch sizes
+        for k in [k for k, v in graphs.items() if not isinstance(v, GraphedCall)][:len(graphs) - 64]:
+            del graphs[k]
+
+
 def expand_candidates(code_rows: torch.Tensor, csr_off: torch.Tensor, csr_rows: torch.Tensor):
     """Ragged expansion ``near codes -> descriptor rows`` on the device.
 
@@ -284,6 +294,8 @@ class DeviceLshIndex:
 
     #: capture the pipeline of a (Q, n) shape into a CUDA graph once it has been asked for this often
     GRAPH_AFTER = 2
+    #: captured shapes kept per index (each holds its workspaces: ~0.3 GB at 4096 queries); oldest evicted
+    MAX_GRAPHS = 4
 
     def query_graphed(self, functor, q: torch.Tensor, n: int, distance_method: str, to_host: bool = False):
         """``query`` through a per-shape CUDA graph (captured on the ``GRAPH_AFTER``-th batch of the
@@ -305,6 +317,7 @@ class DeviceLshIndex:
             q = q.to(self.x.device, non_blocking=True)
         seen = (ent or 0) + 1
         if seen >= self.GRAPH_AFTER:
+            evict_graphs(self._graphs, self.MAX_GRAPHS - 1)
             self._graphs[key] = g = GraphedCall(lambda qq: self.query(functor, qq, n, distance_method), q)
             out = g(q)
         else:
