@@ -369,19 +369,21 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_tc_kernel(const HamTcPa
             unsigned any = 0u;
 #pragma unroll
             for (int g32 = 0; g32 < QB / 32; ++g32) any |= hit[g32];
-            if (any) {                                                 // rare: one atomic per (warp, tile, group) with survivors
+            if (any) {                                                 // rare: survivors in this (warp, tile, block)
+              // one slot reservation per group WITH survivors, all issued at once: lane g reserves for group g
+              // (serial atomics would cost a global round trip each while the next tile's accumulator waits)
+              int mine_cnt = 0;
+#pragma unroll
+              for (int g32 = 0; g32 < QB / 32; ++g32) mine_cnt = (lane == g32) ? __popc(hit[g32]) : mine_cnt;
+              int mine_base = 0;
+              if (lane < QB / 32 && mine_cnt) mine_base = atomicAdd(p.recheck_cnt + (q0 >> 5) + lane, mine_cnt);
 #pragma unroll
               for (int g32 = 0; g32 < QB / 32; ++g32) {
                 const unsigned m = hit[g32];
-                if (m) {                                               // warp-uniform (ballot result)
-                  const int grp = (q0 >> 5) + g32;
-                  int base = 0;
-                  if (lane == 0) base = atomicAdd(p.recheck_cnt + grp, __popc(m));
-                  base = __shfl_sync(0xffffffffu, base, 0);
-                  if ((m >> lane) & 1u) {
-                    const int slot = base + __popc(m & ((1u << lane) - 1u));
-                    if (slot < p.recheck_cap) p.recheck[(size_t)grp * p.recheck_cap + slot] = (unsigned long long)row;
-                  }
+                const int base = __shfl_sync(0xffffffffu, mine_base, g32);
+                if ((m >> lane) & 1u) {
+                  const int slot = base + __popc(m & ((1u << lane) - 1u));
+                  if (slot < p.recheck_cap) p.recheck[(size_t)((q0 >> 5) + g32) * p.recheck_cap + slot] = (unsigned long long)row;
                 }
               }
             }
