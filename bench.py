@@ -116,6 +116,35 @@ def measure_fp8_gemm(dev):
         return None
 
 
+def measure_fp4_gemm(dev):
+    """cuBLASLt MXFP4 (E2M1 x E2M1, UE8M0 scale per 32 elements -> BF16) GEMM, 8192^3, best of 10 with CUDA
+    events: the tensor-pipe denominator of the packed-FP4 scan.  None when this torch / cuBLASLt build has no
+    such GEMM (the caller then uses 2 x the measured FP8 figure and says so)."""
+    import torch
+    try:
+        n = 8192
+        a = torch.randint(0, 256, (n, n // 2), device=dev, dtype=torch.uint8).view(torch.float4_e2m1fn_x2)
+        b = torch.randint(0, 256, (n, n // 2), device=dev, dtype=torch.uint8).view(torch.float4_e2m1fn_x2).t()
+        sc = torch.full((n * (n // 32),), 127, device=dev, dtype=torch.uint8).view(torch.float8_e8m0fnu)   # 2^0 everywhere
+        for _ in range(3):
+            torch._scaled_mm(a, b, scale_a=sc, scale_b=sc, out_dtype=torch.bfloat16)
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._scaled_mm(a, b, scale_a=sc, scale_b=sc, out_dtype=torch.bfloat16)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception as e:                   # pragma: no cover - depends on the torch build
+        sys.stderr.write("fp4 GEMM measurement unavailable: %r\n" % (e,))
+        return None
+
+
+TC4_QUERIES_PER_COLUMN = 2     # hamming_tc4.cu: queries per FP32 accumulator column
+
+
 def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -827,6 +856,9 @@ def run_b200(args):
     ms_dev, ms_e2e, ms_eager = float(t[0]), float(t[1]), float(t[2])
 
     fp8_meas = measure_fp8_gemm(dev) if rank == 0 else None
+    from smqtk_indexing_b200 import device as _devmod
+    scan_fmt = _devmod.TC_SCAN_FORMAT
+    fp4_meas = measure_fp4_gemm(dev) if (rank == 0 and scan_fmt == "fp4") else None
     if rank == 0:
         W = (b + 31) // 32
         per_kernel = {}
@@ -838,31 +870,51 @@ def run_b200(args):
         q_per_rank = (Q + world - 1) // world if (world > 1 and index._by_queries(Q)) else Q
         tc = per_kernel.get("ham_filter_tc_kernel", [])
         if tc:
-            # batched path: +-1 FP8 dot products on tcgen05 (hamming_tc.cu); several launches per step (chunks)
+            # batched path: +-1 dot products on tcgen05; several launches per step (chunks).  Default: packed FP4
+            # operands, TC4_QUERIES_PER_COLUMN queries per FP32 accumulator column (hamming_tc4.cu); SB_TC_SCAN_FORMAT=fp8: E4M3
+            # operands, FP16 accumulators (hamming_tc.cu)
             scan_ms = sum(tc) / args.steps
             alg_flops = 2.0 * q_per_rank * scan_rows * (32 * W)           # this rank's share of 2*Q*U*b
             achieved = alg_flops / (scan_ms * 1e-3) / 1e12
             proxy, proxy_src = fp8_peak()
-            tpeak, tpeak_src = (fp8_meas, "cuBLASLt FP8 E4M3 GEMM 8192^3 (torch._scaled_mm), best of 10, timed in this run") \
-                if fp8_meas else (proxy, proxy_src)
+            if scan_fmt == "fp4":
+                nominal = 9000.0
+                if fp4_meas:
+                    tpeak, tpeak_src = fp4_meas, "cuBLASLt MXFP4 GEMM 8192^3 (torch._scaled_mm), best of 10, timed in this run"
+                elif fp8_meas:
+                    tpeak, tpeak_src = 2.0 * fp8_meas, ("2 x the cuBLASLt FP8 E4M3 GEMM 8192^3 timed in this run (no MXFP4 GEMM in "
+                                                        "this torch build; kind::mxf4 issues at twice the f8f6f4 rate)")
+                else:
+                    tpeak, tpeak_src = 2.0 * proxy, "2 x (" + proxy_src + ")"
+            else:
+                nominal = 4500.0
+                tpeak, tpeak_src = (fp8_meas, "cuBLASLt FP8 E4M3 GEMM 8192^3 (torch._scaled_mm), best of 10, timed in this run") \
+                    if fp8_meas else (proxy, proxy_src)
             traffic = recorded_traffic("scan_tc_traffic.json")
+            # tensor-memory read floor: every (row, query) accumulator leaves TMEM through tcgen05.ld at 64 B/clk/SM
+            # (B300_MICROARCH.md "LDTM throughput"); bytes per pair = 4 / TC4_QUERIES_PER_COLUMN (FP4) or 2 (FP8)
+            tmem_bpp = (4.0 / TC4_QUERIES_PER_COLUMN) if scan_fmt == "fp4" else 2.0
+            sm_hz = (clocks.get("sm_mhz") or 1800.0) * 1e6
+            tmem_floor_ms = float(q_per_rank) * scan_rows * tmem_bpp / (64.0 * 148 * sm_hz) * 1e3
             roofline = {
-                "kernel": "ham_filter_tc_kernel", "bound": "tensor",
+                "kernel": "ham_filter_tc_kernel (%s operands)" % scan_fmt, "bound": "tensor",
                 "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s", "frac": achieved / tpeak,
                 "traffic": traffic.get("dram_bytes_per_step") if traffic else None,
                 "traffic_source": "profiles/scan_tc_traffic.json (ncu dram__bytes_read+write of one batch, N=1 shape)"
                                   if traffic else None,
                 "peak_source": tpeak_src,
                 "frac_of_2x_measured_bf16": achieved / proxy, "proxy_peak": proxy,
-                "nominal_fp8_peak": 4500.0, "frac_of_nominal": achieved / 4500.0,
+                "nominal_peak": nominal, "frac_of_nominal": achieved / nominal,
+                "tmem_read_floor_ms": tmem_floor_ms, "frac_of_tmem_read_floor": tmem_floor_ms / scan_ms,
                 "algorithmic_flops_per_step": alg_flops, "launches_per_step": len(tc) / args.steps,
                 "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / ms_step_eager,
                 "note": "per rank.  algorithmic flops = 2*Q*U*b: one multiply-add per (query, code, bit) of this rank's share; "
-                        "the kernel issues b+32 per pair (the threshold rides in one extra K step).  Durations come from "
-                        "the kernel-by-kernel pass (region B, %.3f ms/step); the reported value is the graph-replayed "
+                        "the kernel issues b+64 (fp4) / b+32 (fp8) per pair (the threshold rides in one extra K step).  Durations "
+                        "come from the kernel-by-kernel pass (region B, %.3f ms/step); the reported value is the graph-replayed "
                         "pass (region A).  A +-1 operand GEMM draws less power than cuBLAS's random-data GEMM and holds a "
-                        "higher clock, so frac can exceed 1 against a measured GEMM peak; frac_of_nominal uses the 4.5 "
-                        "PFLOP/s datasheet figure.  Equivalent algorithmic bytes (Q*U*b/8 per step): %.1f TB/s." % (
+                        "higher clock, so frac can exceed 1 against a measured GEMM peak; frac_of_nominal uses the datasheet "
+                        "figure.  The second ceiling is the tensor-memory read path (tmem_read_floor_ms at the sampled SM "
+                        "clock).  Equivalent algorithmic bytes (Q*U*b/8 per step): %.1f TB/s." % (
                             ms_step_eager, float(q_per_rank) * scan_rows * W * 4 / (scan_ms * 1e-3) / 1e12),
             }
             int_pipe = None
@@ -904,7 +956,7 @@ def run_b200(args):
             "value": Q * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "fp8 (+-1, exact integer distances)" if tc else "u32", "data": "synthetic",
+            "dtype": ("%s (+-1 operands, exact integer distances)" % scan_fmt) if tc else "u32", "data": "synthetic",
             "config": workload_config(args, world, parallelism),
             "clocks": clocks,
             "e2e": {"value": Q * args.steps / (ms_e2e * 1e-3), "unit": "queries/s",
@@ -924,7 +976,7 @@ def run_b200(args):
             "roofline": roofline,
             "rerank": rerank_line,
             "int_pipe": int_pipe,
-            "fp8_gemm_tflops_measured": fp8_meas,
+            "fp8_gemm_tflops_measured": fp8_meas, "fp4_gemm_tflops_measured": fp4_meas,
             "single_query_scan": {
                 "what": "sb_hamming_scan with Q=1 (LinearHashIndex.nn call shape): HBM-bound, whole table",
                 "kernel_ms": statistics.median(prof1) if prof1 else None,

@@ -12,15 +12,23 @@
 //     memory; the whole 16-column SF window is filled with 0x7F in every lane with tcgen05.st once per CTA, so
 //     the (sub-partition replicated) SF layout never matters.  Instruction descriptor: a/b format = 1
 //     (MXF4Format::E2M1; 5 is the kind::mxf8f6f4 code and raises "illegal instruction"), scale format UE8M0.
-//   * Accumulators are FP32 only, and the SF window needs columns too: query blocks are 240 columns
-//     (accumulator 0 = TMEM columns [0, 240), SF window [240, 256), accumulator 1 = [256, 496)).
+//   * Accumulators are FP32 only, and reading 4 bytes per (row, query) pair out of tensor memory would set the
+//     pace (measured: profiles/r2_ham_fp4_full.md).  So every accumulator column carries TWO queries:
+//         acc = t_a + 4096 * t_b,   t = 2 * (tq - d) + 1  (odd, |t| <= 513),
+//     the second query's MMAs use a second scale-factor window that holds 2^12 instead of 2^0 (uniform per MMA, so
+//     the SF layout still does not matter).  2 bytes per pair again, like the FP8 kernel's packed halves.  Decoding:
+//     t_b > 0 <=> acc > 0 (|t_a| < 2048), t_a > 0 <=> bit 11 of the mantissa of acc + (1.5 * 2^23 + 2048) -- one
+//     FADD and two LOP3 per accumulator.
+//   * TMEM: accumulator 0 = columns [0, C), C <= 224; scale factors 2^0 in [224, 240), 2^12 in [240, 256);
+//     accumulator 1 = [256, 256 + C).  A block = C columns = 2 C queries: query jb * 2C + h * C + n sits in column n
+//     as the a (h = 0) or b (h = 1) operand.
 //   * Bit -> nibble expansion is two instructions per 8 elements: out = ((w << s) & 0x88888888) | 0x22222222
 //     for s = 3, 2, 1, 0 takes every 4th bit of a code word as the sign of 8 consecutive elements.  This permutes
 //     the elements inside a row, identically for table rows and query rows -- a dot product does not care.
-//   * The threshold still rides in one extra K step: A_syn = 64 x (+1), B_syn = up to 44 E2M1 slots (values 6, 4,
-//     3, 2, 1) that sum to 2 * tq - K + 1; "d <= tq" stays a sign test on the accumulator.
-//   * Survivor groups are 32 columns of a 240-column block: the re-check list stores the group's first query in
-//     units of 16 (240 = 15 * 16) and a flag for the last, half-width group of a block.
+//   * The threshold still rides in extra K steps (one per query of the column): A_syn = 64 x (+1), B_syn = up to 44
+//     E2M1 slots (values 6, 4, 3, 2, 1) that sum to 2 * tq - K + 1.
+//   * Survivor groups are 32 columns = 32 a-queries and 32 b-queries, flagged separately; the re-check list stores
+//     (row, first query of the group / 16).
 // Warp roles: 0-15 epilogue (lane quadrant x query block x column half), 16 MMA issue + TMEM alloc, 17 B loader,
 // 18-25 producers (half a table row per thread and tile).
 #include <cuda_fp16.h>
@@ -35,12 +43,14 @@ using namespace tcptx;
 namespace {
 
 constexpr int TM = 128;                     // rows per tile (UMMA M)
-constexpr int QB = 224;                     // most query columns per block (UMMA N): 2 FP32 accumulators + SF columns <= 512
+constexpr int QB = 224;                     // most columns per block (UMMA N): 2 FP32 accumulators + 2 SF windows <= 512
 constexpr int A_GROUP = TM * 128;           // 16 KB: 128 rows x 256 E2M1 (8 code words)
 // one query block in shared memory: qb rows x 128 B (SWIZZLE_128B) + B_syn 2 x qb x 16 B (no swizzle), rounded up
 // to the 1024-byte swizzle atom -- 38 KB at qb = 240; two of them (the next block streams in during the current pass)
 constexpr int A_SYN = 2 * TM * 16;          // 4 KB
-constexpr int SF_COL = 240;                 // TMEM columns [240, 256): scale factors (all 2^0)
+constexpr int SF_COL = 224;                 // TMEM columns [224, 240): scale factors 2^0 (SFA at +0, SFB at +8)
+constexpr int SF12_COL = 240;               // TMEM columns [240, 256): scale factors 2^12 (SFB of the b-query MMAs)
+constexpr float DECODE_MAGIC = 12582912.0f + 2048.0f;   // 1.5 * 2^23 + 2048: acc + this has (t_a + 2048) in its low 12 mantissa bits
 constexpr int ACC1_COL = 256;               // second accumulator
 constexpr int MAX_STAGES = 4;
 constexpr int NB = 2;                       // (kept from hamming_tc.cu; unused: one block is resident, its successor streams in)
@@ -66,7 +76,7 @@ struct HamTc4Params {
   const unsigned char* image;  // per block: G x B_GROUP (SW128) then B_SYN
   const int* tq;               // thresholds (Hamming distance) per query column
   unsigned long long* recheck; // (row << 24 | (group width - 1) << 19 | first query of the group / 16) entries
-  int qb, b_block;             // query columns per block (multiple of 16, <= 240), bytes of one block image
+  int qb, b_block;             // columns per block (multiple of 32, <= 224; 2 * qb queries), bytes of one block image
   int* recheck_cnt;
   int recheck_cap;
   unsigned long long* cand_buf;
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int KSTEPS = (W >= 2) ? W / 2 : 1;                    // 64 elements = 2 code words per MMA
   constexpr uint32_t a_stage = (uint32_t)A_GROUP;
-  const int qb = p.qb;                                           // query columns per block (multiple of 16, <= 240)
+  const int qb = p.qb;                                           // columns per block (multiple of 32, <= 224): 2 * qb queries
   const uint32_t b_block = (uint32_t)p.b_block;                  // bytes of one block image (data rows + B_syn), 1024-aligned
   // layout (offsets are multiples of 1024): [B buffer 0][B buffer 1][A_syn][A ring][barriers, thresholds]
   unsigned char* s_b = smem;
@@ -151,7 +161,6 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
   const uint32_t acc_full = a_empty + MAX_STAGES * 8, acc_empty = acc_full + 16;
   const uint32_t b_full = acc_empty + 16, b_empty = b_full + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 8);
-  int* s_tq = reinterpret_cast<int*>(bars + 2 * MAX_STAGES + 10);  // [16 warps][128]: thresholds of the warp's columns
 
   const long long n_gran = p.vg1 - p.vg0;
   const long long n_tiles = (n_gran + 3) / 4;
@@ -185,12 +194,14 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // every UE8M0 block scale = 2^0: 0x7F in every byte of every lane of the SF window (whatever layout the MMA reads)
+  // UE8M0 block scales, uniform per window (whatever layout the MMA reads): 2^0 = 0x7F in every byte of every lane
+  // of columns [224, 240), 2^12 = 0x8B in [240, 256)
   if (warp < 4) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
+    for (int c = 0; c < 32; ++c) {
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(SF_COL + c);
-      asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(0x7F7F7F7Fu) : "memory");
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(c < 16 ? 0x7F7F7F7Fu : 0x8B8B8B8Bu)
+                   : "memory");
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
@@ -217,6 +228,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
       // format UE8M0 (bit 23), M at 24, scale-factor ids 0, K = 64 (bit 31 = 0); accumulator FP32
       const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(qb >> 3) << 17) | (1u << 23) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t tsfa = tmem_base + (uint32_t)SF_COL, tsfb = tmem_base + (uint32_t)(SF_COL + 8);
+      const uint32_t tsfb12 = tmem_base + (uint32_t)SF12_COL;    // the b-queries' products are scaled by 2^12
       const uint64_t asyn_desc = umma_desc(smem_u32(s_asyn), TM * 16, 128);
       const uint64_t a_desc0 = umma_desc_sw128(smem_u32(s_a));
       int stage = 0, it = 0;
@@ -226,8 +238,12 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
         const int sb = it & 1;
         mbar_wait(b_full + sb * 8, (it >> 1) & 1);
         tc_fence_after();
-        const uint64_t b_desc = umma_desc_sw128(smem_u32(s_b) + sb * b_block);
-        const uint64_t bsyn_desc = umma_desc(smem_u32(s_b) + sb * b_block + (uint32_t)qb * 128u, (uint32_t)qb * 16u, 128);
+        // block image: [qb rows x 128 B a-queries][qb x 128 B b-queries][B_syn a: 2 x qb x 16 B][B_syn b]
+        const uint32_t bb = smem_u32(s_b) + sb * b_block;
+        const uint64_t b_desc = umma_desc_sw128(bb);
+        const uint64_t b2_desc = umma_desc_sw128(bb + (uint32_t)qb * 128u);
+        const uint64_t bsyn_desc = umma_desc(bb + (uint32_t)qb * 256u, (uint32_t)qb * 16u, 128);
+        const uint64_t bsyn2_desc = umma_desc(bb + (uint32_t)qb * 288u, (uint32_t)qb * 16u, 128);
         for (long long i = 0; i < my_tiles; ++i, ++t) {
           const int buf = (int)(t & 1);
           mbar_wait(a_full + stage * 8, phase);
@@ -239,7 +255,11 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
           for (int ks = 0; ks < KSTEPS; ++ks)
             umma_fp4(d_tmem, a_desc + (uint64_t)((ks * 32) >> 4), b_desc + (uint64_t)((ks * 32) >> 4), idesc, ks ? 1u : 0u, tsfa,
                      tsfb);
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks)
+            umma_fp4(d_tmem, a_desc + (uint64_t)((ks * 32) >> 4), b2_desc + (uint64_t)((ks * 32) >> 4), idesc, 1u, tsfa, tsfb12);
           umma_fp4(d_tmem, asyn_desc, bsyn_desc, idesc, 1u, tsfa, tsfb);
+          umma_fp4(d_tmem, asyn_desc, bsyn2_desc, idesc, 1u, tsfa, tsfb12);
           umma_commit(acc_full + buf * 8);
           umma_commit(a_empty + stage * 8);
           if (++stage == MAX_STAGES) { stage = 0; phase ^= 1; }
@@ -325,7 +345,6 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
     const int col0 = (warp >> 3) * 128;                          // this warp's columns: [0, 128) or [128, qb)
     constexpr int GRP = 4;                                       // 32-column survivor groups per warp
     const int ngrp = max(0, min(GRP, (qb - col0) >> 5));         // qb is a multiple of 32: whole groups only
-    int* my_tq = s_tq + warp * 128;
     const long long vg_base = p.vg0 + (long long)blockIdx.x * 4 + ew;
     const long long vg_step2 = 8ll * gridDim.x;                  // this warp sees every second tile
     const unsigned long long NGu = (unsigned long long)p.NG;
@@ -333,10 +352,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
     const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * ACC1_COL + col0);
     long long t0 = 0;                                            // global tile counter at the start of this block's pass
     for (int jb = jb0; jb < jb1; ++jb, t0 += my_tiles) {
-      const int q0 = jb * qb + col0;                             // first query of this warp's columns
-      __syncwarp();
-      for (int c = lane; c < 128; c += 32) my_tq[c] = (col0 + c < qb) ? __ldcg(p.tq + q0 + c) : 0;
-      __syncwarp();
+      const int qa0 = jb * 2 * qb + col0;                        // first a-query of this warp's columns; b-queries: + qb
       const long long i_first = ((t0 & 1) == buf) ? 0 : 1;       // first tile of this pass that lands in this warp's buffer
       long long vg = vg_base + i_first * 4 * (long long)gridDim.x;
       long long pg = (long long)(((unsigned long long)vg * (unsigned long long)p.P) % NGu);
@@ -347,22 +363,29 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
         mbar_wait(acc_full + buf * 8, par);
         par ^= 1u;
         tc_fence_after();
-        unsigned hit[GRP];                                         // lanes with a survivor in each 32-column group
+        unsigned hit_a[GRP], hit_b[GRP];                           // lanes with a surviving a- / b-query in each 32-column group
         if (!p.dense) {
 #pragma unroll
           for (int g = 0; g < GRP; ++g) {
-            hit[g] = 0u;
+            hit_a[g] = 0u;
+            hit_b[g] = 0u;
             if (g < ngrp) {                                        // warp-uniform
               uint32_t va[32];
               tmem_ld32_nowait(tbase + (uint32_t)(32 * g), va);
               tmem_ld_wait();
-              // the common case (no survivor among 32 pairs) is an AND tree over the sign bits: 8 independent
-              // 4-input terms, then a 3-level combine (a dependent chain of 32 ANDs costs ~150 cycles of latency)
-              uint32_t r[8];
+              // acc = t_a + 4096 t_b.  b survives <=> acc > 0 (sign bit clear): AND tree over the sign bits.
+              // a survives <=> bit 11 of the mantissa of acc + DECODE_MAGIC: OR tree over those words.
+              uint32_t sa[8], ob[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) r[j] = va[4 * j] & va[4 * j + 1] & va[4 * j + 2] & va[4 * j + 3];
-              const uint32_t a = (r[0] & r[1] & r[2]) & (r[3] & r[4] & r[5]) & (r[6] & r[7]);
-              hit[g] = __ballot_sync(0xffffffffu, rvalid && (a & 0x80000000u) == 0u);
+              for (int j = 0; j < 8; ++j) {
+                sa[j] = va[4 * j] & va[4 * j + 1] & va[4 * j + 2] & va[4 * j + 3];
+                ob[j] = __float_as_uint(__uint_as_float(va[4 * j]) + DECODE_MAGIC) | __float_as_uint(__uint_as_float(va[4 * j + 1]) + DECODE_MAGIC) |
+                        __float_as_uint(__uint_as_float(va[4 * j + 2]) + DECODE_MAGIC) | __float_as_uint(__uint_as_float(va[4 * j + 3]) + DECODE_MAGIC);
+              }
+              const uint32_t s_all = (sa[0] & sa[1] & sa[2]) & (sa[3] & sa[4] & sa[5]) & (sa[6] & sa[7]);
+              const uint32_t o_all = (ob[0] | ob[1] | ob[2]) | (ob[3] | ob[4] | ob[5]) | (ob[6] | ob[7]);
+              hit_b[g] = __ballot_sync(0xffffffffu, rvalid && (s_all & 0x80000000u) == 0u);
+              hit_a[g] = __ballot_sync(0xffffffffu, rvalid && (o_all & 0x800u) != 0u);
             }
           }
         } else {
@@ -377,9 +400,13 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int c = 32 * g + j;
-              const int d = my_tq[c] - (int)(__uint_as_float(va[j]) * 0.5f);
-              p.cand_buf[(long long)(q0 + c) * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)d << 40) | row_key) : ~0ull;
+              // mantissa of acc + magic = (t_a + 2048) + 4096 * (t_b + 1024)
+              const uint32_t mant = __float_as_uint(__uint_as_float(va[j]) + DECODE_MAGIC) & 0x7fffffu;
+              const int ta = (int)(mant & 4095u) - 2048, tb = (int)(mant >> 12) - 1024;
+              const int qa = qa0 + 32 * g + j, qbq = qa + qb;
+              const int da = __ldg(p.tq + qa) - (ta - 1) / 2, db = __ldg(p.tq + qbq) - (tb - 1) / 2;
+              p.cand_buf[(long long)qa * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)da << 40) | row_key) : ~0ull;
+              p.cand_buf[(long long)qbq * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)db << 40) | row_key) : ~0ull;
             }
           }
         }
@@ -388,20 +415,25 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + buf * 8);
         if (!p.dense) {
-          const int total = __popc(hit[0]) + __popc(hit[1]) + __popc(hit[2]) + __popc(hit[3]);
+          int total = 0;
+#pragma unroll
+          for (int g = 0; g < GRP; ++g) total += __popc(hit_a[g]) + __popc(hit_b[g]);
           if (total) {                                               // rare: one atomic per (warp, tile) with survivors
             int base = 0;
             if (lane == 0) base = atomicAdd(p.recheck_cnt, total);
             base = __shfl_sync(0xffffffffu, base, 0);
 #pragma unroll
             for (int g = 0; g < GRP; ++g) {
-              const unsigned m = hit[g];
-              if ((m >> lane) & 1u) {
-                const int slot = base + __popc(m & ((1u << lane) - 1u));
-                if (slot < p.recheck_cap)
-                  p.recheck[slot] = ((unsigned long long)row << 24) | (31ull << 19) | (unsigned long long)((q0 + 32 * g) >> 4);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const unsigned m = h ? hit_b[g] : hit_a[g];
+                if ((m >> lane) & 1u) {
+                  const int slot = base + __popc(m & ((1u << lane) - 1u));
+                  if (slot < p.recheck_cap)
+                    p.recheck[slot] = ((unsigned long long)row << 24) | (31ull << 19) | (unsigned long long)((qa0 + h * qb + 32 * g) >> 4);
+                }
+                base += __popc(m);
               }
-              base += __popc(m);
             }
           }
         }
@@ -442,26 +474,28 @@ ham4_recheck_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict_
   }
 }
 
-// Query codes -> per-block image: [qb rows x 128 B] in the SWIZZLE_128B K-major order (same bit -> nibble expansion
-// as the table rows), then the block's B_syn; columns past Q and K chunks past the code are zero (the image is
-// cleared first).  One thread per (column, word).
+// Query codes -> per-block image: [qb rows x 128 B] of a-queries then [qb rows x 128 B] of b-queries, both in the
+// SWIZZLE_128B K-major order (same bit -> nibble expansion as the table rows), then the two B_syn areas; query slots
+// past Q and K chunks past the code are zero (the image is cleared first).  One thread per (query, word).
 __global__ void ham4_query_image_kernel(const uint32_t* __restrict__ q, int Q, int W, int qb, int b_block,
                                         unsigned char* __restrict__ img) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Q * W) return;
-  const int col = (int)(i / W), j = (int)(i % W);
-  const int jb = col / qb, n = col % qb;
-  *reinterpret_cast<uint4*>(img + (size_t)jb * b_block + sw128_off(n, j)) = expand_word4(q[(long long)col * W + j]);
+  const int qi = (int)(i / W), j = (int)(i % W);
+  const int jb = qi / (2 * qb), r = qi % (2 * qb);
+  const int h = r / qb, n = r % qb;
+  *reinterpret_cast<uint4*>(img + (size_t)jb * b_block + (size_t)h * qb * 128 + sw128_off(n, j)) = expand_word4(q[(long long)qi * W + j]);
 }
 
-// B_syn of every block: up to 64 E2M1 slots per column that sum to s = 2 * tq - K + 1 (|s| <= 257: at most 42 slots of
-// 6 plus two for the remainder); padding columns get -258 (their data nibbles are zero: the accumulator is negative).
+// B_syn of every query slot: up to 64 E2M1 slots that sum to s = 2 * tq - K + 1 (|s| <= 257: at most 42 slots of 6 plus
+// two for the remainder); padding slots get -258 (their data nibbles are zero: that query's term is negative).
 __global__ void ham4_threshold_image_kernel(int Q, int cols, int K, int qb, int b_block, const int* __restrict__ tq,
                                             unsigned char* __restrict__ img, int* __restrict__ list_cnt) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;        // query slot
   if (col == 0) *list_cnt = 0;                                   // the re-check list restarts with every chunk
   if (col >= cols) return;
-  const int jb = col / qb, n = col % qb;
+  const int jb = col / (2 * qb), r = col % (2 * qb);
+  const int h = r / qb, n = r % qb;
   const int s = (col < Q) ? (2 * min(tq[col], K) - K + 1) : -258;
   const uint32_t sign = s < 0 ? 0x8u : 0u;
   const int mag = s < 0 ? -s : s;
@@ -483,7 +517,7 @@ __global__ void ham4_threshold_image_kernel(int Q, int cols, int K, int qb, int 
     }
     words[wd] = v;
   }
-  unsigned char* base = img + (size_t)jb * b_block + (size_t)qb * 128;
+  unsigned char* base = img + (size_t)jb * b_block + (size_t)qb * 256 + (size_t)h * qb * 32;
   *reinterpret_cast<uint4*>(base + n * 16) = make_uint4(words[0], words[1], words[2], words[3]);
   *reinterpret_cast<uint4*>(base + qb * 16 + n * 16) = make_uint4(words[4], words[5], words[6], words[7]);
 }
@@ -568,21 +602,20 @@ int growth_for(int Q) {
 HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
   HamTc4Plan p;
   p.K = 32 * W;
-  // equal blocks of at most 224 columns, a multiple of 32 (whole 32-column survivor groups; the scale factors
-  // sit in TMEM columns [240, 256) between the two accumulators): 4096 queries -> 19 x 224, 512 -> 3 x 192
-  const int nblk = (Q + QB - 1) / QB;
-  p.qb = ((Q + nblk - 1) / nblk + 31) / 32 * 32;
-  p.col_blocks = (Q + p.qb - 1) / p.qb;
-  p.cols = p.col_blocks * p.qb;
-  p.b_block = (p.qb * 160 + 1023) / 1024 * 1024;               // qb rows x 128 B + B_syn (2 x qb x 16 B)
+  // equal blocks of at most 224 columns = 448 queries, columns a multiple of 32 (whole 32-column survivor groups):
+  // 4096 queries -> 10 blocks of 208 columns, 512 -> 2 blocks of 128
+  const int nblk = (Q + 2 * QB - 1) / (2 * QB);
+  p.qb = ((Q + 2 * nblk - 1) / (2 * nblk) + 31) / 32 * 32;
+  p.col_blocks = (Q + 2 * p.qb - 1) / (2 * p.qb);
+  p.cols = p.col_blocks * 2 * p.qb;                            // query slots
+  p.b_block = (p.qb * 320 + 1023) / 1024 * 1024;               // 2 x (qb rows x 128 B) + 2 x B_syn (2 x qb x 16 B)
   p.cap = 4096;
   p.growth = growth_for(Q);
   while (p.cap < 4 * (p.growth + 1) * k) p.cap <<= 1;
   p.first_rows = Q <= SMALL_Q ? 1024 : 256;                    // dense seed chunk: at least 8 k rows (its sort costs Q * rows)
   while (p.first_rows < 8 * k) p.first_rows <<= 1;
   if (p.first_rows > p.cap) p.first_rows = p.cap;
-  p.smem_bytes = 1024 + (size_t)2 * p.b_block + A_SYN + (size_t)MAX_STAGES * A_GROUP + (2 * MAX_STAGES + 10) * 8 +
-                 EPI_WARPS * 128 * sizeof(int);
+  p.smem_bytes = 1024 + (size_t)2 * p.b_block + A_SYN + (size_t)MAX_STAGES * A_GROUP + (2 * MAX_STAGES + 10) * 8;
   size_t o = 0;
   p.off_img = o;  o += align256((size_t)p.col_blocks * p.b_block);
   p.off_tq = o;   o += align256((size_t)p.cols * sizeof(int));

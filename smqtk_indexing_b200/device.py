@@ -219,10 +219,11 @@ def hamming_scan_tc_supported(U: int, W: int, Q: int, k: int) -> bool:
     return bool(_lib.load().sb_hamming_scan_tc_supported(U, W, Q, k))
 
 
-#: operand format of the tensor-core scan: "fp8" (E4M3, kind::f8f6f4, FP16 accumulators read packed: the
-#: default) or "fp4" (packed E2M1, kind::mxf4: half the tensor-pipe time per MMA, but FP32-only accumulators
-#: double the tensor-memory read of the epilogue, which then binds -- measured slower); same keys
-TC_SCAN_FORMAT = os.environ.get("SB_TC_SCAN_FORMAT", "fp8")
+#: operand format of the tensor-core scan: "fp4" (packed E2M1, kind::mxf4: half the tensor-pipe time per MMA;
+#: several queries share one FP32 accumulator column so the tensor-memory read of the epilogue does not grow --
+#: the default) or "fp8" (E4M3, kind::f8f6f4, FP16 accumulators read packed); same keys.  Shapes
+#: the FP4 kernel does not take (k > 256) run the FP8 kernel
+TC_SCAN_FORMAT = os.environ.get("SB_TC_SCAN_FORMAT", "fp4")
 
 
 def hamming_scan_keys_tc(db: torch.Tensor, q: torch.Tensor, k: int, idx_base: int = 0, fmt: Optional[str] = None):
