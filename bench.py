@@ -117,15 +117,16 @@ def measure_fp8_gemm(dev):
 
 
 def measure_fp4_gemm(dev):
-    """cuBLASLt MXFP4 (E2M1 x E2M1, UE8M0 scale per 32 elements -> BF16) GEMM, 8192^3, best of 10 with CUDA
-    events: the tensor-pipe denominator of the packed-FP4 scan.  None when this torch / cuBLASLt build has no
-    such GEMM (the caller then uses 2 x the measured FP8 figure and says so)."""
+    """cuBLASLt block-scaled FP4 (E2M1 x E2M1, one E4M3 scale per 16 elements -> BF16: the FP4 GEMM this torch
+    build exposes; it issues at the same tensor-pipe rate as the kernel's kind::mxf4) GEMM, 8192^3, best of 10
+    with CUDA events: the tensor-pipe denominator of the packed-FP4 scan.  None when the library call is
+    unavailable (the caller then uses 2 x the measured FP8 figure and says so)."""
     import torch
     try:
         n = 8192
         a = torch.randint(0, 256, (n, n // 2), device=dev, dtype=torch.uint8).view(torch.float4_e2m1fn_x2)
         b = torch.randint(0, 256, (n, n // 2), device=dev, dtype=torch.uint8).view(torch.float4_e2m1fn_x2).t()
-        sc = torch.full((n * (n // 32),), 127, device=dev, dtype=torch.uint8).view(torch.float8_e8m0fnu)   # 2^0 everywhere
+        sc = torch.full((n * (n // 16),), 0x38, device=dev, dtype=torch.uint8).view(torch.float8_e4m3fn)   # 1.0 everywhere
         for _ in range(3):
             torch._scaled_mm(a, b, scale_a=sc, scale_b=sc, out_dtype=torch.bfloat16)
         best = float("inf")
@@ -880,7 +881,7 @@ def run_b200(args):
             if scan_fmt == "fp4":
                 nominal = 9000.0
                 if fp4_meas:
-                    tpeak, tpeak_src = fp4_meas, "cuBLASLt MXFP4 GEMM 8192^3 (torch._scaled_mm), best of 10, timed in this run"
+                    tpeak, tpeak_src = fp4_meas, "cuBLASLt block-scaled FP4 (E2M1, 1x16 E4M3 scales) GEMM 8192^3 (torch._scaled_mm), best of 10, timed in this run"
                 elif fp8_meas:
                     tpeak, tpeak_src = 2.0 * fp8_meas, ("2 x the cuBLASLt FP8 E4M3 GEMM 8192^3 timed in this run (no MXFP4 GEMM in "
                                                         "this torch build; kind::mxf4 issues at twice the f8f6f4 rate)")
