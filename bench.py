@@ -143,7 +143,7 @@ def measure_fp4_gemm(dev):
         return None
 
 
-TC4_QUERIES_PER_COLUMN = 2     # hamming_tc4.cu: queries per FP32 accumulator column
+TC4_QUERIES_PER_COLUMN = 3     # hamming_tc4.cu: queries per FP32 accumulator column
 
 
 def hbm_peak():

@@ -12,22 +12,34 @@
 //     memory; the whole 16-column SF window is filled with 0x7F in every lane with tcgen05.st once per CTA, so
 //     the (sub-partition replicated) SF layout never matters.  Instruction descriptor: a/b format = 1
 //     (MXF4Format::E2M1; 5 is the kind::mxf8f6f4 code and raises "illegal instruction"), scale format UE8M0.
-//   * Accumulators are FP32 only, and reading 4 bytes per (row, query) pair out of tensor memory would set the
-//     pace (measured: profiles/r2_ham_fp4_full.md).  So every accumulator column carries TWO queries:
-//         acc = t_a + 4096 * t_b,   t = 2 * (tq - d) + 1  (odd, |t| <= 513),
-//     the second query's MMAs use a second scale-factor window that holds 2^12 instead of 2^0 (uniform per MMA, so
-//     the SF layout still does not matter).  2 bytes per pair again, like the FP8 kernel's packed halves.  Decoding:
-//     t_b > 0 <=> acc > 0 (|t_a| < 2048), t_a > 0 <=> bit 11 of the mantissa of acc + (1.5 * 2^23 + 2048) -- one
-//     FADD and two LOP3 per accumulator.
-//   * TMEM: accumulator 0 = columns [0, C), C <= 224; scale factors 2^0 in [224, 240), 2^12 in [240, 256);
-//     accumulator 1 = [256, 256 + C).  A block = C columns = 2 C queries: query jb * 2C + h * C + n sits in column n
-//     as the a (h = 0) or b (h = 1) operand.
-//   * Bit -> nibble expansion is two instructions per 8 elements: out = ((w << s) & 0x88888888) | 0x22222222
+//   * Accumulators are FP32 only, and every accumulator leaves tensor memory through tcgen05.ld at 64 B/clk/SM:
+//     with one query per column that read sets the pace (measured: profiles/r2_ham_fp4_full.md).  So every
+//     accumulator column carries THREE queries in 8-bit fields (all 24 bits of an FP32 integer):
+//         X = u_a + 256 w_b + 65536 u_c,      acc = X - 2^23,
+//         u_a = tq_a - d_a + beta,  w_b = d_b - tq_b + gamma,  u_c = tq_c - d_c + beta
+//     with T = the largest threshold of the batch (thresholds only tighten, so the value after the seed chunk
+//     stays an upper bound), beta = (254 - T) & ~1 and gamma = T + 1: "d <= tq" is u >= beta / w <= gamma, the
+//     same constants for every column.  Query operands are +-0.5 (a dot product is K/2 - d; the b query has its
+//     signs inverted), the b and c MMAs use scale-factor windows holding 2^8 and 2^16 (uniform per MMA, so the SF
+//     layout still does not matter), and the thresholds ride in one extra K step per field.  4/3 bytes per pair.
+//     Decoding: v = bits(acc +rz 1.5 * 2^24) = 0x4B800000 | (X >> 1); VIMNMX3.U16x2 keeps a running min of v << 1
+//     (low half [w_b : u_a >> 1], high half [exponent : u_c]) and a running max of v << 9 (low half [u_a >> 1],
+//     high half [u_c : w_b]) over a row's 32 columns: 4 instructions per accumulator, three compares per group.
+//     A field can leave its window only for a distance far above the threshold (d > 254 - (T - tq)); the fields
+//     are oriented so that this can only ADD survivors (the exact re-check drops them): u_a < 0 borrows from w_b
+//     (smaller = more likely to pass), w_b > 255 carries into u_c (larger = more likely to pass), and u_c < 0 drops
+//     the exponent of v, which the high half of the running min sees -- the row is then re-checked for the whole
+//     group.  T > 252 (no room for the windows) raises the overflow flag: the caller re-runs the XOR/POPC scan.
+//   * TMEM: accumulator 0 = columns [0, C), C <= 192; scale factors in [224, 256): 2^0 (SFA at 224, SFB at 232),
+//     2^8 at 240, 2^16 at 248; accumulator 1 = [256, 256 + C).  A block = C columns = 3 C queries: query
+//     jb * 3C + h * C + n sits in column n as field h.
+//   * The seed chunk (every pair kept) is a plain XOR/POPC kernel: it is a few hundred rows.
+//   * Bit -> nibble expansion is two instructions per 8 elements (rows: +-1.0; queries: ^ 0x33333333 -> +-0.5):
+//     out = ((w << s) & 0x88888888) | 0x22222222
 //     for s = 3, 2, 1, 0 takes every 4th bit of a code word as the sign of 8 consecutive elements.  This permutes
 //     the elements inside a row, identically for table rows and query rows -- a dot product does not care.
-//   * The threshold still rides in extra K steps (one per query of the column): A_syn = 64 x (+1), B_syn = up to 44
-//     E2M1 slots (values 6, 4, 3, 2, 1) that sum to 2 * tq - K + 1.
-//   * Survivor groups are 32 columns = 32 a-queries and 32 b-queries, flagged separately; the re-check list stores
+//   * Threshold steps: A_syn = 64 x (+1), B_syn = up to 64 E2M1 slots (values 6, 4, 3, 2, 1) summing to the field's offset.
+//   * Survivor groups are 32 columns = 32 queries of each field, flagged separately; the re-check list stores
 //     (row, first query of the group / 16).
 // Warp roles: 0-15 epilogue (lane quadrant x query block x column half), 16 MMA issue + TMEM alloc, 17 B loader,
 // 18-25 producers (half a table row per thread and tile).
@@ -43,17 +55,19 @@ using namespace tcptx;
 namespace {
 
 constexpr int TM = 128;                     // rows per tile (UMMA M)
-constexpr int QB = 224;                     // most columns per block (UMMA N): 2 FP32 accumulators + 2 SF windows <= 512
+constexpr int QB = 192;                     // most columns per block (UMMA N): two block images of 480 B per column in shared memory
+constexpr int QPC = 3;                      // queries per accumulator column
 constexpr int A_GROUP = TM * 128;           // 16 KB: 128 rows x 256 E2M1 (8 code words)
 // one query block in shared memory: qb rows x 128 B (SWIZZLE_128B) + B_syn 2 x qb x 16 B (no swizzle), rounded up
 // to the 1024-byte swizzle atom -- 38 KB at qb = 240; two of them (the next block streams in during the current pass)
 constexpr int A_SYN = 2 * TM * 16;          // 4 KB
 constexpr int SF_COL = 224;                 // TMEM columns [224, 240): scale factors 2^0 (SFA at +0, SFB at +8)
-constexpr int SF12_COL = 240;               // TMEM columns [240, 256): scale factors 2^12 (SFB of the b-query MMAs)
-constexpr float DECODE_MAGIC = 12582912.0f + 2048.0f;   // 1.5 * 2^23 + 2048: acc + this has (t_a + 2048) in its low 12 mantissa bits
+constexpr int SF8_COL = 240;                // [240, 248): 2^8 (SFB of the b-field MMAs)
+constexpr int SF16_COL = 248;               // [248, 256): 2^16 (SFB of the c-field MMAs)
+constexpr float DECODE_MAGIC = 25165824.0f; // 1.5 * 2^24: bits(acc +rz this) = 0x4B800000 | ((acc + 2^23) >> 1)
+constexpr int T_MAX = 252;                  // largest threshold the 8-bit windows take
 constexpr int ACC1_COL = 256;               // second accumulator
-constexpr int MAX_STAGES = 4;
-constexpr int NB = 2;                       // (kept from hamming_tc.cu; unused: one block is resident, its successor streams in)
+constexpr int MAX_STAGES = 2;                 // 16 KB each; a tile is 15 MMAs (~1500 cycles) and the producers prefetch in registers
 constexpr int GRAN = 32;                    // rows per granule of the visiting order
 // 16 epilogue warps: (TMEM lane quadrant) x (accumulator buffer = tile parity) x (column half).  tcgen05.wait::ld
 // waits for ALL of a thread's loads, so tensor-memory latency can only be hidden by other warps -- with FP32
@@ -74,16 +88,16 @@ struct HamTc4Params {
   long long NG, P;             // physical granule = (virtual * P) mod NG
   int col_blocks, cb_per;      // query blocks in total / per blockIdx.y
   const unsigned char* image;  // per block: G x B_GROUP (SW128) then B_SYN
-  const int* tq;               // thresholds (Hamming distance) per query column
+  const int* tq;               // thresholds (Hamming distance) per query slot
+  const int* tqmax;            // T: upper bound of the thresholds (device scalar)
   unsigned long long* recheck; // (row << 24 | (group width - 1) << 19 | first query of the group / 16) entries
-  int qb, b_block;             // columns per block (multiple of 32, <= 224; 2 * qb queries), bytes of one block image
+  int qb, b_block;             // columns per block (multiple of 32, <= 192; 3 * qb queries), bytes of one block image
   int* recheck_cnt;
   int recheck_cap;
   unsigned long long* cand_buf;
   int* cand_cnt;
   int cap;
   long long idx_base;
-  int dense;                   // first chunk: every pair is kept -> key stored at buf[query][virtual row]
   int stages;
 };
 
@@ -137,12 +151,10 @@ __device__ __forceinline__ void ham4_recheck_group(const uint32_t* __restrict__ 
   }
 }
 
-// W = code words per row (1, 2, 4, 8); W / 2 MMAs of K = 64 elements per tile (+ the threshold step).
-// ONE query block (qb <= 240 columns) is resident at a time and the accumulator is DOUBLE-BUFFERED over tiles:
-// the MMAs of tile i + 1 run while the 8 epilogue warps of the other buffer still read tile i.  (With one
-// accumulator per block the critical path per tile was MMA + epilogue latency, ~2000 cycles for 650 cycles of
-// MMA work; the expansion of a table tile is two instructions per 8 elements here, so re-expanding it for every
-// query block is cheap and the table stays L2 / HBM resident: 18 passes x 320 MB per 4096-query batch.)
+// W = code words per row (1, 2, 4, 8); 3 x (W / 2 MMAs of K = 64 elements + the threshold step) per tile.
+// ONE query block is resident at a time, its successor streams into the second buffer.  The expansion of a table
+// tile is two instructions per 8 elements, so re-expanding it for every query block is cheap and the table stays
+// L2 / HBM resident.
 template <int W>
 __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -150,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int KSTEPS = (W >= 2) ? W / 2 : 1;                    // 64 elements = 2 code words per MMA
   constexpr uint32_t a_stage = (uint32_t)A_GROUP;
-  const int qb = p.qb;                                           // columns per block (multiple of 32, <= 224): 2 * qb queries
+  const int qb = p.qb;                                           // columns per block (multiple of 32, <= 192): 3 * qb queries
   const uint32_t b_block = (uint32_t)p.b_block;                  // bytes of one block image (data rows + B_syn), 1024-aligned
   // layout (offsets are multiples of 1024): [B buffer 0][B buffer 1][A_syn][A ring][barriers, thresholds]
   unsigned char* s_b = smem;
@@ -195,12 +207,12 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // UE8M0 block scales, uniform per window (whatever layout the MMA reads): 2^0 = 0x7F in every byte of every lane
-  // of columns [224, 240), 2^12 = 0x8B in [240, 256)
+  // of columns [224, 240), 2^8 = 0x87 in [240, 248), 2^16 = 0x8F in [248, 256)
   if (warp < 4) {
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(SF_COL + c);
-      asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(c < 16 ? 0x7F7F7F7Fu : 0x8B8B8B8Bu)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(c < 16 ? 0x7F7F7F7Fu : (c < 24 ? 0x87878787u : 0x8F8F8F8Fu))
                    : "memory");
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -228,7 +240,8 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
       // format UE8M0 (bit 23), M at 24, scale-factor ids 0, K = 64 (bit 31 = 0); accumulator FP32
       const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(qb >> 3) << 17) | (1u << 23) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t tsfa = tmem_base + (uint32_t)SF_COL, tsfb = tmem_base + (uint32_t)(SF_COL + 8);
-      const uint32_t tsfb12 = tmem_base + (uint32_t)SF12_COL;    // the b-queries' products are scaled by 2^12
+      const uint32_t tsfb8 = tmem_base + (uint32_t)SF8_COL;      // the b field's products are scaled by 2^8,
+      const uint32_t tsfb16 = tmem_base + (uint32_t)SF16_COL;    // the c field's by 2^16
       const uint64_t asyn_desc = umma_desc(smem_u32(s_asyn), TM * 16, 128);
       const uint64_t a_desc0 = umma_desc_sw128(smem_u32(s_a));
       int stage = 0, it = 0;
@@ -238,12 +251,14 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
         const int sb = it & 1;
         mbar_wait(b_full + sb * 8, (it >> 1) & 1);
         tc_fence_after();
-        // block image: [qb rows x 128 B a-queries][qb x 128 B b-queries][B_syn a: 2 x qb x 16 B][B_syn b]
+        // block image: 3 x [qb rows x 128 B] (fields a, b, c), then 3 x B_syn [2 x qb x 16 B]
         const uint32_t bb = smem_u32(s_b) + sb * b_block;
-        const uint64_t b_desc = umma_desc_sw128(bb);
-        const uint64_t b2_desc = umma_desc_sw128(bb + (uint32_t)qb * 128u);
-        const uint64_t bsyn_desc = umma_desc(bb + (uint32_t)qb * 256u, (uint32_t)qb * 16u, 128);
-        const uint64_t bsyn2_desc = umma_desc(bb + (uint32_t)qb * 288u, (uint32_t)qb * 16u, 128);
+        uint64_t b_desc[QPC], bsyn_desc[QPC];
+#pragma unroll
+        for (int h = 0; h < QPC; ++h) {
+          b_desc[h] = umma_desc_sw128(bb + (uint32_t)(h * qb) * 128u);
+          bsyn_desc[h] = umma_desc(bb + (uint32_t)qb * (128u * QPC) + (uint32_t)(h * qb) * 32u, (uint32_t)qb * 16u, 128);
+        }
         for (long long i = 0; i < my_tiles; ++i, ++t) {
           const int buf = (int)(t & 1);
           mbar_wait(a_full + stage * 8, phase);
@@ -252,14 +267,14 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
           const uint64_t a_desc = a_desc0 + (uint64_t)(((uint32_t)stage * a_stage) >> 4);
           const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC1_COL);
 #pragma unroll
-          for (int ks = 0; ks < KSTEPS; ++ks)
-            umma_fp4(d_tmem, a_desc + (uint64_t)((ks * 32) >> 4), b_desc + (uint64_t)((ks * 32) >> 4), idesc, ks ? 1u : 0u, tsfa,
-                     tsfb);
+          for (int h = 0; h < QPC; ++h) {
+            const uint32_t sfb = h == 0 ? tsfb : (h == 1 ? tsfb8 : tsfb16);
 #pragma unroll
-          for (int ks = 0; ks < KSTEPS; ++ks)
-            umma_fp4(d_tmem, a_desc + (uint64_t)((ks * 32) >> 4), b2_desc + (uint64_t)((ks * 32) >> 4), idesc, 1u, tsfa, tsfb12);
-          umma_fp4(d_tmem, asyn_desc, bsyn_desc, idesc, 1u, tsfa, tsfb);
-          umma_fp4(d_tmem, asyn_desc, bsyn2_desc, idesc, 1u, tsfa, tsfb12);
+            for (int ks = 0; ks < KSTEPS; ++ks)
+              umma_fp4(d_tmem, a_desc + (uint64_t)((ks * 32) >> 4), b_desc[h] + (uint64_t)((ks * 32) >> 4), idesc, (h | ks) ? 1u : 0u,
+                       tsfa, sfb);
+            umma_fp4(d_tmem, asyn_desc, bsyn_desc[h], idesc, 1u, tsfa, sfb);
+          }
           umma_commit(acc_full + buf * 8);
           umma_commit(a_empty + stage * 8);
           if (++stage == MAX_STAGES) { stage = 0; phase ^= 1; }
@@ -339,20 +354,27 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
       }
     }
   } else if (warp < EPI_WARPS) {
-    // =========================== epilogue: sign test, survivors queued ===========================
+    // =========================== epilogue: window tests, survivors queued ===========================
     const int ew = warp & 3;                                     // TMEM lane quadrant = granule of the tile
     const int buf = (warp >> 2) & 1;                             // accumulator buffer: this warp takes the tiles t = buf (mod 2)
-    const int col0 = (warp >> 3) * 128;                          // this warp's columns: [0, 128) or [128, qb)
-    constexpr int GRP = 4;                                       // 32-column survivor groups per warp
-    const int ngrp = max(0, min(GRP, (qb - col0) >> 5));         // qb is a multiple of 32: whole groups only
+    constexpr int GRP = 3;                                       // most 32-column survivor groups per warp (qb <= 192)
+    const int split = ((qb + 63) >> 6) << 5;                     // columns of the first half (whole groups)
+    const int col0 = (warp >> 3) * split;                        // this warp's columns: [0, split) or [split, qb)
+    const int ngrp = ((warp >> 3) ? (qb - split) : split) >> 5;
     const long long vg_base = p.vg0 + (long long)blockIdx.x * 4 + ew;
     const long long vg_step2 = 8ll * gridDim.x;                  // this warp sees every second tile
     const unsigned long long NGu = (unsigned long long)p.NG;
     const long long pg_step2 = (long long)(((unsigned long long)vg_step2 * (unsigned long long)p.P) % NGu);
     const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * ACC1_COL + col0);
+    // window constants of this batch (see the header): d <= tq  <=>  u_a >= beta, w_b <= gamma, u_c >= beta
+    const int T = min(__ldg(p.tqmax), T_MAX);
+    const uint32_t beta = (uint32_t)((254 - T) & ~1), gamma = (uint32_t)(T + 1);
+    const uint32_t a_min = (beta >> 1) << 9;                     // low half of max(v << 9) = (u_a >> 1) << 9
+    const uint32_t c_min = beta << 8;                            // high half of max(v << 9) = [u_c : w_b]
+    const uint32_t b_lim = (gamma + 1u) << 8;                    // low half of min(v << 1) = [w_b : u_a >> 1 : 0]
     long long t0 = 0;                                            // global tile counter at the start of this block's pass
     for (int jb = jb0; jb < jb1; ++jb, t0 += my_tiles) {
-      const int qa0 = jb * 2 * qb + col0;                        // first a-query of this warp's columns; b-queries: + qb
+      const int q0 = jb * QPC * qb + col0;                       // first a-field query of this warp's columns; field h: + h * qb
       const long long i_first = ((t0 & 1) == buf) ? 0 : 1;       // first tile of this pass that lands in this warp's buffer
       long long vg = vg_base + i_first * 4 * (long long)gridDim.x;
       long long pg = (long long)(((unsigned long long)vg * (unsigned long long)p.P) % NGu);
@@ -363,77 +385,53 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
         mbar_wait(acc_full + buf * 8, par);
         par ^= 1u;
         tc_fence_after();
-        unsigned hit_a[GRP], hit_b[GRP];                           // lanes with a surviving a- / b-query in each 32-column group
-        if (!p.dense) {
+        unsigned hit[GRP][QPC];                                    // lanes with a surviving query of field h in each 32-column group
 #pragma unroll
-          for (int g = 0; g < GRP; ++g) {
-            hit_a[g] = 0u;
-            hit_b[g] = 0u;
-            if (g < ngrp) {                                        // warp-uniform
-              uint32_t va[32];
-              tmem_ld32_nowait(tbase + (uint32_t)(32 * g), va);
-              tmem_ld_wait();
-              // acc = t_a + 4096 t_b.  b survives <=> acc > 0 (sign bit clear): AND tree over the sign bits.
-              // a survives <=> bit 11 of the mantissa of acc + DECODE_MAGIC: OR tree over those words.
-              uint32_t sa[8], ob[8];
+        for (int g = 0; g < GRP; ++g) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                sa[j] = va[4 * j] & va[4 * j + 1] & va[4 * j + 2] & va[4 * j + 3];
-                ob[j] = __float_as_uint(__uint_as_float(va[4 * j]) + DECODE_MAGIC) | __float_as_uint(__uint_as_float(va[4 * j + 1]) + DECODE_MAGIC) |
-                        __float_as_uint(__uint_as_float(va[4 * j + 2]) + DECODE_MAGIC) | __float_as_uint(__uint_as_float(va[4 * j + 3]) + DECODE_MAGIC);
-              }
-              const uint32_t s_all = (sa[0] & sa[1] & sa[2]) & (sa[3] & sa[4] & sa[5]) & (sa[6] & sa[7]);
-              const uint32_t o_all = (ob[0] | ob[1] | ob[2]) | (ob[3] | ob[4] | ob[5]) | (ob[6] | ob[7]);
-              hit_b[g] = __ballot_sync(0xffffffffu, rvalid && (s_all & 0x80000000u) == 0u);
-              hit_a[g] = __ballot_sync(0xffffffffu, rvalid && (o_all & 0x800u) != 0u);
-            }
-          }
-        } else {
-          // seed chunk: buf[query][virtual row] = key for every pair (virtual row < cap by construction)
-          const long long vt = blockIdx.x + i * gridDim.x;
-          const long long vrow = vt * TM + ew * 32 + lane;
-          const unsigned long long row_key = (unsigned long long)(p.idx_base + row);
-#pragma unroll 1
-          for (int g = 0; g < ngrp; ++g) {
+          for (int h = 0; h < QPC; ++h) hit[g][h] = 0u;
+          if (g < ngrp) {                                          // warp-uniform
             uint32_t va[32];
             tmem_ld32_nowait(tbase + (uint32_t)(32 * g), va);
             tmem_ld_wait();
+            uint32_t mn = 0xffffffffu, mx = 0u;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              // mantissa of acc + magic = (t_a + 2048) + 4096 * (t_b + 1024)
-              const uint32_t mant = __float_as_uint(__uint_as_float(va[j]) + DECODE_MAGIC) & 0x7fffffu;
-              const int ta = (int)(mant & 4095u) - 2048, tb = (int)(mant >> 12) - 1024;
-              const int qa = qa0 + 32 * g + j, qbq = qa + qb;
-              const int da = __ldg(p.tq + qa) - (ta - 1) / 2, db = __ldg(p.tq + qbq) - (tb - 1) / 2;
-              p.cand_buf[(long long)qa * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)da << 40) | row_key) : ~0ull;
-              p.cand_buf[(long long)qbq * p.cap + vrow] = rvalid ? (((unsigned long long)(unsigned)db << 40) | row_key) : ~0ull;
+            for (int j = 0; j < 32; j += 2) {
+              const uint32_t v0 = __float_as_uint(__fadd_rz(__uint_as_float(va[j]), DECODE_MAGIC));
+              const uint32_t v1 = __float_as_uint(__fadd_rz(__uint_as_float(va[j + 1]), DECODE_MAGIC));
+              mn = __vimin3_u16x2(mn, v0 << 1, v1 << 1);
+              mx = __vimax3_u16x2(mx, v0 << 9, v1 << 9);
             }
+            const bool under = (mn >> 16) < 0x9700u;               // a c field below its window: the other fields are unreadable
+            hit[g][0] = __ballot_sync(0xffffffffu, rvalid && (under || (mx & 0xffffu) >= a_min));
+            hit[g][1] = __ballot_sync(0xffffffffu, rvalid && (under || (mn & 0xffffu) < b_lim));
+            hit[g][2] = __ballot_sync(0xffffffffu, rvalid && (under || (mx >> 16) >= c_min));
           }
         }
         // the accumulator buffer is free: let the MMAs of tile t + 2 start, THEN pay for the appends
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + buf * 8);
-        if (!p.dense) {
-          int total = 0;
+        int total = 0;
 #pragma unroll
-          for (int g = 0; g < GRP; ++g) total += __popc(hit_a[g]) + __popc(hit_b[g]);
-          if (total) {                                               // rare: one atomic per (warp, tile) with survivors
-            int base = 0;
-            if (lane == 0) base = atomicAdd(p.recheck_cnt, total);
-            base = __shfl_sync(0xffffffffu, base, 0);
+        for (int g = 0; g < GRP; ++g)
 #pragma unroll
-            for (int g = 0; g < GRP; ++g) {
+          for (int h = 0; h < QPC; ++h) total += __popc(hit[g][h]);
+        if (total) {                                               // rare: one atomic per (warp, tile) with survivors
+          int base = 0;
+          if (lane == 0) base = atomicAdd(p.recheck_cnt, total);
+          base = __shfl_sync(0xffffffffu, base, 0);
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const unsigned m = h ? hit_b[g] : hit_a[g];
-                if ((m >> lane) & 1u) {
-                  const int slot = base + __popc(m & ((1u << lane) - 1u));
-                  if (slot < p.recheck_cap)
-                    p.recheck[slot] = ((unsigned long long)row << 24) | (31ull << 19) | (unsigned long long)((qa0 + h * qb + 32 * g) >> 4);
-                }
-                base += __popc(m);
+          for (int g = 0; g < GRP; ++g) {
+#pragma unroll
+            for (int h = 0; h < QPC; ++h) {
+              const unsigned m = hit[g][h];
+              if ((m >> lane) & 1u) {
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < p.recheck_cap)
+                  p.recheck[slot] = ((unsigned long long)row << 24) | (31ull << 19) | (unsigned long long)((q0 + h * qb + 32 * g) >> 4);
               }
+              base += __popc(m);
             }
           }
         }
@@ -474,29 +472,46 @@ ham4_recheck_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict_
   }
 }
 
-// Query codes -> per-block image: [qb rows x 128 B] of a-queries then [qb rows x 128 B] of b-queries, both in the
-// SWIZZLE_128B K-major order (same bit -> nibble expansion as the table rows), then the two B_syn areas; query slots
-// past Q and K chunks past the code are zero (the image is cleared first).  One thread per (query, word).
+// Query codes -> per-block image: 3 x [qb rows x 128 B] (fields a, b, c) in the SWIZZLE_128B K-major order (same
+// bit -> nibble order as the table rows; values +-0.5, the b field with inverted signs), then the three B_syn areas;
+// query slots past Q and K chunks past the code are zero (the image is cleared first).  One thread per (query, word).
 __global__ void ham4_query_image_kernel(const uint32_t* __restrict__ q, int Q, int W, int qb, int b_block,
                                         unsigned char* __restrict__ img) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Q * W) return;
   const int qi = (int)(i / W), j = (int)(i % W);
-  const int jb = qi / (2 * qb), r = qi % (2 * qb);
+  const int jb = qi / (QPC * qb), r = qi % (QPC * qb);
   const int h = r / qb, n = r % qb;
-  *reinterpret_cast<uint4*>(img + (size_t)jb * b_block + (size_t)h * qb * 128 + sw128_off(n, j)) = expand_word4(q[(long long)qi * W + j]);
+  uint4 o = expand_word4(q[(long long)qi * W + j]);
+  const uint32_t fix = (h == 1) ? 0xbbbbbbbbu : 0x33333333u;    // 1.0 (0x2) -> 0.5 (0x1); field b: sign flipped as well
+  o.x ^= fix; o.y ^= fix; o.z ^= fix; o.w ^= fix;
+  *reinterpret_cast<uint4*>(img + (size_t)jb * b_block + (size_t)h * qb * 128 + sw128_off(n, j)) = o;
 }
 
-// B_syn of every query slot: up to 64 E2M1 slots that sum to s = 2 * tq - K + 1 (|s| <= 257: at most 42 slots of 6 plus
-// two for the remainder); padding slots get -258 (their data nibbles are zero: that query's term is negative).
+// B_syn of every query slot: 64 E2M1 slots that sum to the field's offset (|s| <= 381: at most 63 slots of 6 plus
+// the remainder), see the header:  a: tq - K/2 + beta,  b: gamma - tq + K/2,  c: tq - K/2 + beta - 128.
+// Padding slots (their data nibbles are zero) sit inside their window on the failing side.
 __global__ void ham4_threshold_image_kernel(int Q, int cols, int K, int qb, int b_block, const int* __restrict__ tq,
-                                            unsigned char* __restrict__ img, int* __restrict__ list_cnt) {
+                                            const int* __restrict__ tqmax, unsigned char* __restrict__ img,
+                                            int* __restrict__ list_cnt, int* __restrict__ overflow) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;        // query slot
-  if (col == 0) *list_cnt = 0;                                   // the re-check list restarts with every chunk
+  const int T_raw = *tqmax;
+  if (col == 0) {
+    *list_cnt = 0;                                               // the re-check list restarts with every chunk
+    if (T_raw > T_MAX) *overflow = 1;                            // no room for the windows: the caller falls back
+  }
   if (col >= cols) return;
-  const int jb = col / (2 * qb), r = col % (2 * qb);
+  const int T = min(T_raw, T_MAX);
+  const int beta = (254 - T) & ~1, gamma = T + 1;
+  const int jb = col / (QPC * qb), r = col % (QPC * qb);
   const int h = r / qb, n = r % qb;
-  const int s = (col < Q) ? (2 * min(tq[col], K) - K + 1) : -258;
+  int s;
+  if (col < Q) {
+    const int t = min(tq[col], T);
+    s = (h == 1) ? (gamma - t + K / 2) : (t - K / 2 + beta - (h == 2 ? 128 : 0));
+  } else {
+    s = (h == 0) ? 0 : (h == 1 ? 255 : -128);
+  }
   const uint32_t sign = s < 0 ? 0x8u : 0u;
   const int mag = s < 0 ? -s : s;
   const int n6 = mag / 6, rem = mag - 6 * n6;
@@ -517,22 +532,43 @@ __global__ void ham4_threshold_image_kernel(int Q, int cols, int K, int qb, int 
     }
     words[wd] = v;
   }
-  unsigned char* base = img + (size_t)jb * b_block + (size_t)qb * 256 + (size_t)h * qb * 32;
+  unsigned char* base = img + (size_t)jb * b_block + (size_t)qb * (128 * QPC) + (size_t)h * qb * 32;
   *reinterpret_cast<uint4*>(base + n * 16) = make_uint4(words[0], words[1], words[2], words[3]);
   *reinterpret_cast<uint4*>(base + qb * 16 + n * 16) = make_uint4(words[4], words[5], words[6], words[7]);
 }
 
-__global__ void ham4_init_kernel(int cols, int K, int* __restrict__ tq, int* __restrict__ cnt, int* __restrict__ overflow) {
+__global__ void ham4_init_kernel(int cols, int K, int* __restrict__ tq, int* __restrict__ cnt, int* __restrict__ flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *overflow = 0;
+  if (i == 0) { flags[0] = 0; flags[2] = 0; }                    // overflow flag, T (largest threshold)
   if (i >= cols) return;
   tq[i] = K;
   cnt[i] = 0;
 }
 
-__global__ void ham4_set_count_kernel(int* __restrict__ cnt, int Q, int v) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < Q) cnt[i] = v;
+// Seed chunk: buf[query][virtual row] = key for EVERY pair of the first `n_vrows` rows of the visiting order
+// (rows past the table: empty keys, they sort last).  Thread = one row, 32 queries per blockIdx.y.
+template <int W>
+__global__ void __launch_bounds__(128)
+ham4_seed_kernel(const uint32_t* __restrict__ db, long long U, long long NG, long long P, int n_vrows, const uint32_t* __restrict__ q,
+                 int Q, long long idx_base, unsigned long long* __restrict__ cand_buf, int* __restrict__ cand_cnt, int cap) {
+  const int vrow = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q0 = blockIdx.y * 32;
+  if (vrow == 0)
+    for (int j = 0; j < 32 && q0 + j < Q; ++j) cand_cnt[q0 + j] = n_vrows;
+  if (vrow >= n_vrows) return;
+  const long long pg = (long long)(((unsigned long long)(vrow / GRAN) * (unsigned long long)P) % (unsigned long long)NG);
+  const long long row = pg * GRAN + (vrow % GRAN);
+  const bool valid = row < U;
+  uint32_t x[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) x[w] = valid ? __ldg(db + row * W + w) : 0u;
+  const unsigned long long row_key = (unsigned long long)(idx_base + row);
+  for (int j = 0; j < 32 && q0 + j < Q; ++j) {
+    int d = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) d += __popc(x[w] ^ __ldg(q + (long long)(q0 + j) * W + w));
+    cand_buf[(long long)(q0 + j) * cap + vrow] = valid ? (((unsigned long long)(unsigned)d << 40) | row_key) : ~0ull;
+  }
 }
 
 // One CTA per query: sort the survivors (canonical keys: distance, row), keep the best k, tighten
@@ -540,7 +576,7 @@ __global__ void ham4_set_count_kernel(int* __restrict__ cnt, int Q, int v) {
 // the test stays "<="); `final` writes keys_out.
 __global__ void __launch_bounds__(CP_THREADS)
 ham4_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt, int cap, int k, int K, int* __restrict__ tq,
-                    int* __restrict__ overflow, int final, unsigned long long* __restrict__ keys_out) {
+                    int* __restrict__ overflow, int* __restrict__ tqmax, int final, unsigned long long* __restrict__ keys_out) {
   extern __shared__ unsigned long long s_key[];   // P = next pow2 >= min(count, cap)
   const int qi = blockIdx.x, tid = threadIdx.x;
   const int raw = cnt[qi];
@@ -576,7 +612,9 @@ ham4_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt,
   for (int i = tid; i < keep; i += CP_THREADS) mine[i] = s_key[i];
   if (tid == 0) {
     cnt[qi] = keep;
-    tq[qi] = (keep >= k) ? (int)(s_key[k - 1] >> 40) : K;
+    const int t = (keep >= k) ? (int)(s_key[k - 1] >> 40) : K;
+    tq[qi] = t;
+    if (tqmax) atomicMax(tqmax, t);                              // after the seed chunk: the batch's T
   }
   if (final)
     for (int i = tid; i < k; i += CP_THREADS) keys_out[(size_t)qi * k + i] = (i < keep) ? s_key[i] : ~0ull;
@@ -602,13 +640,18 @@ int growth_for(int Q) {
 HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
   HamTc4Plan p;
   p.K = 32 * W;
-  // equal blocks of at most 224 columns = 448 queries, columns a multiple of 32 (whole 32-column survivor groups):
-  // 4096 queries -> 10 blocks of 208 columns, 512 -> 2 blocks of 128
-  const int nblk = (Q + 2 * QB - 1) / (2 * QB);
-  p.qb = ((Q + 2 * nblk - 1) / (2 * nblk) + 31) / 32 * 32;
-  p.col_blocks = (Q + 2 * p.qb - 1) / (2 * p.qb);
-  p.cols = p.col_blocks * 2 * p.qb;                            // query slots
-  p.b_block = (p.qb * 320 + 1023) / 1024 * 1024;               // 2 x (qb rows x 128 B) + 2 x B_syn (2 x qb x 16 B)
+  // blocks of qb columns = 3 qb queries, qb a multiple of 32 (whole 32-column survivor groups) and <= 192: the
+  // width that pads least (a block costs about 8 columns of fixed work): 4096 queries -> 11 x 128, 512 -> 1 x 192
+  const int need = (Q + QPC - 1) / QPC;
+  long long best = -1;
+  p.qb = 32;
+  for (int c = 32; c <= QB; c += 32) {
+    const long long blocks = (need + c - 1) / c, cost = blocks * (c + 8);
+    if (best < 0 || cost <= best) { best = cost; p.qb = c; }
+  }
+  p.col_blocks = (need + p.qb - 1) / p.qb;
+  p.cols = p.col_blocks * QPC * p.qb;                          // query slots
+  p.b_block = (p.qb * 160 * QPC + 1023) / 1024 * 1024;         // 3 x (qb rows x 128 B) + 3 x B_syn (2 x qb x 16 B)
   p.cap = 4096;
   p.growth = growth_for(Q);
   while (p.cap < 4 * (p.growth + 1) * k) p.cap <<= 1;
@@ -620,7 +663,7 @@ HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
   p.off_img = o;  o += align256((size_t)p.col_blocks * p.b_block);
   p.off_tq = o;   o += align256((size_t)p.cols * sizeof(int));
   p.off_cnt = o;  o += align256((size_t)p.cols * sizeof(int));
-  p.off_flag = o; o += 256;                                   // [0] overflow flag, [1] re-check list length
+  p.off_flag = o; o += 256;                                   // [0] overflow flag, [1] re-check list length, [2] T
   p.list_cap = 1 << 22;
   p.off_list = o; o += align256((size_t)p.list_cap * sizeof(unsigned long long));
   p.off_buf = o;  o += align256((size_t)p.cols * p.cap * sizeof(unsigned long long));
@@ -705,27 +748,38 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
     long long len = (done == 0) ? p.first_rows / GRAN : done * (p.growth - 1);
     if (len > NG - done) len = NG - done;
     const int dense = (done == 0) ? 1 : 0;
-    ham4_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.K, p.qb, p.b_block, tq, img, flag + 1);
-    sb::count_launch();
-    if (int rc = sb::check_launch("ham4_threshold_image_kernel")) return rc;
-    HamTc4Params hp;
-    hp.db = db; hp.U = U; hp.W = W; hp.G = 1; hp.ksteps = 0; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
-    hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.recheck = list; hp.recheck_cnt = flag + 1; hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
-    hp.idx_base = idx_base; hp.dense = dense; hp.stages = MAX_STAGES; hp.qb = p.qb; hp.b_block = p.b_block;
-    const long long n_tiles = (len + 3) / 4;
-    const int gx = (int)(n_tiles < sms ? n_tiles : sms);
-    int gy = sms / gx;
-    if (gy < 1) gy = 1;
-    if (gy > p.col_blocks) gy = p.col_blocks;
-    hp.cb_per = (p.col_blocks + gy - 1) / gy;
-    gy = (p.col_blocks + hp.cb_per - 1) / hp.cb_per;
-    {
-      sb::ProfScope prof("ham_filter_tc_kernel", st);
-      kernel<<<dim3(gx, gy), THREADS, p.smem_bytes, st>>>(hp);
+    if (dense) {
+      // seed chunk: every pair kept (a few hundred rows): plain XOR / POPC
+      const int n_vrows = (int)(len * GRAN);
+      const dim3 grid((unsigned)((n_vrows + 127) / 128), (unsigned)((Q + 31) / 32));
+      if (W == 8) ham4_seed_kernel<8><<<grid, 128, 0, st>>>(db, U, NG, P, n_vrows, q, Q, idx_base, buf, cnt, p.cap);
+      else if (W == 4) ham4_seed_kernel<4><<<grid, 128, 0, st>>>(db, U, NG, P, n_vrows, q, Q, idx_base, buf, cnt, p.cap);
+      else if (W == 2) ham4_seed_kernel<2><<<grid, 128, 0, st>>>(db, U, NG, P, n_vrows, q, Q, idx_base, buf, cnt, p.cap);
+      else ham4_seed_kernel<1><<<grid, 128, 0, st>>>(db, U, NG, P, n_vrows, q, Q, idx_base, buf, cnt, p.cap);
       sb::count_launch();
-      if (int rc = sb::check_launch("ham_filter_fp4_kernel")) return rc;
-    }
-    if (!dense) {
+      if (int rc = sb::check_launch("ham4_seed_kernel")) return rc;
+    } else {
+      ham4_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.K, p.qb, p.b_block, tq, flag + 2, img, flag + 1, flag);
+      sb::count_launch();
+      if (int rc = sb::check_launch("ham4_threshold_image_kernel")) return rc;
+      HamTc4Params hp;
+      hp.db = db; hp.U = U; hp.W = W; hp.G = 1; hp.ksteps = 0; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
+      hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.tqmax = flag + 2; hp.recheck = list; hp.recheck_cnt = flag + 1;
+      hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
+      hp.idx_base = idx_base; hp.stages = MAX_STAGES; hp.qb = p.qb; hp.b_block = p.b_block;
+      const long long n_tiles = (len + 3) / 4;
+      const int gx = (int)(n_tiles < sms ? n_tiles : sms);
+      int gy = sms / gx;
+      if (gy < 1) gy = 1;
+      if (gy > p.col_blocks) gy = p.col_blocks;
+      hp.cb_per = (p.col_blocks + gy - 1) / gy;
+      gy = (p.col_blocks + hp.cb_per - 1) / hp.cb_per;
+      {
+        sb::ProfScope prof("ham_filter_tc_kernel", st);
+        kernel<<<dim3(gx, gy), THREADS, p.smem_bytes, st>>>(hp);
+        sb::count_launch();
+        if (int rc = sb::check_launch("ham_filter_fp4_kernel")) return rc;
+      }
       sb::ProfScope prof("ham_recheck_kernel", st);
       const int blocks = 8 * sms;                               // 64 warps per SM: the re-check is load-latency bound
       if (W == 8) ham4_recheck_kernel<8><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
@@ -735,16 +789,11 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
       sb::count_launch();
       if (int rc = sb::check_launch("ham4_recheck_kernel")) return rc;
     }
-    if (dense) {
-      ham4_set_count_kernel<<<(Q + 255) / 256, 256, 0, st>>>(cnt, Q, (int)(len * GRAN));
-      sb::count_launch();
-      if (int rc = sb::check_launch("ham4_set_count_kernel")) return rc;
-    }
     done += len;
     const int final = (done >= NG) ? 1 : 0;
     sb::ProfScope prof("ham_compact_kernel", st);
-    ham4_compact_kernel<<<Q, CP_THREADS, p.cap * sizeof(unsigned long long), st>>>(buf, cnt, p.cap, k, p.K, tq, flag, final,
-                                                                                   reinterpret_cast<unsigned long long*>(keys_out));
+    ham4_compact_kernel<<<Q, CP_THREADS, p.cap * sizeof(unsigned long long), st>>>(buf, cnt, p.cap, k, p.K, tq, flag, dense ? flag + 2 : nullptr,
+                                                                                   final, reinterpret_cast<unsigned long long*>(keys_out));
     sb::count_launch();
     if (int rc = sb::check_launch("ham4_compact_kernel")) return rc;
   }
