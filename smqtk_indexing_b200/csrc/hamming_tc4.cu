@@ -42,7 +42,7 @@
 //   * Survivor groups are 32 columns = 32 queries of each field, flagged separately; the re-check list stores
 //     (row, first query of the group / 16).
 // Warp roles: 0-15 epilogue (lane quadrant x query block x column half), 16 MMA issue + TMEM alloc, 17 B loader,
-// 18-25 producers (half a table row per thread and tile).
+// 18-21 producers (one warp per stage of the A ring).
 #include <cuda_fp16.h>
 
 #include <stdlib.h>
@@ -67,14 +67,14 @@ constexpr int SF16_COL = 248;               // [248, 256): 2^16 (SFB of the c-fi
 constexpr float DECODE_MAGIC = 25165824.0f; // 1.5 * 2^24: bits(acc +rz this) = 0x4B800000 | ((acc + 2^23) >> 1)
 constexpr int T_MAX = 252;                  // largest threshold the 8-bit windows take
 constexpr int ACC1_COL = 256;               // second accumulator
-constexpr int MAX_STAGES = 2;                 // 16 KB each; a tile is 15 MMAs (~1500 cycles) and the producers prefetch in registers
+constexpr int MAX_STAGES = 4;               // A ring: 16 KB per stage; 4 stages when the two block images leave room, else 2 (HamTc4Params::stages)
 constexpr int GRAN = 32;                    // rows per granule of the visiting order
 // 16 epilogue warps: (TMEM lane quadrant) x (accumulator buffer = tile parity) x (column half).  tcgen05.wait::ld
 // waits for ALL of a thread's loads, so tensor-memory latency can only be hidden by other warps -- with FP32
 // accumulators (twice the registers per column of the FP8 kernel's packed halves) and half the MMA time per
 // tile, four epilogue warps were the bottleneck (measured: 6.8 ms vs the FP8 kernel's 6.3 ms).
-constexpr int EPI_WARPS = 16, EPI_PER_BUF = 8, MMA_WARP = 16, B_WARP = 17, PROD_WARP0 = 18, PROD_WARPS = 8;
-constexpr int THREADS = (PROD_WARP0 + PROD_WARPS) * 32;   // 832
+constexpr int EPI_WARPS = 16, EPI_PER_BUF = 8, MMA_WARP = 16, B_WARP = 17, PROD_WARP0 = 18, PROD_WARPS = MAX_STAGES;
+constexpr int THREADS = (PROD_WARP0 + PROD_WARPS) * 32;   // 704
 constexpr int GROWTH = 4;                   // rows of a chunk = 3 x the rows before it: ~3 (k + ties) survivors per query
 constexpr int GROWTH_SMALL_Q = 8;           // few queries: every chunk's launch / fill / drain weighs more than the
 constexpr int SMALL_Q = 1024;               // extra survivors -- 6 chunks of 7 (k + ties) instead of 9 of 3 (k + ties)
@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
   unsigned char* s_b = smem;
   unsigned char* s_asyn = s_b + 2 * b_block;
   unsigned char* s_a = s_asyn + A_SYN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + (size_t)MAX_STAGES * a_stage);
+  const int stages = p.stages;                                   // 2 or 4
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + (size_t)stages * a_stage);
   const uint32_t a_full = smem_u32(bars), a_empty = a_full + MAX_STAGES * 8;
   const uint32_t acc_full = a_empty + MAX_STAGES * 8, acc_empty = acc_full + 16;
   const uint32_t b_full = acc_empty + 16, b_empty = b_full + 16;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
   const int jb1 = min(p.col_blocks, jb0 + p.cb_per);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(a_full + s * 8, PROD_WARPS); mbar_init(a_empty + s * 8, 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(a_full + s * 8, 1); mbar_init(a_empty + s * 8, 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full + b * 8, 1);
       mbar_init(acc_empty + b * 8, EPI_PER_BUF);
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
   // the ring once (a zero nibble is +0.0)
   for (int i = threadIdx.x; i < A_SYN / 4; i += THREADS) reinterpret_cast<uint32_t*>(s_asyn)[i] = 0x22222222u;
   if (W < 8)
-    for (int i = threadIdx.x; i < (int)(MAX_STAGES * a_stage / 16); i += THREADS)
+    for (int i = threadIdx.x; i < (int)(stages * a_stage / 16); i += THREADS)
       reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   tc_fence_before();
@@ -277,80 +278,67 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
           }
           umma_commit(acc_full + buf * 8);
           umma_commit(a_empty + stage * 8);
-          if (++stage == MAX_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(b_empty + sb * 8);                          // this B buffer may be replaced once these MMAs retire
       }
     }
   } else if (warp >= PROD_WARP0) {
     // =========================== A: packed codes -> +-1 E2M1, swizzled ===========================
-    // thread -> (row r of the tile, half h of its words); a code word becomes one 16-byte chunk
-    constexpr int WH = (W >= 2) ? W / 2 : 1;                     // words per thread
-    const int pt = threadIdx.x - PROD_WARP0 * 32;
-    const int r = pt & (TM - 1), h = pt >> 7;
-    const bool worker = (W >= 2) || h == 0;
-    int stage = 0;
-    uint32_t phase = 0;
-    // PF tiles of packed words are in flight per thread: a tile is consumed every ~650 cycles (its MMAs), one
-    // HBM / L2 round trip is 1000+, and the 320 MB table does not stay in L2 between the passes
-    constexpr int PF = 4;
-    uint32_t cw[PF][WH];
-    bool cv[PF];
-    // granule of tile i for this thread: vg = vg_first + i * 4 * gridDim.x, physical pg = vg * P mod NG, kept incrementally
-    const long long vg_first = p.vg0 + (long long)blockIdx.x * 4 + (r >> 5);
-    const long long pg_first = (long long)(((unsigned long long)vg_first * (unsigned long long)p.P) % (unsigned long long)p.NG);
-    const long long pg_step = (long long)(((unsigned long long)(4 * gridDim.x) * (unsigned long long)p.P) % (unsigned long long)p.NG);
-    long long vg_ld = vg_first, pg_ld = pg_first;
-    auto load = [&](uint32_t (&w)[WH]) {                        // loads the NEXT tile in sequence
-      const bool in_chunk = vg_ld < p.vg1;
-      const long long row = pg_ld * GRAN + lane;
-      const bool valid = in_chunk && row < p.U;
-      vg_ld += 4 * gridDim.x;
-      pg_ld += pg_step;
-      if (pg_ld >= p.NG) pg_ld -= p.NG;
+    // One warp per ring stage: warp pw expands the WHOLE tiles t = pw (mod MAX_STAGES) -- lane = row of each of the
+    // tile's four 32-row granules, all W words -- so that the generic -> async proxy fence (several hundred cycles:
+    // it was more than half of a producer's time when every producer thread touched every tile, and with ~1000-cycle
+    // tiles it set the pace) is paid once per warp and MAX_STAGES tiles, not once per tile.
+    const int pw = warp - PROD_WARP0;
+    const unsigned long long NGu = (unsigned long long)p.NG;
+    const long long Pm = (long long)((unsigned long long)p.P % NGu);
+    uint32_t cw[4][W];                                           // the warp's next tile: granule g, word j of this lane's row
+    unsigned char* dst = s_a + (size_t)pw * a_stage;
+    long long t0 = 0;                                            // global tile counter at the start of this block's pass
+    auto load = [&](long long i) {                               // tile i of the pass: granules (blockIdx.x + i * gridDim.x) * 4 + g
+      const long long vg = p.vg0 + ((long long)blockIdx.x + i * gridDim.x) * 4;
+      long long pg = (long long)(((unsigned long long)vg * (unsigned long long)p.P) % NGu);
 #pragma unroll
-      for (int j = 0; j < WH; ++j) w[j] = 0u;
-      if (valid && worker) {
-        const uint32_t* src = p.db + row * W + h * WH;
-        if (WH == 4) {
-          const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(src));
-          w[0] = x0.x; w[1] = x0.y; w[2 % WH] = x0.z; w[3 % WH] = x0.w;
-        } else if (WH == 2) {
-          const uint2 x0 = __ldg(reinterpret_cast<const uint2*>(src));
-          w[0] = x0.x; w[1 % WH] = x0.y;
+      for (int g = 0; g < 4; ++g) {
+        const long long row = pg * GRAN + lane;
+        const bool valid = (vg + g < p.vg1) && row < p.U;
+        const uint32_t* src = p.db + row * W;
+        if (W == 8) {
+          uint4 x0 = make_uint4(0u, 0u, 0u, 0u), x1 = x0;
+          if (valid) { x0 = __ldg(reinterpret_cast<const uint4*>(src)); x1 = __ldg(reinterpret_cast<const uint4*>(src) + 1); }
+          cw[g][0] = x0.x; cw[g][1 % W] = x0.y; cw[g][2 % W] = x0.z; cw[g][3 % W] = x0.w;
+          cw[g][4 % W] = x1.x; cw[g][5 % W] = x1.y; cw[g][6 % W] = x1.z; cw[g][7 % W] = x1.w;
+        } else if (W == 4) {
+          uint4 x0 = make_uint4(0u, 0u, 0u, 0u);
+          if (valid) x0 = __ldg(reinterpret_cast<const uint4*>(src));
+          cw[g][0] = x0.x; cw[g][1 % W] = x0.y; cw[g][2 % W] = x0.z; cw[g][3 % W] = x0.w;
+        } else if (W == 2) {
+          uint2 x0 = make_uint2(0u, 0u);
+          if (valid) x0 = __ldg(reinterpret_cast<const uint2*>(src));
+          cw[g][0] = x0.x; cw[g][1 % W] = x0.y;
         } else {
-          w[0] = __ldg(src);
+          cw[g][0] = valid ? __ldg(src) : 0u;
         }
+        pg += Pm;
+        if (pg >= p.NG) pg -= p.NG;
       }
-      return valid;
     };
-    for (int jb = jb0; jb < jb1; ++jb) {
-      vg_ld = vg_first;
-      pg_ld = pg_first;
+    for (int jb = jb0; jb < jb1 && pw < stages; ++jb, t0 += my_tiles) {
+      const long long i_first = (pw - t0) & (stages - 1);        // first tile of this pass that lands in this warp's stage
+      uint32_t phase = (uint32_t)(((t0 + i_first) / stages) & 1);
+      if (i_first < my_tiles) load(i_first);
+      for (long long i = i_first; i < my_tiles; i += stages) {
+        mbar_wait(a_empty + pw * 8, phase ^ 1);
+        phase ^= 1u;
 #pragma unroll
-      for (int d = 0; d < PF; ++d) cv[d] = (d < my_tiles) ? load(cw[d]) : false;
-      for (long long i0 = 0; i0 < my_tiles; i0 += PF) {
+        for (int g = 0; g < 4; ++g)
 #pragma unroll
-        for (int d = 0; d < PF; ++d) {
-          if (i0 + d < my_tiles) {
-            mbar_wait(a_empty + stage * 8, phase ^ 1);
-            unsigned char* dst = s_a + (size_t)stage * a_stage;
-            if (worker) {
-#pragma unroll
-              for (int j = 0; j < WH; ++j) {
-                const int wj = h * WH + j;                         // word of the row = 16-byte chunk of the 128-byte row
-                uint4 o = expand_word4(cw[d][j]);
-                if (!cv[d]) o = make_uint4(0u, 0u, 0u, 0u);        // rows past the table: all-zero operand
-                *reinterpret_cast<uint4*>(dst + sw128_off(r, wj)) = o;
-              }
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full + stage * 8);
-            cv[d] = (i0 + d + PF < my_tiles) ? load(cw[d]) : false;   // refill this slot with the tile PF ahead
-            if (++stage == MAX_STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
+          for (int j = 0; j < W; ++j)                              // (rows past the table expand to some code: the epilogue masks them)
+            *reinterpret_cast<uint4*>(dst + sw128_off(g * 32 + lane, j)) = expand_word4(cw[g][j]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + pw * 8);
+        if (i + stages < my_tiles) load(i + stages);               // in flight while the ring turns
       }
     }
   } else if (warp < EPI_WARPS) {
@@ -621,7 +609,7 @@ ham4_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt,
 }
 
 struct HamTc4Plan {
-  int K, qb, b_block, col_blocks, cols, cap, first_rows, growth;
+  int K, qb, b_block, col_blocks, cols, cap, first_rows, growth, stages;
   size_t smem_bytes;
   size_t off_img, off_tq, off_cnt, off_flag, off_list, off_buf, total;
   int list_cap;
@@ -641,13 +629,20 @@ HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
   HamTc4Plan p;
   p.K = 32 * W;
   // blocks of qb columns = 3 qb queries, qb a multiple of 32 (whole 32-column survivor groups) and <= 192: the
-  // width that pads least (a block costs about 8 columns of fixed work): 4096 queries -> 11 x 128, 512 -> 1 x 192
+  // width with the least MMA time.  A kind::mxf4 MMA of N columns takes about 100 + 0.15 N cycles here (tile time
+  // measured at N = 64 ... 192: 1700, 1810, 1970, 2060, 2080 cycles for 15 MMAs; 138 cycles at N = 256 in
+  // tools/experiments/mxf4_probe2.cu), i.e. mostly a fixed cost per instruction: few wide blocks beat many narrow
+  // ones even when they pad more.  4096 queries -> 8 x 192, 512 -> 1 x 192
   const int need = (Q + QPC - 1) / QPC;
   long long best = -1;
   p.qb = 32;
   for (int c = 32; c <= QB; c += 32) {
-    const long long blocks = (need + c - 1) / c, cost = blocks * (c + 8);
+    const long long blocks = (need + c - 1) / c, cost = blocks * (c + 667);
     if (best < 0 || cost <= best) { best = cost; p.qb = c; }
+  }
+  if (const char* e = getenv("SB_TC4_QB")) {                    // tuning knob
+    const int c = atoi(e);
+    if (c >= 32 && c <= QB && c % 32 == 0) p.qb = c;
   }
   p.col_blocks = (need + p.qb - 1) / p.qb;
   p.cols = p.col_blocks * QPC * p.qb;                          // query slots
@@ -658,7 +653,12 @@ HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
   p.first_rows = Q <= SMALL_Q ? 1024 : 256;                    // dense seed chunk: at least 8 k rows (its sort costs Q * rows)
   while (p.first_rows < 8 * k) p.first_rows <<= 1;
   if (p.first_rows > p.cap) p.first_rows = p.cap;
-  p.smem_bytes = 1024 + (size_t)2 * p.b_block + A_SYN + (size_t)MAX_STAGES * A_GROUP + (2 * MAX_STAGES + 10) * 8;
+  p.stages = MAX_STAGES;
+  p.smem_bytes = 1024 + (size_t)2 * p.b_block + A_SYN + (size_t)p.stages * A_GROUP + (2 * MAX_STAGES + 10) * 8;
+  if (p.smem_bytes > 227 * 1024) {                             // the widest blocks leave room for two stages only
+    p.stages = 2;
+    p.smem_bytes -= (size_t)2 * A_GROUP;
+  }
   size_t o = 0;
   p.off_img = o;  o += align256((size_t)p.col_blocks * p.b_block);
   p.off_tq = o;   o += align256((size_t)p.cols * sizeof(int));
@@ -766,7 +766,7 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
       hp.db = db; hp.U = U; hp.W = W; hp.G = 1; hp.ksteps = 0; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
       hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.tqmax = flag + 2; hp.recheck = list; hp.recheck_cnt = flag + 1;
       hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
-      hp.idx_base = idx_base; hp.stages = MAX_STAGES; hp.qb = p.qb; hp.b_block = p.b_block;
+      hp.idx_base = idx_base; hp.stages = p.stages; hp.qb = p.qb; hp.b_block = p.b_block;
       const long long n_tiles = (len + 3) / 4;
       const int gx = (int)(n_tiles < sms ? n_tiles : sms);
       int gy = sms / gx;
