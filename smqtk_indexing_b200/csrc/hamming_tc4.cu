@@ -17,8 +17,8 @@
 //     accumulator column carries THREE queries in 8-bit fields (all 24 bits of an FP32 integer):
 //         X = u_a + 256 w_b + 65536 u_c,      acc = X - 2^23,
 //         u_a = tq_a - d_a + beta,  w_b = d_b - tq_b + gamma,  u_c = tq_c - d_c + beta
-//     with T = the largest threshold of the batch (thresholds only tighten, so the value after the seed chunk
-//     stays an upper bound), beta = (254 - T) & ~1 and gamma = T + 1: "d <= tq" is u >= beta / w <= gamma, the
+//     with T = the largest threshold of the batch when the chunk starts (collected by the compaction kernel behind
+//     the previous chunk), beta = (254 - T) & ~1 and gamma = T + 1: "d <= tq" is u >= beta / w <= gamma, the
 //     same constants for every column.  Query operands are +-0.5 (a dot product is K/2 - d; the b query has its
 //     signs inverted), the b and c MMAs use scale-factor windows holding 2^8 and 2^16 (uniform per MMA, so the SF
 //     layout still does not matter), and the thresholds ride in one extra K step per field.  4/3 bytes per pair.
@@ -41,7 +41,7 @@
 //   * Threshold steps: A_syn = 64 x (+1), B_syn = up to 64 E2M1 slots (values 6, 4, 3, 2, 1) summing to the field's offset.
 //   * Survivor groups are 32 columns = 32 queries of each field, flagged separately; the re-check list stores
 //     (row, first query of the group / 16).
-// Warp roles: 0-15 epilogue (lane quadrant x query block x column half), 16 MMA issue + TMEM alloc, 17 B loader,
+// Warp roles: 0-15 epilogue (lane quadrant x tile parity x column half), 16 MMA issue + TMEM alloc, 17 B loader,
 // 18-21 producers (one warp per stage of the A ring).
 #include <cuda_fp16.h>
 
@@ -480,12 +480,14 @@ __global__ void ham4_query_image_kernel(const uint32_t* __restrict__ q, int Q, i
 // the remainder), see the header:  a: tq - K/2 + beta,  b: gamma - tq + K/2,  c: tq - K/2 + beta - 128.
 // Padding slots (their data nibbles are zero) sit inside their window on the failing side.
 __global__ void ham4_threshold_image_kernel(int Q, int cols, int K, int qb, int b_block, const int* __restrict__ tq,
-                                            const int* __restrict__ tqmax, unsigned char* __restrict__ img,
-                                            int* __restrict__ list_cnt, int* __restrict__ overflow) {
+                                            const int* __restrict__ tqmax, int* __restrict__ tqmax_next,
+                                            unsigned char* __restrict__ img, int* __restrict__ list_cnt,
+                                            int* __restrict__ overflow) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;        // query slot
   const int T_raw = *tqmax;
   if (col == 0) {
     *list_cnt = 0;                                               // the re-check list restarts with every chunk
+    *tqmax_next = 0;                                             // the compaction behind this chunk collects the next T here
     if (T_raw > T_MAX) *overflow = 1;                            // no room for the windows: the caller falls back
   }
   if (col >= cols) return;
@@ -527,7 +529,7 @@ __global__ void ham4_threshold_image_kernel(int Q, int cols, int K, int qb, int 
 
 __global__ void ham4_init_kernel(int cols, int K, int* __restrict__ tq, int* __restrict__ cnt, int* __restrict__ flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { flags[0] = 0; flags[2] = 0; }                    // overflow flag, T (largest threshold)
+  if (i == 0) { flags[0] = 0; flags[2] = 0; flags[3] = 0; }      // overflow flag, T (largest threshold) of odd / even chunks
   if (i >= cols) return;
   tq[i] = K;
   cnt[i] = 0;
@@ -602,7 +604,7 @@ ham4_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt,
     cnt[qi] = keep;
     const int t = (keep >= k) ? (int)(s_key[k - 1] >> 40) : K;
     tq[qi] = t;
-    if (tqmax) atomicMax(tqmax, t);                              // after the seed chunk: the batch's T
+    atomicMax(tqmax, t);                                         // T of the next chunk: its windows sit as tight as they can
   }
   if (final)
     for (int i = tid; i < k; i += CP_THREADS) keys_out[(size_t)qi * k + i] = (i < keep) ? s_key[i] : ~0ull;
@@ -663,7 +665,7 @@ HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
   p.off_img = o;  o += align256((size_t)p.col_blocks * p.b_block);
   p.off_tq = o;   o += align256((size_t)p.cols * sizeof(int));
   p.off_cnt = o;  o += align256((size_t)p.cols * sizeof(int));
-  p.off_flag = o; o += 256;                                   // [0] overflow flag, [1] re-check list length, [2] T
+  p.off_flag = o; o += 256;                                   // [0] overflow flag, [1] re-check list length, [2], [3] T (by chunk parity)
   p.list_cap = 1 << 22;
   p.off_list = o; o += align256((size_t)p.list_cap * sizeof(unsigned long long));
   p.off_buf = o;  o += align256((size_t)p.cols * p.cap * sizeof(unsigned long long));
@@ -744,7 +746,9 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
                                    (int)(p.cap * sizeof(unsigned long long))));
   const int sms = sb::sm_count();
   long long done = 0;                                         // granules
-  while (done < NG) {
+  for (int chunk = 0; done < NG; ++chunk) {
+    int* const T_cur = flag + 2 + (chunk & 1);                  // written by the compaction behind the previous chunk
+    int* const T_next = flag + 2 + ((chunk + 1) & 1);
     long long len = (done == 0) ? p.first_rows / GRAN : done * (p.growth - 1);
     if (len > NG - done) len = NG - done;
     const int dense = (done == 0) ? 1 : 0;
@@ -759,12 +763,12 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
       sb::count_launch();
       if (int rc = sb::check_launch("ham4_seed_kernel")) return rc;
     } else {
-      ham4_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.K, p.qb, p.b_block, tq, flag + 2, img, flag + 1, flag);
+      ham4_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.K, p.qb, p.b_block, tq, T_cur, T_next, img, flag + 1, flag);
       sb::count_launch();
       if (int rc = sb::check_launch("ham4_threshold_image_kernel")) return rc;
       HamTc4Params hp;
       hp.db = db; hp.U = U; hp.W = W; hp.G = 1; hp.ksteps = 0; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
-      hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.tqmax = flag + 2; hp.recheck = list; hp.recheck_cnt = flag + 1;
+      hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.tqmax = T_cur; hp.recheck = list; hp.recheck_cnt = flag + 1;
       hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
       hp.idx_base = idx_base; hp.stages = p.stages; hp.qb = p.qb; hp.b_block = p.b_block;
       const long long n_tiles = (len + 3) / 4;
@@ -792,7 +796,7 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
     done += len;
     const int final = (done >= NG) ? 1 : 0;
     sb::ProfScope prof("ham_compact_kernel", st);
-    ham4_compact_kernel<<<Q, CP_THREADS, p.cap * sizeof(unsigned long long), st>>>(buf, cnt, p.cap, k, p.K, tq, flag, dense ? flag + 2 : nullptr,
+    ham4_compact_kernel<<<Q, CP_THREADS, p.cap * sizeof(unsigned long long), st>>>(buf, cnt, p.cap, k, p.K, tq, flag, T_next,
                                                                                    final, reinterpret_cast<unsigned long long*>(keys_out));
     sb::count_launch();
     if (int rc = sb::check_launch("ham4_compact_kernel")) return rc;
