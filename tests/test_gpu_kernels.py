@@ -195,6 +195,47 @@ def test_hamming_tensor_core_scan_ties_and_clusters(dev, tc_fmt):
     assert flag == 0 and np.array_equal(d, od) and np.array_equal(i, oi)
 
 
+def test_hamming_tensor_core_scan_far_codes_and_mixed_thresholds(dev, tc_fmt):
+    """The FP4 scan packs three queries into 8-bit fields of one FP32 accumulator; a field leaves its window for
+    pairs far above the threshold (d > 254 - (T - tq)).  Build exactly that: half of the queries have duplicates
+    and neighbours at d <= 5 in the table (thresholds -> 0), the others only random codes (thresholds ~ 100),
+    and the table holds complements / near-complements of the queries (d = 230 ... 256).  Borrows, carries and
+    exponent drops may only ADD re-check work: the keys must equal the oracle's, without the fallback."""
+    rng = np.random.RandomState(41)
+    b, W, Q, k = 256, 8, 300, 10
+    qbits = rng.rand(Q, b) > 0.5
+    rows = [rng.rand(100000, b) > 0.5]
+    for j in range(0, Q, 2):                                    # near neighbours of every second query
+        near = np.repeat(qbits[j:j + 1], 14, axis=0)
+        for r in range(4, 14):
+            near[r, rng.choice(b, rng.randint(1, 6), replace=False)] ^= True
+        rows.append(near)
+    far = ~qbits[rng.randint(0, Q, 20000)]                      # complements, most with a few bits flipped back
+    flips = rng.rand(20000, b) < (rng.rand(20000, 1) * 0.1)
+    flips[:200] = False                                         # exact complements: d = 256
+    rows.append(far ^ flips)
+    bits = np.concatenate(rows)
+    bits = bits[rng.permutation(len(bits))]
+    table, q = O.pack_codes(bits, W), O.pack_codes(qbits, W)
+    od, oi = O.hamming_topk(table, q, k)
+    assert od[0, 3] == 0 and od[1, 0] > 60 and od[0, -1] <= 5   # the two kinds of query
+    d, i, flag = _tc_keys(dev, table, q, k)
+    assert flag == 0
+    assert np.array_equal(d, od) and np.array_equal(i, oi)
+    # every query close to one centre, 30000 rows close to its complement: millions of far pairs at once.  The
+    # re-check list may overflow (-> flag, XOR/POPC scan through the dispatcher); the keys are exact either way
+    centre = rng.rand(1, b) > 0.5
+    qbits = centre ^ (rng.rand(Q, b) < 0.02)
+    bits = np.concatenate([rng.rand(60000, b) > 0.5, (~centre) ^ (rng.rand(30000, b) < 0.03),
+                           centre ^ (rng.rand(3000, b) < 0.05)])
+    bits = bits[rng.permutation(len(bits))]
+    table, q = O.pack_codes(bits, W), O.pack_codes(qbits, W)
+    od, oi = O.hamming_topk(table, q, k)
+    keys = dev.hamming_scan_keys(dev.codes_to_device(table), dev.codes_to_device(q), k, variant=dev.SCAN_VARIANT_TC)
+    d, i = (t.cpu().numpy() for t in dev.topk_merge(keys.unsqueeze(0).contiguous()))
+    assert np.array_equal(d, od) and np.array_equal(i, oi)
+
+
 def test_hamming_scan_dispatch_and_overflow_fallback(dev):
     """hamming_scan_keys picks the tensor-core scan for large batches; identical keys either way.
     A table of identical rows overflows the candidate buffers (every row ties): the flag is raised

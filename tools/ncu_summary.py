@@ -48,8 +48,9 @@ def launches(src, dst):
         for _, k, blk, grd, ms in step:
             out.append("| `%s` | %s | %s | %.4f | %.2f%% |" % (k, grd, blk, ms, 100 * ms / st))
         out.append("")
-        out.append("step total %.3f ms; `hamming_scan_kernel` share %.2f%%" %
-                   (st, 100 * sum(r[4] for r in step if r[1].startswith("hamming_scan_kernel")) / st))
+        out.append("step total %.3f ms; `ham_filter_*` (tensor-core scan) share %.2f%%; `hamming_scan_kernel` share %.2f%%" %
+                   (st, 100 * sum(r[4] for r in step if r[1].startswith("ham_filter")) / st,
+                    100 * sum(r[4] for r in step if r[1].startswith("hamming_scan_kernel")) / st))
     open(dst, "w").write("\n".join(out) + "\n")
     print("wrote", dst)
 
