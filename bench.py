@@ -492,9 +492,12 @@ def _timed_steps(torch, dist, world, fn, steps, flush):
         torch.cuda.synchronize()
     evs = []
     barrier()
+    token = torch.zeros(1, dtype=torch.int32, device=flush.device)
     for _ in range(steps):
         flush.zero_()
         flush.view(torch.int64).sum()
+        if world > 1:
+            dist.all_reduce(token)                             # ranks start the step together (stream-ordered)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
@@ -783,6 +786,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_token = torch.zeros(1, dtype=torch.int32, device=dev)
+
     def timed(fn, arg, steps, on_step=None):
         """EXACTLY `steps` steps; per-step CUDA events (the L2 flush between steps is
         outside the events); returns the summed milliseconds.  `on_step` runs after each step has
@@ -791,6 +796,11 @@ def run_b200(args):
         barrier()
         for _ in range(steps):
             flush_l2()
+            if world > 1:
+                # line the ranks up ON THE DEVICE before the step's first event: a step contains a collective, so a
+                # rank whose host is late (rank 0 samples the clocks after every step) would otherwise be waited for
+                # inside the other ranks' events.  Stream-ordered, no host synchronisation.
+                dist.all_reduce(step_token)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn(arg)
