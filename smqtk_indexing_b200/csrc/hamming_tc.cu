@@ -418,7 +418,7 @@ ham_recheck_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__
   const int raw = list_cnt[grp];
   if (raw > list_cap && blockIdx.y == 0 && threadIdx.x == 0) *overflow = 1;
   const int n = min(raw, list_cap);
-  if (n == 0) return;
+  if ((blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 >= n) return;   // no entries for this warp: leave before any load
   const int qg = grp * 32 + lane;
   const bool qvalid = qg < Q;
   uint32_t qw[W];

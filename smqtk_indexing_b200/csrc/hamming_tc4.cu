@@ -39,8 +39,8 @@
 //     for s = 3, 2, 1, 0 takes every 4th bit of a code word as the sign of 8 consecutive elements.  This permutes
 //     the elements inside a row, identically for table rows and query rows -- a dot product does not care.
 //   * Threshold steps: A_syn = 64 x (+1), B_syn = up to 64 E2M1 slots (values 6, 4, 3, 2, 1) summing to the field's offset.
-//   * Survivor groups are 32 columns = 32 queries of each field, flagged separately; the re-check list stores
-//     (row, first query of the group / 16).
+//   * Survivor groups are 32 columns = 32 queries of each field, flagged separately; every 32-query group has its own
+//     re-check list of rows.
 // Warp roles: 0-15 epilogue (lane quadrant x tile parity x column half), 16 MMA issue + TMEM alloc, 17 B loader,
 // 18-21 producers (one warp per stage of the A ring).
 #include <cuda_fp16.h>
@@ -90,9 +90,9 @@ struct HamTc4Params {
   const unsigned char* image;  // per block: G x B_GROUP (SW128) then B_SYN
   const int* tq;               // thresholds (Hamming distance) per query slot
   const int* tqmax;            // T: upper bound of the thresholds (device scalar)
-  unsigned long long* recheck; // (row << 24 | (group width - 1) << 19 | first query of the group / 16) entries
+  unsigned long long* recheck; // per 32-query group: recheck_cap rows to re-check
   int qb, b_block;             // columns per block (multiple of 32, <= 192; 3 * qb queries), bytes of one block image
-  int* recheck_cnt;
+  int* recheck_cnt;            // entries per 32-query group
   int recheck_cap;
   unsigned long long* cand_buf;
   int* cand_cnt;
@@ -127,28 +127,6 @@ __device__ __forceinline__ void umma_fp4(uint32_t d_tmem, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n"
       "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
       : "memory");
-}
-
-// One re-check entry = (row, group of up to 32 queries starting at `qg0`): exact distances from the packed codes
-// (see hamming_tc.cu for why survivors are not decoded from the accumulator registers).
-template <int W>
-__device__ __forceinline__ void ham4_recheck_group(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qcodes, int Q,
-                                                   long long row, unsigned long long row_key, int qg0, int width,
-                                                   const int* __restrict__ tq, unsigned long long* cand_buf, int* cand_cnt,
-                                                   int cap, int lane) {
-  uint32_t x[W];
-#pragma unroll
-  for (int w = 0; w < W; ++w) x[w] = __ldg(db + row * W + w);
-  const int qg = qg0 + lane;
-  if (lane < width && qg < Q) {
-    int d = 0;
-#pragma unroll
-    for (int w = 0; w < W; ++w) d += __popc(x[w] ^ __ldg(qcodes + (long long)qg * W + w));
-    if (d <= tq[qg]) {
-      const int slot = atomicAdd(cand_cnt + qg, 1);
-      if (slot < cap) cand_buf[(long long)qg * cap + slot] = ((unsigned long long)(unsigned)d << 40) | row_key;
-    }
-  }
 }
 
 // W = code words per row (1, 2, 4, 8); 3 x (W / 2 MMAs of K = 64 elements + the threshold step) per tile.
@@ -400,26 +378,33 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + buf * 8);
-        int total = 0;
+        unsigned any = 0u;
 #pragma unroll
         for (int g = 0; g < GRP; ++g)
 #pragma unroll
-          for (int h = 0; h < QPC; ++h) total += __popc(hit[g][h]);
-        if (total) {                                               // rare: one atomic per (warp, tile) with survivors
-          int base = 0;
-          if (lane == 0) base = atomicAdd(p.recheck_cnt, total);
-          base = __shfl_sync(0xffffffffu, base, 0);
+          for (int h = 0; h < QPC; ++h) any |= hit[g][h];
+        if (any) {                                                 // rare: survivors in this (warp, tile)
+          // one slot reservation per (group, field) WITH survivors, all issued at once: lane c reserves for combination
+          // c = g * 3 + h (serial atomics would cost a global round trip each)
+          int mine_cnt = 0;
+#pragma unroll
+          for (int g = 0; g < GRP; ++g)
+#pragma unroll
+            for (int h = 0; h < QPC; ++h) mine_cnt = (lane == g * QPC + h) ? __popc(hit[g][h]) : mine_cnt;
+          int mine_base = 0;
+          if (lane < GRP * QPC && mine_cnt)
+            mine_base = atomicAdd(p.recheck_cnt + ((q0 + (lane % QPC) * qb + 32 * (lane / QPC)) >> 5), mine_cnt);
 #pragma unroll
           for (int g = 0; g < GRP; ++g) {
 #pragma unroll
             for (int h = 0; h < QPC; ++h) {
               const unsigned m = hit[g][h];
+              const int base = __shfl_sync(0xffffffffu, mine_base, g * QPC + h);
               if ((m >> lane) & 1u) {
                 const int slot = base + __popc(m & ((1u << lane) - 1u));
                 if (slot < p.recheck_cap)
-                  p.recheck[slot] = ((unsigned long long)row << 24) | (31ull << 19) | (unsigned long long)((q0 + h * qb + 32 * g) >> 4);
+                  p.recheck[(size_t)((q0 + h * qb + 32 * g) >> 5) * p.recheck_cap + slot] = (unsigned long long)row;
               }
-              base += __popc(m);
             }
           }
         }
@@ -438,8 +423,11 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
   }
 }
 
-// One warp per re-check entry (row, group of 32 or 16 queries): exact distances from the packed codes, survivors
-// appended to their query's candidate buffer.
+// Re-check, one CTA column per 32-query group (blockIdx.x = group, blockIdx.y splits the group's list): every lane
+// keeps ITS query of the group in registers for the whole kernel, so an entry costs one row read instead of the row
+// plus the group's 32 query codes.  A warp takes 32 entries at a time: lane l loads entry l's row, then the 32 rows
+// are broadcast one after the other with shuffles and every lane tests its own query.  (Same scheme as
+// ham_recheck_kernel of hamming_tc.cu.)
 template <int W>
 __global__ void __launch_bounds__(256)
 ham4_recheck_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qcodes, int Q, long long idx_base,
@@ -447,16 +435,49 @@ ham4_recheck_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict_
                     const int* __restrict__ tq, unsigned long long* __restrict__ cand_buf, int* __restrict__ cand_cnt, int cap,
                     int* __restrict__ overflow) {
   const int lane = threadIdx.x & 31;
-  const int raw = *list_cnt;
-  if (raw > list_cap && blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+  const int grp = blockIdx.x;
+  const int raw = list_cnt[grp];
+  if (raw > list_cap && blockIdx.y == 0 && threadIdx.x == 0) *overflow = 1;
   const int n = min(raw, list_cap);
-  const int warps = gridDim.x * (blockDim.x >> 5);
-  for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
-    const unsigned long long ent = list[e];
-    const long long row = (long long)(ent >> 24);
-    const int qg0 = (int)(ent & 0x7ffffull) * 16;
-    const int width = (int)((ent >> 19) & 31ull) + 1;
-    ham4_recheck_group<W>(db, qcodes, Q, row, (unsigned long long)(idx_base + row), qg0, width, tq, cand_buf, cand_cnt, cap, lane);
+  if ((blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 >= n) return;   // no entries for this warp: leave before any load
+  const int qg = grp * 32 + lane;
+  const bool qvalid = qg < Q;
+  uint32_t qw[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) qw[w] = qvalid ? __ldg(qcodes + (long long)qg * W + w) : 0u;
+  const int my_tq = qvalid ? tq[qg] : -1;
+  const unsigned long long* mine = list + (size_t)grp * list_cap;
+  const int warps = gridDim.y * (blockDim.x >> 5);
+  for (int e0 = (blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; e0 < n; e0 += warps * 32) {
+    const int cnt = min(32, n - e0);
+    long long row = 0;
+    uint32_t x[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) x[w] = 0u;
+    if (lane < cnt) {
+      row = (long long)mine[e0 + lane];
+      const uint32_t* src = db + row * W;
+      if (W >= 4) {
+#pragma unroll
+        for (int w = 0; w < W; w += 4) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + w));
+          x[w] = v.x; x[(w + 1) % W] = v.y; x[(w + 2) % W] = v.z; x[(w + 3) % W] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < W; ++w) x[w] = __ldg(src + w);
+      }
+    }
+    for (int i = 0; i < cnt; ++i) {
+      int d = 0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) d += __popc(__shfl_sync(0xffffffffu, x[w], i) ^ qw[w]);
+      const long long ri = __shfl_sync(0xffffffffu, row, i);
+      if (d <= my_tq) {
+        const int slot = atomicAdd(cand_cnt + qg, 1);
+        if (slot < cap) cand_buf[(long long)qg * cap + slot] = ((unsigned long long)(unsigned)d << 40) | (unsigned long long)(idx_base + ri);
+      }
+    }
   }
 }
 
@@ -485,8 +506,8 @@ __global__ void ham4_threshold_image_kernel(int Q, int cols, int K, int qb, int 
                                             int* __restrict__ overflow) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;        // query slot
   const int T_raw = *tqmax;
+  if (col < cols && (col & 31) == 0) list_cnt[col >> 5] = 0;     // the re-check lists restart with every chunk
   if (col == 0) {
-    *list_cnt = 0;                                               // the re-check list restarts with every chunk
     *tqmax_next = 0;                                             // the compaction behind this chunk collects the next T here
     if (T_raw > T_MAX) *overflow = 1;                            // no room for the windows: the caller falls back
   }
@@ -613,7 +634,7 @@ ham4_compact_kernel(unsigned long long* __restrict__ buf, int* __restrict__ cnt,
 struct HamTc4Plan {
   int K, qb, b_block, col_blocks, cols, cap, first_rows, growth, stages;
   size_t smem_bytes;
-  size_t off_img, off_tq, off_cnt, off_flag, off_list, off_buf, total;
+  size_t off_img, off_tq, off_cnt, off_flag, off_gcnt, off_list, off_buf, total;
   int list_cap;
 };
 
@@ -665,9 +686,15 @@ HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
   p.off_img = o;  o += align256((size_t)p.col_blocks * p.b_block);
   p.off_tq = o;   o += align256((size_t)p.cols * sizeof(int));
   p.off_cnt = o;  o += align256((size_t)p.cols * sizeof(int));
-  p.off_flag = o; o += 256;                                   // [0] overflow flag, [1] re-check list length, [2], [3] T (by chunk parity)
-  p.list_cap = 1 << 22;
-  p.off_list = o; o += align256((size_t)p.list_cap * sizeof(unsigned long long));
+  p.off_flag = o; o += 256;                                   // [0] overflow flag, [2], [3] T (by chunk parity)
+  p.off_gcnt = o; o += align256((size_t)(p.cols / 32) * sizeof(int));   // re-check entries per 32-query group
+  // entries per group list: a chunk yields ~(growth - 1) * (k + ties) survivors per query, 32 queries per group
+  {
+    const long long need = 32ll * p.growth * (k + 32) * 4 / 3;
+    p.list_cap = 8192;
+    while (p.list_cap < need && p.list_cap < (1 << 16)) p.list_cap <<= 1;
+  }
+  p.off_list = o; o += align256((size_t)(p.cols / 32) * p.list_cap * sizeof(unsigned long long));
   p.off_buf = o;  o += align256((size_t)p.cols * p.cap * sizeof(unsigned long long));
   p.total = o;
   return p;
@@ -714,6 +741,7 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
   int* flag = reinterpret_cast<int*>(ws + p.off_flag);
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(ws + p.off_buf);
   unsigned long long* list = reinterpret_cast<unsigned long long*>(ws + p.off_list);
+  int* gcnt = reinterpret_cast<int*>(ws + p.off_gcnt);
 
   SB_CUDA_TRY(cudaMemsetAsync(img, 0, (size_t)p.col_blocks * p.b_block, st));
   {
@@ -763,12 +791,12 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
       sb::count_launch();
       if (int rc = sb::check_launch("ham4_seed_kernel")) return rc;
     } else {
-      ham4_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.K, p.qb, p.b_block, tq, T_cur, T_next, img, flag + 1, flag);
+      ham4_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.K, p.qb, p.b_block, tq, T_cur, T_next, img, gcnt, flag);
       sb::count_launch();
       if (int rc = sb::check_launch("ham4_threshold_image_kernel")) return rc;
       HamTc4Params hp;
       hp.db = db; hp.U = U; hp.W = W; hp.G = 1; hp.ksteps = 0; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
-      hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.tqmax = T_cur; hp.recheck = list; hp.recheck_cnt = flag + 1;
+      hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.tqmax = T_cur; hp.recheck = list; hp.recheck_cnt = gcnt;
       hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
       hp.idx_base = idx_base; hp.stages = p.stages; hp.qb = p.qb; hp.b_block = p.b_block;
       const long long n_tiles = (len + 3) / 4;
@@ -785,11 +813,16 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
         if (int rc = sb::check_launch("ham_filter_fp4_kernel")) return rc;
       }
       sb::ProfScope prof("ham_recheck_kernel", st);
-      const int blocks = 8 * sms;                               // 64 warps per SM: the re-check is load-latency bound
-      if (W == 8) ham4_recheck_kernel<8><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
-      else if (W == 4) ham4_recheck_kernel<4><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
-      else if (W == 2) ham4_recheck_kernel<2><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
-      else ham4_recheck_kernel<1><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, flag + 1, p.list_cap, tq, buf, cnt, p.cap, flag);
+      // one CTA column per 32-query group, split so that the grid fills the GPU about four times over
+      const int groups = (Q + 31) / 32;
+      int split = (4 * sms + groups - 1) / groups;
+      if (split < 1) split = 1;
+      if (split > 32) split = 32;
+      const dim3 blocks((unsigned)groups, (unsigned)split);
+      if (W == 8) ham4_recheck_kernel<8><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
+      else if (W == 4) ham4_recheck_kernel<4><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
+      else if (W == 2) ham4_recheck_kernel<2><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
+      else ham4_recheck_kernel<1><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
       sb::count_launch();
       if (int rc = sb::check_launch("ham4_recheck_kernel")) return rc;
     }
