@@ -92,8 +92,9 @@ struct HamTc4Params {
   const int* tqmax;            // T: upper bound of the thresholds (device scalar)
   unsigned long long* recheck; // per 32-query group: recheck_cap rows to re-check
   int qb, b_block;             // columns per block (multiple of 32, <= 192; 3 * qb queries), bytes of one block image
-  int* recheck_cnt;            // entries per 32-query group
+  int* recheck_cnt;            // entries per 32-query group (by_group) / of the one list
   int recheck_cap;
+  int by_group;                // per-group lists (many queries) or one list of (row << 24 | 31 << 19 | group first query / 16) entries
   unsigned long long* cand_buf;
   int* cand_cnt;
   int cap;
@@ -129,11 +130,33 @@ __device__ __forceinline__ void umma_fp4(uint32_t d_tmem, uint64_t adesc, uint64
       : "memory");
 }
 
+// One re-check entry = (row, group of up to 32 queries starting at `qg0`): exact distances from the packed codes
+// (see hamming_tc.cu for why survivors are not decoded from the accumulator registers).
+template <int W>
+__device__ __forceinline__ void ham4_recheck_group(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qcodes, int Q,
+                                                   long long row, unsigned long long row_key, int qg0, int width,
+                                                   const int* __restrict__ tq, unsigned long long* cand_buf, int* cand_cnt,
+                                                   int cap, int lane) {
+  uint32_t x[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) x[w] = __ldg(db + row * W + w);
+  const int qg = qg0 + lane;
+  if (lane < width && qg < Q) {
+    int d = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) d += __popc(x[w] ^ __ldg(qcodes + (long long)qg * W + w));
+    if (d <= tq[qg]) {
+      const int slot = atomicAdd(cand_cnt + qg, 1);
+      if (slot < cap) cand_buf[(long long)qg * cap + slot] = ((unsigned long long)(unsigned)d << 40) | row_key;
+    }
+  }
+}
+
 // W = code words per row (1, 2, 4, 8); 3 x (W / 2 MMAs of K = 64 elements + the threshold step) per tile.
 // ONE query block is resident at a time, its successor streams into the second buffer.  The expansion of a table
 // tile is two instructions per 8 elements, so re-expanding it for every query block is cheap and the table stays
 // L2 / HBM resident.
-template <int W>
+template <int W, bool BY_GROUP>
 __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms: align by hand
@@ -383,7 +406,29 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
         for (int g = 0; g < GRP; ++g)
 #pragma unroll
           for (int h = 0; h < QPC; ++h) any |= hit[g][h];
-        if (any) {                                                 // rare: survivors in this (warp, tile)
+        if (any && !BY_GROUP) {                                    // one list, one atomic per (warp, tile) with survivors
+          int total = 0;
+#pragma unroll
+          for (int g = 0; g < GRP; ++g)
+#pragma unroll
+            for (int h = 0; h < QPC; ++h) total += __popc(hit[g][h]);
+          int base = 0;
+          if (lane == 0) base = atomicAdd(p.recheck_cnt, total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+          for (int g = 0; g < GRP; ++g) {
+#pragma unroll
+            for (int h = 0; h < QPC; ++h) {
+              const unsigned m = hit[g][h];
+              if ((m >> lane) & 1u) {
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < p.recheck_cap)
+                  p.recheck[slot] = ((unsigned long long)row << 24) | (31ull << 19) | (unsigned long long)((q0 + h * qb + 32 * g) >> 4);
+              }
+              base += __popc(m);
+            }
+          }
+        } else if (any) {                                          // rare: survivors in this (warp, tile)
           // one slot reservation per (group, field) WITH survivors, all issued at once: lane c reserves for combination
           // c = g * 3 + h (serial atomics would cost a global round trip each)
           int mine_cnt = 0;
@@ -420,6 +465,29 @@ __global__ void __launch_bounds__(THREADS, 1) ham_filter_fp4_kernel(const HamTc4
   if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// Few queries (<= 1024: the per-rank share of a batch on 4-8 GPUs): ONE unordered list of (row, 32-query group)
+// entries, one warp per entry -- every entry re-reads its group's query codes (1 KB from L2), but the kernel is a
+// few microseconds shorter than the per-group one when there are only a handful of groups.
+template <int W>
+__global__ void __launch_bounds__(256)
+ham4_recheck_flat_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qcodes, int Q, long long idx_base,
+                    const unsigned long long* __restrict__ list, const int* __restrict__ list_cnt, int list_cap,
+                    const int* __restrict__ tq, unsigned long long* __restrict__ cand_buf, int* __restrict__ cand_cnt, int cap,
+                    int* __restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const int raw = *list_cnt;
+  if (raw > list_cap && blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+  const int n = min(raw, list_cap);
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
+    const unsigned long long ent = list[e];
+    const long long row = (long long)(ent >> 24);
+    const int qg0 = (int)(ent & 0x7ffffull) * 16;
+    const int width = (int)((ent >> 19) & 31ull) + 1;
+    ham4_recheck_group<W>(db, qcodes, Q, row, (unsigned long long)(idx_base + row), qg0, width, tq, cand_buf, cand_cnt, cap, lane);
   }
 }
 
@@ -635,7 +703,7 @@ struct HamTc4Plan {
   int K, qb, b_block, col_blocks, cols, cap, first_rows, growth, stages;
   size_t smem_bytes;
   size_t off_img, off_tq, off_cnt, off_flag, off_gcnt, off_list, off_buf, total;
-  int list_cap;
+  int list_cap, by_group;
 };
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -689,12 +757,16 @@ HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
   p.off_flag = o; o += 256;                                   // [0] overflow flag, [2], [3] T (by chunk parity)
   p.off_gcnt = o; o += align256((size_t)(p.cols / 32) * sizeof(int));   // re-check entries per 32-query group
   // entries per group list: a chunk yields ~(growth - 1) * (k + ties) survivors per query, 32 queries per group
-  {
+  p.by_group = Q > SMALL_Q;
+  if (p.by_group) {
     const long long need = 32ll * p.growth * (k + 32) * 4 / 3;
     p.list_cap = 8192;
     while (p.list_cap < need && p.list_cap < (1 << 16)) p.list_cap <<= 1;
+    p.off_list = o; o += align256((size_t)(p.cols / 32) * p.list_cap * sizeof(unsigned long long));
+  } else {
+    p.list_cap = 1 << 21;                                      // one list for all (<= 1024) queries
+    p.off_list = o; o += align256((size_t)p.list_cap * sizeof(unsigned long long));
   }
-  p.off_list = o; o += align256((size_t)(p.cols / 32) * p.list_cap * sizeof(unsigned long long));
   p.off_buf = o;  o += align256((size_t)p.cols * p.cap * sizeof(unsigned long long));
   p.total = o;
   return p;
@@ -765,10 +837,11 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
     if (P >= NG) P = 1;
   }
 
-  void (*kernel)(const HamTc4Params) = W == 8   ? ham_filter_fp4_kernel<8>
-                                       : W == 4 ? ham_filter_fp4_kernel<4>
-                                       : W == 2 ? ham_filter_fp4_kernel<2>
-                                                : ham_filter_fp4_kernel<1>;
+  void (*kernel)(const HamTc4Params) =
+      p.by_group ? (W == 8 ? ham_filter_fp4_kernel<8, true> : W == 4 ? ham_filter_fp4_kernel<4, true>
+                    : W == 2 ? ham_filter_fp4_kernel<2, true> : ham_filter_fp4_kernel<1, true>)
+                 : (W == 8 ? ham_filter_fp4_kernel<8, false> : W == 4 ? ham_filter_fp4_kernel<4, false>
+                    : W == 2 ? ham_filter_fp4_kernel<2, false> : ham_filter_fp4_kernel<1, false>);
   SB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
   SB_CUDA_TRY(cudaFuncSetAttribute(ham4_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(p.cap * sizeof(unsigned long long))));
@@ -796,7 +869,7 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
       if (int rc = sb::check_launch("ham4_threshold_image_kernel")) return rc;
       HamTc4Params hp;
       hp.db = db; hp.U = U; hp.W = W; hp.G = 1; hp.ksteps = 0; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
-      hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.tqmax = T_cur; hp.recheck = list; hp.recheck_cnt = gcnt;
+      hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.tqmax = T_cur; hp.recheck = list; hp.recheck_cnt = gcnt; hp.by_group = p.by_group;
       hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
       hp.idx_base = idx_base; hp.stages = p.stages; hp.qb = p.qb; hp.b_block = p.b_block;
       const long long n_tiles = (len + 3) / 4;
@@ -813,6 +886,15 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
         if (int rc = sb::check_launch("ham_filter_fp4_kernel")) return rc;
       }
       sb::ProfScope prof("ham_recheck_kernel", st);
+      if (!p.by_group) {
+        const int blocks = 8 * sms;                             // 64 warps per SM: load-latency bound
+        if (W == 8) ham4_recheck_flat_kernel<8><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
+        else if (W == 4) ham4_recheck_flat_kernel<4><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
+        else if (W == 2) ham4_recheck_flat_kernel<2><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
+        else ham4_recheck_flat_kernel<1><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
+        sb::count_launch();
+        if (int rc = sb::check_launch("ham4_recheck_flat_kernel")) return rc;
+      } else {
       // one CTA column per 32-query group, split so that the grid fills the GPU about four times over
       const int groups = (Q + 31) / 32;
       int split = (4 * sms + groups - 1) / groups;
@@ -825,6 +907,7 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
       else ham4_recheck_kernel<1><<<blocks, 256, 0, st>>>(db, q, Q, idx_base, list, gcnt, p.list_cap, tq, buf, cnt, p.cap, flag);
       sb::count_launch();
       if (int rc = sb::check_launch("ham4_recheck_kernel")) return rc;
+      }
     }
     done += len;
     const int final = (done >= NG) ? 1 : 0;
