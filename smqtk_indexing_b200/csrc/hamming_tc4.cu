@@ -757,14 +757,14 @@ HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
   p.off_flag = o; o += 256;                                   // [0] overflow flag, [2], [3] T (by chunk parity)
   p.off_gcnt = o; o += align256((size_t)(p.cols / 32) * sizeof(int));   // re-check entries per 32-query group
   // entries per group list: a chunk yields ~(growth - 1) * (k + ties) survivors per query, 32 queries per group
-  p.by_group = Q > SMALL_Q;
+  p.by_group = Q > SMALL_Q || k >= 32;                         // (many survivors per query: the group's queries in registers pay)
   if (p.by_group) {
     const long long need = 32ll * p.growth * (k + 32) * 4 / 3;
     p.list_cap = 8192;
     while (p.list_cap < need && p.list_cap < (1 << 16)) p.list_cap <<= 1;
     p.off_list = o; o += align256((size_t)(p.cols / 32) * p.list_cap * sizeof(unsigned long long));
   } else {
-    p.list_cap = 1 << 21;                                      // one list for all (<= 1024) queries
+    p.list_cap = 1 << 21;                                      // one list for all (<= 1024) queries, k < 32
     p.off_list = o; o += align256((size_t)p.list_cap * sizeof(unsigned long long));
   }
   p.off_buf = o;  o += align256((size_t)p.cols * p.cap * sizeof(unsigned long long));
