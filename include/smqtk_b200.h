@@ -150,9 +150,11 @@ SB_API int sb_hamming_scan_tc(const uint32_t* db, int64_t U, int32_t W,
                        const uint32_t* q, int32_t Q, int32_t k, int64_t idx_base,
                        uint64_t* keys_out, int32_t* overflow_out,
                        void* workspace, size_t workspace_bytes, void* stream);
-/* The same scan with PACKED FP4 operands (hamming_tc4.cu): bits -> +-1 E2M1, tcgen05.mma kind::mxf4.block_scale
- * (every block scale 2^0), K = 64 per MMA at the cycle count of kind::f8f6f4's K = 32 -- half the tensor-pipe
- * time, the same exact integer distances and the same keys.  Same contract as sb_hamming_scan_tc. */
+/* The same scan with PACKED FP4 operands (hamming_tc4.cu; the one the host side calls by default): bits -> +-1
+ * E2M1, tcgen05.mma kind::mxf4.block_scale, K = 64 per MMA at the cycle count of kind::f8f6f4's K = 32, three
+ * queries per FP32 accumulator column (8-bit fields; the b / c queries' products scaled by 2^8 / 2^16 through the
+ * block scales).  The same exact integer distances, the same keys, the same overflow flag (also raised when a
+ * threshold above 252 leaves no room for the field windows).  Same contract as sb_hamming_scan_tc; k <= 256. */
 SB_API int sb_hamming_scan_tc4_supported(int64_t U, int32_t W, int32_t Q, int32_t k);
 SB_API size_t sb_hamming_scan_tc4_workspace_bytes(int64_t U, int32_t W, int32_t Q, int32_t k);
 SB_API int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t* q, int32_t Q, int32_t k,
