@@ -234,6 +234,17 @@ def test_hamming_tensor_core_scan_far_codes_and_mixed_thresholds(dev, tc_fmt):
     keys = dev.hamming_scan_keys(dev.codes_to_device(table), dev.codes_to_device(q), k, variant=dev.SCAN_VARIANT_TC)
     d, i = (t.cpu().numpy() for t in dev.topk_merge(keys.unsqueeze(0).contiguous()))
     assert np.array_equal(d, od) and np.array_equal(i, oi)
+    # EVERY row far from every query (thresholds of 240 ... 256 bits: no room for the 8-bit windows above 252 --
+    # the FP4 kernel must raise the flag rather than answer) and a batch whose thresholds straddle that limit
+    for flip in (0.0, 0.03):
+        bits = (~centre) ^ (rng.rand(70000, b) < flip)
+        if flip:
+            bits[:35000] = rng.rand(35000, b) > 0.5
+        table = O.pack_codes(bits[rng.permutation(len(bits))], W)
+        od, oi = O.hamming_topk(table, q, k)
+        keys = dev.hamming_scan_keys(dev.codes_to_device(table), dev.codes_to_device(q), k, variant=dev.SCAN_VARIANT_TC)
+        d, i = (t.cpu().numpy() for t in dev.topk_merge(keys.unsqueeze(0).contiguous()))
+        assert np.array_equal(d, od) and np.array_equal(i, oi)
 
 
 def test_hamming_scan_dispatch_and_overflow_fallback(dev):
