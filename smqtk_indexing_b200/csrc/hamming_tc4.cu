@@ -568,14 +568,16 @@ __global__ void ham4_query_image_kernel(const uint32_t* __restrict__ q, int Q, i
 // B_syn of every query slot: 64 E2M1 slots that sum to the field's offset (|s| <= 381: at most 63 slots of 6 plus
 // the remainder), see the header:  a: tq - K/2 + beta,  b: gamma - tq + K/2,  c: tq - K/2 + beta - 128.
 // Padding slots (their data nibbles are zero) sit inside their window on the failing side.
+// One thread per (slot, 8-element word): the kernel runs between every two chunks, its latency is on the critical path.
 __global__ void ham4_threshold_image_kernel(int Q, int cols, int K, int qb, int b_block, const int* __restrict__ tq,
                                             const int* __restrict__ tqmax, int* __restrict__ tqmax_next,
                                             unsigned char* __restrict__ img, int* __restrict__ list_cnt,
                                             int* __restrict__ overflow) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;        // query slot
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = tid >> 3, wd = tid & 7;                       // query slot, word (8 slots of 4 bits) of its 64 B_syn slots
   const int T_raw = *tqmax;
-  if (col < cols && (col & 31) == 0) list_cnt[col >> 5] = 0;     // the re-check lists restart with every chunk
-  if (col == 0) {
+  if (col < cols && wd == 0 && (col & 31) == 0) list_cnt[col >> 5] = 0;   // the re-check lists restart with every chunk
+  if (tid == 0) {
     *tqmax_next = 0;                                             // the compaction behind this chunk collects the next T here
     if (T_raw > T_MAX) *overflow = 1;                            // no room for the windows: the caller falls back
   }
@@ -596,24 +598,19 @@ __global__ void ham4_threshold_image_kernel(int Q, int cols, int K, int qb, int 
   const int n6 = mag / 6, rem = mag - 6 * n6;
   // E2M1 magnitude codes: 1.0 = 2, 2.0 = 4, 3.0 = 5, 4.0 = 6, 6.0 = 7; remainder 5 = 4 + 1 (two slots)
   const uint32_t rem_code[6] = {0u, 2u, 4u, 5u, 6u, 6u};
-  uint32_t words[8];
+  uint32_t v = 0u;
 #pragma unroll
-  for (int wd = 0; wd < 8; ++wd) {
-    uint32_t v = 0u;
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const int slot = wd * 8 + b;
-      uint32_t nib = 0u;
-      if (slot < n6) nib = 7u | sign;
-      else if (slot == n6 && rem) nib = rem_code[rem] | sign;
-      else if (slot == n6 + 1 && rem == 5) nib = 2u | sign;
-      v |= nib << (4 * b);
-    }
-    words[wd] = v;
+  for (int b = 0; b < 8; ++b) {
+    const int slot = wd * 8 + b;
+    uint32_t nib = 0u;
+    if (slot < n6) nib = 7u | sign;
+    else if (slot == n6 && rem) nib = rem_code[rem] | sign;
+    else if (slot == n6 + 1 && rem == 5) nib = 2u | sign;
+    v |= nib << (4 * b);
   }
+  // B_syn of a field: two K-chunk planes of [qb x 16 B]; word wd of the 64 slots = plane wd / 4, word wd % 4
   unsigned char* base = img + (size_t)jb * b_block + (size_t)qb * (128 * QPC) + (size_t)h * qb * 32;
-  *reinterpret_cast<uint4*>(base + n * 16) = make_uint4(words[0], words[1], words[2], words[3]);
-  *reinterpret_cast<uint4*>(base + qb * 16 + n * 16) = make_uint4(words[4], words[5], words[6], words[7]);
+  reinterpret_cast<uint32_t*>(base + (size_t)(wd >> 2) * qb * 16 + n * 16)[wd & 3] = v;
 }
 
 __global__ void ham4_init_kernel(int cols, int K, int* __restrict__ tq, int* __restrict__ cnt, int* __restrict__ flags) {
@@ -741,7 +738,11 @@ HamTc4Plan make_plan(int32_t W, int32_t Q, int32_t k) {
   p.cap = 4096;
   p.growth = growth_for(Q);
   while (p.cap < 4 * (p.growth + 1) * k) p.cap <<= 1;
-  p.first_rows = Q <= SMALL_Q ? 1024 : 256;                    // dense seed chunk: at least 8 k rows (its sort costs Q * rows)
+  p.first_rows = Q <= SMALL_Q ? 512 : 256;                     // dense seed chunk: at least 8 k rows (its sort costs Q * rows)
+  if (const char* e = getenv("SB_TC4_FIRST_ROWS")) {            // tuning knob
+    const int r = atoi(e);
+    if (r >= 32 && r <= 4096 && (r & (r - 1)) == 0) p.first_rows = r;
+  }
   while (p.first_rows < 8 * k) p.first_rows <<= 1;
   if (p.first_rows > p.cap) p.first_rows = p.cap;
   p.stages = MAX_STAGES;
@@ -864,7 +865,7 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
       sb::count_launch();
       if (int rc = sb::check_launch("ham4_seed_kernel")) return rc;
     } else {
-      ham4_threshold_image_kernel<<<(p.cols + 255) / 256, 256, 0, st>>>(Q, p.cols, p.K, p.qb, p.b_block, tq, T_cur, T_next, img, gcnt, flag);
+      ham4_threshold_image_kernel<<<(p.cols * 8 + 255) / 256, 256, 0, st>>>(Q, p.cols, p.K, p.qb, p.b_block, tq, T_cur, T_next, img, gcnt, flag);
       sb::count_launch();
       if (int rc = sb::check_launch("ham4_threshold_image_kernel")) return rc;
       HamTc4Params hp;
