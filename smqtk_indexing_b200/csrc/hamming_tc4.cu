@@ -8,9 +8,9 @@
 // HALF the tensor-pipe time for the same dot products, still exact: every product is +-1 and the FP32
 // accumulator holds the integers.  A 256-bit code is ONE 128-byte SWIZZLE_128B row (4 MMAs, start address
 // advancing 32 bytes), so a tile has one K group instead of two.
-//   * Block scaling cannot be switched off: every UE8M0 block scale is 2^0.  The scale factors live in tensor
-//     memory; the whole 16-column SF window is filled with 0x7F in every lane with tcgen05.st once per CTA, so
-//     the (sub-partition replicated) SF layout never matters.  Instruction descriptor: a/b format = 1
+//   * Block scaling cannot be switched off, so it is put to use (below).  The scale factors live in tensor memory;
+//     every SF window is filled with ONE value in every byte of every lane with tcgen05.st once per CTA, so the
+//     (sub-partition replicated) SF layout never matters.  Instruction descriptor: a/b format = 1
 //     (MXF4Format::E2M1; 5 is the kind::mxf8f6f4 code and raises "illegal instruction"), scale format UE8M0.
 //   * Accumulators are FP32 only, and every accumulator leaves tensor memory through tcgen05.ld at 64 B/clk/SM:
 //     with one query per column that read sets the pace (measured: profiles/r2_ham_fp4_full.md).  So every
@@ -40,7 +40,7 @@
 //     the elements inside a row, identically for table rows and query rows -- a dot product does not care.
 //   * Threshold steps: A_syn = 64 x (+1), B_syn = up to 64 E2M1 slots (values 6, 4, 3, 2, 1) summing to the field's offset.
 //   * Survivor groups are 32 columns = 32 queries of each field, flagged separately; every 32-query group has its own
-//     re-check list of rows.
+//     re-check list of rows (batches of <= 1024 queries with k < 32: one list of (row, group) entries, see make_plan).
 // Warp roles: 0-15 epilogue (lane quadrant x tile parity x column half), 16 MMA issue + TMEM alloc, 17 B loader,
 // 18-21 producers (one warp per stage of the A ring).
 #include <cuda_fp16.h>
@@ -83,7 +83,7 @@ constexpr int CP_THREADS = 256;            // 7-8 compaction CTAs per SM: most q
 struct HamTc4Params {
   const uint32_t* db;          // u32[U][W]
   long long U;
-  int W, G, ksteps;            // G = 128-byte K groups per row, ksteps = MMAs per group
+  int W;                       // code words per row
   long long vg0, vg1;          // virtual granules of this chunk
   long long NG, P;             // physical granule = (virtual * P) mod NG
   int col_blocks, cb_per;      // query blocks in total / per blockIdx.y
@@ -99,7 +99,7 @@ struct HamTc4Params {
   int* cand_cnt;
   int cap;
   long long idx_base;
-  int stages;
+  int stages;                  // stages of the A ring in use (2 or 4)
 };
 
 // 32 code bits -> 32 E2M1 elements (16 bytes): +1.0 = 0x2, -1.0 = 0xA.  Output word s holds the bits
@@ -869,7 +869,7 @@ int sb_hamming_scan_tc4(const uint32_t* db, int64_t U, int32_t W, const uint32_t
       sb::count_launch();
       if (int rc = sb::check_launch("ham4_threshold_image_kernel")) return rc;
       HamTc4Params hp;
-      hp.db = db; hp.U = U; hp.W = W; hp.G = 1; hp.ksteps = 0; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
+      hp.db = db; hp.U = U; hp.W = W; hp.vg0 = done; hp.vg1 = done + len; hp.NG = NG; hp.P = P;
       hp.col_blocks = p.col_blocks; hp.image = img; hp.tq = tq; hp.tqmax = T_cur; hp.recheck = list; hp.recheck_cnt = gcnt; hp.by_group = p.by_group;
       hp.recheck_cap = p.list_cap; hp.cand_buf = buf; hp.cand_cnt = cnt; hp.cap = p.cap;
       hp.idx_base = idx_base; hp.stages = p.stages; hp.qb = p.qb; hp.b_block = p.b_block;
