@@ -222,7 +222,7 @@ def hamming_scan_tc_supported(U: int, W: int, Q: int, k: int) -> bool:
 #: operand format of the tensor-core scan: "fp4" (packed E2M1, kind::mxf4: half the tensor-pipe time per MMA;
 #: several queries share one FP32 accumulator column so the tensor-memory read of the epilogue does not grow --
 #: the default) or "fp8" (E4M3, kind::f8f6f4, FP16 accumulators read packed); same keys.  Shapes
-#: the FP4 kernel does not take (k > 256) run the FP8 kernel
+#: neither kernel takes (k > 256, codes wider than 256 bits) run the XOR/POPC scan
 TC_SCAN_FORMAT = os.environ.get("SB_TC_SCAN_FORMAT", "fp4")
 
 
