@@ -521,3 +521,54 @@ def test_simple_rp_functor_config_and_errors():
     assert not f.has_model()
     with pytest.raises(RuntimeError):
         f.get_hash(np.zeros(4))
+
+
+# ------------------------------------------------------------------ FP4 scan: the 8-bit field windows, modelled on the host
+def _fp4_window_model(T, tq, d, K=256):
+    """Arithmetic of hamming_tc4.cu's epilogue for ONE accumulator column (three queries a, b, c), restated with
+    numpy: the accumulator the MMAs produce, `v = bits(acc +rz 1.5 * 2^24)`, and the three window tests.
+    tq, d: int arrays [..., 3].  Returns (pass_a, pass_b, pass_c) as the kernel would flag them."""
+    beta, gamma = (254 - T) & ~1, T + 1
+    t = np.minimum(tq, T)
+    u_a = t[..., 0] - d[..., 0] + beta
+    w_b = d[..., 1] - t[..., 1] + gamma
+    u_c = t[..., 2] - d[..., 2] + beta
+    acc = (u_a + 256 * w_b + 65536 * (u_c - 128)).astype(np.int64)      # exact in FP32: |acc| < 2^25 here, see below
+    x = acc + 25165824                                                   # acc + 1.5 * 2^24
+    # round toward zero to FP32: ulp 2 in [2^24, 2^25), ulp 1 in [2^23, 2^24), ...
+    xf = np.where(x >= (1 << 24), (x >> 1) << 1, x).astype(np.float64)
+    v = xf.astype(np.float32).view(np.uint32).astype(np.uint64)
+    w1, w9 = (v << np.uint64(1)) & np.uint64(0xffffffff), (v << np.uint64(9)) & np.uint64(0xffffffff)
+    under = (w1 >> np.uint64(16)) < 0x9700
+    a_min, c_min, b_lim = (beta >> 1) << 9, beta << 8, (gamma + 1) << 8
+    pa = under | ((w9 & np.uint64(0xffff)) >= a_min)
+    pb = under | ((w1 & np.uint64(0xffff)) < b_lim)
+    pc = under | ((w9 >> np.uint64(16)) >= c_min)
+    return pa, pb, pc
+
+
+def test_fp4_scan_field_windows_never_lose_a_survivor():
+    """Whatever the three queries' distances are -- including distances that push a field out of its window
+    (borrow into the b field, carry into the c field, exponent drop of the c field) -- a pair with d <= tq is
+    flagged for the re-check; and while every field is inside its window the test is exact."""
+    rng = np.random.RandomState(5)
+    for T in (0, 1, 7, 64, 100, 127, 128, 200, 251, 252):
+        n = 200000
+        tq = rng.randint(0, T + 1, size=(n, 3))
+        d = rng.randint(0, 257, size=(n, 3))
+        # edge values: on / next to the threshold, the extremes of the distance range
+        edge = rng.randint(0, 6, size=(n, 3))
+        d = np.where(edge == 0, tq, d)
+        d = np.where(edge == 1, np.minimum(tq + 1, 256), d)
+        d = np.where(edge == 2, rng.choice([0, 255, 256], size=(n, 3)), d)
+        tq[:1000] = T
+        tq[1000:2000] = 0
+        passed = _fp4_window_model(T, tq, d)
+        truth = d <= tq
+        beta, gamma = (254 - T) & ~1, T + 1
+        inside = np.stack([(tq[:, 0] - d[:, 0] + beta >= 0), (d[:, 1] - tq[:, 1] + gamma <= 255),
+                           (tq[:, 2] - d[:, 2] + beta >= 0)], axis=1).all(axis=1)
+        for h in range(3):
+            assert not (truth[:, h] & ~passed[h]).any(), (T, h)          # never a false negative
+            assert np.array_equal(passed[h][inside], truth[inside, h]), (T, h)   # exact inside the windows
+        assert inside.mean() > 0.2                                       # (the sample covers both regimes)
