@@ -783,7 +783,7 @@ long long gcd_ll(long long a, long long b) {
 extern "C" {
 
 int sb_hamming_scan_tc4_supported(int64_t U, int32_t W, int32_t Q, int32_t k) {
-  return U >= 1 && (W == 1 || W == 2 || W == 4 || W == 8) && Q >= 1 && k >= 1 && k <= 256 && U < (1ll << 38) && Q < (1 << 22);
+  return U >= 1 && (W == 1 || W == 2 || W == 4 || W == 8) && Q >= 1 && k >= 1 && k <= 256 && U < (1ll << 38) && Q <= (1 << 21);   // (Q / 32 is a grid.y)
 }
 
 size_t sb_hamming_scan_tc4_workspace_bytes(int64_t U, int32_t W, int32_t Q, int32_t k) {
