@@ -8,7 +8,7 @@ Headline benchmark: LSH kNN queries/s @k=10 over 10M x 256-bit ITQ codes
     python bench.py --impl reference --gpus N --steps K ...   # reference CPU path (rank 0 only)
 
 One "step" = one batch of Q queries through the whole query path
-(sb_itq_hash_tc -> sb_hamming_scan_tc over the unique-code table -> candidate
+(sb_itq_hash_tc -> sb_hamming_scan_tc4 over the unique-code table -> candidate
 expansion -> sb_rerank -> sb_rerank_select), i.e. LSHNearestNeighborIndex.nn
 (reference smqtk_indexing/impls/nn_index/lsh.py:452-519) for Q queries.
 
@@ -16,10 +16,12 @@ expansion -> sb_rerank -> sb_rerank_select), i.e. LSHNearestNeighborIndex.nn
           default path (the pipeline replayed as one CUDA graph once the batch shape repeats)
   e2e     the same through the public plugin call LSHNearestNeighborIndex.nn_batch
           with pinned HOST query buffers in and host result arrays out
-  roofline  the dominant kernel (ham_filter_tc_kernel, tcgen05 +-1 FP8 dot products): algorithmic
-          flops 2*Q*U*b per step over its CUDA-event duration -- measured in a second, kernel-by-kernel
-          pass of the same K steps --, against a cuBLASLt FP8 GEMM timed in this very run and 2 x the
-          measured bf16 figure; `rerank` and `single_query_scan` carry the HBM-bound kernels' GB/s
+  roofline  the dominant kernel (ham_filter_tc_kernel: tcgen05 +-1 dot products, packed FP4 operands by
+          default, FP8 with SB_TC_SCAN_FORMAT=fp8): algorithmic flops 2*Q*U*b per step over its CUDA-event
+          duration -- measured in a second, kernel-by-kernel pass of the same K steps --, against a cuBLASLt
+          GEMM of the same operand format timed in this very run (2 x the measured bf16 figure and the
+          tensor-memory read floor beside it); `rerank` and `single_query_scan` carry the HBM-bound
+          kernels' GB/s
   cpu_baseline  the reference's algorithm (oracle/ref_port.py, literal port) on
           this box's host cores, bounded sample
   parity_checked  8 queries of the timed batch re-derived with plain torch (float64 hash, byte-LUT
